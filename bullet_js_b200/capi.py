@@ -1,0 +1,147 @@
+"""ctypes view of include/bullet_b200.h and the loader for libbulletb200.so.
+
+There is NO CPU fallback: `load()` raises if the CUDA library has not been built
+(run `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C bullet_js_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import codec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libbulletb200.so")
+
+ABI_VERSION = 1
+
+OK, ERR_ARG, ERR_CUDA, ERR_DOMAIN, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5
+_ERR_NAMES = {
+    ERR_ARG: "BB_ERR_ARG", ERR_CUDA: "BB_ERR_CUDA", ERR_DOMAIN: "BB_ERR_DOMAIN",
+    ERR_CAPACITY: "BB_ERR_CAPACITY", ERR_STATE: "BB_ERR_STATE",
+}
+
+
+class BBConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("device", C.c_int32), ("n_fields", C.c_uint32),
+        ("local_peer", C.c_uint32), ("capacity", C.c_uint64), ("rank_object", C.c_uint64),
+        ("rank_true", C.c_uint64), ("rank_false", C.c_uint64), ("rank_nan", C.c_uint64),
+        ("flags", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class BBBatch(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64), ("path_id", C.c_void_p), ("head", C.c_void_p),
+        ("clk", C.c_void_p), ("val", C.c_void_p),
+    ]
+
+
+class BBChanges(C.Structure):
+    _fields_ = [
+        ("cap", C.c_uint64), ("decision", C.c_void_p), ("n_changes", C.c_void_p),
+        ("idx", C.c_void_p), ("head", C.c_void_p), ("clk", C.c_void_p), ("val", C.c_void_p),
+    ]
+
+
+class BulletB200Error(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}")
+
+
+# Every symbol include/bullet_b200.h declares (tests check the .so exports them all).
+EXPORTS = [
+    "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
+    "bb_table_load", "bb_table_read", "bb_table_clear",
+    "bb_merge_batch", "bb_merge_batch_dev",
+    "bb_launch_count", "bb_last_phase_ms",
+]
+
+_lib = None
+
+
+def load():
+    """dlopen libbulletb200.so (no GPU needed just to load it)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension must be built "
+            "(__graft_entry__.build()); bullet_js_b200 has no CPU fallback"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    lib.bb_abi_version.restype = i32
+    lib.bb_create.argtypes = [C.POINTER(BBConfig), C.POINTER(vp)]
+    lib.bb_create.restype = i32
+    lib.bb_destroy.argtypes = [vp]
+    lib.bb_destroy.restype = i32
+    lib.bb_last_error.argtypes = [vp]
+    lib.bb_last_error.restype = C.c_char_p
+    lib.bb_table_load.argtypes = [vp, u64, vp, vp]
+    lib.bb_table_load.restype = i32
+    lib.bb_table_read.argtypes = [vp, u64, vp, vp, i32]
+    lib.bb_table_read.restype = i32
+    lib.bb_table_clear.argtypes = [vp]
+    lib.bb_table_clear.restype = i32
+    lib.bb_merge_batch.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges)]
+    lib.bb_merge_batch.restype = i32
+    lib.bb_merge_batch_dev.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges), vp]
+    lib.bb_merge_batch_dev.restype = i32
+    lib.bb_launch_count.argtypes = [vp]
+    lib.bb_launch_count.restype = u64
+    lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]
+    lib.bb_last_phase_ms.restype = C.c_double
+    _lib = lib
+    return lib
+
+
+def make_config(capacity, n_fields=codec.MAX_FIELDS, local_peer=0, device=0, flags=0,
+                rank_object=0, rank_true=0, rank_false=0, rank_nan=0) -> BBConfig:
+    return BBConfig(
+        abi_version=ABI_VERSION, device=device, n_fields=n_fields, local_peer=local_peer,
+        capacity=capacity, rank_object=rank_object, rank_true=rank_true,
+        rank_false=rank_false, rank_nan=rank_nan, flags=flags, reserved=0,
+    )
+
+
+def _ptr(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def batch_struct(b: codec.Batch) -> BBBatch:
+    assert b.path_id.dtype == np.uint64 and b.head.dtype == codec.HEAD_DTYPE
+    assert b.clk.dtype == np.uint32 and b.val.dtype == np.uint64
+    return BBBatch(n=b.n, path_id=_ptr(b.path_id), head=_ptr(b.head), clk=_ptr(b.clk),
+                   val=_ptr(b.val))
+
+
+class ChangeBuffers:
+    """Caller-owned output buffers for bb_merge_batch (reusable across calls)."""
+
+    def __init__(self, cap: int):
+        cap = max(int(cap), 1)
+        self.cap = cap
+        self.decision = np.zeros(cap, np.uint8)
+        self.n_changes = np.zeros(1, np.uint64)
+        self.idx = np.zeros(cap, np.uint32)
+        self.head = np.zeros(cap, codec.HEAD_DTYPE)
+        self.clk = np.zeros((cap, codec.MAX_PEERS), np.uint32)
+        self.val = np.zeros((cap, codec.MAX_FIELDS), np.uint64)
+
+    def struct(self) -> BBChanges:
+        return BBChanges(cap=self.cap, decision=_ptr(self.decision), n_changes=_ptr(self.n_changes),
+                         idx=_ptr(self.idx), head=_ptr(self.head), clk=_ptr(self.clk),
+                         val=_ptr(self.val))
+
+    def result(self, n: int) -> codec.Changes:
+        k = int(self.n_changes[0])
+        return codec.Changes(self.decision[:n].copy(), self.idx[:k].copy(), self.head[:k].copy(),
+                             self.clk[:k].copy(), self.val[:k].copy())

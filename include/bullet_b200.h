@@ -1,0 +1,204 @@
+/*
+ * bullet_b200.h - C ABI of libbulletb200.so, the B200-native drop-in for ONE hot
+ * path of KORandi/bullet-js: batched conflict-resolution merge of graph updates
+ * (src/bullet-crt.js as driven by src/bullet-network-sync.js:551-569 through
+ * src/bullet.js:139-220) plus index build and equals/range/count
+ * (src/bullet-query.js).  Paths below are relative to the reference repo root.
+ *
+ * The reference has NO FFI / addon / operator registry for this path
+ * (SURVEY.md 8b), so there is nothing to mirror symbol-for-symbol; each entry
+ * point names the reference function(s) whose batched equivalent it is.  The
+ * reference-side binding (N-API addon + JS shim that swaps `bullet.crt`,
+ * `bullet.query` and `sync._processSyncEntries`) is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; returns 0 or a negative BB_ERR_*;
+ * never aborts, never calls back into the host; host buffers are caller-owned
+ * (pinned memory recommended); the library owns all device memory; outputs are
+ * only defined on success; a bb_ctx is not thread-safe; results are
+ * deterministic (bit-identical across runs).  There is NO CPU fallback: every
+ * compute entry point fails with BB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BULLET_B200_H
+#define BULLET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+#define BB_MAX_PEERS 8   /* clock slots per path (peer ids interned by the host) */
+#define BB_MAX_FIELDS 4  /* value slots per record in this build (128-byte rows) */
+
+/* ---- error codes ------------------------------------------------------- */
+#define BB_OK 0
+#define BB_ERR_ARG (-1)      /* null pointer, bad size, bad handle */
+#define BB_ERR_CUDA (-2)     /* CUDA runtime / no device; see bb_last_error */
+#define BB_ERR_DOMAIN (-3)   /* input outside the bit-exact domain */
+#define BB_ERR_CAPACITY (-4) /* path id >= capacity, or output buffer too small */
+#define BB_ERR_STATE (-5)    /* e.g. query on an index that was never built */
+
+/* ---- typed JS values ---------------------------------------------------
+ * A field slot is (tag, 64-bit payload):
+ *   ABSENT  the key is not an own property of the record
+ *   NUM     IEEE-754 binary64 bits (NaN, +-0, +-Infinity allowed)
+ *   STR     id in the host's order-preserving string dictionary: id order ==
+ *           UTF-16 code-unit order (what JS `<` uses for two strings).  The
+ *           dictionary must not contain strings Number() can parse, nor
+ *           "true", "false", "NaN", "[object Object]" (SURVEY 8a restriction 6)
+ *   BOOL    payload 0 / 1
+ *   NULL    JS null
+ */
+#define BB_TAG_ABSENT 0u
+#define BB_TAG_NUM 1u
+#define BB_TAG_STR 2u
+#define BB_TAG_BOOL 3u
+#define BB_TAG_NULL 4u
+
+/* A whole value is a flat record (KIND_OBJ: the slots with tag != ABSENT are its
+ * own keys; zero keys is `{}`) or a primitive (KIND_PRIM: slot 0).  KIND_NONE is
+ * "the path was never written" and only occurs in table rows. */
+#define BB_KIND_NONE 0u
+#define BB_KIND_OBJ 1u
+#define BB_KIND_PRIM 2u
+
+/* Value header word (`hdr`), used by updates, change-set entries and rows:
+ *   bit  0      flavour, updates only: 1 = from the network WITH a clock
+ *               (src/bullet-crt.js:339-344), 0 = local flavour (also what a
+ *               primitive arriving from the network gets, sync:560-563)
+ *   bits 1-2    BB_KIND_*
+ *   bits 8-31   3-bit tag of slot f at bit 8+3f
+ *   bits 32-63  own-key order: nibble i (bit 32+4i) = slot id of the i-th key,
+ *               for i < (number of non-ABSENT slots); unused nibbles are 0.
+ *               (JS object key order is part of the emitted value.)
+ */
+#define BB_HDR_FLAVOUR_NET 1ull
+#define BB_HDR_KIND_SHIFT 1
+#define BB_HDR_TAG_SHIFT 8
+#define BB_HDR_ORDER_SHIFT 32
+
+/* Clock: cnt[s] > 0 <=> peer slot s is a key of the clock object; `order` holds
+ * the key order (nibble i = slot of the i-th key, unused nibbles 0).  Key order
+ * matters: it decides "identical" vs "concurrent" (src/bullet-crt.js:200-203). */
+
+/* 16-byte per-update / per-change head. */
+typedef struct bb_head {
+  uint64_t hdr;       /* value header word, see above */
+  uint32_t clk_order; /* key order of the clock that travels with it */
+  uint32_t user;      /* opaque to the library; copied from update to change entry */
+} bb_head;
+
+/* Device-resident table row, one per interned path id; 128 bytes, 128-aligned.
+ * State per path is (S, M, V, a) of SURVEY.md 8a:
+ *   S = val/hdr, M = meta[path].vectorClock, V = crt.vectorClocks.get(path),
+ *   a = M and V are the same JS object (src/bullet.js:198-203 stores the
+ *   object the resolver keeps, so in-place increments are shared). */
+#define BB_ROW_M_PRESENT 1u
+#define BB_ROW_V_PRESENT 2u
+#define BB_ROW_ALIAS 4u
+typedef struct bb_row {
+  uint64_t val[BB_MAX_FIELDS];   /*   0 */
+  uint32_t m_cnt[BB_MAX_PEERS];  /*  32 */
+  uint32_t v_cnt[BB_MAX_PEERS];  /*  64 */
+  uint32_t m_order;              /*  96 */
+  uint32_t v_order;              /* 100 */
+  uint64_t hdr;                  /* 104: kind, tags, key order (flavour bit unused) */
+  uint32_t flags;                /* 112: BB_ROW_* */
+  uint32_t reserved;             /* 116 */
+  uint64_t cseq;                 /* 120: 1 + global sequence of the update that first
+                                         touched the row (== key order of the parent
+                                         collection object, query:61); 0 = never */
+} bb_row;
+
+/* Decision codes: the 6 `reason` strings of src/bullet-crt.js:182,216,230,245,
+ * 260,276; the :230 one split by the sign of the value comparison. */
+#define BB_DEC_NO_CURRENT 0u    /* accepted */
+#define BB_DEC_IDENTICAL 1u     /* rejected */
+#define BB_DEC_TIE_INCOMING 2u  /* accepted */
+#define BB_DEC_TIE_CURRENT 3u   /* rejected */
+#define BB_DEC_INCOMING 4u      /* accepted */
+#define BB_DEC_HISTORICAL 5u    /* rejected */
+#define BB_DEC_CONCURRENT 6u    /* accepted (field-wise max merge) */
+#define BB_DEC_ACCEPTED(d) ((0x55u >> (d)) & 1u) /* doUpdate, crt:383 */
+
+typedef struct bb_config {
+  uint32_t abi_version; /* BB_ABI_VERSION */
+  int32_t device;       /* CUDA ordinal */
+  uint32_t n_fields;    /* 1..BB_MAX_FIELDS */
+  uint32_t local_peer;  /* slot of bullet.id (`me`) */
+  uint64_t capacity;    /* rows; path ids are 0..capacity-1 */
+  /* Where the strings JS manufactures on this path would sort in the host's
+   * dictionary: the smallest dictionary id that is greater than the string.
+   * "[object Object]" is what `<` sees for an object operand (ToPrimitive). */
+  uint64_t rank_object;
+  uint64_t rank_true;   /* String(true)  as a range() bucket key */
+  uint64_t rank_false;  /* String(false) */
+  uint64_t rank_nan;    /* String(NaN)   */
+  uint32_t flags;       /* BB_CFG_* */
+  uint32_t reserved;
+} bb_config;
+/* The index hook is installed for these paths: `_updateIndices` re-reads the node
+ * with `_getData` after every setData (query:151,169), which turns a falsy stored
+ * primitive into `{}` right after the write instead of at the next update. */
+#define BB_CFG_POST_GETDATA 1u
+
+typedef struct bb_ctx bb_ctx;
+
+/* One batch of updates in arrival order == the `entries` argument of
+ * BulletNetworkSync._processSyncEntries (sync:551-569), or a run of
+ * BulletNode.put / _handlePut calls. Struct-of-arrays, n elements each. */
+typedef struct bb_batch {
+  uint64_t n;
+  const uint64_t* path_id; /* [n] interned path */
+  const bb_head* head;     /* [n] */
+  const uint32_t* clk;     /* [n][BB_MAX_PEERS] incoming clock counts (net flavour) */
+  const uint64_t* val;     /* [n][BB_MAX_FIELDS] */
+} bb_batch;
+
+/* The emitted change set == the ordered _applyUpdate calls (src/bullet.js:184-220):
+ * one entry per accepted update, in arrival order. */
+typedef struct bb_changes {
+  uint64_t cap;       /* capacity of idx/head/clk/val in entries (n always suffices) */
+  uint8_t* decision;  /* [n] BB_DEC_* per update (every update, accepted or not) */
+  uint64_t* n_changes;/* [1] */
+  uint32_t* idx;      /* [cap] index of the update in the batch */
+  bb_head* head;      /* [cap] stored value header + order of the stored clock */
+  uint32_t* clk;      /* [cap][BB_MAX_PEERS] stored clock == decision.vectorClock */
+  uint64_t* val;      /* [cap][BB_MAX_FIELDS] stored value == decision.value */
+} bb_changes;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int bb_abi_version(void);
+/* new BulletCRT(bullet) + empty store/meta (src/bullet.js:28-31,62-64) */
+int bb_create(const bb_config* cfg, bb_ctx** out);
+int bb_destroy(bb_ctx* ctx);
+const char* bb_last_error(const bb_ctx* ctx); /* ctx may be NULL: last create error */
+
+/* ---- table import / export (meta.json + store.json shaped state, and the
+ *      read side of Bullet._getData, src/bullet.js:115-129) ------------------ */
+int bb_table_load(bb_ctx* ctx, uint64_t n, const uint64_t* path_id, const bb_row* rows);
+/* materialise != 0 reproduces _getData's side effect (falsy/missing -> {}). */
+int bb_table_read(bb_ctx* ctx, uint64_t n, const uint64_t* path_id, bb_row* rows_out,
+                  int materialise);
+int bb_table_clear(bb_ctx* ctx);
+
+/* ---- the merge: n x [BulletCRT.handleUpdate (crt:329-385) -> resolve (164-279)
+ *      -> Bullet._applyUpdate (src/bullet.js:184-220)] in arrival order per path.
+ *      Host buffers; H2D / D2H copies are part of the call. ------------------- */
+int bb_merge_batch(bb_ctx* ctx, const bb_batch* in, bb_changes* out);
+/* Same, all pointers are device pointers on ctx's device, work is enqueued on
+ * `stream` (a cudaStream_t; 0 = ctx's own stream) and NOT synchronised. */
+int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* stream);
+
+/* ---- telemetry ---------------------------------------------------------- */
+/* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
+uint64_t bb_launch_count(const bb_ctx* ctx);
+/* Device time of the named phase of the most recent *_dev / host call, in ms,
+ * from CUDA events on the launching stream; -1 if unknown. Synchronises. */
+double bb_last_phase_ms(bb_ctx* ctx, const char* phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BULLET_B200_H */

@@ -1,0 +1,469 @@
+/*
+ * bullet_oracle.c - typed CPU restatement of the bullet-js merge path.
+ * TEST INFRASTRUCTURE ONLY (checker + cpu_baseline); never linked into
+ * libbulletb200.so and never called from the product path.
+ *
+ * PARITY UNPINNED BY THE REFERENCE: bullet-js has no tests or golden vectors
+ * (SURVEY.md 8c).  This file is validated against oracle/js_literal.py (the
+ * JS-object-level restatement, itself pinned by the KATs of SURVEY.md 8c) on
+ * random streams by tests/test_oracle_typed.py.
+ *
+ * It consumes the same typed struct-of-arrays format as the library
+ * (include/bullet_b200.h describes the encoding) but shares no code with the CUDA
+ * kernels: values and clocks are unpacked into ordered key lists - the shape of
+ * the JS objects they stand for - and the reference is followed statement by
+ * statement:
+ *   Bullet._getData            src/bullet.js:115-129
+ *   BulletCRT.handleUpdate     src/bullet-crt.js:329-385
+ *   incrementVectorClock       src/bullet-crt.js:56-60 (+33-49)
+ *   compareVectorClocks        src/bullet-crt.js:68-95
+ *   mergeVectorClocks          src/bullet-crt.js:103-114
+ *   compare (default)          src/bullet-crt.js:11-15
+ *   mergeValues                src/bullet-crt.js:122-153
+ *   resolve                    src/bullet-crt.js:164-279
+ *   Bullet._applyUpdate        src/bullet.js:184-220
+ *   _processSyncEntries loop   src/bullet-network-sync.js:551-569
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/bullet_b200.h"
+
+/* ---- JS-object-shaped working types ------------------------------------- */
+typedef struct {
+  int present;  /* the clock object exists (not undefined) */
+  int n;        /* number of own keys */
+  uint8_t key[BB_MAX_PEERS];
+  uint32_t cnt[BB_MAX_PEERS];
+} oclock;
+
+typedef struct {
+  int kind; /* BB_KIND_* */
+  int n;    /* own keys (OBJ) */
+  uint8_t key[BB_MAX_FIELDS];
+  uint8_t tag[BB_MAX_FIELDS];
+  uint64_t pay[BB_MAX_FIELDS];
+} ovalue;
+
+static void clock_unpack(oclock* c, const uint32_t* cnt, uint32_t order, int present) {
+  int n = 0;
+  for (int s = 0; s < BB_MAX_PEERS; ++s) n += cnt[s] != 0;
+  c->present = present;
+  c->n = n;
+  for (int i = 0; i < n; ++i) {
+    c->key[i] = (order >> (4 * i)) & 0xF;
+    c->cnt[i] = cnt[c->key[i] & 7];
+  }
+}
+
+static void clock_pack(const oclock* c, uint32_t* cnt, uint32_t* order) {
+  uint32_t o = 0;
+  memset(cnt, 0, sizeof(uint32_t) * BB_MAX_PEERS);
+  for (int i = 0; i < c->n; ++i) {
+    cnt[c->key[i]] = c->cnt[i];
+    o |= (uint32_t)c->key[i] << (4 * i);
+  }
+  *order = o;
+}
+
+static int clock_find(const oclock* c, int key) {
+  for (int i = 0; i < c->n; ++i)
+    if (c->key[i] == key) return i;
+  return -1;
+}
+
+/* clock[key] || 0 */
+static uint32_t clock_get(const oclock* c, int key) {
+  int i = clock_find(c, key);
+  return i < 0 ? 0 : c->cnt[i];
+}
+
+/* clock[key] = v  (existing key keeps its position, new key is appended) */
+static void clock_set(oclock* c, int key, uint32_t v) {
+  int i = clock_find(c, key);
+  if (i < 0) {
+    i = c->n++;
+    c->key[i] = (uint8_t)key;
+  }
+  c->cnt[i] = v;
+}
+
+static void value_unpack(ovalue* v, uint64_t hdr, const uint64_t* val) {
+  v->kind = (int)((hdr >> BB_HDR_KIND_SHIFT) & 3);
+  v->n = 0;
+  if (v->kind == BB_KIND_PRIM) {
+    v->n = 1;
+    v->key[0] = 0;
+    v->tag[0] = (hdr >> BB_HDR_TAG_SHIFT) & 7;
+    v->pay[0] = val[0];
+  } else if (v->kind == BB_KIND_OBJ) {
+    int n = 0;
+    for (int f = 0; f < BB_MAX_FIELDS; ++f) n += ((hdr >> (BB_HDR_TAG_SHIFT + 3 * f)) & 7) != 0;
+    v->n = n;
+    for (int i = 0; i < n; ++i) {
+      int f = (hdr >> (BB_HDR_ORDER_SHIFT + 4 * i)) & 0xF;
+      v->key[i] = (uint8_t)f;
+      v->tag[i] = (hdr >> (BB_HDR_TAG_SHIFT + 3 * f)) & 7;
+      v->pay[i] = val[f];
+    }
+  }
+}
+
+static uint64_t value_pack(const ovalue* v, uint64_t* val) {
+  uint64_t hdr = (uint64_t)v->kind << BB_HDR_KIND_SHIFT;
+  memset(val, 0, sizeof(uint64_t) * BB_MAX_FIELDS);
+  if (v->kind == BB_KIND_PRIM) {
+    hdr |= (uint64_t)v->tag[0] << BB_HDR_TAG_SHIFT;
+    val[0] = v->pay[0];
+  } else if (v->kind == BB_KIND_OBJ) {
+    for (int i = 0; i < v->n; ++i) {
+      int f = v->key[i];
+      hdr |= (uint64_t)v->tag[i] << (BB_HDR_TAG_SHIFT + 3 * f);
+      hdr |= (uint64_t)f << (BB_HDR_ORDER_SHIFT + 4 * i);
+      val[f] = v->pay[i];
+    }
+  }
+  return hdr;
+}
+
+/* ---- JS primitive semantics on typed slots ------------------------------ */
+static double as_double(uint64_t bits) {
+  double d;
+  memcpy(&d, &bits, 8);
+  return d;
+}
+
+/* ToBoolean(v) == false */
+static int prim_falsy(int tag, uint64_t pay) {
+  switch (tag) {
+    case BB_TAG_NUM: {
+      double d = as_double(pay);
+      return d == 0.0 || d != d;
+    }
+    case BB_TAG_BOOL: return pay == 0;
+    case BB_TAG_NULL: return 1;
+    default: return 0; /* dictionary strings are never "" */
+  }
+}
+
+/* ToNumber for NUM / BOOL / NULL */
+static double prim_number(int tag, uint64_t pay) {
+  if (tag == BB_TAG_NUM) return as_double(pay);
+  if (tag == BB_TAG_BOOL) return pay ? 1.0 : 0.0;
+  return 0.0;
+}
+
+/* crt:11-15 on two primitives: a===b -> 0 ; a<b -> -1 ; else +1 */
+static int compare_prim(int ta, uint64_t pa, int tb, uint64_t pb) {
+  if (ta == tb) {
+    if (ta == BB_TAG_NUM) {
+      if (as_double(pa) == as_double(pb)) return 0;
+    } else if (ta == BB_TAG_NULL) {
+      return 0;
+    } else if (pa == pb) {
+      return 0;
+    }
+  }
+  if (ta == BB_TAG_STR && tb == BB_TAG_STR) return pa < pb ? -1 : 1;
+  if (ta == BB_TAG_STR || tb == BB_TAG_STR) return 1; /* ToNumber(non-numeric string) = NaN */
+  return prim_number(ta, pa) < prim_number(tb, pb) ? -1 : 1;
+}
+
+/* crt:11-15 on two whole values; an object operand is "[object Object]" to `<`
+ * and two distinct objects are never === */
+static int compare_whole(const bb_config* cfg, const ovalue* x, const ovalue* cur) {
+  int xo = x->kind == BB_KIND_OBJ, co = cur->kind == BB_KIND_OBJ;
+  if (xo && co) return 1;
+  if (xo) return (cur->tag[0] == BB_TAG_STR && cur->pay[0] >= cfg->rank_object) ? -1 : 1;
+  if (co) return (x->tag[0] == BB_TAG_STR && x->pay[0] < cfg->rank_object) ? -1 : 1;
+  return compare_prim(x->tag[0], x->pay[0], cur->tag[0], cur->pay[0]);
+}
+
+static int value_find(const ovalue* v, int key) {
+  for (int i = 0; i < v->n; ++i)
+    if (v->key[i] == key) return i;
+  return -1;
+}
+
+/* crt:122-153 */
+static void merge_values(const bb_config* cfg, const ovalue* inc, const ovalue* cur, ovalue* out) {
+  if (inc->kind != BB_KIND_OBJ || cur->kind != BB_KIND_OBJ) {
+    *out = compare_whole(cfg, inc, cur) >= 0 ? *inc : *cur;
+    return;
+  }
+  *out = *cur; /* {...currentValue} */
+  for (int i = 0; i < inc->n; ++i) {
+    int j = value_find(out, inc->key[i]);
+    if (j >= 0) { /* key in result: both leaves are primitives in the flat domain */
+      if (compare_prim(inc->tag[i], inc->pay[i], out->tag[j], out->pay[j]) >= 0) {
+        out->tag[j] = inc->tag[i];
+        out->pay[j] = inc->pay[i];
+      }
+    } else {
+      j = out->n++;
+      out->key[j] = inc->key[i];
+      out->tag[j] = inc->tag[i];
+      out->pay[j] = inc->pay[i];
+    }
+  }
+}
+
+/* crt:68-95 */
+static int compare_clocks(const oclock* c1, const oclock* c2, int* same_text) {
+  int d1 = 0, d2 = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const oclock* c = pass ? c2 : c1;
+    for (int i = 0; i < c->n; ++i) {
+      uint32_t v1 = clock_get(c1, c->key[i]), v2 = clock_get(c2, c->key[i]);
+      if (v1 > v2) d1 = 1;
+      else if (v2 > v1) d2 = 1;
+    }
+  }
+  /* JSON.stringify(c1) === JSON.stringify(c2): same keys, same order, same counts */
+  int same = c1->n == c2->n;
+  for (int i = 0; same && i < c1->n; ++i)
+    same = c1->key[i] == c2->key[i] && c1->cnt[i] == c2->cnt[i];
+  *same_text = same;
+  if (d1 && d2) return 0;
+  if (d1) return 1;
+  if (d2) return -1;
+  return 0;
+}
+
+/* crt:103-114 */
+static void merge_clocks(const oclock* c1, const oclock* c2, oclock* out) {
+  *out = *c1;
+  out->present = 1;
+  for (int i = 0; i < c2->n; ++i) {
+    uint32_t r = clock_get(out, c2->key[i]);
+    clock_set(out, c2->key[i], r > c2->cnt[i] ? r : c2->cnt[i]);
+  }
+}
+
+/* crt:56-60 with getVectorClock/createVectorClock 33-49 */
+static void increment_clock(oclock* v, int me) {
+  if (!v->present) {
+    v->present = 1;
+    v->n = 0;
+    clock_set(v, me, 1);
+  }
+  clock_set(v, me, clock_get(v, me) + 1);
+}
+
+/* One setData call. Returns the decision code; *accepted = doUpdate. */
+static int step(const bb_config* cfg, bb_row* row, uint64_t seq, const bb_head* uh,
+                const uint32_t* uclk, const uint64_t* uval, ovalue* out_val, oclock* out_clk,
+                int* accepted) {
+  const int me = (int)cfg->local_peer;
+  ovalue cur, x, res;
+  oclock M, V, I, N;
+  int alias = (row->flags & BB_ROW_ALIAS) != 0;
+  int code;
+
+  value_unpack(&cur, row->hdr, row->val);
+  clock_unpack(&M, row->m_cnt, row->m_order, (row->flags & BB_ROW_M_PRESENT) != 0);
+  clock_unpack(&V, row->v_cnt, row->v_order, (row->flags & BB_ROW_V_PRESENT) != 0);
+  value_unpack(&x, uh->hdr, uval);
+
+  /* _getData: a missing or falsy value is replaced by {} (src/bullet.js:122-124) */
+  if (cur.kind == BB_KIND_NONE) {
+    row->cseq = seq + 1;
+    cur.kind = BB_KIND_OBJ;
+    cur.n = 0;
+  } else if (cur.kind == BB_KIND_PRIM && prim_falsy(cur.tag[0], cur.pay[0])) {
+    cur.kind = BB_KIND_OBJ;
+    cur.n = 0;
+  }
+
+  if (uh->hdr & BB_HDR_FLAVOUR_NET) {
+    clock_unpack(&I, uclk, uh->clk_order, 1);
+  } else {
+    increment_clock(&V, me); /* crt:358, in place */
+    if (alias) M = V;        /* same object */
+    I = V;
+  }
+
+  if (!M.present) { /* crt:172-185 */
+    increment_clock(&V, me);
+    res = x;
+    *out_clk = V;
+    code = BB_DEC_NO_CURRENT;
+    *accepted = 1;
+  } else {
+    int same_text;
+    int c = compare_clocks(&I, &M, &same_text);
+    merge_clocks(&I, &M, &N);
+    V = N; /* crt:197 */
+    alias = 0;
+    *out_clk = N;
+    if (c == 0 && same_text) {
+      int vc = compare_whole(cfg, &x, &cur);
+      if (vc == 0) {
+        code = BB_DEC_IDENTICAL;
+        res = cur;
+      } else if (vc > 0) {
+        code = BB_DEC_TIE_INCOMING;
+        res = x;
+      } else {
+        code = BB_DEC_TIE_CURRENT;
+        res = cur;
+      }
+    } else if (c > 0) {
+      code = BB_DEC_INCOMING;
+      res = x;
+    } else if (c < 0) {
+      code = BB_DEC_HISTORICAL;
+      res = cur;
+    } else {
+      code = BB_DEC_CONCURRENT;
+      merge_values(cfg, &x, &cur, &res);
+    }
+    *accepted = code == BB_DEC_TIE_INCOMING || code == BB_DEC_INCOMING || code == BB_DEC_CONCURRENT;
+  }
+
+  if (*accepted) { /* _applyUpdate: store value, meta.vectorClock = the resolver's object */
+    cur = res;
+    M = *out_clk;
+    V = *out_clk;
+    alias = 1;
+  }
+  if ((cfg->flags & BB_CFG_POST_GETDATA) && cur.kind == BB_KIND_PRIM &&
+      prim_falsy(cur.tag[0], cur.pay[0])) {
+    cur.kind = BB_KIND_OBJ; /* the index hook's _getData (query:151,169) */
+    cur.n = 0;
+  }
+  *out_val = res;
+
+  row->hdr = value_pack(&cur, row->val);
+  clock_pack(&M, row->m_cnt, &row->m_order);
+  clock_pack(&V, row->v_cnt, &row->v_order);
+  row->flags = (M.present ? BB_ROW_M_PRESENT : 0) | (V.present ? BB_ROW_V_PRESENT : 0) |
+               (alias ? BB_ROW_ALIAS : 0);
+  return code;
+}
+
+static void emit(bb_changes* out, uint64_t k, uint64_t i, const bb_head* uh, const ovalue* v,
+                 const oclock* c) {
+  out->idx[k] = (uint32_t)i;
+  out->head[k].hdr = value_pack(v, out->val + k * BB_MAX_FIELDS);
+  clock_pack(c, out->clk + k * BB_MAX_PEERS, &out->head[k].clk_order);
+  out->head[k].user = uh->user;
+}
+
+/* The sequential driver: for (const entry of entries) setData(...)  (sync:551-569). */
+int bo_merge_batch(const bb_config* cfg, bb_row* table, uint64_t seq_base, const bb_batch* in,
+                   bb_changes* out) {
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < in->n; ++i) {
+    ovalue v;
+    oclock c;
+    int acc;
+    if (in->path_id[i] >= cfg->capacity) return BB_ERR_CAPACITY;
+    int code = step(cfg, &table[in->path_id[i]], seq_base + i, &in->head[i],
+                    in->clk + i * BB_MAX_PEERS, in->val + i * BB_MAX_FIELDS, &v, &c, &acc);
+    out->decision[i] = (uint8_t)code;
+    if (acc) {
+      if (k >= out->cap) return BB_ERR_CAPACITY;
+      emit(out, k++, i, &in->head[i], &v, &c);
+    }
+  }
+  *out->n_changes = k;
+  return BB_OK;
+}
+
+/* ---- "all host threads" variant for bench.py --impl reference ------------
+ * Paths are independent, so thread t replays, in arrival order,
+ * the updates whose path id is congruent to t; the change set is compacted in
+ * arrival order afterwards.  Same results as bo_merge_batch. */
+typedef struct {
+  const bb_config* cfg;
+  bb_row* table;
+  uint64_t seq_base;
+  const bb_batch* in;
+  bb_changes* out;
+  bb_head* thead;
+  uint32_t* tclk;
+  uint64_t* tval;
+  int t, nt, err;
+} mt_arg;
+
+static void* mt_worker(void* p) {
+  mt_arg* a = (mt_arg*)p;
+  const bb_batch* in = a->in;
+  for (uint64_t i = 0; i < in->n; ++i) {
+    uint64_t pid = in->path_id[i];
+    if (pid % (uint64_t)a->nt != (uint64_t)a->t) continue;
+    if (pid >= a->cfg->capacity) {
+      a->err = BB_ERR_CAPACITY;
+      return 0;
+    }
+    ovalue v;
+    oclock c;
+    int acc;
+    int code = step(a->cfg, &a->table[pid], a->seq_base + i, &in->head[i],
+                    in->clk + i * BB_MAX_PEERS, in->val + i * BB_MAX_FIELDS, &v, &c, &acc);
+    a->out->decision[i] = (uint8_t)code;
+    if (acc) {
+      a->thead[i].hdr = value_pack(&v, a->tval + i * BB_MAX_FIELDS);
+      clock_pack(&c, a->tclk + i * BB_MAX_PEERS, &a->thead[i].clk_order);
+      a->thead[i].user = in->head[i].user;
+    }
+  }
+  return 0;
+}
+
+int bo_merge_batch_mt(const bb_config* cfg, bb_row* table, uint64_t seq_base, const bb_batch* in,
+                      bb_changes* out, int nthreads) {
+  if (nthreads <= 1) return bo_merge_batch(cfg, table, seq_base, in, out);
+  if (nthreads > 256) nthreads = 256;
+  uint64_t n = in->n;
+  bb_head* thead = (bb_head*)malloc(sizeof(bb_head) * (n ? n : 1));
+  uint32_t* tclk = (uint32_t*)malloc(sizeof(uint32_t) * BB_MAX_PEERS * (n ? n : 1));
+  uint64_t* tval = (uint64_t*)malloc(sizeof(uint64_t) * BB_MAX_FIELDS * (n ? n : 1));
+  pthread_t th[256];
+  mt_arg args[256];
+  int err = BB_OK;
+  for (int t = 0; t < nthreads; ++t) {
+    mt_arg a = {cfg, table, seq_base, in, out, thead, tclk, tval, t, nthreads, 0};
+    args[t] = a;
+    pthread_create(&th[t], 0, mt_worker, &args[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) {
+    pthread_join(th[t], 0);
+    if (args[t].err) err = args[t].err;
+  }
+  uint64_t k = 0;
+  for (uint64_t i = 0; err == BB_OK && i < n; ++i) {
+    if (!BB_DEC_ACCEPTED(out->decision[i])) continue;
+    if (k >= out->cap) {
+      err = BB_ERR_CAPACITY;
+      break;
+    }
+    out->idx[k] = (uint32_t)i;
+    out->head[k] = thead[i];
+    memcpy(out->clk + k * BB_MAX_PEERS, tclk + i * BB_MAX_PEERS, sizeof(uint32_t) * BB_MAX_PEERS);
+    memcpy(out->val + k * BB_MAX_FIELDS, tval + i * BB_MAX_FIELDS, sizeof(uint64_t) * BB_MAX_FIELDS);
+    ++k;
+  }
+  *out->n_changes = k;
+  free(thead);
+  free(tclk);
+  free(tval);
+  return err;
+}
+
+/* _getData's read-side materialisation for bb_table_read(materialise=1). */
+void bo_materialise(bb_row* row, uint64_t seq) {
+  ovalue cur;
+  value_unpack(&cur, row->hdr, row->val);
+  if (cur.kind == BB_KIND_NONE) {
+    row->cseq = seq + 1;
+  } else if (!(cur.kind == BB_KIND_PRIM && prim_falsy(cur.tag[0], cur.pay[0]))) {
+    return;
+  }
+  cur.kind = BB_KIND_OBJ;
+  cur.n = 0;
+  row->hdr = value_pack(&cur, row->val);
+}
