@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - the BASELINE.json metric on BASELINE.json's config.
+
+A "step" = one pass of the hot path over one synthetic batch: 1 M conflicting
+updates (F=4 fields each => 4 M field-merges) merged into a resident table of
+2.5 M records (10 M fields) per GPU  (BASELINE.json configs[1]; SURVEY.md 8d
+"Config 2", uniform-key variant - the one the 8d roofline figure is worked on).
+
+  value   field-merges/s, whole job, inputs already resident in HBM
+          (bb_merge_batch_dev; CUDA events on the launching stream, max over ranks)
+  e2e     same metric through the reference-facing C-ABI call bb_merge_batch with
+          pinned HOST buffers: H2D of the batch and D2H of decisions + change set
+          inside the timed region
+  roofline      the dominant kernel (k_merge): algorithmic bytes / its mean launch
+                duration inside the timed region / measured HBM peak
+  cpu_baseline  the typed C oracle (oracle/bullet_oracle.c, a restatement of the
+                reference's JS: kind "port"), 1 thread, bounded sample
+  --impl reference   the same oracle on every host thread (the reference itself is
+                JavaScript and there is no JS engine on the box: see DESIGN.md)
+
+N > 1 (torchrun, one rank per GPU): the table is sharded by path id, every rank
+submits its own 1 M batch, updates are routed to their owner with one NCCL
+all-to-all, merged there; weak scaling (per-GPU work fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RECORDS = 2_500_000   # per GPU: 10 M fields
+BATCH = 1_000_000       # updates per step per GPU
+N_BATCHES = 4           # distinct pre-generated batches, cycled
+F = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--records", type=int, default=N_RECORDS)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--keys", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        loaded = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {
+            "sm_mhz": float(np.median(loaded)) if loaded else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def make_workload(args, rank):
+    from bullet_js_b200 import synth
+
+    rng = synth.rng_for(2, salt=rank)
+    table = synth.make_table(args.records, rng)
+    batches = [synth.make_batch(table, args.batch, rng, keys=args.keys) for _ in range(N_BATCHES)]
+    return table, batches
+
+
+def run_reference(args, rank, world):
+    """The reference's algorithm on the host cores: typed C restatement, all threads."""
+    if rank != 0:
+        return
+    from bullet_js_b200 import capi, synth
+    from oracle.typed import TypedOracle
+
+    table, batches = make_workload(args, 0)
+    cores = os.cpu_count() or 1
+    cfg = capi.make_config(args.records, **synth.synth_ranks(args.records))
+    orc = TypedOracle(cfg)
+    out = capi.ChangeBuffers(args.batch)
+    dt = 0.0
+    for i in range(args.warmup + args.steps):
+        orc.table[:] = table.rows  # every step merges into the pristine table (not timed)
+        t0 = time.perf_counter()
+        orc.merge(batches[i % N_BATCHES], threads=cores, out=out)
+        if i >= args.warmup:
+            dt += time.perf_counter() - t0
+    v = args.steps * args.batch * F / dt
+    line = {
+        "impl": "reference", "metric": "crdt_field_merges_per_sec", "value": v, "unit": "field-merges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
+        "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": "field-merges/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x {args.batch} updates on the same table, path-sharded over {cores} threads"},
+        "e2e": {"value": v, "unit": "field-merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is JavaScript; no JS engine on the box, so this is the C restatement (oracle/bullet_oracle.c)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"config2: {args.records * F // 1_000_000}M-field table/GPU ({args.records} records x {F} fields, 128 B rows), "
+                    f"{args.batch}-update conflicting batch/GPU/step, {args.keys} keys, clock mix 40/20/25/5/5/5",
+        "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
+        "keys": args.keys, "sharding": f"path_id % {world}" if world > 1 else "none",
+        "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2",
+    }
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    from bullet_js_b200 import capi, codec, synth
+    from bullet_js_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bullet_js_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    table, batches = make_workload(args, rank)
+    n, K, W = args.batch, args.steps, args.warmup
+    # Every step merges into a PRISTINE copy of the table (one bb_ctx per step, all
+    # loaded with the same image): the batches' clocks are built relative to that image,
+    # so re-merging into an already-merged table would turn the workload into "all
+    # historical".  It also means no step ever finds its table in L2.
+    ids = np.arange(args.records, dtype=np.uint64)
+    engines = []
+    for _ in range(W + K):
+        e = Engine(args.records, device=local_rank, **synth.synth_ranks(args.records))
+        e.table_load(ids, table.rows)
+        engines.append(e)
+    eng = engines[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- device-resident inputs and outputs
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+    d_in = [(to_dev(b.path_id), to_dev(b.head), to_dev(b.clk), to_dev(b.val)) for b in batches]
+    cap = n * (world if world > 1 else 1)  # a rank may receive more than it sent
+    o_dec = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    o_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    o_idx = torch.zeros(cap, dtype=torch.int32, device=dev)
+    o_head = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
+    o_clk = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+    o_val = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+    cs = capi.BBChanges(cap=cap, decision=o_dec.data_ptr(), n_changes=o_n.data_ptr(), idx=o_idx.data_ptr(),
+                        head=o_head.data_ptr(), clk=o_clk.data_ptr(), val=o_val.data_ptr())
+
+    router = None
+    if world > 1:
+        from bullet_js_b200.shard import Router
+
+        router = Router(eng, world, rank, n, dev)
+
+    def step_dev(i):
+        p, h, c, v = d_in[i % N_BATCHES]
+        if router is None:
+            bs = capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
+            engines[i].merge_dev(bs, cs, stream)
+            return n
+        return router.route_and_merge(engines[i], p, h, c, v, cs, stream)
+
+    sampler = ClockSampler(local_rank)
+    for i in range(W):
+        step_dev(i)
+    eng.sync(stream)
+    barrier()
+    sampler.start()
+    launches0 = sum(e.launch_count() for e in engines)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    merged = 0
+    for i in range(K):
+        merged += step_dev(W + i)
+    e1.record()
+    barrier()
+    launches = sum(e.launch_count() for e in engines) - launches0
+    for e in engines:
+        e.sync(stream)
+    dev_ms = e0.elapsed_time(e1)
+    # phase timings of the timed steps (events recorded inside the library on the same stream)
+    ph = {name: float(np.mean([engines[W + j].phase_ms(name) for j in range(K)]))
+          for name in ("sort", "merge", "compact", "device")}
+    acc_frac = float(o_n.item()) / max(1, (merged // K))
+
+    # ---- e2e through bb_merge_batch with pinned host buffers
+    def pinned(a):
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
+        return t
+
+    e2e = None
+    if world == 1:
+        h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
+        hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        h_dec, h_n, h_idx, h_head, h_clk, h_val = hp(n), hp(8), hp(4 * n), hp(16 * n), hp(32 * n), hp(32 * n)
+        hcs = capi.BBChanges(cap=n, decision=h_dec.data_ptr(), n_changes=h_n.data_ptr(), idx=h_idx.data_ptr(),
+                             head=h_head.data_ptr(), clk=h_clk.data_ptr(), val=h_val.data_ptr())
+        hbs = [capi.BBBatch(n=n, path_id=a.data_ptr(), head=b_.data_ptr(), clk=c_.data_ptr(), val=d_.data_ptr())
+               for a, b_, c_, d_ in h_in]
+        Ke = min(K, 20)
+        for e in engines[: W + Ke]:
+            e.table_load(ids, table.rows)  # pristine again
+        for i in range(W):
+            engines[i].merge_raw(hbs[i % N_BATCHES], hcs)
+        torch.cuda.synchronize()
+        d2h = 0
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            engines[W + i].merge_raw(hbs[(W + i) % N_BATCHES], hcs)
+            k = int(h_n.view(torch.int64)[0])
+            d2h += n + 8 + k * 84
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
+               "d2h_bytes_per_step": d2h // Ke, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
+               "api": "bb_merge_batch (pinned host buffers, synchronous)"}
+    clocks = sampler.stop()
+
+    # ---- max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_ms, float(merged)], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, merged_total = float(tmax[0]), float(tsum[1])
+    else:
+        merged_total = float(merged)
+
+    # ---- roofline of the dominant kernel (k_merge), SURVEY 8d figure
+    peak, peak_src = peaks()
+    distinct = float(np.mean([np.unique(b.path_id).size for b in batches])) / n
+    bytes_per_update = 84 + 68 * acc_frac + 256 * distinct
+    per_launch_updates = merged / K
+    achieved = bytes_per_update * per_launch_updates / (ph["merge"] * 1e-3) / 1e9
+    pipeline = bytes_per_update * per_launch_updates / (ph["device"] * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.typed import TypedOracle
+
+        orc = TypedOracle(eng.cfg)
+        out = capi.ChangeBuffers(n)
+        done, dtc = 0, 0.0
+        while dtc < args.cpu_seconds and done < 64:
+            orc.table[:] = table.rows  # pristine table, not timed
+            t0 = time.perf_counter()
+            orc.merge(batches[done % N_BATCHES], out=out)
+            dtc += time.perf_counter() - t0
+            done += 1
+        cpu = {"value": done * n * F / dtc, "unit": "field-merges/s", "cores": 1, "kind": "port",
+               "sample": f"{done} x {n}-update batches of the same workload on the same table, "
+                         f"oracle/bullet_oracle.c single thread, {dtc:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "crdt_field_merges_per_sec", "value": merged_total * F / (dev_ms * 1e-3),
+            "unit": "field-merges/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "updates_per_sec": merged_total / (dev_ms * 1e-3),
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_merge", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_update": bytes_per_update, "accepted_frac": acc_frac,
+                         "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],
+                         "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
+                         "phase_ms": ph},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    for e in engines:
+        e.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

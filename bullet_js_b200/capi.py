@@ -58,8 +58,8 @@ class BulletB200Error(RuntimeError):
 EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear",
-    "bb_merge_batch", "bb_merge_batch_dev",
-    "bb_launch_count", "bb_last_phase_ms",
+    "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
+    "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
 ]
 
 _lib = None
@@ -94,10 +94,14 @@ def load():
     lib.bb_merge_batch.restype = i32
     lib.bb_merge_batch_dev.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges), vp]
     lib.bb_merge_batch_dev.restype = i32
+    lib.bb_sync.argtypes = [vp, vp]
+    lib.bb_sync.restype = i32
     lib.bb_launch_count.argtypes = [vp]
     lib.bb_launch_count.restype = u64
     lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]
     lib.bb_last_phase_ms.restype = C.c_double
+    lib.bb_phase_ms.argtypes = [vp, C.c_char_p, C.c_uint32]
+    lib.bb_phase_ms.restype = C.c_double
     _lib = lib
     return lib
 

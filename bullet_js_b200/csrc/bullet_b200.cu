@@ -1,0 +1,434 @@
+// bullet_b200.cu - the C ABI of include/bullet_b200.h over the sm_100a kernels.
+// One bb_ctx == one GPU-resident shard of the graph table (rows of 128 bytes,
+// row index == interned path id) plus the scratch the pipeline needs.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "bb_kernels.cuh"
+
+static_assert(sizeof(bb_row) == 128, "table rows are one 128-byte line");
+static_assert(sizeof(bb_head) == 16, "heads are one 16-byte vector");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_COMPACT, EV_D2H, EV_COUNT };
+constexpr int EV_RING = 64;  // merge calls whose phase timings can still be queried
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 1024;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct bb_ctx {
+  bb_config cfg{};
+  cudaStream_t stream = nullptr;
+  uint4* table = nullptr;
+  uint64_t seq = 0;  // updates (and materialising reads) seen so far
+  int key_bits = 0;
+  uint64_t launches = 0;
+  std::string err;
+  cudaEvent_t ev[EV_RING][EV_COUNT]{};
+  bool ev_valid[EV_RING][EV_COUNT]{};
+  uint64_t calls = 0;  // merge calls started; ring slot = (calls - 1) % EV_RING
+  // pipeline scratch
+  DevBuf<uint64_t> items_a, items_b;
+  DevBuf<uint32_t> counts, tile_sums, tile_cnt;
+  DevBuf<uint4> st_head, st_clk, st_val;
+  uint32_t* d_err = nullptr;    // bit0: path id out of range, bit1: change buffer too small
+  uint32_t* h_err = nullptr;    // pinned
+  // device mirrors of the host-call buffers
+  DevBuf<uint64_t> io_path;
+  DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
+  DevBuf<uint8_t> io_decision;
+  DevBuf<uint32_t> io_out_idx;
+  uint64_t* d_nchanges = nullptr;
+  uint64_t* h_nchanges = nullptr;  // pinned
+};
+
+namespace {
+
+int fail(bb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) {
+      c->err += ": ";
+      c->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+#define BB_CUDA(c, call)                                         \
+  do {                                                           \
+    cudaError_t e_ = (call);                                     \
+    if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #call, e_); \
+  } while (0)
+
+#define BB_LAUNCH(c, kernel, grid, block, stream, ...)                  \
+  do {                                                                  \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);              \
+    ++(c)->launches;                                                    \
+    cudaError_t e_ = cudaGetLastError();                                \
+    if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);  \
+  } while (0)
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+void begin_call(bb_ctx* c) {
+  ++c->calls;
+  const int slot = (int)((c->calls - 1) % EV_RING);
+  for (int i = 0; i < EV_COUNT; ++i) c->ev_valid[slot][i] = false;
+}
+
+void mark(bb_ctx* c, int which, cudaStream_t s) {
+  const int slot = (int)((c->calls - 1) % EV_RING);
+  cudaEventRecord(c->ev[slot][which], s);
+  c->ev_valid[slot][which] = true;
+}
+
+// exclusive scan of data[0..m) in place on stream s (m up to 2^32)
+int scan_u32(bb_ctx* c, uint32_t* data, uint64_t m, uint64_t* total64, cudaStream_t s) {
+  using namespace bb;
+  if (m <= 4096) {
+    BB_LAUNCH(c, k_scan_small, 1, 1024, s, data, m, total64);
+    return BB_OK;
+  }
+  const uint32_t tiles = div_up(m, SCAN_TILE);
+  BB_CUDA(c, c->tile_sums.ensure(tiles));
+  BB_LAUNCH(c, k_scan_reduce, tiles, SCAN_THREADS, s, data, m, c->tile_sums.p);
+  BB_LAUNCH(c, k_scan_small, 1, 1024, s, c->tile_sums.p, (uint64_t)tiles, total64);
+  BB_LAUNCH(c, k_scan_apply, tiles, SCAN_THREADS, s, data, m, c->tile_sums.p);
+  return BB_OK;
+}
+
+int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
+  using namespace bb;
+  const uint64_t n = in->n;
+  if (n >= 0xFFFFFFFFull) return fail(c, BB_ERR_ARG, "batch larger than 2^32-1 updates");
+  mark(c, EV_START, s);
+  if (n == 0) {
+    BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+    mark(c, EV_SORT, s);
+    mark(c, EV_MERGE, s);
+    mark(c, EV_COMPACT, s);
+    return BB_OK;
+  }
+  const uint32_t sort_tiles = div_up(n, SORT_TILE);
+  BB_CUDA(c, c->items_a.ensure(n));
+  BB_CUDA(c, c->items_b.ensure(n));
+  BB_CUDA(c, c->counts.ensure((size_t)RADIX * sort_tiles));
+  BB_CUDA(c, c->st_head.ensure(n));
+  BB_CUDA(c, c->st_clk.ensure(2 * n));
+  BB_CUDA(c, c->st_val.ensure(2 * n));
+
+  // K0 + K1: stable sort of (path id, arrival index) by path id
+  BB_LAUNCH(c, k_make_keys, div_up(n, 256), 256, s, in->path_id, n, c->cfg.capacity, c->items_a.p, c->d_err);
+  uint64_t* src = c->items_a.p;
+  uint64_t* dst = c->items_b.p;
+  for (int shift = 0; shift < c->key_bits; shift += 8) {
+    BB_LAUNCH(c, k_sort_count, sort_tiles, SORT_THREADS, s, src, n, shift, sort_tiles, c->counts.p);
+    int rc = scan_u32(c, c->counts.p, (uint64_t)RADIX * sort_tiles, nullptr, s);
+    if (rc) return rc;
+    BB_LAUNCH(c, k_sort_scatter, sort_tiles, SORT_THREADS, s, src, dst, n, shift, sort_tiles, c->counts.p);
+    uint64_t* t = src;
+    src = dst;
+    dst = t;
+  }
+  mark(c, EV_SORT, s);
+
+  // K2: per-path sequential replay against the table
+  MergeArgs ma;
+  ma.sorted = src;
+  ma.n = n;
+  ma.table = c->table;
+  ma.head = reinterpret_cast<const uint4*>(in->head);
+  ma.clk = reinterpret_cast<const uint4*>(in->clk);
+  ma.val = reinterpret_cast<const uint4*>(in->val);
+  ma.decision = out->decision;
+  ma.st_head = c->st_head.p;
+  ma.st_clk = c->st_clk.p;
+  ma.st_val = c->st_val.p;
+  ma.seq_base = c->seq;
+  ma.err = c->d_err;
+  ma.p.rank_object = c->cfg.rank_object;
+  ma.p.me = c->cfg.local_peer;
+  ma.p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
+  BB_LAUNCH(c, k_merge, div_up(n, MERGE_THREADS), MERGE_THREADS, s, ma);
+  mark(c, EV_MERGE, s);
+
+  // K3: change set in arrival order
+  const uint32_t ctiles = div_up(n, COMPACT_TILE);
+  BB_CUDA(c, c->tile_cnt.ensure(ctiles));
+  BB_LAUNCH(c, k_accept_count, ctiles, COMPACT_THREADS, s, out->decision, n, c->tile_cnt.p, c->d_err);
+  int rc = scan_u32(c, c->tile_cnt.p, ctiles, out->n_changes, s);
+  if (rc) return rc;
+  CompactArgs ca;
+  ca.decision = out->decision;
+  ca.n = n;
+  ca.tile_base = c->tile_cnt.p;
+  ca.st_head = c->st_head.p;
+  ca.st_clk = c->st_clk.p;
+  ca.st_val = c->st_val.p;
+  ca.out_idx = out->idx;
+  ca.out_head = reinterpret_cast<uint4*>(out->head);
+  ca.out_clk = reinterpret_cast<uint4*>(out->clk);
+  ca.out_val = reinterpret_cast<uint4*>(out->val);
+  ca.cap = out->cap;
+  ca.err = c->d_err;
+  BB_LAUNCH(c, k_compact, ctiles, COMPACT_THREADS, s, ca);
+  mark(c, EV_COMPACT, s);
+  c->seq += n;
+  return BB_OK;
+}
+
+// fetch + clear the deferred device error word; stream must be idle afterwards
+int collect_device_error(bb_ctx* c, cudaStream_t s) {
+  BB_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), s));
+  BB_CUDA(c, cudaStreamSynchronize(s));
+  const uint32_t e = *c->h_err;
+  if (e & 1u) return fail(c, BB_ERR_CAPACITY, "path id >= capacity (batch rejected, table unchanged)");
+  if (e & 2u) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
+  return BB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bb_abi_version(void) { return BB_ABI_VERSION; }
+
+const char* bb_last_error(const bb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int bb_create(const bb_config* cfg, bb_ctx** out) {
+  if (!cfg || !out) {
+    g_create_error = "null argument";
+    return BB_ERR_ARG;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != BB_ABI_VERSION || cfg->n_fields < 1 || cfg->n_fields > BB_MAX_FIELDS ||
+      cfg->local_peer >= BB_MAX_PEERS || cfg->capacity == 0 || cfg->capacity >= 0xFFFFFFFFull) {
+    g_create_error = "bad bb_config (abi_version / n_fields / local_peer / capacity)";
+    return BB_ERR_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range");
+    return BB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+    g_create_error = "device is not sm_100 (this library is built for B200 only)";
+    return BB_ERR_CUDA;
+  }
+  bb_ctx* c = new (std::nothrow) bb_ctx();
+  if (!c) {
+    g_create_error = "out of host memory";
+    return BB_ERR_ARG;
+  }
+  c->cfg = *cfg;
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
+  c->key_bits = bits;
+  bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc((void**)&c->table, cfg->capacity * sizeof(bb_row)) == cudaSuccess &&
+            cudaMemsetAsync(c->table, 0, cfg->capacity * sizeof(bb_row), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&c->h_err, sizeof(uint32_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&c->h_nchanges, sizeof(uint64_t)) == cudaSuccess;
+  for (int r = 0; ok && r < EV_RING; ++r)
+    for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&c->ev[r][i]) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    bb_destroy(c);
+    return BB_ERR_CUDA;
+  }
+  *out = c;
+  return BB_OK;
+}
+
+int bb_destroy(bb_ctx* c) {
+  if (!c) return BB_ERR_ARG;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->items_a.release(); c->items_b.release(); c->counts.release(); c->tile_sums.release();
+  c->tile_cnt.release(); c->st_head.release(); c->st_clk.release(); c->st_val.release();
+  c->io_path.release(); c->io_head.release(); c->io_clk.release(); c->io_val.release();
+  c->io_out_head.release(); c->io_out_clk.release(); c->io_out_val.release(); c->io_rows.release();
+  c->io_decision.release(); c->io_out_idx.release();
+  if (c->table) cudaFree(c->table);
+  if (c->d_err) cudaFree(c->d_err);
+  if (c->d_nchanges) cudaFree(c->d_nchanges);
+  if (c->h_err) cudaFreeHost(c->h_err);
+  if (c->h_nchanges) cudaFreeHost(c->h_nchanges);
+  for (int r = 0; r < EV_RING; ++r)
+    for (int i = 0; i < EV_COUNT; ++i)
+      if (c->ev[r][i]) cudaEventDestroy(c->ev[r][i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return BB_OK;
+}
+
+int bb_table_clear(bb_ctx* c) {
+  if (!c) return BB_ERR_ARG;
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  BB_CUDA(c, cudaMemsetAsync(c->table, 0, c->cfg.capacity * sizeof(bb_row), c->stream));
+  BB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->seq = 0;
+  return BB_OK;
+}
+
+int bb_table_load(bb_ctx* c, uint64_t n, const uint64_t* path_id, const bb_row* rows) {
+  if (!c || (n && (!path_id || !rows))) return fail(c, BB_ERR_ARG, "null argument");
+  if (n == 0) return BB_OK;
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  BB_CUDA(c, c->io_path.ensure(n));
+  BB_CUDA(c, c->io_rows.ensure(n * 8));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, path_id, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_rows.p, rows, n * sizeof(bb_row), cudaMemcpyHostToDevice, s));
+  BB_LAUNCH(c, bb::k_table_scatter, div_up(n * 8, 256), 256, s, c->table, c->io_path.p, c->io_rows.p, n,
+            c->cfg.capacity, c->d_err);
+  return collect_device_error(c, s);
+}
+
+int bb_table_read(bb_ctx* c, uint64_t n, const uint64_t* path_id, bb_row* rows_out, int materialise) {
+  if (!c || (n && (!path_id || !rows_out))) return fail(c, BB_ERR_ARG, "null argument");
+  if (n == 0) return BB_OK;
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  BB_CUDA(c, c->io_path.ensure(n));
+  BB_CUDA(c, c->io_rows.ensure(n * 8));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, path_id, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  BB_CUDA(c, cudaMemsetAsync(c->io_rows.p, 0, n * sizeof(bb_row), s));
+  BB_LAUNCH(c, bb::k_table_gather, div_up(n, 256), 256, s, c->table, c->io_path.p, c->io_rows.p, n,
+            c->cfg.capacity, materialise, c->seq, c->d_err);
+  BB_CUDA(c, cudaMemcpyAsync(rows_out, c->io_rows.p, n * sizeof(bb_row), cudaMemcpyDeviceToHost, s));
+  if (materialise) c->seq += n;
+  return collect_device_error(c, s);
+}
+
+int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* stream) {
+  if (!c || !in || !out) return fail(c, BB_ERR_ARG, "null argument");
+  if (in->n && (!in->path_id || !in->head || !in->clk || !in->val || !out->decision || !out->idx ||
+                !out->head || !out->clk || !out->val))
+    return fail(c, BB_ERR_ARG, "null buffer");
+  if (!out->n_changes) return fail(c, BB_ERR_ARG, "null n_changes");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  begin_call(c);
+  return merge_dev(c, in, out, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int bb_sync(bb_ctx* c, void* stream) {
+  if (!c) return BB_ERR_ARG;
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  return collect_device_error(c, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
+  if (!c || !in || !out || !out->n_changes) return fail(c, BB_ERR_ARG, "null argument");
+  const uint64_t n = in->n;
+  if (n && (!in->path_id || !in->head || !in->clk || !in->val || !out->decision))
+    return fail(c, BB_ERR_ARG, "null buffer");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  begin_call(c);
+  mark(c, EV_H2D0, s);
+  if (n == 0) {
+    *out->n_changes = 0;
+    mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_COMPACT, s); mark(c, EV_D2H, s);
+    return BB_OK;
+  }
+  BB_CUDA(c, c->io_path.ensure(n));
+  BB_CUDA(c, c->io_head.ensure(n));
+  BB_CUDA(c, c->io_clk.ensure(2 * n));
+  BB_CUDA(c, c->io_val.ensure(2 * n));
+  BB_CUDA(c, c->io_decision.ensure(n));
+  BB_CUDA(c, c->io_out_idx.ensure(n));
+  BB_CUDA(c, c->io_out_head.ensure(n));
+  BB_CUDA(c, c->io_out_clk.ensure(2 * n));
+  BB_CUDA(c, c->io_out_val.ensure(2 * n));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, in->path_id, n * 8, cudaMemcpyHostToDevice, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_head.p, in->head, n * 16, cudaMemcpyHostToDevice, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_clk.p, in->clk, n * 32, cudaMemcpyHostToDevice, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->io_val.p, in->val, n * 32, cudaMemcpyHostToDevice, s));
+  bb_batch din{n, c->io_path.p, reinterpret_cast<const bb_head*>(c->io_head.p),
+               reinterpret_cast<const uint32_t*>(c->io_clk.p), reinterpret_cast<const uint64_t*>(c->io_val.p)};
+  bb_changes dout{n, c->io_decision.p, c->d_nchanges, c->io_out_idx.p,
+                  reinterpret_cast<bb_head*>(c->io_out_head.p), reinterpret_cast<uint32_t*>(c->io_out_clk.p),
+                  reinterpret_cast<uint64_t*>(c->io_out_val.p)};
+  int rc = merge_dev(c, &din, &dout, s);
+  if (rc) return rc;
+  BB_CUDA(c, cudaMemcpyAsync(out->decision, c->io_decision.p, n, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges, c->d_nchanges, 8, cudaMemcpyDeviceToHost, s));
+  rc = collect_device_error(c, s);  // synchronises
+  if (rc) return rc;
+  const uint64_t k = *c->h_nchanges;
+  if (k > out->cap) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
+  if (k && (!out->idx || !out->head || !out->clk || !out->val)) return fail(c, BB_ERR_ARG, "null buffer");
+  if (k) {
+    BB_CUDA(c, cudaMemcpyAsync(out->idx, c->io_out_idx.p, k * 4, cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaMemcpyAsync(out->head, c->io_out_head.p, k * 16, cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaMemcpyAsync(out->clk, c->io_out_clk.p, k * 32, cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaMemcpyAsync(out->val, c->io_out_val.p, k * 32, cudaMemcpyDeviceToHost, s));
+  }
+  mark(c, EV_D2H, s);
+  BB_CUDA(c, cudaStreamSynchronize(s));
+  *out->n_changes = k;
+  return BB_OK;
+}
+
+uint64_t bb_launch_count(const bb_ctx* c) { return c ? c->launches : 0; }
+
+double bb_last_phase_ms(bb_ctx* c, const char* phase) { return bb_phase_ms(c, phase, 0); }
+
+double bb_phase_ms(bb_ctx* c, const char* phase, uint32_t calls_ago) {
+  if (!c || !phase || calls_ago >= EV_RING || calls_ago >= c->calls) return -1.0;
+  const int slot = (int)((c->calls - 1 - calls_ago) % EV_RING);
+  int a = -1, b = -1;
+  if (!strcmp(phase, "h2d")) { a = EV_H2D0; b = EV_START; }
+  else if (!strcmp(phase, "sort")) { a = EV_START; b = EV_SORT; }
+  else if (!strcmp(phase, "merge")) { a = EV_SORT; b = EV_MERGE; }
+  else if (!strcmp(phase, "compact")) { a = EV_MERGE; b = EV_COMPACT; }
+  else if (!strcmp(phase, "d2h")) { a = EV_COMPACT; b = EV_D2H; }
+  else if (!strcmp(phase, "device")) { a = EV_START; b = EV_COMPACT; }
+  else if (!strcmp(phase, "total")) { a = EV_H2D0; b = EV_D2H; }
+  if (a < 0 || !c->ev_valid[slot][a] || !c->ev_valid[slot][b]) return -1.0;
+  cudaSetDevice(c->cfg.device);
+  if (cudaEventSynchronize(c->ev[slot][b]) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev[slot][a], c->ev[slot][b]) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+"""Thin object wrapper over the C ABI (include/bullet_b200.h).
+
+`Engine` owns one bb_ctx == one GPU-resident shard of the graph table.  All
+compute goes through libbulletb200.so; a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi, codec
+
+
+class Engine:
+    def __init__(self, capacity: int, *, local_peer: int = 0, n_fields: int = codec.MAX_FIELDS,
+                 device: int = 0, post_getdata: bool = False, rank_object: int = 0, rank_true: int = 0,
+                 rank_false: int = 0, rank_nan: int = 0):
+        self.lib = capi.load()
+        self.cfg = capi.make_config(
+            capacity, n_fields=n_fields, local_peer=local_peer, device=device,
+            flags=codec.CFG_POST_GETDATA if post_getdata else 0, rank_object=rank_object,
+            rank_true=rank_true, rank_false=rank_false, rank_nan=rank_nan)
+        h = C.c_void_p()
+        rc = self.lib.bb_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0:
+            raise capi.BulletB200Error(rc, (self.lib.bb_last_error(None) or b"").decode())
+        self._h = h
+        self.capacity = int(capacity)
+        self.device = device
+
+    @classmethod
+    def for_schema(cls, schema: codec.Schema, capacity: int, **kw):
+        return cls(capacity, local_peer=schema.peers.index(schema.local_peer), **schema.config_ranks(), **kw)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise capi.BulletB200Error(rc, (self.lib.bb_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.bb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- table
+    def table_load(self, path_id, rows):
+        path_id = np.ascontiguousarray(path_id, np.uint64)
+        rows = np.ascontiguousarray(rows, codec.ROW_DTYPE)
+        assert path_id.shape[0] == rows.shape[0]
+        self._check(self.lib.bb_table_load(self._h, path_id.shape[0], path_id.ctypes.data, rows.ctypes.data))
+
+    def table_read(self, path_id, materialise=False):
+        path_id = np.ascontiguousarray(path_id, np.uint64)
+        rows = np.zeros(path_id.shape[0], codec.ROW_DTYPE)
+        self._check(self.lib.bb_table_read(self._h, path_id.shape[0], path_id.ctypes.data, rows.ctypes.data,
+                                           1 if materialise else 0))
+        return rows
+
+    def table_clear(self):
+        self._check(self.lib.bb_table_clear(self._h))
+
+    # ---- merge, host buffers (the reference-facing call)
+    def merge(self, batch: codec.Batch, out: capi.ChangeBuffers | None = None) -> codec.Changes:
+        out = out or capi.ChangeBuffers(batch.n)
+        bs, cs = capi.batch_struct(batch), out.struct()
+        self._check(self.lib.bb_merge_batch(self._h, C.byref(bs), C.byref(cs)))
+        return out.result(batch.n)
+
+    def merge_raw(self, bs: capi.BBBatch, cs: capi.BBChanges):
+        """bb_merge_batch on prebuilt structs (pinned buffers, no numpy copies)."""
+        self._check(self.lib.bb_merge_batch(self._h, C.byref(bs), C.byref(cs)))
+
+    # ---- merge, device pointers (inputs already resident in HBM)
+    def merge_dev(self, bs: capi.BBBatch, cs: capi.BBChanges, stream: int = 0):
+        self._check(self.lib.bb_merge_batch_dev(self._h, C.byref(bs), C.byref(cs), C.c_void_p(stream)))
+
+    def sync(self, stream: int = 0):
+        self._check(self.lib.bb_sync(self._h, C.c_void_p(stream)))
+
+    # ---- telemetry
+    def launch_count(self) -> int:
+        return int(self.lib.bb_launch_count(self._h))
+
+    def phase_ms(self, phase: str, calls_ago: int = 0) -> float:
+        return float(self.lib.bb_phase_ms(self._h, phase.encode(), calls_ago))

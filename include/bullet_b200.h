@@ -190,6 +190,11 @@ int bb_merge_batch(bb_ctx* ctx, const bb_batch* in, bb_changes* out);
 /* Same, all pointers are device pointers on ctx's device, work is enqueued on
  * `stream` (a cudaStream_t; 0 = ctx's own stream) and NOT synchronised. */
 int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* stream);
+/* Synchronise `stream` (0 = ctx's own) and return the deferred status of the
+ * *_dev calls enqueued since the last bb_sync: BB_ERR_CAPACITY if a batch held a
+ * path id >= capacity (that batch was rejected whole, table unchanged) or a
+ * change buffer was too small. */
+int bb_sync(bb_ctx* ctx, void* stream);
 
 /* ---- telemetry ---------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
@@ -197,6 +202,10 @@ uint64_t bb_launch_count(const bb_ctx* ctx);
 /* Device time of the named phase of the most recent *_dev / host call, in ms,
  * from CUDA events on the launching stream; -1 if unknown. Synchronises. */
 double bb_last_phase_ms(bb_ctx* ctx, const char* phase);
+/* Same for the merge call issued `calls_ago` calls before the most recent one
+ * (0 = most recent; the last 64 calls are kept).  Phases: "h2d", "sort", "merge",
+ * "compact", "d2h", "device" (sort+merge+compact), "total". */
+double bb_phase_ms(bb_ctx* ctx, const char* phase, uint32_t calls_ago);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,195 @@
+"""GPU parity: libbulletb200.so (through the C ABI) == the typed oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from bullet_js_b200 import capi, codec, synth
+from oracle.typed import TypedOracle
+from tests import streamgen
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_and_oracle(schema=None, capacity=256, post_getdata=False, **kw):
+    from bullet_js_b200.engine import Engine
+
+    if schema is not None:
+        eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata)
+    else:
+        eng = Engine(capacity, post_getdata=post_getdata, **kw)
+    return eng, TypedOracle(eng.cfg)
+
+
+def assert_same_table(eng, orc, n):
+    ids = np.arange(n, dtype=np.uint64)
+    got, want = eng.table_read(ids), orc.read(ids)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (bad[:5], got[bad[:2]], want[bad[:2]])
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("indexed", [False, True])
+def test_random_js_streams(seed, indexed):
+    ops, _ref = streamgen.generate(100 + seed, 4000, 37, index_fields=("age",) if indexed else ())
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    eng, orc = engine_and_oracle(schema, 64, post_getdata=indexed)
+    cuts = [0, 1, 2, 35, 36, 1000, 1001, 3000, len(ops)]
+    seen = set()
+    for lo, hi in zip(cuts, cuts[1:]):
+        got, want = eng.merge(batch.slice(lo, hi)), orc.merge(batch.slice(lo, hi))
+        assert got.same_as(want), (seed, lo, hi)
+        seen |= set(got.decision.tolist())
+    assert seen == set(range(7))
+    assert_same_table(eng, orc, 64)
+    eng.close()
+
+
+def test_kat_l_on_gpu():
+    schema = codec.Schema(["v"], ["A"], codec.StringDict([]), "A")
+    ops = [("k/v", float(x), None) for x in (5, 3, 3, 3, 7, 9, 0, 0, 4)]
+    batch = codec.encode_updates(schema, ops)
+    eng, _ = engine_and_oracle(schema, 4)
+    ch = eng.merge(batch)
+    assert ch.decision.tolist() == [0, 3, 4, 1, 4, 2, 3, 4, 2]
+    assert ch.idx.tolist() == [0, 2, 4, 5, 7, 8]
+    d = codec.decode_row(schema, eng.table_read([0])[0])
+    assert d["value"] == 4.0 and d["M"] == {"A": 11.0} and d["alias"]
+    eng.close()
+
+
+@pytest.mark.parametrize("keys", ["uniform", "zipf"])
+def test_synthetic_schema_stream(keys):
+    """SURVEY 8d schema at a size the oracle replays in a second: 50k records, 3 x 200k updates."""
+    n_rec = 50_000
+    rng = synth.rng_for(2, salt=1)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec, **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    assert_same_table(eng, orc, n_rec)
+    for _ in range(3):
+        b = synth.make_batch(table, 200_000, rng, keys=keys)
+        got, want = eng.merge(b), orc.merge(b)
+        assert got.same_as(want)
+        assert len(set(got.decision.tolist())) >= 4
+    assert_same_table(eng, orc, n_rec)
+    eng.close()
+
+
+def test_fresh_table_and_local_only():
+    """Every update lands on a path that was never written (M absent) or is a local put."""
+    n_rec = 10_000
+    rng = synth.rng_for(1, salt=3)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec, local_peer=3, **synth.synth_ranks(n_rec))
+    for mix in (synth.MIX, dict(synth.MIX, local=0.7, dominating=0.1, historical=0.05, concurrent=0.05)):
+        tot = sum(mix.values())
+        mix = {k: v / tot for k, v in mix.items()}
+        b = synth.make_batch(table, 50_000, rng, mix=mix)
+        assert eng.merge(b).same_as(orc.merge(b))
+    assert_same_table(eng, orc, n_rec)
+    eng.close()
+
+
+def test_empty_and_single():
+    eng, orc = engine_and_oracle(None, 16)
+    e = codec.Batch.empty(0)
+    got = eng.merge(e)
+    assert got.decision.size == 0 and got.idx.size == 0
+    table = synth.make_table(16, synth.rng_for(0))
+    b = synth.make_batch(table, 1, synth.rng_for(0, 1))
+    assert eng.merge(b).same_as(orc.merge(b))
+    eng.close()
+
+
+def test_out_of_range_path_rejects_batch_and_keeps_table():
+    n_rec = 1000
+    rng = synth.rng_for(0, salt=9)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec)
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    b = synth.make_batch(table, 5000, rng)
+    b.path_id[1234] = n_rec  # one bad id
+    with pytest.raises(capi.BulletB200Error) as ei:
+        eng.merge(b)
+    assert ei.value.code == capi.ERR_CAPACITY
+    assert np.array_equal(eng.table_read(ids), table.rows)
+    b.path_id[1234] = 0
+    orc.load(ids, table.rows)
+    assert eng.merge(b).same_as(orc.merge(b))  # the context stays usable
+    eng.close()
+
+
+def test_change_buffer_too_small():
+    n_rec = 100
+    rng = synth.rng_for(0, salt=5)
+    table = synth.make_table(n_rec, rng)
+    eng, _ = engine_and_oracle(None, n_rec)
+    b = synth.make_batch(table, 2000, rng)
+    out = capi.ChangeBuffers(2000)
+    out.cap = 10
+    with pytest.raises(capi.BulletB200Error) as ei:
+        eng.merge(b, out)
+    assert ei.value.code == capi.ERR_CAPACITY
+    eng.close()
+
+
+def test_table_read_materialise_matches_getdata():
+    schema = streamgen.make_schema()
+    ops = [("users/a", 0.0, None), ("users/b", {"age": 1.0}, None), ("users/c", False, None)]
+    batch = codec.encode_updates(schema, ops)
+    schema.paths.id("users/never")
+    eng, orc = engine_and_oracle(schema, 8)
+    assert eng.merge(batch).same_as(orc.merge(batch))
+    ids = np.arange(4, dtype=np.uint64)
+    got, want = eng.table_read(ids, materialise=True), orc.read(ids, materialise=True)
+    kinds = [codec.decode_row(schema, r)["kind"] for r in got]
+    assert kinds == [codec.KIND_OBJ] * 4
+    assert [codec.decode_row(schema, r)["value"] for r in got] == [{}, {"age": 1.0}, {}, {}]
+    assert np.array_equal(got["hdr"], want["hdr"]) and np.array_equal(got["val"], want["val"])
+    eng.close()
+
+
+def test_device_pointer_entry_matches_host_entry():
+    import ctypes as C
+
+    import torch
+
+    n_rec = 20_000
+    rng = synth.rng_for(2, salt=7)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec)
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    b = synth.make_batch(table, 100_000, rng, keys="zipf")
+    want = orc.merge(b)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+    d_path, d_head, d_clk, d_val = t(b.path_id), t(b.head), t(b.clk), t(b.val)
+    n = b.n
+    o_dec = torch.zeros(n, dtype=torch.uint8, device=dev)
+    o_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    o_idx = torch.zeros(n, dtype=torch.int32, device=dev)
+    o_head = torch.zeros(n * 16, dtype=torch.uint8, device=dev)
+    o_clk = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
+    o_val = torch.zeros(n * 32, dtype=torch.uint8, device=dev)
+    bs = capi.BBBatch(n=n, path_id=d_path.data_ptr(), head=d_head.data_ptr(), clk=d_clk.data_ptr(),
+                      val=d_val.data_ptr())
+    cs = capi.BBChanges(cap=n, decision=o_dec.data_ptr(), n_changes=o_n.data_ptr(), idx=o_idx.data_ptr(),
+                        head=o_head.data_ptr(), clk=o_clk.data_ptr(), val=o_val.data_ptr())
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.merge_dev(bs, cs, stream)
+    eng.sync(stream)
+    k = int(o_n.item())
+    got = codec.Changes(
+        o_dec.cpu().numpy(), o_idx[:k].cpu().numpy().view(np.uint32),
+        o_head[: k * 16].cpu().numpy().view(codec.HEAD_DTYPE),
+        o_clk[: k * 32].cpu().numpy().view(np.uint32).reshape(k, 8),
+        o_val[: k * 32].cpu().numpy().view(np.uint64).reshape(k, 4))
+    assert got.same_as(want)
+    assert_same_table(eng, orc, n_rec)
+    assert eng.launch_count() > 0 and eng.phase_ms("merge") >= 0
+    eng.close()
