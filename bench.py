@@ -211,6 +211,7 @@ def main():
     for _ in range(W + K):
         e = Engine(args.records, device=local_rank, **synth.synth_ranks(args.records))
         e.table_load(ids, table.rows)
+        e.reserve(args.batch * world, host_entry=(world == 1))
         engines.append(e)
     eng = engines[0]
 

@@ -57,7 +57,7 @@ class BulletB200Error(RuntimeError):
 # Every symbol include/bullet_b200.h declares (tests check the .so exports them all).
 EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
-    "bb_table_load", "bb_table_read", "bb_table_clear",
+    "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
     "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
 ]
@@ -94,6 +94,8 @@ def load():
     lib.bb_merge_batch.restype = i32
     lib.bb_merge_batch_dev.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges), vp]
     lib.bb_merge_batch_dev.restype = i32
+    lib.bb_reserve.argtypes = [vp, u64, i32]
+    lib.bb_reserve.restype = i32
     lib.bb_sync.argtypes = [vp, vp]
     lib.bb_sync.restype = i32
     lib.bb_launch_count.argtypes = [vp]

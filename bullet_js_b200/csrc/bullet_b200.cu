@@ -125,6 +125,34 @@ int scan_u32(bb_ctx* c, uint32_t* data, uint64_t m, uint64_t* total64, cudaStrea
   return BB_OK;
 }
 
+// size every scratch buffer of the device pipeline for batches of up to n updates
+int reserve_dev(bb_ctx* c, uint64_t n) {
+  using namespace bb;
+  const uint32_t sort_tiles = div_up(n, SORT_TILE);
+  BB_CUDA(c, c->items_a.ensure(n));
+  BB_CUDA(c, c->items_b.ensure(n));
+  BB_CUDA(c, c->counts.ensure((size_t)RADIX * sort_tiles));
+  BB_CUDA(c, c->tile_sums.ensure(div_up((uint64_t)RADIX * sort_tiles, SCAN_TILE)));
+  BB_CUDA(c, c->tile_cnt.ensure(div_up(n, COMPACT_TILE)));
+  BB_CUDA(c, c->st_head.ensure(n));
+  BB_CUDA(c, c->st_clk.ensure(2 * n));
+  BB_CUDA(c, c->st_val.ensure(2 * n));
+  return BB_OK;
+}
+
+int reserve_io(bb_ctx* c, uint64_t n) {
+  BB_CUDA(c, c->io_path.ensure(n));
+  BB_CUDA(c, c->io_head.ensure(n));
+  BB_CUDA(c, c->io_clk.ensure(2 * n));
+  BB_CUDA(c, c->io_val.ensure(2 * n));
+  BB_CUDA(c, c->io_decision.ensure(n));
+  BB_CUDA(c, c->io_out_idx.ensure(n));
+  BB_CUDA(c, c->io_out_head.ensure(n));
+  BB_CUDA(c, c->io_out_clk.ensure(2 * n));
+  BB_CUDA(c, c->io_out_val.ensure(2 * n));
+  return BB_OK;
+}
+
 int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   using namespace bb;
   const uint64_t n = in->n;
@@ -138,12 +166,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
     return BB_OK;
   }
   const uint32_t sort_tiles = div_up(n, SORT_TILE);
-  BB_CUDA(c, c->items_a.ensure(n));
-  BB_CUDA(c, c->items_b.ensure(n));
-  BB_CUDA(c, c->counts.ensure((size_t)RADIX * sort_tiles));
-  BB_CUDA(c, c->st_head.ensure(n));
-  BB_CUDA(c, c->st_clk.ensure(2 * n));
-  BB_CUDA(c, c->st_val.ensure(2 * n));
+  {
+    int rc = reserve_dev(c, n);  // no-op once the scratch is large enough
+    if (rc) return rc;
+  }
 
   // K0 + K1: stable sort of (path id, arrival index) by path id
   BB_LAUNCH(c, k_make_keys, div_up(n, 256), 256, s, in->path_id, n, c->cfg.capacity, c->items_a.p, c->d_err);
@@ -349,6 +375,14 @@ int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* str
   return merge_dev(c, in, out, stream ? (cudaStream_t)stream : c->stream);
 }
 
+int bb_reserve(bb_ctx* c, uint64_t max_batch, int host_entry) {
+  if (!c || max_batch >= 0xFFFFFFFFull) return fail(c, BB_ERR_ARG, "bad argument");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  int rc = reserve_dev(c, max_batch);
+  if (rc == BB_OK && host_entry) rc = reserve_io(c, max_batch);
+  return rc;
+}
+
 int bb_sync(bb_ctx* c, void* stream) {
   if (!c) return BB_ERR_ARG;
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
@@ -369,15 +403,12 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
     mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_COMPACT, s); mark(c, EV_D2H, s);
     return BB_OK;
   }
-  BB_CUDA(c, c->io_path.ensure(n));
-  BB_CUDA(c, c->io_head.ensure(n));
-  BB_CUDA(c, c->io_clk.ensure(2 * n));
-  BB_CUDA(c, c->io_val.ensure(2 * n));
-  BB_CUDA(c, c->io_decision.ensure(n));
-  BB_CUDA(c, c->io_out_idx.ensure(n));
-  BB_CUDA(c, c->io_out_head.ensure(n));
-  BB_CUDA(c, c->io_out_clk.ensure(2 * n));
-  BB_CUDA(c, c->io_out_val.ensure(2 * n));
+  {
+    int rc = reserve_io(c, n);
+    if (rc) return rc;
+    rc = reserve_dev(c, n);
+    if (rc) return rc;
+  }
   BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, in->path_id, n * 8, cudaMemcpyHostToDevice, s));
   BB_CUDA(c, cudaMemcpyAsync(c->io_head.p, in->head, n * 16, cudaMemcpyHostToDevice, s));
   BB_CUDA(c, cudaMemcpyAsync(c->io_clk.p, in->clk, n * 32, cudaMemcpyHostToDevice, s));

@@ -62,6 +62,9 @@ class Engine:
                                            1 if materialise else 0))
         return rows
 
+    def reserve(self, max_batch: int, host_entry: bool = True):
+        self._check(self.lib.bb_reserve(self._h, int(max_batch), 1 if host_entry else 0))
+
     def table_clear(self):
         self._check(self.lib.bb_table_clear(self._h))
 

@@ -183,6 +183,11 @@ int bb_table_read(bb_ctx* ctx, uint64_t n, const uint64_t* path_id, bb_row* rows
                   int materialise);
 int bb_table_clear(bb_ctx* ctx);
 
+/* Pre-size the device scratch for batches of up to max_batch updates so that no
+ * merge call allocates (host_entry != 0: also the device mirrors bb_merge_batch
+ * copies through).  Optional: buffers otherwise grow on first use. */
+int bb_reserve(bb_ctx* ctx, uint64_t max_batch, int host_entry);
+
 /* ---- the merge: n x [BulletCRT.handleUpdate (crt:329-385) -> resolve (164-279)
  *      -> Bullet._applyUpdate (src/bullet.js:184-220)] in arrival order per path.
  *      Host buffers; H2D / D2H copies are part of the call. ------------------- */
