@@ -11,7 +11,7 @@ updates (F=4 fields each => 4 M field-merges) merged into a resident table of
   e2e     same metric through the reference-facing C-ABI call bb_merge_batch with
           pinned HOST buffers: H2D of the batch and D2H of decisions + change set
           inside the timed region
-  roofline      the dominant kernel (k_merge): algorithmic bytes / its mean launch
+  roofline      the dominant kernel (k_merge_tiles): algorithmic bytes / its mean launch
                 duration inside the timed region / measured HBM peak
   cpu_baseline  the typed C oracle (oracle/bullet_oracle.c, a restatement of the
                 reference's JS: kind "port"), 1 thread, bounded sample
@@ -220,7 +220,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit stream: the library treats handle 0 as "the ctx's own stream"
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
 
     # ---- device-resident inputs and outputs
     def to_dev(a):
@@ -228,13 +231,13 @@ def main():
 
     d_in = [(to_dev(b.path_id), to_dev(b.head), to_dev(b.clk), to_dev(b.val)) for b in batches]
     cap = n * (world if world > 1 else 1)  # a rank may receive more than it sent
-    o_dec = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    o_ver = torch.zeros(cap, dtype=torch.int32, device=dev)
     o_n = torch.zeros(1, dtype=torch.int64, device=dev)
     o_idx = torch.zeros(cap, dtype=torch.int32, device=dev)
     o_head = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
     o_clk = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
     o_val = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
-    cs = capi.BBChanges(cap=cap, decision=o_dec.data_ptr(), n_changes=o_n.data_ptr(), idx=o_idx.data_ptr(),
+    cs = capi.BBChanges(cap=cap, verdict=o_ver.data_ptr(), n_changes=o_n.data_ptr(), idx=o_idx.data_ptr(),
                         head=o_head.data_ptr(), clk=o_clk.data_ptr(), val=o_val.data_ptr())
 
     router = None
@@ -271,7 +274,7 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     # phase timings of the timed steps (events recorded inside the library on the same stream)
     ph = {name: float(np.mean([engines[W + j].phase_ms(name) for j in range(K)]))
-          for name in ("sort", "merge", "compact", "device")}
+          for name in ("sort", "merge", "device")}
     acc_frac = float(o_n.item()) / max(1, (merged // K))
 
     # ---- e2e through bb_merge_batch with pinned host buffers
@@ -283,8 +286,8 @@ def main():
     if world == 1:
         h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
         hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
-        h_dec, h_n, h_idx, h_head, h_clk, h_val = hp(n), hp(8), hp(4 * n), hp(16 * n), hp(32 * n), hp(32 * n)
-        hcs = capi.BBChanges(cap=n, decision=h_dec.data_ptr(), n_changes=h_n.data_ptr(), idx=h_idx.data_ptr(),
+        h_ver, h_n, h_idx, h_head, h_clk, h_val = hp(4 * n), hp(8), hp(4 * n), hp(16 * n), hp(32 * n), hp(32 * n)
+        hcs = capi.BBChanges(cap=n, verdict=h_ver.data_ptr(), n_changes=h_n.data_ptr(), idx=h_idx.data_ptr(),
                              head=h_head.data_ptr(), clk=h_clk.data_ptr(), val=h_val.data_ptr())
         hbs = [capi.BBBatch(n=n, path_id=a.data_ptr(), head=b_.data_ptr(), clk=c_.data_ptr(), val=d_.data_ptr())
                for a, b_, c_, d_ in h_in]
@@ -299,7 +302,7 @@ def main():
         for i in range(Ke):
             engines[W + i].merge_raw(hbs[(W + i) % N_BATCHES], hcs)
             k = int(h_n.view(torch.int64)[0])
-            d2h += n + 8 + k * 84
+            d2h += 4 * n + 8 + k * 84
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
@@ -318,7 +321,7 @@ def main():
     else:
         merged_total = float(merged)
 
-    # ---- roofline of the dominant kernel (k_merge), SURVEY 8d figure
+    # ---- roofline of the dominant kernel (k_merge_tiles), SURVEY 8d figure
     peak, peak_src = peaks()
     distinct = float(np.mean([np.unique(b.path_id).size for b in batches])) / n
     bytes_per_update = 84 + 68 * acc_frac + 256 * distinct
@@ -351,7 +354,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world),
             "updates_per_sec": merged_total / (dev_ms * 1e-3),
             "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_merge", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_merge_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_update": bytes_per_update, "accepted_frac": acc_frac,
                          "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],

@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libbulletb200.so")
 
 ABI_VERSION = 1
+NO_SLOT = 0x1FFFFFFF
 
 OK, ERR_ARG, ERR_CUDA, ERR_DOMAIN, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5
 _ERR_NAMES = {
@@ -43,7 +44,7 @@ class BBBatch(C.Structure):
 
 class BBChanges(C.Structure):
     _fields_ = [
-        ("cap", C.c_uint64), ("decision", C.c_void_p), ("n_changes", C.c_void_p),
+        ("cap", C.c_uint64), ("verdict", C.c_void_p), ("n_changes", C.c_void_p),
         ("idx", C.c_void_p), ("head", C.c_void_p), ("clk", C.c_void_p), ("val", C.c_void_p),
     ]
 
@@ -135,7 +136,7 @@ class ChangeBuffers:
     def __init__(self, cap: int):
         cap = max(int(cap), 1)
         self.cap = cap
-        self.decision = np.zeros(cap, np.uint8)
+        self.verdict = np.zeros(cap, np.uint32)
         self.n_changes = np.zeros(1, np.uint64)
         self.idx = np.zeros(cap, np.uint32)
         self.head = np.zeros(cap, codec.HEAD_DTYPE)
@@ -143,11 +144,11 @@ class ChangeBuffers:
         self.val = np.zeros((cap, codec.MAX_FIELDS), np.uint64)
 
     def struct(self) -> BBChanges:
-        return BBChanges(cap=self.cap, decision=_ptr(self.decision), n_changes=_ptr(self.n_changes),
+        return BBChanges(cap=self.cap, verdict=_ptr(self.verdict), n_changes=_ptr(self.n_changes),
                          idx=_ptr(self.idx), head=_ptr(self.head), clk=_ptr(self.clk),
                          val=_ptr(self.val))
 
     def result(self, n: int) -> codec.Changes:
         k = int(self.n_changes[0])
-        return codec.Changes(self.decision[:n].copy(), self.idx[:k].copy(), self.head[:k].copy(),
-                             self.clk[:k].copy(), self.val[:k].copy())
+        return codec.Changes.from_verdicts(self.verdict[:n], self.idx[:k], self.head[:k], self.clk[:k],
+                                           self.val[:k])

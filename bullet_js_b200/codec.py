@@ -272,15 +272,35 @@ class Batch:
         return Batch(self.path_id[lo:hi], self.head[lo:hi], self.clk[lo:hi], self.val[lo:hi])
 
 
+NO_SLOT = 0x1FFFFFFF
+
+
 @dataclass
 class Changes:
-    """Decisions + emitted change set (bb_changes), trimmed to n_changes."""
+    """Decisions + emitted change set in ARRIVAL order (the reference's order)."""
 
     decision: np.ndarray  # u8[n]
     idx: np.ndarray       # u32[k]
     head: np.ndarray      # HEAD_DTYPE[k]
     clk: np.ndarray       # u32[k, 8]
     val: np.ndarray       # u64[k, 4]
+
+    @staticmethod
+    def from_verdicts(verdict, idx, head, clk, val) -> "Changes":
+        """bb_changes -> arrival order: walk verdict[] and follow the slots (the
+        library stores entries path-major; include/bullet_b200.h)."""
+        verdict = np.asarray(verdict, np.uint32)
+        decision = (verdict >> 29).astype(np.uint8)
+        slot = verdict & NO_SLOT
+        acc = np.nonzero(slot != NO_SLOT)[0]
+        order = slot[acc].astype(np.int64)
+        k = len(idx)
+        if acc.size != k or (k and (np.sort(order) != np.arange(k)).any()):
+            raise ValueError("verdict slots are not a permutation of the change set")
+        if k and not np.array_equal(np.asarray(idx)[order], acc.astype(np.uint32)):
+            raise ValueError("verdict slot does not point at the update's own entry")
+        return Changes(decision, np.asarray(idx)[order].copy(), np.asarray(head)[order].copy(),
+                       np.asarray(clk)[order].copy(), np.asarray(val)[order].copy())
 
     def same_as(self, other: "Changes") -> bool:
         return (

@@ -1,53 +1,67 @@
 // bb_kernels.cuh - sm_100a kernels of the merge pipeline.
 //
-//   K0  make_keys      (path id, arrival index) -> 64-bit sort items, bounds check
-//   K1  radix sort     stable LSD, 8-bit digits, only as many passes as the
-//                      table's row-index width needs; moves 8-byte items, never payloads
-//   K2  merge          one thread per path segment replays its updates in arrival
-//                      order against the 128-byte table row (bb_merge.cuh)
-//   K3  compaction     accepted updates -> dense change set in arrival order
+//   K0  k_keys_hist    (path id, arrival index) -> 64-bit sort items, bounds check,
+//                      digit histograms of every radix pass in the same read
+//   K1  k_sort_pass    stable LSD radix sort, 8-bit digits, ONE kernel per pass
+//                      (chained-scan / decoupled look-back across tiles); only as many
+//                      passes as the table's row-index width needs; moves 8-byte items,
+//                      never payloads
+//   K2  k_merge_tiles  one WARP per tile of 32 sorted positions, warps fully independent;
+//                      one 8-lane GROUP per path segment (lane g owns clock slot g and
+//                      value slot g & 3, bb_group.cuh), four segments in lockstep per warp:
+//                      every row / payload access is a coalesced 32-byte piece, a clock
+//                      compare is one compare per lane + two ballots.  Accepted updates
+//                      are ranked by ballot, tile totals chained with a decoupled
+//                      look-back scan, entries written straight to the change set
 //
 // All of it is integer / f64 compare-and-move work: HBM-bound, no tensor cores.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "bb_group.cuh"
 #include "bb_merge.cuh"
 
 namespace bb {
 
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 items per CTA
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048 items per CTA: a 1 M batch is one wave
 constexpr int RADIX = 256;
+constexpr int MAX_PASSES = 4;
 
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int UPD_Q = 5;         // 16-byte chunks per update payload (head 1 + clk 2 + val 2)
+constexpr int ROW_Q = 8;         // 16-byte chunks per table row
 
-constexpr int MERGE_THREADS = 128;
-constexpr int COMPACT_THREADS = 256;
-constexpr int COMPACT_TILE = 4096;
+// chained-scan tile states: 2 flag bits + 30 value bits in one word
+constexpr uint32_t ST_AGG = 1u << 30, ST_PRE = 2u << 30, ST_MASK = 3u << 30, ST_VAL = ~ST_MASK;
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
-
-// ---------------------------------------------------------------- K0
-__global__ void __launch_bounds__(256) k_make_keys(const uint64_t* __restrict__ path_id, uint64_t n,
-                                                   uint64_t capacity, uint64_t* __restrict__ items,
-                                                   uint32_t* __restrict__ err) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t p = path_id[i];
-  if (p >= capacity) atomicOr(err, 1u);  // the whole batch is rejected: K2/K3 see the flag and do nothing
-  items[i] = (p << 32) | i;
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-
-// ---------------------------------------------------------------- generic exclusive scan (u32)
+__device__ __forceinline__ void st_volatile(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -78,86 +92,95 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint64_t n,
-                                                              uint32_t* __restrict__ tile_sum) {
-  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
-    if (i < n) s += in[i];
+// Exclusive prefix of `agg` over tiles 0..tile-1, published tile by tile (decoupled
+// look-back). Called by all 32 lanes of one warp; tile ids come from an atomic ticket
+// so every predecessor is already running.
+__device__ __forceinline__ uint32_t tile_prefix(uint32_t* state, uint32_t tile, uint32_t agg) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) st_volatile(state, ST_PRE | agg);
+    return 0;
   }
-  uint32_t total;
-  block_exclusive_scan<SCAN_THREADS>(s, &total);
-  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+  if (lane == 0) st_volatile(state + tile, ST_AGG | agg);
+  uint32_t excl = 0;
+  int look = (int)tile - 1;
+  while (true) {
+    const int i = look - lane;
+    uint32_t v = ST_PRE;  // virtual zero prefix in front of tile 0
+    if (i >= 0) {
+      do {
+        v = ld_volatile(state + i);
+      } while ((v & ST_MASK) == 0);
+    }
+    const uint32_t pre = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_PRE);
+    if (pre) {
+      const int first = __ffs(pre) - 1;
+      excl += warp_sum(lane <= first ? (v & ST_VAL) : 0u);
+      break;
+    }
+    excl += warp_sum(v & ST_VAL);
+    look -= 32;
+  }
+  if (lane == 0) st_volatile(state + tile, ST_PRE | (excl + agg));
+  return excl;
 }
 
-// single CTA: exclusive scan of m values in place; writes the grand total to *total_out
-__global__ void __launch_bounds__(1024) k_scan_small(uint32_t* __restrict__ data, uint64_t m,
-                                                     uint64_t* __restrict__ total_out) {
-  uint32_t carry = 0;
-  for (uint64_t base = 0; base < m; base += 1024) {
-    const uint64_t i = base + threadIdx.x;
-    const uint32_t v = i < m ? data[i] : 0;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_scan<1024>(v, &total);
-    if (i < m) data[i] = carry + ex;
-    carry += total;
-  }
-  if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restrict__ data, uint64_t n,
-                                                             const uint32_t* __restrict__ tile_base) {
-  // each thread owns SCAN_ITEMS consecutive elements so the scan is in index order
-  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS];
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    v[k] = base + k < n ? data[base + k] : 0;
-    s += v[k];
-  }
-  uint32_t total;
-  uint32_t run = tile_base[blockIdx.x] + block_exclusive_scan<SCAN_THREADS>(s, &total);
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    if (base + k < n) data[base + k] = run;
-    run += v[k];
-  }
-}
-
-// ---------------------------------------------------------------- K1 radix sort
-// counts layout: counts[digit * num_tiles + tile]  (digit-major so one exclusive scan
-// over the whole array yields every (digit, tile) base)
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_count(const uint64_t* __restrict__ items, uint64_t n,
-                                                             int shift, uint32_t num_tiles,
-                                                             uint32_t* __restrict__ counts) {
-  __shared__ uint32_t hist[RADIX];
-  hist[threadIdx.x] = 0;
+// ---------------------------------------------------------------- K0
+// items[i] = path_id[i] << 32 | i ; ghist[pass][digit] += 1 for every pass
+__global__ void __launch_bounds__(SORT_THREADS) k_keys_hist(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                            uint64_t capacity, int passes,
+                                                            uint64_t* __restrict__ items,
+                                                            uint32_t* __restrict__ ghist,
+                                                            uint32_t* __restrict__ err) {
+  __shared__ uint32_t hist[MAX_PASSES][RADIX];
+  for (int p = 0; p < passes; ++p) hist[p][threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * SORT_TILE;
-#pragma unroll
+  bool bad = false;
+#pragma unroll 4
   for (int k = 0; k < SORT_ITEMS; ++k) {
     const uint64_t i = base + (uint64_t)k * SORT_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&hist[(uint32_t)(items[i] >> (32 + shift)) & (RADIX - 1)], 1u);
+    if (i < n) {
+      const uint64_t pid = path_id[i];
+      bad |= pid >= capacity;
+      items[i] = (pid << 32) | i;
+      for (int p = 0; p < passes; ++p) atomicAdd(&hist[p][(uint32_t)(pid >> (8 * p)) & (RADIX - 1)], 1u);
+    }
   }
+  if (bad) atomicOr(err, 1u);  // the whole batch is rejected: K2 sees the flag and does nothing
   __syncthreads();
-  counts[(uint64_t)threadIdx.x * num_tiles + blockIdx.x] = hist[threadIdx.x];
+  for (int p = 0; p < passes; ++p) {
+    const uint32_t c = hist[p][threadIdx.x];
+    if (c) atomicAdd(&ghist[p * RADIX + threadIdx.x], c);
+  }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* __restrict__ in,
-                                                               uint64_t* __restrict__ out, uint64_t n, int shift,
-                                                               uint32_t num_tiles,
-                                                               const uint32_t* __restrict__ bases) {
+// one CTA per pass: exclusive scan of its 256-bin histogram, in place
+__global__ void __launch_bounds__(RADIX) k_hist_scan(uint32_t* __restrict__ ghist) {
+  uint32_t* h = ghist + blockIdx.x * RADIX;
+  uint32_t total;
+  const uint32_t v = h[threadIdx.x];
+  h[threadIdx.x] = block_exclusive_scan<RADIX>(v, &total);
+}
+
+// ---------------------------------------------------------------- K1
+__global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const uint64_t* __restrict__ in,
+                                                            uint64_t* __restrict__ out, uint64_t n, int shift,
+                                                            const uint32_t* __restrict__ gbase,  // [256]
+                                                            uint32_t* __restrict__ state,         // [tiles][256]
+                                                            uint32_t* __restrict__ ticket) {
   __shared__ uint32_t whist[SORT_WARPS][RADIX];
+  __shared__ uint32_t s_base[RADIX];
+  __shared__ uint32_t s_tile;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   for (int d = threadIdx.x; d < SORT_WARPS * RADIX; d += SORT_THREADS) (&whist[0][0])[d] = 0;
   __syncthreads();
+  const uint32_t tile = s_tile;
 
-  // warp w owns the contiguous run [tile + w*512, +512): arrival order inside the
+  // warp w owns the contiguous run [tile*TILE + w*ITEMS*32, +ITEMS*32): arrival order inside the
   // tile is (warp, round, lane), which is what makes the pass stable
-  const uint64_t wbase = (uint64_t)blockIdx.x * SORT_TILE + (uint64_t)w * (SORT_ITEMS * 32);
+  const uint64_t wbase = (uint64_t)tile * SORT_TILE + (uint64_t)w * (SORT_ITEMS * 32);
   uint64_t kv[SORT_ITEMS];
   uint32_t rank[SORT_ITEMS];
 #pragma unroll
@@ -182,27 +205,44 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint64_t* _
     __syncwarp();
   }
   __syncthreads();
-  {  // thread d: turn per-warp counts into global bases
+  {  // thread d: per-warp exclusive offsets, tile count, chained scan over tiles for digit d
     const int d = threadIdx.x;
-    uint32_t b = bases[(uint64_t)d * num_tiles + blockIdx.x];
+    uint32_t cnt = 0;
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ++ww) {
       const uint32_t t = whist[ww][d];
-      whist[ww][d] = b;
-      b += t;
+      whist[ww][d] = cnt;
+      cnt += t;
     }
+    uint32_t excl = 0;
+    uint32_t* st = state + d;
+    if (tile == 0) {
+      st_volatile(st, ST_PRE | cnt);
+    } else {
+      st_volatile(st + (uint64_t)tile * RADIX, ST_AGG | cnt);
+      for (int look = (int)tile - 1;; --look) {
+        uint32_t v;
+        do {
+          v = ld_volatile(st + (uint64_t)look * RADIX);
+        } while ((v & ST_MASK) == 0);
+        excl += v & ST_VAL;
+        if ((v & ST_MASK) == ST_PRE) break;
+      }
+      st_volatile(st + (uint64_t)tile * RADIX, ST_PRE | (excl + cnt));
+    }
+    s_base[d] = gbase[d] + excl;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < SORT_ITEMS; ++k) {
     if (wbase + k * 32 + lane < n) {
       const uint32_t d = (uint32_t)(kv[k] >> (32 + shift)) & (RADIX - 1);
-      out[whist[w][d] + rank[k]] = kv[k];
+      out[s_base[d] + whist[w][d] + rank[k]] = kv[k];
     }
   }
 }
 
-// ---------------------------------------------------------------- K2 merge
+// ---------------------------------------------------------------- K2
 struct MergeArgs {
   const uint64_t* sorted;  // [n] (path id << 32 | arrival index), stable-sorted by path id
   uint64_t n;
@@ -210,166 +250,234 @@ struct MergeArgs {
   const uint4* head;       // [n]
   const uint4* clk;        // [n][2]
   const uint4* val;        // [n][2]
-  uint8_t* decision;       // [n]
-  uint4* st_head;          // staging at arrival index: [n], [n][2], [n][2]
-  uint4* st_clk;
-  uint4* st_val;
+  uint32_t* verdict;       // [n] arrival order: code << 29 | slot
+  uint64_t* n_changes;
+  uint32_t* out_idx;       // change set, path-major order
+  uint4* out_head;
+  uint4* out_clk;
+  uint4* out_val;
+  uint64_t cap;
+  uint32_t* st_idx;        // staging for the part of a segment that runs past its tile,
+  uint4* st_ent;           // [n][5] indexed by sorted position
+  uint32_t* tile_state;    // [num_tiles], zeroed per launch
+  uint32_t* ticket;        // zeroed per launch
+  uint32_t num_tiles;
   uint64_t seq_base;
-  const uint32_t* err;     // non-zero: the batch was rejected by K0, leave the table alone
+  uint32_t* err;           // bit0 in: batch rejected by K0; bit1 out: cap too small
   Params p;
 };
 
-__device__ __forceinline__ void load_row(const uint4* __restrict__ row, RowState& r) {
-  const uint4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
-  const uint4 q4 = row[4], q5 = row[5], q6 = row[6], q7 = row[7];
-  r.s.val[0] = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
-  r.s.val[1] = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
-  r.s.val[2] = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
-  r.s.val[3] = (uint64_t)q1.z | ((uint64_t)q1.w << 32);
+__device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+__device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
+  const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+  r.s.val[0] = u64_of(q0.x, q0.y); r.s.val[1] = u64_of(q0.z, q0.w);
+  r.s.val[2] = u64_of(q1.x, q1.y); r.s.val[3] = u64_of(q1.z, q1.w);
   r.m.cnt[0] = q2.x; r.m.cnt[1] = q2.y; r.m.cnt[2] = q2.z; r.m.cnt[3] = q2.w;
   r.m.cnt[4] = q3.x; r.m.cnt[5] = q3.y; r.m.cnt[6] = q3.z; r.m.cnt[7] = q3.w;
   r.v.cnt[0] = q4.x; r.v.cnt[1] = q4.y; r.v.cnt[2] = q4.z; r.v.cnt[3] = q4.w;
   r.v.cnt[4] = q5.x; r.v.cnt[5] = q5.y; r.v.cnt[6] = q5.z; r.v.cnt[7] = q5.w;
   r.m.order = q6.x;
   r.v.order = q6.y;
-  r.s.hdr = (uint64_t)q6.z | ((uint64_t)q6.w << 32);
+  r.s.meta = q6.z;
+  r.s.ord = q6.w;
   r.m.present = (q7.x & BB_ROW_M_PRESENT) != 0;
   r.v.present = (q7.x & BB_ROW_V_PRESENT) != 0;
   r.alias = (q7.x & BB_ROW_ALIAS) != 0;
-  r.cseq = (uint64_t)q7.z | ((uint64_t)q7.w << 32);
+  r.cseq = u64_of(q7.z, q7.w);
 }
 
-__device__ __forceinline__ void store_row(uint4* __restrict__ row, const RowState& r) {
-  row[0] = make_uint4((uint32_t)r.s.val[0], (uint32_t)(r.s.val[0] >> 32), (uint32_t)r.s.val[1],
-                      (uint32_t)(r.s.val[1] >> 32));
-  row[1] = make_uint4((uint32_t)r.s.val[2], (uint32_t)(r.s.val[2] >> 32), (uint32_t)r.s.val[3],
-                      (uint32_t)(r.s.val[3] >> 32));
-  row[2] = make_uint4(r.m.cnt[0], r.m.cnt[1], r.m.cnt[2], r.m.cnt[3]);
-  row[3] = make_uint4(r.m.cnt[4], r.m.cnt[5], r.m.cnt[6], r.m.cnt[7]);
-  row[4] = make_uint4(r.v.cnt[0], r.v.cnt[1], r.v.cnt[2], r.v.cnt[3]);
-  row[5] = make_uint4(r.v.cnt[4], r.v.cnt[5], r.v.cnt[6], r.v.cnt[7]);
-  row[6] = make_uint4(r.m.order, r.v.order, (uint32_t)r.s.hdr, (uint32_t)(r.s.hdr >> 32));
+__device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
+  q[0] = make_uint4((uint32_t)r.s.val[0], (uint32_t)(r.s.val[0] >> 32), (uint32_t)r.s.val[1], (uint32_t)(r.s.val[1] >> 32));
+  q[1] = make_uint4((uint32_t)r.s.val[2], (uint32_t)(r.s.val[2] >> 32), (uint32_t)r.s.val[3], (uint32_t)(r.s.val[3] >> 32));
+  q[2] = make_uint4(r.m.cnt[0], r.m.cnt[1], r.m.cnt[2], r.m.cnt[3]);
+  q[3] = make_uint4(r.m.cnt[4], r.m.cnt[5], r.m.cnt[6], r.m.cnt[7]);
+  q[4] = make_uint4(r.v.cnt[0], r.v.cnt[1], r.v.cnt[2], r.v.cnt[3]);
+  q[5] = make_uint4(r.v.cnt[4], r.v.cnt[5], r.v.cnt[6], r.v.cnt[7]);
+  q[6] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
   const uint32_t flags = (r.m.present ? BB_ROW_M_PRESENT : 0u) | (r.v.present ? BB_ROW_V_PRESENT : 0u) |
                          (r.alias ? BB_ROW_ALIAS : 0u);
-  row[7] = make_uint4(flags, 0u, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
+  q[7] = make_uint4(flags, 0u, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
 }
 
-__device__ __forceinline__ void load_update(const MergeArgs& a, uint32_t idx, uint64_t& uhdr, uint32_t& user,
-                                            Clock& c, Value& x) {
-  const uint4 h = a.head[idx];
-  const uint4 c0 = a.clk[2 * (uint64_t)idx], c1 = a.clk[2 * (uint64_t)idx + 1];
-  const uint4 v0 = a.val[2 * (uint64_t)idx], v1 = a.val[2 * (uint64_t)idx + 1];
-  uhdr = (uint64_t)h.x | ((uint64_t)h.y << 32);
-  user = h.w;
+// update payload / change entry as 5 x uint4: [head][clk lo][clk hi][val lo][val hi]
+__device__ __forceinline__ bool unpack_update(uint4 h, uint4 c0, uint4 c1, uint4 v0, uint4 v1, Clock& c, Value& x) {
   c.cnt[0] = c0.x; c.cnt[1] = c0.y; c.cnt[2] = c0.z; c.cnt[3] = c0.w;
   c.cnt[4] = c1.x; c.cnt[5] = c1.y; c.cnt[6] = c1.z; c.cnt[7] = c1.w;
   c.order = h.z;
   c.present = 1;
-  x.val[0] = (uint64_t)v0.x | ((uint64_t)v0.y << 32);
-  x.val[1] = (uint64_t)v0.z | ((uint64_t)v0.w << 32);
-  x.val[2] = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
-  x.val[3] = (uint64_t)v1.z | ((uint64_t)v1.w << 32);
-  x.hdr = uhdr & ~(uint64_t)BB_HDR_FLAVOUR_NET;
+  x.val[0] = u64_of(v0.x, v0.y); x.val[1] = u64_of(v0.z, v0.w);
+  x.val[2] = u64_of(v1.x, v1.y); x.val[3] = u64_of(v1.z, v1.w);
+  x.meta = h.x & ~(uint32_t)BB_HDR_FLAVOUR_NET;
+  x.ord = h.y;
+  return (h.x & (uint32_t)BB_HDR_FLAVOUR_NET) != 0;
 }
 
-__device__ __forceinline__ void store_change(const MergeArgs& a, uint32_t idx, uint32_t user, const Value& v,
-                                             const Clock& c) {
-  a.st_head[idx] = make_uint4((uint32_t)v.hdr, (uint32_t)(v.hdr >> 32), c.order, user);
-  a.st_clk[2 * (uint64_t)idx] = make_uint4(c.cnt[0], c.cnt[1], c.cnt[2], c.cnt[3]);
-  a.st_clk[2 * (uint64_t)idx + 1] = make_uint4(c.cnt[4], c.cnt[5], c.cnt[6], c.cnt[7]);
-  a.st_val[2 * (uint64_t)idx] = make_uint4((uint32_t)v.val[0], (uint32_t)(v.val[0] >> 32), (uint32_t)v.val[1],
-                                           (uint32_t)(v.val[1] >> 32));
-  a.st_val[2 * (uint64_t)idx + 1] = make_uint4((uint32_t)v.val[2], (uint32_t)(v.val[2] >> 32),
-                                               (uint32_t)v.val[3], (uint32_t)(v.val[3] >> 32));
+__device__ __forceinline__ void pack_change(uint4* q, uint32_t user, const Value& v, const Clock& c) {
+  q[0] = make_uint4(v.meta, v.ord, c.order, user);
+  q[1] = make_uint4(c.cnt[0], c.cnt[1], c.cnt[2], c.cnt[3]);
+  q[2] = make_uint4(c.cnt[4], c.cnt[5], c.cnt[6], c.cnt[7]);
+  q[3] = make_uint4((uint32_t)v.val[0], (uint32_t)(v.val[0] >> 32), (uint32_t)v.val[1], (uint32_t)(v.val[1] >> 32));
+  q[4] = make_uint4((uint32_t)v.val[2], (uint32_t)(v.val[2] >> 32), (uint32_t)v.val[3], (uint32_t)(v.val[3] >> 32));
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS) k_merge(const MergeArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n || (*a.err & 1u)) return;
-  const uint64_t item = a.sorted[i];
-  const uint32_t key = (uint32_t)(item >> 32);
-  if (i > 0 && (uint32_t)(a.sorted[i - 1] >> 32) == key) return;  // not a segment head
+constexpr uint32_t NO_SLOT = BB_NO_SLOT;
+constexpr int WT = 32;          // sorted positions per warp tile
+constexpr int MERGE_WARPS = 8;  // independent warp tiles per CTA
 
-  uint4* row = a.table + (uint64_t)key * 8;
-  RowState r;
-  load_row(row, r);
-  uint64_t j = i;
-  uint64_t cur = item;
-  while (true) {
-    const uint32_t idx = (uint32_t)cur;
-    uint64_t uhdr;
-    uint32_t user;
-    Clock uc, oc;
-    Value x, ov;
-    load_update(a, idx, uhdr, user, uc, x);
-    const uint32_t code = resolve_step(a.p, r, uhdr, uc, x, a.seq_base + idx, ov, oc);
-    a.decision[idx] = (uint8_t)code;
-    if (BB_DEC_ACCEPTED(code)) store_change(a, idx, user, ov, oc);
-    if (++j >= a.n) break;
-    cur = a.sorted[j];
-    if ((uint32_t)(cur >> 32) != key) break;
-  }
-  store_row(row, r);
-}
+// One warp == one tile of 32 sorted positions; warps never wait for each other (one
+// __syncthreads to hand out tile ids).  Inside a tile the path segments are taken four
+// at a time, one 8-lane group per segment (bb_group.cuh); a group replays its segment's
+// updates in arrival order straight from global memory (32-byte coalesced pieces),
+// parks accepted entries in the warp's shared-memory staging slot, and writes the row
+// back.  Then lane == position again: accepted positions are ranked by ballot, tile
+// totals are chained with a decoupled look-back, and the entries leave for the change
+// set in path-major order.
+#ifndef BB_MERGE_MIN_CTAS
+#define BB_MERGE_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(MERGE_WARPS * 32, BB_MERGE_MIN_CTAS) k_merge_tiles(const MergeArgs a) {
+  __shared__ uint4 s_ent_all[MERGE_WARPS][WT * UPD_Q];
+  __shared__ uint32_t s_idx_all[MERGE_WARPS][WT];
+  __shared__ uint32_t s_res_all[MERGE_WARPS][WT];
+  __shared__ uint32_t s_ticket;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (*a.err & 1u) return;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_ticket * MERGE_WARPS + w;
+  if (tile >= a.num_tiles) return;
+  uint4* s_ent = s_ent_all[w];
+  uint32_t* s_idx = s_idx_all[w];
+  uint32_t* s_res = s_res_all[w];
 
-// ---------------------------------------------------------------- K3 compaction
-__global__ void __launch_bounds__(COMPACT_THREADS) k_accept_count(const uint8_t* __restrict__ decision,
-                                                                  uint64_t n, uint32_t* __restrict__ tile_cnt,
-                                                                  const uint32_t* __restrict__ err) {
-  const uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE;
-  uint32_t s = 0;
-  const bool rejected = (*err & 1u) != 0;
-  for (int k = threadIdx.x; k < COMPACT_TILE; k += COMPACT_THREADS) {
-    const uint64_t i = base + k;
-    if (!rejected && i < n) s += BB_DEC_ACCEPTED(decision[i]);
-  }
-  uint32_t total;
-  block_exclusive_scan<COMPACT_THREADS>(s, &total);
-  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
-}
+  const uint64_t base = (uint64_t)tile * WT;
+  const uint64_t pos = base + lane;
+  const bool valid = pos < a.n;
+  const uint64_t item = valid ? a.sorted[pos] : ~0ull;
+  const uint32_t key = (uint32_t)(item >> 32), idx = (uint32_t)item;
+  uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  if (lane == 0) prev = base > 0 ? (uint32_t)(a.sorted[base - 1] >> 32) : ~key;
+  const bool is_head = valid && key != prev;
+  const uint32_t hmask = __ballot_sync(0xffffffffu, is_head);
+  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+  // positions before the first head continue a segment that an earlier tile owns
+  const uint32_t omask = hmask ? (vmask & ~((hmask & (0u - hmask)) - 1u)) : 0u;
+  const bool owned = (omask >> lane) & 1u;
+  const int nvalid = __popc(vmask);
+  s_idx[lane] = idx;
+  __syncwarp();
 
-struct CompactArgs {
-  const uint8_t* decision;
-  uint64_t n;
-  const uint32_t* tile_base;  // exclusive scan of tile counts
-  const uint4* st_head;
-  const uint4* st_clk;
-  const uint4* st_val;
-  uint32_t* out_idx;
-  uint4* out_head;
-  uint4* out_clk;
-  uint4* out_val;
-  uint64_t cap;
-  uint32_t* err;  // bit0 in: batch rejected; bit1 out: cap too small
-};
-
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact(const CompactArgs a) {
-  // thread t owns the 16 consecutive updates [tile + 16t, +16): arrival order is kept
-  constexpr int PER = COMPACT_TILE / COMPACT_THREADS;
-  const uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE + (uint64_t)threadIdx.x * PER;
-  uint32_t flags = 0;
-  const bool rejected = (*a.err & 1u) != 0;
-#pragma unroll
-  for (int k = 0; k < PER; ++k)
-    if (!rejected && base + k < a.n && BB_DEC_ACCEPTED(a.decision[base + k])) flags |= 1u << k;
-  uint32_t total;
-  uint64_t pos = (uint64_t)a.tile_base[blockIdx.x] + block_exclusive_scan<COMPACT_THREADS>(__popc(flags), &total);
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    if (!((flags >> k) & 1u)) continue;
-    const uint64_t i = base + k;
-    if (pos >= a.cap) {
-      atomicOr(a.err, 2u);
-      return;
+  GLane L;
+  L.sh = lane & 24;
+  L.g = lane & 7;
+  L.lane0 = L.sh;
+  L.gm = 0xFFu << L.sh;
+  const int G = lane >> 3;
+  const int nh = __popc(hmask);
+  uint32_t over = 0;
+  for (int round = 0; round * 4 < nh; ++round) {
+    const int hi = round * 4 + G;
+    const bool has = hi < nh;
+    const int hp = has ? (int)__fns(hmask, 0, hi + 1) : 0;  // position of my group's segment head
+    const uint32_t rkey = __shfl_sync(0xffffffffu, key, hp);
+    if (has) {
+      const uint32_t above = hp < 31 ? (hmask & ~((2u << hp) - 1u)) : 0u;
+      const int end = above ? __ffs(above) - 1 : nvalid;
+      uint4* row = a.table + (uint64_t)rkey * ROW_Q;
+      GState r;
+      g_load_row(row, L, r);
+      for (int p = hp; p < end; ++p) {
+        const uint32_t ui = s_idx[p];
+        const uint4 h = a.head[ui];
+        const uint32_t icnt = reinterpret_cast<const uint32_t*>(a.clk)[8 * (uint64_t)ui + L.g];
+        const uint64_t xval = reinterpret_cast<const uint64_t*>(a.val)[4 * (uint64_t)ui + (L.g & 3)];
+        uint32_t ocnt, oorder, ometa, oord;
+        uint64_t oval;
+        const uint32_t code = g_step(a.p, L, r, (h.x & 1u) != 0, icnt, h.z, h.x & ~1u, h.y, xval,
+                                     a.seq_base + ui, ocnt, oorder, ometa, oord, oval);
+        if (BB_DEC_ACCEPTED(code)) g_store_entry(s_ent + p * UPD_Q, L, h.w, ocnt, oorder, ometa, oord, oval);
+        if (L.g == 0) s_res[p] = code;
+      }
+      if (!above && nvalid == WT) {  // last segment of a full tile: it may run on into the next tiles
+        for (uint64_t gp = base + WT; gp < a.n; ++gp) {
+          const uint64_t it = a.sorted[gp];
+          if ((uint32_t)(it >> 32) != rkey) break;
+          const uint32_t ui = (uint32_t)it;
+          const uint4 h = a.head[ui];
+          const uint32_t icnt = reinterpret_cast<const uint32_t*>(a.clk)[8 * (uint64_t)ui + L.g];
+          const uint64_t xval = reinterpret_cast<const uint64_t*>(a.val)[4 * (uint64_t)ui + (L.g & 3)];
+          uint32_t ocnt, oorder, ometa, oord;
+          uint64_t oval;
+          const uint32_t code = g_step(a.p, L, r, (h.x & 1u) != 0, icnt, h.z, h.x & ~1u, h.y, xval,
+                                       a.seq_base + ui, ocnt, oorder, ometa, oord, oval);
+          if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
+            const uint64_t sp = base + WT + over;
+            g_store_entry(a.st_ent + sp * UPD_Q, L, h.w, ocnt, oorder, ometa, oord, oval);
+            if (L.g == 0) a.st_idx[sp] = ui | (code << 29);
+            ++over;
+          } else if (L.g == 0) {
+            a.verdict[ui] = (code << 29) | NO_SLOT;
+          }
+        }
+      }
+      g_store_row(row, L, r);
     }
-    a.out_idx[pos] = (uint32_t)i;
-    a.out_head[pos] = a.st_head[i];
-    a.out_clk[2 * pos] = a.st_clk[2 * i];
-    a.out_clk[2 * pos + 1] = a.st_clk[2 * i + 1];
-    a.out_val[2 * pos] = a.st_val[2 * i];
-    a.out_val[2 * pos + 1] = a.st_val[2 * i + 1];
-    ++pos;
+    __syncwarp();
   }
+
+  // ---- compaction: rank accepted positions inside the tile, chain the tile totals
+  const uint32_t code = owned ? s_res[lane] : 0xFFu;
+  const bool acc = owned && BB_DEC_ACCEPTED(code);
+  const uint32_t amask = __ballot_sync(0xffffffffu, acc);
+  const uint32_t rank = __popc(amask & lanemask_lt());
+  const uint32_t in_cnt = __popc(amask);
+  uint32_t over_cnt = (L.g == 0) ? over : 0u;  // at most one group ran past the tile
+  over_cnt = warp_sum(over_cnt);
+  const uint32_t ex = tile_prefix(a.tile_state, tile, in_cnt + over_cnt);
+  if (lane == 0 && tile == a.num_tiles - 1) *a.n_changes = (uint64_t)ex + in_cnt + over_cnt;
+  const uint64_t obase = ex;
+
+  // ---- verdicts (arrival order) and the change set (path-major order)
+  bool overflow = false;
+  const uint64_t dest = obase + rank;
+  if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : NO_SLOT);
+  if (acc) {
+    if (dest < a.cap) {
+      a.out_idx[dest] = idx;
+      a.out_head[dest] = s_ent[lane * UPD_Q];
+    } else {
+      overflow = true;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {  // lanes 2k, 2k+1 move the two halves of a 32-byte clock / value
+    const int e = j * 16 + (lane >> 1), half = lane & 1;
+    const uint64_t edest = obase + __popc(amask & ((1u << e) - 1u));
+    if (((amask >> e) & 1u) && edest < a.cap) {
+      a.out_clk[2 * edest + half] = s_ent[e * UPD_Q + 1 + half];
+      a.out_val[2 * edest + half] = s_ent[e * UPD_Q + 3 + half];
+    }
+  }
+  // ---- entries of a segment tail that ran past the tile
+  for (uint32_t k = lane; k < over_cnt; k += 32) {
+    const uint64_t sp = base + WT + k, odest = obase + in_cnt + k;
+    const uint32_t packed = a.st_idx[sp];
+    const uint32_t gi = packed & NO_SLOT;
+    a.verdict[gi] = (packed & ~NO_SLOT) | (uint32_t)odest;
+    if (odest < a.cap) {
+      const uint4* q = a.st_ent + sp * UPD_Q;
+      a.out_idx[odest] = gi;
+      a.out_head[odest] = q[0];
+      a.out_clk[2 * odest] = q[1];
+      a.out_clk[2 * odest + 1] = q[2];
+      a.out_val[2 * odest] = q[3];
+      a.out_val[2 * odest + 1] = q[4];
+    } else {
+      overflow = true;
+    }
+  }
+  if (overflow) atomicOr(a.err, 2u);
 }
 
 // ---------------------------------------------------------------- table import / export
@@ -400,12 +508,12 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
   uint4* row = table + p * 8;
   if (materialise) {  // Bullet._getData's side effect (src/bullet.js:122-124)
     RowState r;
-    load_row(row, r);
-    const uint32_t k = kind_of(r.s.hdr);
-    if (k == BB_KIND_NONE || (k == BB_KIND_PRIM && prim_falsy(tag_of(r.s.hdr, 0), r.s.val[0]))) {
+    unpack_row(row, r);
+    const uint32_t k = kind_of(r.s.meta);
+    if (k == BB_KIND_NONE || falsy_primitive(r.s)) {
       if (k == BB_KIND_NONE) r.cseq = seq + i + 1;
       materialise_empty_object(r.s);
-      store_row(row, r);
+      pack_row(row, r);
     }
   }
 #pragma unroll

@@ -11,7 +11,9 @@
 //
 // Everything is kept in registers: clock counts and value payloads are fixed
 // arrays that are only ever indexed by unrolled loop counters; key orders and
-// tags are bit fields (layout: include/bullet_b200.h).
+// tags are 32-bit bit fields (layout: include/bullet_b200.h; the 64-bit header
+// word is split into `meta` = low half (kind, tags) and `ord` = high half (key
+// order) so that no 64-bit shifts are needed).
 #pragma once
 #include <stdint.h>
 
@@ -30,7 +32,8 @@ struct Clock {
 
 struct Value {
   uint64_t val[F];
-  uint64_t hdr;  // kind | tags | key order (flavour bit stripped)
+  uint32_t meta;  // low half of the header word, flavour bit stripped
+  uint32_t ord;   // high half: own-key order nibbles
 };
 
 struct Params {
@@ -39,11 +42,13 @@ struct Params {
   uint32_t post_getdata;
 };
 
-__device__ __forceinline__ uint32_t kind_of(uint64_t hdr) { return (uint32_t)(hdr >> BB_HDR_KIND_SHIFT) & 3u; }
-__device__ __forceinline__ uint32_t tag_of(uint64_t hdr, int f) {
-  return (uint32_t)(hdr >> (BB_HDR_TAG_SHIFT + 3 * f)) & 7u;
+__device__ __forceinline__ uint32_t kind_of(uint32_t meta) { return (meta >> BB_HDR_KIND_SHIFT) & 3u; }
+__device__ __forceinline__ uint32_t tag_of(uint32_t meta, int f) { return (meta >> (BB_HDR_TAG_SHIFT + 3 * f)) & 7u; }
+// one bit per own key, at bit 3f
+__device__ __forceinline__ uint32_t present_bits(uint32_t meta) {
+  const uint32_t t = meta >> BB_HDR_TAG_SHIFT;
+  return (t | (t >> 1) | (t >> 2)) & 0x249249u;
 }
-__device__ __forceinline__ uint32_t tags_of(uint64_t hdr) { return (uint32_t)(hdr >> BB_HDR_TAG_SHIFT) & 0xFFFFFFu; }
 
 __device__ __forceinline__ uint32_t clock_mask(const Clock& c) {
   uint32_t m = 0;
@@ -68,16 +73,18 @@ __device__ __forceinline__ void clock_increment(Clock& v, uint32_t me) {
 
 // crt:103-114: {...c1}, then c2's keys (max); keys new to c1 appended in c2's order
 __device__ __forceinline__ void clock_merge(const Clock& c1, const Clock& c2, Clock& out) {
-  uint32_t m1 = clock_mask(c1);
-  const uint32_t n2 = __popc(clock_mask(c2));
-  uint32_t n = __popc(m1);
+  const uint32_t m1 = clock_mask(c1), m2 = clock_mask(c2);
   uint32_t order = c1.order;
-  for (uint32_t i = 0; i < n2; ++i) {
-    const uint32_t s = (c2.order >> (4 * i)) & 0xFu;
-    if (!((m1 >> s) & 1u)) {
-      order |= s << (4 * n);
-      ++n;
-      m1 |= 1u << s;
+  uint32_t fresh = m2 & ~m1;
+  if (fresh) {  // rare: the key sets usually coincide
+    uint32_t n = __popc(m1);
+    const uint32_t n2 = __popc(m2);
+    for (uint32_t i = 0; i < n2; ++i) {
+      const uint32_t s = (c2.order >> (4 * i)) & 0xFu;
+      if ((fresh >> s) & 1u) {
+        order |= s << (4 * n);
+        ++n;
+      }
     }
   }
 #pragma unroll
@@ -87,76 +94,76 @@ __device__ __forceinline__ void clock_merge(const Clock& c1, const Clock& c2, Cl
 }
 
 __device__ __forceinline__ bool prim_falsy(uint32_t tag, uint64_t pay) {
-  if (tag == BB_TAG_NUM) {
-    const double d = __longlong_as_double((long long)pay);
-    return d == 0.0 || d != d;
-  }
+  if (tag == BB_TAG_NUM) return (pay << 1) == 0 || (pay << 1) > 0xFFE0000000000000ull;  // +-0 or NaN
   if (tag == BB_TAG_BOOL) return pay == 0;
   return tag == BB_TAG_NULL;
 }
 
 // crt:11-15 on two primitives (=== then <; anything else, NaN included, is +1)
 __device__ __forceinline__ int compare_prim(uint32_t ta, uint64_t pa, uint32_t tb, uint64_t pb) {
-  const double da = __longlong_as_double((long long)pa), db = __longlong_as_double((long long)pb);
+  if (ta == BB_TAG_NUM && tb == BB_TAG_NUM) {
+    const double da = __longlong_as_double((long long)pa), db = __longlong_as_double((long long)pb);
+    return da == db ? 0 : (da < db ? -1 : 1);
+  }
   if (ta == tb) {
-    const bool eq = ta == BB_TAG_NUM ? (da == db) : (ta == BB_TAG_NULL ? true : pa == pb);
-    if (eq) return 0;
+    if (ta == BB_TAG_NULL || pa == pb) return 0;
+    return pa < pb ? -1 : 1;  // STR: dictionary id order == UTF-16 order; BOOL: false < true
   }
-  if (ta == BB_TAG_STR || tb == BB_TAG_STR) {
-    if (ta == tb) return pa < pb ? -1 : 1;  // UTF-16 order == dictionary id order
-    return 1;                               // ToNumber(non-numeric string) is NaN
-  }
-  const double na = ta == BB_TAG_NUM ? da : (double)(ta == BB_TAG_BOOL && pa != 0);
-  const double nb = tb == BB_TAG_NUM ? db : (double)(tb == BB_TAG_BOOL && pb != 0);
+  if (ta == BB_TAG_STR || tb == BB_TAG_STR) return 1;  // ToNumber(non-numeric string) is NaN
+  const double na = ta == BB_TAG_NUM ? __longlong_as_double((long long)pa) : (double)(ta == BB_TAG_BOOL && pa != 0);
+  const double nb = tb == BB_TAG_NUM ? __longlong_as_double((long long)pb) : (double)(tb == BB_TAG_BOOL && pb != 0);
   return na < nb ? -1 : 1;
 }
 
 // crt:11-15 on whole values: distinct objects are never ===, and `<` sees an
 // object operand as the string "[object Object]".
 __device__ __forceinline__ int compare_whole(const Params& p, const Value& x, const Value& cur) {
-  const bool xo = kind_of(x.hdr) == BB_KIND_OBJ, co = kind_of(cur.hdr) == BB_KIND_OBJ;
+  const bool xo = kind_of(x.meta) == BB_KIND_OBJ, co = kind_of(cur.meta) == BB_KIND_OBJ;
   if (xo && co) return 1;
-  if (xo) return (tag_of(cur.hdr, 0) == BB_TAG_STR && cur.val[0] >= p.rank_object) ? -1 : 1;
-  if (co) return (tag_of(x.hdr, 0) == BB_TAG_STR && x.val[0] < p.rank_object) ? -1 : 1;
-  return compare_prim(tag_of(x.hdr, 0), x.val[0], tag_of(cur.hdr, 0), cur.val[0]);
-}
-
-__device__ __forceinline__ uint32_t nkeys(uint64_t hdr) {
-  const uint32_t t = tags_of(hdr);
-  return __popc((t | (t >> 1) | (t >> 2)) & 0x249249u);  // one bit per non-ABSENT slot
+  if (xo) return (tag_of(cur.meta, 0) == BB_TAG_STR && cur.val[0] >= p.rank_object) ? -1 : 1;
+  if (co) return (tag_of(x.meta, 0) == BB_TAG_STR && x.val[0] < p.rank_object) ? -1 : 1;
+  return compare_prim(tag_of(x.meta, 0), x.val[0], tag_of(cur.meta, 0), cur.val[0]);
 }
 
 // crt:122-153 (flat records: every leaf compare is primitive vs primitive)
 __device__ __forceinline__ void merge_values(const Params& p, const Value& x, const Value& cur, Value& out) {
-  if (kind_of(x.hdr) != BB_KIND_OBJ || kind_of(cur.hdr) != BB_KIND_OBJ) {
+  if (kind_of(x.meta) != BB_KIND_OBJ || kind_of(cur.meta) != BB_KIND_OBJ) {
     out = compare_whole(p, x, cur) >= 0 ? x : cur;
     return;
   }
   out = cur;  // {...currentValue}
-  const uint32_t nx = nkeys(x.hdr);
-  uint32_t n = nkeys(cur.hdr);
-  for (uint32_t i = 0; i < nx; ++i) {  // own keys of incoming that are new: appended in its order
-    const uint32_t f = (uint32_t)(x.hdr >> (BB_HDR_ORDER_SHIFT + 4 * i)) & 0xFu;
-    if (tag_of(cur.hdr, f) == BB_TAG_ABSENT) {
-      out.hdr |= (uint64_t)f << (BB_HDR_ORDER_SHIFT + 4 * n);
-      ++n;
+  const uint32_t px = present_bits(x.meta), pc = present_bits(cur.meta);
+  const uint32_t fresh = px & ~pc;
+  if (fresh) {  // own keys of incoming that current lacks: appended in incoming's order
+    uint32_t n = __popc(pc);
+    const uint32_t nx = __popc(px);
+    for (uint32_t i = 0; i < nx; ++i) {
+      const uint32_t f = (x.ord >> (4 * i)) & 0xFu;
+      if ((fresh >> (3 * f)) & 1u) {
+        out.ord |= f << (4 * n);
+        ++n;
+      }
     }
   }
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    const uint32_t tx = tag_of(x.hdr, f), tc = tag_of(cur.hdr, f);
-    if (tx == BB_TAG_ABSENT) continue;
-    if (tc == BB_TAG_ABSENT || compare_prim(tx, x.val[f], tc, cur.val[f]) >= 0) {
-      out.hdr = (out.hdr & ~(7ull << (BB_HDR_TAG_SHIFT + 3 * f))) | ((uint64_t)tx << (BB_HDR_TAG_SHIFT + 3 * f));
+    const uint32_t tx = tag_of(x.meta, f), tc = tag_of(cur.meta, f);
+    if (tx != BB_TAG_ABSENT && (tc == BB_TAG_ABSENT || compare_prim(tx, x.val[f], tc, cur.val[f]) >= 0)) {
+      out.meta = (out.meta & ~(7u << (BB_HDR_TAG_SHIFT + 3 * f))) | (tx << (BB_HDR_TAG_SHIFT + 3 * f));
       out.val[f] = x.val[f];
     }
   }
 }
 
 __device__ __forceinline__ void materialise_empty_object(Value& v) {
-  v.hdr = (uint64_t)BB_KIND_OBJ << BB_HDR_KIND_SHIFT;
+  v.meta = BB_KIND_OBJ << BB_HDR_KIND_SHIFT;
+  v.ord = 0;
 #pragma unroll
   for (int f = 0; f < F; ++f) v.val[f] = 0;
+}
+
+__device__ __forceinline__ bool falsy_primitive(const Value& v) {
+  return kind_of(v.meta) == BB_KIND_PRIM && prim_falsy(tag_of(v.meta, 0), v.val[0]);
 }
 
 struct RowState {
@@ -167,22 +174,19 @@ struct RowState {
 };
 
 // One setData(): mutates the row state, returns the decision code, fills the
-// emitted (value, clock) when accepted.
-__device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, uint64_t uhdr,
-                                                 const Clock& uclk, const Value& x, uint64_t seq,
-                                                 Value& out_val, Clock& out_clk) {
-  const uint32_t ck = kind_of(r.s.hdr);
-  if (ck == BB_KIND_NONE) {
+// emitted (value, clock) when accepted.  `net` = network-with-clock flavour.
+__device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, bool net, const Clock& uclk,
+                                                 const Value& x, uint64_t seq, Value& out_val, Clock& out_clk) {
+  if (kind_of(r.s.meta) == BB_KIND_NONE) {
     r.cseq = seq + 1;
     materialise_empty_object(r.s);
-  } else if (ck == BB_KIND_PRIM && prim_falsy(tag_of(r.s.hdr, 0), r.s.val[0])) {
+  } else if (falsy_primitive(r.s)) {
     materialise_empty_object(r.s);
   }
 
   Clock inc;
-  if (uhdr & BB_HDR_FLAVOUR_NET) {
+  if (net) {
     inc = uclk;
-    inc.present = 1;
   } else {
     clock_increment(r.v, p.me);  // crt:358, in place
     if (r.alias) r.m = r.v;      // M is the same object
@@ -190,10 +194,10 @@ __device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, u
   }
 
   uint32_t code;
+  out_val = x;
   if (!r.m.present) {  // crt:172-185
     clock_increment(r.v, p.me);
     out_clk = r.v;
-    out_val = x;
     code = BB_DEC_NO_CURRENT;
   } else {
     bool d1 = false, d2 = false;
@@ -205,16 +209,11 @@ __device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, u
     clock_merge(inc, r.m, out_clk);
     r.v = out_clk;  // crt:197
     r.alias = 0;
-    if (!d1 && !d2 && inc.order == r.m.order) {  // JSON.stringify equal (crt:200-203)
+    if (d1 != d2) {
+      code = d1 ? BB_DEC_INCOMING : BB_DEC_HISTORICAL;
+    } else if (!d1 && inc.order == r.m.order) {  // JSON.stringify equal (crt:200-203)
       const int vc = compare_whole(p, x, r.s);
       code = vc == 0 ? BB_DEC_IDENTICAL : (vc > 0 ? BB_DEC_TIE_INCOMING : BB_DEC_TIE_CURRENT);
-      out_val = x;
-    } else if (d1 && !d2) {
-      code = BB_DEC_INCOMING;
-      out_val = x;
-    } else if (d2 && !d1) {
-      code = BB_DEC_HISTORICAL;
-      out_val = x;
     } else {
       code = BB_DEC_CONCURRENT;
       merge_values(p, x, r.s, out_val);
@@ -226,8 +225,7 @@ __device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, u
     r.v = out_clk;
     r.alias = 1;
   }
-  if (p.post_getdata && kind_of(r.s.hdr) == BB_KIND_PRIM && prim_falsy(tag_of(r.s.hdr, 0), r.s.val[0]))
-    materialise_empty_object(r.s);  // the index hook's _getData (query:151,169)
+  if (p.post_getdata && falsy_primitive(r.s)) materialise_empty_object(r.s);  // hook's _getData (query:151,169)
   return code;
 }
 

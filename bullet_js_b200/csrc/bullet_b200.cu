@@ -17,7 +17,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_COMPACT, EV_D2H, EV_COUNT };
+enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_D2H, EV_COUNT };
 constexpr int EV_RING = 64;  // merge calls whose phase timings can still be queried
 
 template <class T>
@@ -56,15 +56,15 @@ struct bb_ctx {
   uint64_t calls = 0;  // merge calls started; ring slot = (calls - 1) % EV_RING
   // pipeline scratch
   DevBuf<uint64_t> items_a, items_b;
-  DevBuf<uint32_t> counts, tile_sums, tile_cnt;
-  DevBuf<uint4> st_head, st_clk, st_val;
+  DevBuf<uint32_t> zero;  // zeroed per call: [digit histograms | tickets | sort tile states | merge tile states]
+  DevBuf<uint32_t> st_idx;
+  DevBuf<uint4> st_ent;
   uint32_t* d_err = nullptr;    // bit0: path id out of range, bit1: change buffer too small
   uint32_t* h_err = nullptr;    // pinned
   // device mirrors of the host-call buffers
   DevBuf<uint64_t> io_path;
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
-  DevBuf<uint8_t> io_decision;
-  DevBuf<uint32_t> io_out_idx;
+  DevBuf<uint32_t> io_verdict, io_out_idx;
   uint64_t* d_nchanges = nullptr;
   uint64_t* h_nchanges = nullptr;  // pinned
 };
@@ -110,33 +110,33 @@ void mark(bb_ctx* c, int which, cudaStream_t s) {
   c->ev_valid[slot][which] = true;
 }
 
-// exclusive scan of data[0..m) in place on stream s (m up to 2^32)
-int scan_u32(bb_ctx* c, uint32_t* data, uint64_t m, uint64_t* total64, cudaStream_t s) {
+struct ZeroLayout {
+  uint32_t passes, sort_tiles, merge_tiles;
+  size_t hist, tickets, sort_state, merge_state, total;  // offsets in uint32_t units
+};
+
+ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   using namespace bb;
-  if (m <= 4096) {
-    BB_LAUNCH(c, k_scan_small, 1, 1024, s, data, m, total64);
-    return BB_OK;
-  }
-  const uint32_t tiles = div_up(m, SCAN_TILE);
-  BB_CUDA(c, c->tile_sums.ensure(tiles));
-  BB_LAUNCH(c, k_scan_reduce, tiles, SCAN_THREADS, s, data, m, c->tile_sums.p);
-  BB_LAUNCH(c, k_scan_small, 1, 1024, s, c->tile_sums.p, (uint64_t)tiles, total64);
-  BB_LAUNCH(c, k_scan_apply, tiles, SCAN_THREADS, s, data, m, c->tile_sums.p);
-  return BB_OK;
+  ZeroLayout z;
+  z.passes = (uint32_t)((c->key_bits + 7) / 8);
+  z.sort_tiles = div_up(n, SORT_TILE);
+  z.merge_tiles = div_up(n, WT);
+  z.hist = 0;
+  z.tickets = z.hist + (size_t)MAX_PASSES * RADIX;
+  z.sort_state = z.tickets + 8;
+  z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
+  z.total = z.merge_state + z.merge_tiles;
+  return z;
 }
 
 // size every scratch buffer of the device pipeline for batches of up to n updates
 int reserve_dev(bb_ctx* c, uint64_t n) {
-  using namespace bb;
-  const uint32_t sort_tiles = div_up(n, SORT_TILE);
+  const ZeroLayout z = zero_layout(c, n);
   BB_CUDA(c, c->items_a.ensure(n));
   BB_CUDA(c, c->items_b.ensure(n));
-  BB_CUDA(c, c->counts.ensure((size_t)RADIX * sort_tiles));
-  BB_CUDA(c, c->tile_sums.ensure(div_up((uint64_t)RADIX * sort_tiles, SCAN_TILE)));
-  BB_CUDA(c, c->tile_cnt.ensure(div_up(n, COMPACT_TILE)));
-  BB_CUDA(c, c->st_head.ensure(n));
-  BB_CUDA(c, c->st_clk.ensure(2 * n));
-  BB_CUDA(c, c->st_val.ensure(2 * n));
+  BB_CUDA(c, c->zero.ensure(z.total));
+  BB_CUDA(c, c->st_idx.ensure(n));
+  BB_CUDA(c, c->st_ent.ensure(5 * n));
   return BB_OK;
 }
 
@@ -145,7 +145,7 @@ int reserve_io(bb_ctx* c, uint64_t n) {
   BB_CUDA(c, c->io_head.ensure(n));
   BB_CUDA(c, c->io_clk.ensure(2 * n));
   BB_CUDA(c, c->io_val.ensure(2 * n));
-  BB_CUDA(c, c->io_decision.ensure(n));
+  BB_CUDA(c, c->io_verdict.ensure(n));
   BB_CUDA(c, c->io_out_idx.ensure(n));
   BB_CUDA(c, c->io_out_head.ensure(n));
   BB_CUDA(c, c->io_out_clk.ensure(2 * n));
@@ -156,37 +156,39 @@ int reserve_io(bb_ctx* c, uint64_t n) {
 int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   using namespace bb;
   const uint64_t n = in->n;
-  if (n >= 0xFFFFFFFFull) return fail(c, BB_ERR_ARG, "batch larger than 2^32-1 updates");
+  if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
   mark(c, EV_START, s);
+  BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
   if (n == 0) {
-    BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
     mark(c, EV_SORT, s);
     mark(c, EV_MERGE, s);
-    mark(c, EV_COMPACT, s);
     return BB_OK;
   }
-  const uint32_t sort_tiles = div_up(n, SORT_TILE);
   {
     int rc = reserve_dev(c, n);  // no-op once the scratch is large enough
     if (rc) return rc;
   }
+  const ZeroLayout z = zero_layout(c, n);
+  uint32_t* zp = c->zero.p;
+  BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
 
   // K0 + K1: stable sort of (path id, arrival index) by path id
-  BB_LAUNCH(c, k_make_keys, div_up(n, 256), 256, s, in->path_id, n, c->cfg.capacity, c->items_a.p, c->d_err);
+  BB_LAUNCH(c, k_keys_hist, z.sort_tiles, SORT_THREADS, s, in->path_id, n, c->cfg.capacity, (int)z.passes,
+            c->items_a.p, zp + z.hist, c->d_err);
+  BB_LAUNCH(c, k_hist_scan, z.passes, RADIX, s, zp + z.hist);
   uint64_t* src = c->items_a.p;
   uint64_t* dst = c->items_b.p;
-  for (int shift = 0; shift < c->key_bits; shift += 8) {
-    BB_LAUNCH(c, k_sort_count, sort_tiles, SORT_THREADS, s, src, n, shift, sort_tiles, c->counts.p);
-    int rc = scan_u32(c, c->counts.p, (uint64_t)RADIX * sort_tiles, nullptr, s);
-    if (rc) return rc;
-    BB_LAUNCH(c, k_sort_scatter, sort_tiles, SORT_THREADS, s, src, dst, n, shift, sort_tiles, c->counts.p);
+  for (uint32_t pass = 0; pass < z.passes; ++pass) {
+    BB_LAUNCH(c, k_sort_pass, z.sort_tiles, SORT_THREADS, s, src, dst, n, (int)(8 * pass),
+              zp + z.hist + (size_t)pass * RADIX, zp + z.sort_state + (size_t)pass * z.sort_tiles * RADIX,
+              zp + z.tickets + pass);
     uint64_t* t = src;
     src = dst;
     dst = t;
   }
   mark(c, EV_SORT, s);
 
-  // K2: per-path sequential replay against the table
+  // K2: per-path sequential replay against the table + change-set compaction
   MergeArgs ma;
   ma.sorted = src;
   ma.n = n;
@@ -194,39 +196,25 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   ma.head = reinterpret_cast<const uint4*>(in->head);
   ma.clk = reinterpret_cast<const uint4*>(in->clk);
   ma.val = reinterpret_cast<const uint4*>(in->val);
-  ma.decision = out->decision;
-  ma.st_head = c->st_head.p;
-  ma.st_clk = c->st_clk.p;
-  ma.st_val = c->st_val.p;
+  ma.verdict = out->verdict;
+  ma.n_changes = out->n_changes;
+  ma.out_idx = out->idx;
+  ma.out_head = reinterpret_cast<uint4*>(out->head);
+  ma.out_clk = reinterpret_cast<uint4*>(out->clk);
+  ma.out_val = reinterpret_cast<uint4*>(out->val);
+  ma.cap = out->cap;
+  ma.st_idx = c->st_idx.p;
+  ma.st_ent = c->st_ent.p;
+  ma.tile_state = zp + z.merge_state;
+  ma.ticket = zp + z.tickets + MAX_PASSES;
+  ma.num_tiles = z.merge_tiles;
   ma.seq_base = c->seq;
   ma.err = c->d_err;
   ma.p.rank_object = c->cfg.rank_object;
   ma.p.me = c->cfg.local_peer;
   ma.p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
-  BB_LAUNCH(c, k_merge, div_up(n, MERGE_THREADS), MERGE_THREADS, s, ma);
+  BB_LAUNCH(c, k_merge_tiles, div_up(z.merge_tiles, MERGE_WARPS), MERGE_WARPS * 32, s, ma);
   mark(c, EV_MERGE, s);
-
-  // K3: change set in arrival order
-  const uint32_t ctiles = div_up(n, COMPACT_TILE);
-  BB_CUDA(c, c->tile_cnt.ensure(ctiles));
-  BB_LAUNCH(c, k_accept_count, ctiles, COMPACT_THREADS, s, out->decision, n, c->tile_cnt.p, c->d_err);
-  int rc = scan_u32(c, c->tile_cnt.p, ctiles, out->n_changes, s);
-  if (rc) return rc;
-  CompactArgs ca;
-  ca.decision = out->decision;
-  ca.n = n;
-  ca.tile_base = c->tile_cnt.p;
-  ca.st_head = c->st_head.p;
-  ca.st_clk = c->st_clk.p;
-  ca.st_val = c->st_val.p;
-  ca.out_idx = out->idx;
-  ca.out_head = reinterpret_cast<uint4*>(out->head);
-  ca.out_clk = reinterpret_cast<uint4*>(out->clk);
-  ca.out_val = reinterpret_cast<uint4*>(out->val);
-  ca.cap = out->cap;
-  ca.err = c->d_err;
-  BB_LAUNCH(c, k_compact, ctiles, COMPACT_THREADS, s, ca);
-  mark(c, EV_COMPACT, s);
   c->seq += n;
   return BB_OK;
 }
@@ -307,11 +295,11 @@ int bb_destroy(bb_ctx* c) {
   if (!c) return BB_ERR_ARG;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  c->items_a.release(); c->items_b.release(); c->counts.release(); c->tile_sums.release();
-  c->tile_cnt.release(); c->st_head.release(); c->st_clk.release(); c->st_val.release();
+  c->items_a.release(); c->items_b.release(); c->zero.release(); c->st_idx.release();
+  c->st_ent.release();
   c->io_path.release(); c->io_head.release(); c->io_clk.release(); c->io_val.release();
   c->io_out_head.release(); c->io_out_clk.release(); c->io_out_val.release(); c->io_rows.release();
-  c->io_decision.release(); c->io_out_idx.release();
+  c->io_verdict.release(); c->io_out_idx.release();
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_nchanges) cudaFree(c->d_nchanges);
@@ -366,7 +354,7 @@ int bb_table_read(bb_ctx* c, uint64_t n, const uint64_t* path_id, bb_row* rows_o
 
 int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* stream) {
   if (!c || !in || !out) return fail(c, BB_ERR_ARG, "null argument");
-  if (in->n && (!in->path_id || !in->head || !in->clk || !in->val || !out->decision || !out->idx ||
+  if (in->n && (!in->path_id || !in->head || !in->clk || !in->val || !out->verdict || !out->idx ||
                 !out->head || !out->clk || !out->val))
     return fail(c, BB_ERR_ARG, "null buffer");
   if (!out->n_changes) return fail(c, BB_ERR_ARG, "null n_changes");
@@ -392,7 +380,7 @@ int bb_sync(bb_ctx* c, void* stream) {
 int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   if (!c || !in || !out || !out->n_changes) return fail(c, BB_ERR_ARG, "null argument");
   const uint64_t n = in->n;
-  if (n && (!in->path_id || !in->head || !in->clk || !in->val || !out->decision))
+  if (n && (!in->path_id || !in->head || !in->clk || !in->val || !out->verdict))
     return fail(c, BB_ERR_ARG, "null buffer");
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
@@ -400,7 +388,7 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   mark(c, EV_H2D0, s);
   if (n == 0) {
     *out->n_changes = 0;
-    mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_COMPACT, s); mark(c, EV_D2H, s);
+    mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_D2H, s);
     return BB_OK;
   }
   {
@@ -415,12 +403,12 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   BB_CUDA(c, cudaMemcpyAsync(c->io_val.p, in->val, n * 32, cudaMemcpyHostToDevice, s));
   bb_batch din{n, c->io_path.p, reinterpret_cast<const bb_head*>(c->io_head.p),
                reinterpret_cast<const uint32_t*>(c->io_clk.p), reinterpret_cast<const uint64_t*>(c->io_val.p)};
-  bb_changes dout{n, c->io_decision.p, c->d_nchanges, c->io_out_idx.p,
+  bb_changes dout{n, c->io_verdict.p, c->d_nchanges, c->io_out_idx.p,
                   reinterpret_cast<bb_head*>(c->io_out_head.p), reinterpret_cast<uint32_t*>(c->io_out_clk.p),
                   reinterpret_cast<uint64_t*>(c->io_out_val.p)};
   int rc = merge_dev(c, &din, &dout, s);
   if (rc) return rc;
-  BB_CUDA(c, cudaMemcpyAsync(out->decision, c->io_decision.p, n, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaMemcpyAsync(out->verdict, c->io_verdict.p, n * 4, cudaMemcpyDeviceToHost, s));
   BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges, c->d_nchanges, 8, cudaMemcpyDeviceToHost, s));
   rc = collect_device_error(c, s);  // synchronises
   if (rc) return rc;
@@ -450,9 +438,8 @@ double bb_phase_ms(bb_ctx* c, const char* phase, uint32_t calls_ago) {
   if (!strcmp(phase, "h2d")) { a = EV_H2D0; b = EV_START; }
   else if (!strcmp(phase, "sort")) { a = EV_START; b = EV_SORT; }
   else if (!strcmp(phase, "merge")) { a = EV_SORT; b = EV_MERGE; }
-  else if (!strcmp(phase, "compact")) { a = EV_MERGE; b = EV_COMPACT; }
-  else if (!strcmp(phase, "d2h")) { a = EV_COMPACT; b = EV_D2H; }
-  else if (!strcmp(phase, "device")) { a = EV_START; b = EV_COMPACT; }
+  else if (!strcmp(phase, "d2h")) { a = EV_MERGE; b = EV_D2H; }
+  else if (!strcmp(phase, "device")) { a = EV_START; b = EV_MERGE; }
   else if (!strcmp(phase, "total")) { a = EV_H2D0; b = EV_D2H; }
   if (a < 0 || !c->ev_valid[slot][a] || !c->ev_valid[slot][b]) return -1.0;
   cudaSetDevice(c->cfg.device);

@@ -156,16 +156,26 @@ typedef struct bb_batch {
   const uint64_t* val;     /* [n][BB_MAX_FIELDS] */
 } bb_batch;
 
-/* The emitted change set == the ordered _applyUpdate calls (src/bullet.js:184-220):
- * one entry per accepted update, in arrival order. */
+/* Per-update verdict + the emitted change set.
+ * verdict[i] (arrival order, every update) = BB_DEC_* code << 29 | slot, where slot
+ * is the position of update i's entry in idx/head/clk/val, or BB_NO_SLOT when the
+ * update was rejected (doUpdate == false, src/bullet-crt.js:383).
+ * The change set == the _applyUpdate calls (src/bullet.js:184-220), one entry per
+ * accepted update.  Entries are stored in PATH-MAJOR order (ascending path id,
+ * arrival order within a path) because that is the order the device resolves them
+ * in; the reference's arrival order is recovered without a sort by walking
+ * verdict[] and following the slots.  A batch is limited to 2^29-2 updates. */
+#define BB_NO_SLOT 0x1FFFFFFFu
+#define BB_VERDICT_CODE(v) ((uint32_t)(v) >> 29)
+#define BB_VERDICT_SLOT(v) ((uint32_t)(v) & BB_NO_SLOT)
 typedef struct bb_changes {
-  uint64_t cap;       /* capacity of idx/head/clk/val in entries (n always suffices) */
-  uint8_t* decision;  /* [n] BB_DEC_* per update (every update, accepted or not) */
-  uint64_t* n_changes;/* [1] */
-  uint32_t* idx;      /* [cap] index of the update in the batch */
-  bb_head* head;      /* [cap] stored value header + order of the stored clock */
-  uint32_t* clk;      /* [cap][BB_MAX_PEERS] stored clock == decision.vectorClock */
-  uint64_t* val;      /* [cap][BB_MAX_FIELDS] stored value == decision.value */
+  uint64_t cap;        /* capacity of idx/head/clk/val in entries (n always suffices) */
+  uint32_t* verdict;   /* [n] */
+  uint64_t* n_changes; /* [1] */
+  uint32_t* idx;       /* [cap] index of the update in the batch */
+  bb_head* head;       /* [cap] stored value header + key order of the stored clock */
+  uint32_t* clk;       /* [cap][BB_MAX_PEERS] stored clock == decision.vectorClock */
+  uint64_t* val;       /* [cap][BB_MAX_FIELDS] stored value == decision.value */
 } bb_changes;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -193,7 +203,8 @@ int bb_reserve(bb_ctx* ctx, uint64_t max_batch, int host_entry);
  *      Host buffers; H2D / D2H copies are part of the call. ------------------- */
 int bb_merge_batch(bb_ctx* ctx, const bb_batch* in, bb_changes* out);
 /* Same, all pointers are device pointers on ctx's device, work is enqueued on
- * `stream` (a cudaStream_t; 0 = ctx's own stream) and NOT synchronised. */
+ * `stream` (a cudaStream_t; 0 = ctx's own stream - pass cudaStreamLegacy (0x1) to
+ * name the legacy default stream) and NOT synchronised. */
 int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* stream);
 /* Synchronise `stream` (0 = ctx's own) and return the deferred status of the
  * *_dev calls enqueued since the last bb_sync: BB_ERR_CAPACITY if a batch held a
@@ -209,7 +220,7 @@ uint64_t bb_launch_count(const bb_ctx* ctx);
 double bb_last_phase_ms(bb_ctx* ctx, const char* phase);
 /* Same for the merge call issued `calls_ago` calls before the most recent one
  * (0 = most recent; the last 64 calls are kept).  Phases: "h2d", "sort", "merge",
- * "compact", "d2h", "device" (sort+merge+compact), "total". */
+ * "d2h", "device" (sort+merge), "total". */
 double bb_phase_ms(bb_ctx* ctx, const char* phase, uint32_t calls_ago);
 
 #ifdef __cplusplus

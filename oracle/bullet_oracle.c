@@ -363,7 +363,7 @@ int bo_merge_batch(const bb_config* cfg, bb_row* table, uint64_t seq_base, const
     if (in->path_id[i] >= cfg->capacity) return BB_ERR_CAPACITY;
     int code = step(cfg, &table[in->path_id[i]], seq_base + i, &in->head[i],
                     in->clk + i * BB_MAX_PEERS, in->val + i * BB_MAX_FIELDS, &v, &c, &acc);
-    out->decision[i] = (uint8_t)code;
+    out->verdict[i] = ((uint32_t)code << 29) | (acc ? (uint32_t)k : BB_NO_SLOT);
     if (acc) {
       if (k >= out->cap) return BB_ERR_CAPACITY;
       emit(out, k++, i, &in->head[i], &v, &c);
@@ -404,7 +404,7 @@ static void* mt_worker(void* p) {
     int acc;
     int code = step(a->cfg, &a->table[pid], a->seq_base + i, &in->head[i],
                     in->clk + i * BB_MAX_PEERS, in->val + i * BB_MAX_FIELDS, &v, &c, &acc);
-    a->out->decision[i] = (uint8_t)code;
+    a->out->verdict[i] = ((uint32_t)code << 29) | BB_NO_SLOT;
     if (acc) {
       a->thead[i].hdr = value_pack(&v, a->tval + i * BB_MAX_FIELDS);
       clock_pack(&c, a->tclk + i * BB_MAX_PEERS, &a->thead[i].clk_order);
@@ -436,11 +436,12 @@ int bo_merge_batch_mt(const bb_config* cfg, bb_row* table, uint64_t seq_base, co
   }
   uint64_t k = 0;
   for (uint64_t i = 0; err == BB_OK && i < n; ++i) {
-    if (!BB_DEC_ACCEPTED(out->decision[i])) continue;
+    if (!BB_DEC_ACCEPTED(BB_VERDICT_CODE(out->verdict[i]))) continue;
     if (k >= out->cap) {
       err = BB_ERR_CAPACITY;
       break;
     }
+    out->verdict[i] = (out->verdict[i] & ~BB_NO_SLOT) | (uint32_t)k;
     out->idx[k] = (uint32_t)i;
     out->head[k] = thead[i];
     memcpy(out->clk + k * BB_MAX_PEERS, tclk + i * BB_MAX_PEERS, sizeof(uint32_t) * BB_MAX_PEERS);
