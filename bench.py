@@ -11,7 +11,7 @@ updates (F=4 fields each => 4 M field-merges) merged into a resident table of
   e2e     same metric through the reference-facing C-ABI call bb_merge_batch with
           pinned HOST buffers: H2D of the batch and D2H of decisions + change set
           inside the timed region
-  roofline      the dominant kernel (k_merge_tiles): algorithmic bytes / its mean launch
+  roofline      the dominant kernel (k_merge_stage): algorithmic bytes / its mean launch
                 duration inside the timed region / measured HBM peak
   cpu_baseline  the typed C oracle (oracle/bullet_oracle.c, a restatement of the
                 reference's JS: kind "port"), 1 thread, bounded sample
@@ -321,7 +321,7 @@ def main():
     else:
         merged_total = float(merged)
 
-    # ---- roofline of the dominant kernel (k_merge_tiles), SURVEY 8d figure
+    # ---- roofline of the dominant kernel (k_merge_stage), SURVEY 8d figure
     peak, peak_src = peaks()
     distinct = float(np.mean([np.unique(b.path_id).size for b in batches])) / n
     bytes_per_update = 84 + 68 * acc_frac + 256 * distinct
@@ -354,7 +354,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world),
             "updates_per_sec": merged_total / (dev_ms * 1e-3),
             "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_merge_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_merge_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_update": bytes_per_update, "accepted_frac": acc_frac,
                          "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],

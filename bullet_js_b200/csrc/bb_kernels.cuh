@@ -19,7 +19,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "bb_group.cuh"
 #include "bb_merge.cuh"
 
 namespace bb {
@@ -322,146 +321,198 @@ __device__ __forceinline__ void pack_change(uint4* q, uint32_t user, const Value
 }
 
 constexpr uint32_t NO_SLOT = BB_NO_SLOT;
-constexpr int WT = 32;          // sorted positions per warp tile
-constexpr int MERGE_WARPS = 8;  // independent warp tiles per CTA
+constexpr int MT = 128;    // sorted positions per CTA tile == threads per CTA
+constexpr int MT_WARPS = MT / 32;
+constexpr int ROW_S = 9;   // staged row stride in uint4 (144 B): LDS.128 / STS.128 by 32 rows at once is conflict-free
 
-// One warp == one tile of 32 sorted positions; warps never wait for each other (one
-// __syncthreads to hand out tile ids).  Inside a tile the path segments are taken four
-// at a time, one 8-lane group per segment (bb_group.cuh); a group replays its segment's
-// updates in arrival order straight from global memory (32-byte coalesced pieces),
-// parks accepted entries in the warp's shared-memory staging slot, and writes the row
-// back.  Then lane == position again: accepted positions are ranked by ballot, tile
-// totals are chained with a decoupled look-back, and the entries leave for the change
-// set in path-major order.
+// One CTA == one tile of MT sorted positions, in three phases with all global traffic
+// asynchronous and coalesced and all resolver work out of shared memory:
+//   stage    every update payload of the tile (5 x 16 B, by arrival index) and the table row of
+//            every path segment that starts in the tile (8 x 16 B) go global -> shared with
+//            cp.async (LDGSTS): ~24 KB in flight per CTA, no registers held
+//   resolve  one thread per segment replays its updates in arrival order on the staged row
+//            (bb_merge.cuh), overwriting each accepted update's payload slot with its change entry
+//   drain    accepted positions ranked by a block scan, tile totals chained with a decoupled
+//            look-back, then verdicts (arrival order), change entries (path-major, compacted)
+//            and the rows leave with warp-cooperative 16-byte stores
+// A segment that runs past its tile is finished by its owner straight from global memory.
 #ifndef BB_MERGE_MIN_CTAS
-#define BB_MERGE_MIN_CTAS 4
+#define BB_MERGE_MIN_CTAS 7
 #endif
-__global__ void __launch_bounds__(MERGE_WARPS * 32, BB_MERGE_MIN_CTAS) k_merge_tiles(const MergeArgs a) {
-  __shared__ uint4 s_ent_all[MERGE_WARPS][WT * UPD_Q];
-  __shared__ uint32_t s_idx_all[MERGE_WARPS][WT];
-  __shared__ uint32_t s_res_all[MERGE_WARPS][WT];
-  __shared__ uint32_t s_ticket;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+template <bool ORDERED>
+__global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const MergeArgs a) {
+  __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
+  __shared__ __align__(16) uint4 s_row[MT * ROW_S];
+  __shared__ uint32_t s_idx[MT], s_res[MT];
+  __shared__ uint32_t s_hmask[MT_WARPS], s_wsum[MT_WARPS];
+  __shared__ uint32_t s_tile, s_over, s_ex;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wbase = w * 32;
   if (*a.err & 1u) return;
-  if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+  if (tid == 0) {
+    s_tile = atomicAdd(a.ticket, 1u);
+    s_over = 0;
+  }
   __syncthreads();
-  const uint32_t tile = s_ticket * MERGE_WARPS + w;
-  if (tile >= a.num_tiles) return;
-  uint4* s_ent = s_ent_all[w];
-  uint32_t* s_idx = s_idx_all[w];
-  uint32_t* s_res = s_res_all[w];
-
-  const uint64_t base = (uint64_t)tile * WT;
-  const uint64_t pos = base + lane;
+  const uint32_t tile = s_tile;
+  const uint64_t base = (uint64_t)tile * MT;
+  const uint64_t pos = base + tid;
   const bool valid = pos < a.n;
+  const int nvalid = (int)min((uint64_t)MT, a.n - base);
   const uint64_t item = valid ? a.sorted[pos] : ~0ull;
   const uint32_t key = (uint32_t)(item >> 32), idx = (uint32_t)item;
   uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-  if (lane == 0) prev = base > 0 ? (uint32_t)(a.sorted[base - 1] >> 32) : ~key;
+  if (lane == 0) prev = (valid && pos > 0) ? (uint32_t)(a.sorted[pos - 1] >> 32) : ~key;
   const bool is_head = valid && key != prev;
   const uint32_t hmask = __ballot_sync(0xffffffffu, is_head);
-  const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-  // positions before the first head continue a segment that an earlier tile owns
-  const uint32_t omask = hmask ? (vmask & ~((hmask & (0u - hmask)) - 1u)) : 0u;
-  const bool owned = (omask >> lane) & 1u;
-  const int nvalid = __popc(vmask);
-  s_idx[lane] = idx;
-  __syncwarp();
+  if (lane == 0) s_hmask[w] = hmask;
+  s_idx[tid] = idx;
 
-  GLane L;
-  L.sh = lane & 24;
-  L.g = lane & 7;
-  L.lane0 = L.sh;
-  L.gm = 0xFFu << L.sh;
-  const int G = lane >> 3;
-  const int nh = __popc(hmask);
-  uint32_t over = 0;
-  for (int round = 0; round * 4 < nh; ++round) {
-    const int hi = round * 4 + G;
-    const bool has = hi < nh;
-    const int hp = has ? (int)__fns(hmask, 0, hi + 1) : 0;  // position of my group's segment head
-    const uint32_t rkey = __shfl_sync(0xffffffffu, key, hp);
-    if (has) {
-      const uint32_t above = hp < 31 ? (hmask & ~((2u << hp) - 1u)) : 0u;
-      const int end = above ? __ffs(above) - 1 : nvalid;
-      uint4* row = a.table + (uint64_t)rkey * ROW_Q;
-      GState r;
-      g_load_row(row, L, r);
-      for (int p = hp; p < end; ++p) {
-        const uint32_t ui = s_idx[p];
-        const uint4 h = a.head[ui];
-        const uint32_t icnt = reinterpret_cast<const uint32_t*>(a.clk)[8 * (uint64_t)ui + L.g];
-        const uint64_t xval = reinterpret_cast<const uint64_t*>(a.val)[4 * (uint64_t)ui + (L.g & 3)];
-        uint32_t ocnt, oorder, ometa, oord;
-        uint64_t oval;
-        const uint32_t code = g_step(a.p, L, r, (h.x & 1u) != 0, icnt, h.z, h.x & ~1u, h.y, xval,
-                                     a.seq_base + ui, ocnt, oorder, ometa, oord, oval);
-        if (BB_DEC_ACCEPTED(code)) g_store_entry(s_ent + p * UPD_Q, L, h.w, ocnt, oorder, ometa, oord, oval);
-        if (L.g == 0) s_res[p] = code;
-      }
-      if (!above && nvalid == WT) {  // last segment of a full tile: it may run on into the next tiles
-        for (uint64_t gp = base + WT; gp < a.n; ++gp) {
-          const uint64_t it = a.sorted[gp];
-          if ((uint32_t)(it >> 32) != rkey) break;
-          const uint32_t ui = (uint32_t)it;
-          const uint4 h = a.head[ui];
-          const uint32_t icnt = reinterpret_cast<const uint32_t*>(a.clk)[8 * (uint64_t)ui + L.g];
-          const uint64_t xval = reinterpret_cast<const uint64_t*>(a.val)[4 * (uint64_t)ui + (L.g & 3)];
-          uint32_t ocnt, oorder, ometa, oord;
-          uint64_t oval;
-          const uint32_t code = g_step(a.p, L, r, (h.x & 1u) != 0, icnt, h.z, h.x & ~1u, h.y, xval,
-                                       a.seq_base + ui, ocnt, oorder, ometa, oord, oval);
-          if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
-            const uint64_t sp = base + WT + over;
-            g_store_entry(a.st_ent + sp * UPD_Q, L, h.w, ocnt, oorder, ometa, oord, oval);
-            if (L.g == 0) a.st_idx[sp] = ui | (code << 29);
-            ++over;
-          } else if (L.g == 0) {
-            a.verdict[ui] = (code << 29) | NO_SLOT;
-          }
+  // ---- stage: lane pairs fetch whole 32-byte clocks / values, 8 lanes fetch one 128-byte row
+  if (valid) cp_async16(&s_upd[tid * UPD_Q], a.head + idx);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int e = j * 16 + (lane >> 1), half = lane & 1;
+    const uint32_t eidx = __shfl_sync(0xffffffffu, idx, e);
+    if (wbase + e < nvalid) {
+      cp_async16(&s_upd[(wbase + e) * UPD_Q + 1 + half], a.clk + 2 * (uint64_t)eidx + half);
+      cp_async16(&s_upd[(wbase + e) * UPD_Q + 3 + half], a.val + 2 * (uint64_t)eidx + half);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+    if ((hmask >> e) & 1u) cp_async16(&s_row[(wbase + e) * ROW_S + chunk], a.table + (uint64_t)ekey * ROW_Q + chunk);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- resolve: thread == segment head
+  if (is_head) {
+    int end = nvalid;
+    bool last = true;  // no later head in this tile
+    const uint32_t above = lane < 31 ? (hmask & ~((2u << lane) - 1u)) : 0u;
+    if (above) {
+      end = wbase + __ffs(above) - 1;
+      last = false;
+    } else {
+      for (int ww = w + 1; ww < MT_WARPS; ++ww) {
+        const uint32_t m = s_hmask[ww];
+        if (m) {
+          end = ww * 32 + __ffs(m) - 1;
+          last = false;
+          break;
         }
       }
-      g_store_row(row, L, r);
     }
-    __syncwarp();
+    RowState r;
+    unpack_row(&s_row[tid * ROW_S], r);
+    for (int p = tid; p < end; ++p) {
+      uint4* u = &s_upd[p * UPD_Q];
+      const uint4 h = u[0];
+      Clock c, oc;
+      Value x, ov;
+      const bool net = unpack_update(h, u[1], u[2], u[3], u[4], c, x);
+      const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + s_idx[p], ov, oc);
+      if (BB_DEC_ACCEPTED(code)) pack_change(u, h.w, ov, oc);
+      s_res[p] = code;
+    }
+    if (last && nvalid == MT) {  // last segment of a full tile: it may run on into the next tiles
+      uint32_t over = 0;
+      for (uint64_t gp = base + MT; gp < a.n; ++gp) {
+        const uint64_t it = a.sorted[gp];
+        if ((uint32_t)(it >> 32) != key) break;
+        const uint32_t ui = (uint32_t)it;
+        const uint4 h = a.head[ui];
+        Clock c, oc;
+        Value x, ov;
+        const bool net = unpack_update(h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1],
+                                       a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
+        const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
+        if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
+          const uint64_t sp = base + MT + over;
+          pack_change(a.st_ent + sp * UPD_Q, h.w, ov, oc);
+          a.st_idx[sp] = ui | (code << 29);
+          ++over;
+        } else {
+          a.verdict[ui] = (code << 29) | NO_SLOT;
+        }
+      }
+      s_over = over;
+    }
+    pack_row(&s_row[tid * ROW_S], r);
   }
+  __syncthreads();
 
-  // ---- compaction: rank accepted positions inside the tile, chain the tile totals
-  const uint32_t code = owned ? s_res[lane] : 0xFFu;
+  // ---- drain: rank the accepted positions, chain the tile totals
+  int first = MT;  // positions before the tile's first head continue a segment an earlier tile owns
+#pragma unroll
+  for (int ww = MT_WARPS - 1; ww >= 0; --ww)
+    if (s_hmask[ww]) first = ww * 32 + __ffs(s_hmask[ww]) - 1;
+  const bool owned = valid && tid >= first;
+  const uint32_t code = owned ? s_res[tid] : 0xFFu;
   const bool acc = owned && BB_DEC_ACCEPTED(code);
   const uint32_t amask = __ballot_sync(0xffffffffu, acc);
-  const uint32_t rank = __popc(amask & lanemask_lt());
-  const uint32_t in_cnt = __popc(amask);
-  uint32_t over_cnt = (L.g == 0) ? over : 0u;  // at most one group ran past the tile
-  over_cnt = warp_sum(over_cnt);
-  const uint32_t ex = tile_prefix(a.tile_state, tile, in_cnt + over_cnt);
-  if (lane == 0 && tile == a.num_tiles - 1) *a.n_changes = (uint64_t)ex + in_cnt + over_cnt;
-  const uint64_t obase = ex;
+  if (lane == 0) s_wsum[w] = __popc(amask);
+  __syncthreads();
+  uint32_t rank = __popc(amask & lanemask_lt()), in_cnt = 0;
+#pragma unroll
+  for (int ww = 0; ww < MT_WARPS; ++ww) {
+    const uint32_t c = s_wsum[ww];
+    if (ww < w) rank += c;
+    in_cnt += c;
+  }
+  const uint32_t over_cnt = s_over;
+  // rows first: nothing below them depends on where the tile's entries land
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+    if ((hmask >> e) & 1u) a.table[(uint64_t)ekey * ROW_Q + chunk] = s_row[(wbase + e) * ROW_S + chunk];
+  }
+  if (ORDERED) {  // change set in path-major order: chain the tile totals (decoupled look-back)
+    if (w == 0) {
+      const uint32_t ex = tile_prefix(a.tile_state, tile, in_cnt + over_cnt);
+      if (lane == 0) {
+        s_ex = ex;
+        if (tile == a.num_tiles - 1) *a.n_changes = (uint64_t)ex + in_cnt + over_cnt;
+      }
+    }
+  } else if (tid == 0) {  // tiles claim their slice of the change set as they finish
+    s_ex = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes),
+                               (unsigned long long)(in_cnt + over_cnt));
+  }
+  __syncthreads();
+  const uint64_t obase = s_ex;
 
-  // ---- verdicts (arrival order) and the change set (path-major order)
+  // ---- verdicts (arrival order), change set (path-major order), rows
   bool overflow = false;
   const uint64_t dest = obase + rank;
   if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : NO_SLOT);
   if (acc) {
     if (dest < a.cap) {
       a.out_idx[dest] = idx;
-      a.out_head[dest] = s_ent[lane * UPD_Q];
+      a.out_head[dest] = s_upd[tid * UPD_Q];
     } else {
       overflow = true;
     }
   }
+  uint32_t wex = 0;  // accepted positions in earlier warps of the tile
+#pragma unroll
+  for (int ww = 0; ww < MT_WARPS; ++ww)
+    if (ww < w) wex += s_wsum[ww];
 #pragma unroll
   for (int j = 0; j < 2; ++j) {  // lanes 2k, 2k+1 move the two halves of a 32-byte clock / value
     const int e = j * 16 + (lane >> 1), half = lane & 1;
-    const uint64_t edest = obase + __popc(amask & ((1u << e) - 1u));
+    const uint64_t edest = obase + wex + __popc(amask & ((1u << e) - 1u));
     if (((amask >> e) & 1u) && edest < a.cap) {
-      a.out_clk[2 * edest + half] = s_ent[e * UPD_Q + 1 + half];
-      a.out_val[2 * edest + half] = s_ent[e * UPD_Q + 3 + half];
+      a.out_clk[2 * edest + half] = s_upd[(wbase + e) * UPD_Q + 1 + half];
+      a.out_val[2 * edest + half] = s_upd[(wbase + e) * UPD_Q + 3 + half];
     }
   }
   // ---- entries of a segment tail that ran past the tile
-  for (uint32_t k = lane; k < over_cnt; k += 32) {
-    const uint64_t sp = base + WT + k, odest = obase + in_cnt + k;
+  for (uint32_t k = tid; k < over_cnt; k += MT) {
+    const uint64_t sp = base + MT + k, odest = obase + in_cnt + k;
     const uint32_t packed = a.st_idx[sp];
     const uint32_t gi = packed & NO_SLOT;
     a.verdict[gi] = (packed & ~NO_SLOT) | (uint32_t)odest;

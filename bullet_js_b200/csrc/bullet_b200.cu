@@ -120,7 +120,7 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   ZeroLayout z;
   z.passes = (uint32_t)((c->key_bits + 7) / 8);
   z.sort_tiles = div_up(n, SORT_TILE);
-  z.merge_tiles = div_up(n, WT);
+  z.merge_tiles = div_up(n, MT);
   z.hist = 0;
   z.tickets = z.hist + (size_t)MAX_PASSES * RADIX;
   z.sort_state = z.tickets + 8;
@@ -213,7 +213,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   ma.p.rank_object = c->cfg.rank_object;
   ma.p.me = c->cfg.local_peer;
   ma.p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
-  BB_LAUNCH(c, k_merge_tiles, div_up(z.merge_tiles, MERGE_WARPS), MERGE_WARPS * 32, s, ma);
+  if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
+    BB_LAUNCH(c, k_merge_stage<true>, z.merge_tiles, MT, s, ma);
+  else
+    BB_LAUNCH(c, k_merge_stage<false>, z.merge_tiles, MT, s, ma);
   mark(c, EV_MERGE, s);
   c->seq += n;
   return BB_OK;

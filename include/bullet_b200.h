@@ -15,7 +15,8 @@
  * never aborts, never calls back into the host; host buffers are caller-owned
  * (pinned memory recommended); the library owns all device memory; outputs are
  * only defined on success; a bb_ctx is not thread-safe; results are
- * deterministic (bit-identical across runs).  There is NO CPU fallback: every
+ * deterministic (decisions, stored rows and the change set reached through
+ * verdict[] are bit-identical across runs).  There is NO CPU fallback: every
  * compute entry point fails with BB_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef BULLET_B200_H
@@ -142,6 +143,12 @@ typedef struct bb_config {
  * with `_getData` after every setData (query:151,169), which turns a falsy stored
  * primitive into `{}` right after the write instead of at the next update. */
 #define BB_CFG_POST_GETDATA 1u
+/* Lay the change set out in path-major order (ascending path id, arrival order
+ * within a path), bit-identical from run to run.  Without it tiles of 128 sorted
+ * updates claim their slice of the change set as they finish: the same entries,
+ * each still found through verdict[], but the tiles' order in the buffers is not
+ * fixed - and no tile ever waits for another one. */
+#define BB_CFG_ORDERED_CHANGES 2u
 
 typedef struct bb_ctx bb_ctx;
 
@@ -161,10 +168,11 @@ typedef struct bb_batch {
  * is the position of update i's entry in idx/head/clk/val, or BB_NO_SLOT when the
  * update was rejected (doUpdate == false, src/bullet-crt.js:383).
  * The change set == the _applyUpdate calls (src/bullet.js:184-220), one entry per
- * accepted update.  Entries are stored in PATH-MAJOR order (ascending path id,
- * arrival order within a path) because that is the order the device resolves them
- * in; the reference's arrival order is recovered without a sort by walking
- * verdict[] and following the slots.  A batch is limited to 2^29-2 updates. */
+ * accepted update.  Entries are stored in the order the device resolves them in
+ * (runs of ascending path id, arrival order within a path; see
+ * BB_CFG_ORDERED_CHANGES); the reference's arrival order is recovered without a
+ * sort by walking verdict[] and following the slots.  A batch is limited to
+ * 2^29-2 updates. */
 #define BB_NO_SLOT 0x1FFFFFFFu
 #define BB_VERDICT_CODE(v) ((uint32_t)(v) >> 29)
 #define BB_VERDICT_SLOT(v) ((uint32_t)(v) & BB_NO_SLOT)

@@ -9,13 +9,13 @@ from tests import streamgen
 pytestmark = pytest.mark.gpu
 
 
-def engine_and_oracle(schema=None, capacity=256, post_getdata=False, **kw):
+def engine_and_oracle(schema=None, capacity=256, post_getdata=False, ordered=False, **kw):
     from bullet_js_b200.engine import Engine
 
     if schema is not None:
-        eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata)
+        eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata, ordered_changes=ordered)
     else:
-        eng = Engine(capacity, post_getdata=post_getdata, **kw)
+        eng = Engine(capacity, post_getdata=post_getdata, ordered_changes=ordered, **kw)
     return eng, TypedOracle(eng.cfg)
 
 
@@ -57,21 +57,27 @@ def test_kat_l_on_gpu():
     eng.close()
 
 
+@pytest.mark.parametrize("ordered", [False, True])
 @pytest.mark.parametrize("keys", ["uniform", "zipf"])
-def test_synthetic_schema_stream(keys):
+def test_synthetic_schema_stream(keys, ordered):
     """SURVEY 8d schema at a size the oracle replays in a second: 50k records, 3 x 200k updates."""
     n_rec = 50_000
     rng = synth.rng_for(2, salt=1)
     table = synth.make_table(n_rec, rng)
-    eng, orc = engine_and_oracle(None, n_rec, **synth.synth_ranks(n_rec))
+    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, **synth.synth_ranks(n_rec))
     ids = np.arange(n_rec, dtype=np.uint64)
     eng.table_load(ids, table.rows)
     orc.load(ids, table.rows)
     assert_same_table(eng, orc, n_rec)
     for _ in range(3):
         b = synth.make_batch(table, 200_000, rng, keys=keys)
-        got, want = eng.merge(b), orc.merge(b)
+        out = capi.ChangeBuffers(b.n)
+        got, want = eng.merge(b, out), orc.merge(b)
         assert got.same_as(want)
+        if ordered:  # BB_CFG_ORDERED_CHANGES: raw buffers are path-major, arrival order within a path
+            raw = out.idx[: len(got.idx)].astype(np.int64)
+            k = b.path_id[raw].astype(np.int64) * b.n + raw
+            assert (np.diff(k) > 0).all()
         assert len(set(got.decision.tolist())) >= 4
     assert_same_table(eng, orc, n_rec)
     eng.close()
