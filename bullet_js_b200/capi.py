@@ -49,6 +49,14 @@ class BBChanges(C.Structure):
     ]
 
 
+class BBBound(C.Structure):
+    _fields_ = [("num", C.c_double), ("rank", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class BBHits(C.Structure):
+    _fields_ = [("cap", C.c_uint64), ("node", C.c_void_p), ("n_dense", C.c_void_p), ("n_extra", C.c_void_p)]
+
+
 class BulletB200Error(RuntimeError):
     def __init__(self, code, msg=""):
         self.code = code
@@ -60,6 +68,8 @@ EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
     "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
+    "bb_index_create", "bb_query_equals", "bb_query_count", "bb_query_range",
+    "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
 ]
 
@@ -99,6 +109,21 @@ def load():
     lib.bb_reserve.restype = i32
     lib.bb_sync.argtypes = [vp, vp]
     lib.bb_sync.restype = i32
+    u32 = C.c_uint32
+    lib.bb_index_create.argtypes = [vp, u32, u64]
+    lib.bb_index_create.restype = i32
+    lib.bb_query_equals.argtypes = [vp, u32, u64, C.POINTER(BBHits)]
+    lib.bb_query_equals.restype = i32
+    lib.bb_query_count.argtypes = [vp, u32, u64, C.POINTER(u64)]
+    lib.bb_query_count.restype = i32
+    lib.bb_query_range.argtypes = [vp, u32, C.POINTER(BBBound), C.POINTER(BBBound), C.POINTER(BBHits)]
+    lib.bb_query_range.restype = i32
+    lib.bb_query_equals_dev.argtypes = [vp, u32, u64, C.POINTER(BBHits), vp]
+    lib.bb_query_equals_dev.restype = i32
+    lib.bb_query_range_dev.argtypes = [vp, u32, C.POINTER(BBBound), C.POINTER(BBBound), C.POINTER(BBHits), vp]
+    lib.bb_query_range_dev.restype = i32
+    lib.bb_index_stats.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64)]
+    lib.bb_index_stats.restype = i32
     lib.bb_launch_count.argtypes = [vp]
     lib.bb_launch_count.restype = u64
     lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]
@@ -116,6 +141,27 @@ def make_config(capacity, n_fields=codec.MAX_FIELDS, local_peer=0, device=0, fla
         capacity=capacity, rank_object=rank_object, rank_true=rank_true,
         rank_false=rank_false, rank_nan=rank_nan, flags=flags, reserved=0,
     )
+
+
+def bound_struct(b) -> BBBound:
+    """codec.Schema.bound() record -> bb_bound."""
+    return BBBound(num=float(b["num"]), rank=int(b["rank"]), flags=int(b["flags"]), reserved=0)
+
+
+class HitBuffers:
+    """Caller-owned output of bb_query_equals / bb_query_range."""
+
+    def __init__(self, cap: int):
+        self.cap = max(int(cap), 1)
+        self.node = np.zeros(self.cap, np.uint32)
+        self.n_dense = np.zeros(1, np.uint64)
+        self.n_extra = np.zeros(1, np.uint64)
+
+    def struct(self) -> BBHits:
+        return BBHits(cap=self.cap, node=_ptr(self.node), n_dense=_ptr(self.n_dense), n_extra=_ptr(self.n_extra))
+
+    def result(self) -> np.ndarray:
+        return self.node[: int(self.n_dense[0]) + int(self.n_extra[0])].copy()
 
 
 def _ptr(a: np.ndarray):

@@ -43,7 +43,7 @@ ROW_DTYPE = np.dtype(
         ("v_order", "<u4"),
         ("hdr", "<u8"),
         ("flags", "<u4"),
-        ("reserved", "<u4"),
+        ("xcnt", "<u4"),
         ("cseq", "<u8"),
     ]
 )
@@ -76,6 +76,63 @@ _JS_WS = (
     "\u2009\u200a\u2028\u2029\u202f\u205f\u3000\ufeff"
 )
 _FORBIDDEN = ("true", "false", "NaN", "[object Object]")
+
+
+def js_string_to_number(s: str) -> float:
+    """ToNumber of a JS string (ECMA-262 7.1.4.1.1): what `<`, `>=` and Number() apply."""
+    import re
+
+    t = s.strip(_JS_WS)
+    if t == "":
+        return 0.0
+    if t in ("Infinity", "+Infinity"):
+        return float("inf")
+    if t == "-Infinity":
+        return float("-inf")
+    m = re.fullmatch(r"0[xX]([0-9a-fA-F]+)|0[oO]([0-7]+)|0[bB]([01]+)", t)
+    if m:
+        return float(int(m.group(1) or m.group(2) or m.group(3), 16 if m.group(1) else 8 if m.group(2) else 2))
+    if re.fullmatch(r"[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?)", t):
+        return float(t)
+    return float("nan")
+
+
+def js_number_to_string(x: float) -> str:
+    """String(x) for a JS number (Number::toString, radix 10): shortest digits that
+    round-trip, plain notation for 1e-7 <= |x| < 1e21, exponent form otherwise."""
+    if x != x:
+        return "NaN"
+    if x == 0:
+        return "0"
+    if x < 0:
+        return "-" + js_number_to_string(-x)
+    if x == float("inf"):
+        return "Infinity"
+    mant, _, e10 = ("%r" % x).partition("e")           # repr() is shortest round-trip
+    ip, _, fp = mant.partition(".")
+    digits = (ip + fp).lstrip("0")
+    point = len(ip) + (int(e10) if e10 else 0)           # x = 0.<ip fp> * 10**point before stripping
+    point -= len(ip + fp) - len((ip + fp).lstrip("0"))   # leading zeros removed
+    digits = digits.rstrip("0") or "0"
+    k, n = len(digits), point
+    if k <= n <= 21:
+        return digits + "0" * (n - k)
+    if 0 < n <= 21:
+        return digits[:n] + "." + digits[n:]
+    if -6 < n <= 0:
+        return "0." + "0" * (-n) + digits
+    e = n - 1
+    es = ("+" if e > 0 else "-") + str(abs(e))
+    return (digits if k == 1 else digits[0] + "." + digits[1:]) + "e" + es
+
+
+KEY_NAN = 0x7FF8000000000000
+KEY_STR = 0xFFF9000000000000
+KEY_BOOL = 0xFFFA000000000000
+KEY_NONE = 0xFFFFFFFFFFFFFFFF
+BOUND_IS_STRING, BOUND_TRUE, BOUND_FALSE, BOUND_NAN = 1, 2, 4, 8
+
+BOUND_DTYPE = np.dtype([("num", "<f8"), ("rank", "<u8"), ("flags", "<u4"), ("reserved", "<u4")])
 
 
 class StringDict:
@@ -239,6 +296,57 @@ class Schema:
             s = (order >> (4 * i)) & 0xF
             out[self.peers[s]] = float(cnt[s])
         return out
+
+    # ---- query arguments (src/bullet-query.js:126-131, 238-252)
+    def index_key(self, value):
+        """The 64-bit key of String(value) (include/bullet_b200.h), or None when no
+        stored value can have that string.  equals/count are type-blind: 25 and "25"
+        name the same bucket (query:130)."""
+        if isinstance(value, bool):
+            return KEY_BOOL | int(value)
+        if isinstance(value, (int, float)):
+            x = float(value)
+            if x != x:
+                return KEY_NAN
+            return 0 if x == 0 else _f64_bits(x)
+        if value is None:
+            value = "null"
+        if isinstance(value, dict):
+            return None  # JSON.stringify(object): nested values are outside the typed domain
+        if not isinstance(value, str):
+            raise DomainError(f"unsupported query value {value!r}")
+        if value in ("true", "false"):
+            return KEY_BOOL | int(value == "true")
+        if value == "NaN":
+            return KEY_NAN
+        x = js_string_to_number(value)
+        if x == x and js_number_to_string(x) == value:
+            return 0 if x == 0 else _f64_bits(x)
+        i = self.strings._ids.get(value)
+        return None if i is None else KEY_STR | i
+
+    def bound(self, value, upper: bool):
+        """One side of range() as a bb_bound record (query:246-251)."""
+        b = np.zeros((), BOUND_DTYPE)
+        if isinstance(value, str):
+            k = _utf16_key(value)
+            b["num"] = js_string_to_number(value)
+            b["rank"] = (bisect.bisect_right if upper else bisect.bisect_left)(self.strings._keys, k)
+            fl = BOUND_IS_STRING
+            for name, bit in (("true", BOUND_TRUE), ("false", BOUND_FALSE), ("NaN", BOUND_NAN)):
+                kk = _utf16_key(name)
+                if (kk <= k) if upper else (kk >= k):
+                    fl |= bit
+            b["flags"] = fl
+        elif isinstance(value, bool):
+            b["num"] = float(value)
+        elif value is None:
+            b["num"] = 0.0  # ToNumber(null)
+        elif isinstance(value, (int, float)):
+            b["num"] = float(value)
+        else:
+            b["num"] = float("nan")  # objects: ToNumber("[object Object]")
+        return b
 
     def config_ranks(self):
         return dict(

@@ -6,13 +6,11 @@
 //                      (chained-scan / decoupled look-back across tiles); only as many
 //                      passes as the table's row-index width needs; moves 8-byte items,
 //                      never payloads
-//   K2  k_merge_tiles  one WARP per tile of 32 sorted positions, warps fully independent;
-//                      one 8-lane GROUP per path segment (lane g owns clock slot g and
-//                      value slot g & 3, bb_group.cuh), four segments in lockstep per warp:
-//                      every row / payload access is a coalesced 32-byte piece, a clock
-//                      compare is one compare per lane + two ballots.  Accepted updates
-//                      are ranked by ballot, tile totals chained with a decoupled
-//                      look-back scan, entries written straight to the change set
+//   K2  k_merge_stage  one CTA per tile of 128 sorted positions: payloads and rows staged in
+//                      shared memory with cp.async, one thread per path segment replays its
+//                      updates in arrival order, accepted entries compacted into the change
+//                      set, rows written back with 16-byte stores (see the kernel's comment)
+//   K4/K5               index build and the equals / range / count scans: bb_index.cuh
 //
 // All of it is integer / f64 compare-and-move work: HBM-bound, no tensor cores.
 #pragma once
@@ -241,6 +239,12 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const uint64_t* _
   }
 }
 
+}  // namespace bb
+
+#include "bb_index.cuh"  // needs the warp / look-back helpers above
+
+namespace bb {
+
 // ---------------------------------------------------------------- K2
 struct MergeArgs {
   const uint64_t* sorted;  // [n] (path id << 32 | arrival index), stable-sorted by path id
@@ -264,6 +268,7 @@ struct MergeArgs {
   uint64_t seq_base;
   uint32_t* err;           // bit0 in: batch rejected by K0; bit1 out: cap too small
   Params p;
+  IndexArgs ix;
 };
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
@@ -283,6 +288,7 @@ __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
   r.m.present = (q7.x & BB_ROW_M_PRESENT) != 0;
   r.v.present = (q7.x & BB_ROW_V_PRESENT) != 0;
   r.alias = (q7.x & BB_ROW_ALIAS) != 0;
+  r.xcnt = q7.y;
   r.cseq = u64_of(q7.z, q7.w);
 }
 
@@ -296,7 +302,7 @@ __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
   q[6] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
   const uint32_t flags = (r.m.present ? BB_ROW_M_PRESENT : 0u) | (r.v.present ? BB_ROW_V_PRESENT : 0u) |
                          (r.alias ? BB_ROW_ALIAS : 0u);
-  q[7] = make_uint4(flags, 0u, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
+  q[7] = make_uint4(flags, r.xcnt, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
 }
 
 // update payload / change entry as 5 x uint4: [head][clk lo][clk hi][val lo][val hi]
@@ -339,7 +345,7 @@ constexpr int ROW_S = 9;   // staged row stride in uint4 (144 B): LDS.128 / STS.
 #ifndef BB_MERGE_MIN_CTAS
 #define BB_MERGE_MIN_CTAS 7
 #endif
-template <bool ORDERED>
+template <bool ORDERED, bool INDEXED>
 __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * ROW_S];
@@ -405,6 +411,11 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
         }
       }
     }
+    uint64_t prim[F], prim0[F];  // the node's entries in the dense index columns
+    if (INDEXED) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) prim0[f] = prim[f] = ((a.ix.mask >> f) & 1u) ? a.ix.pcol[f][key] : BB_KEY_NONE;
+    }
     RowState r;
     unpack_row(&s_row[tid * ROW_S], r);
     for (int p = tid; p < end; ++p) {
@@ -414,6 +425,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
       Value x, ov;
       const bool net = unpack_update(h, u[1], u[2], u[3], u[4], c, x);
       const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + s_idx[p], ov, oc);
+      if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
       if (BB_DEC_ACCEPTED(code)) pack_change(u, h.w, ov, oc);
       s_res[p] = code;
     }
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
         const bool net = unpack_update(h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1],
                                        a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
         const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
+        if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
         if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
           const uint64_t sp = base + MT + over;
           pack_change(a.st_ent + sp * UPD_Q, h.w, ov, oc);
@@ -441,6 +454,11 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
       s_over = over;
     }
     pack_row(&s_row[tid * ROW_S], r);
+    if (INDEXED) {
+#pragma unroll
+      for (int f = 0; f < F; ++f)
+        if (prim[f] != prim0[f]) a.ix.pcol[f][key] = prim[f];
+    }
   }
   __syncthreads();
 

@@ -170,6 +170,7 @@ struct RowState {
   Value s;
   Clock m, v;
   uint32_t alias;
+  uint32_t xcnt;  // per-field entry counts in the index overflow sets (bb_index.cuh)
   uint64_t cseq;
 };
 

@@ -17,7 +17,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_D2H, EV_COUNT };
+enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_D2H, EV_Q0, EV_Q1, EV_COUNT };
 constexpr int EV_RING = 64;  // merge calls whose phase timings can still be queried
 
 template <class T>
@@ -67,6 +67,20 @@ struct bb_ctx {
   DevBuf<uint32_t> io_verdict, io_out_idx;
   uint64_t* d_nchanges = nullptr;
   uint64_t* h_nchanges = nullptr;  // pinned
+  // indices (bb_index.cuh): dense key column + overflow set per indexed field
+  struct IndexDev {
+    bool live = false;
+    uint64_t* pcol = nullptr;
+    uint64_t* xkey = nullptr;
+    uint32_t* xnode = nullptr;
+    uint64_t xslots = 0;
+  } index[BB_MAX_FIELDS];
+  uint32_t index_mask = 0;
+  uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
+  unsigned long long* d_counters = nullptr;  // [2] dense / overflow matches of the running query
+  unsigned long long* h_counters = nullptr;  // pinned [2]
+  DevBuf<uint32_t> scan_zero;              // [ticket x 2 | tile states of both scans]
+  DevBuf<uint32_t> io_hits;
 };
 
 namespace {
@@ -213,10 +227,22 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   ma.p.rank_object = c->cfg.rank_object;
   ma.p.me = c->cfg.local_peer;
   ma.p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
-  if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
-    BB_LAUNCH(c, k_merge_stage<true>, z.merge_tiles, MT, s, ma);
-  else
-    BB_LAUNCH(c, k_merge_stage<false>, z.merge_tiles, MT, s, ma);
+  ma.ix.mask = c->index_mask;
+  ma.ix.xused = c->d_xused;
+  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+    ma.ix.pcol[f] = c->index[f].pcol;
+    ma.ix.xkey[f] = c->index[f].xkey;
+    ma.ix.xnode[f] = c->index[f].xnode;
+    ma.ix.xmask[f] = c->index[f].live ? (uint32_t)(c->index[f].xslots - 1) : 0u;
+  }
+  const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
+  if (c->index_mask) {
+    if (ordered) BB_LAUNCH(c, (k_merge_stage<true, true>), z.merge_tiles, MT, s, ma);
+    else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
+  } else {
+    if (ordered) BB_LAUNCH(c, (k_merge_stage<true, false>), z.merge_tiles, MT, s, ma);
+    else BB_LAUNCH(c, (k_merge_stage<false, false>), z.merge_tiles, MT, s, ma);
+  }
   mark(c, EV_MERGE, s);
   c->seq += n;
   return BB_OK;
@@ -228,8 +254,91 @@ int collect_device_error(bb_ctx* c, cudaStream_t s) {
   BB_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), s));
   BB_CUDA(c, cudaStreamSynchronize(s));
   const uint32_t e = *c->h_err;
-  if (e & 1u) return fail(c, BB_ERR_CAPACITY, "path id >= capacity (batch rejected, table unchanged)");
-  if (e & 2u) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
+  if (e & bb::ERR_RANGE) return fail(c, BB_ERR_CAPACITY, "path id >= capacity (batch rejected, table unchanged)");
+  if (e & bb::ERR_CHANGES) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
+  if (e & bb::ERR_XFULL) return fail(c, BB_ERR_CAPACITY, "index overflow set is full (bb_index_create extra_capacity)");
+  if (e & bb::ERR_HITS) return fail(c, BB_ERR_CAPACITY, "hit buffer too small");
+  return BB_OK;
+}
+
+// (re)initialise the index on field f from the current table
+int index_fill(bb_ctx* c, int f, cudaStream_t s) {
+  bb_ctx::IndexDev& ix = c->index[f];
+  const uint64_t cap2 = (c->cfg.capacity + 1) & ~1ull;
+  BB_CUDA(c, cudaMemsetAsync(ix.pcol, 0xFF, cap2 * sizeof(uint64_t), s));
+  BB_CUDA(c, cudaMemsetAsync(ix.xkey, 0xFF, ix.xslots * sizeof(uint64_t), s));
+  BB_CUDA(c, cudaMemsetAsync(ix.xnode, 0xFF, ix.xslots * sizeof(uint32_t), s));
+  BB_CUDA(c, cudaMemsetAsync(c->d_xused + f, 0, sizeof(uint32_t), s));
+  BB_LAUNCH(c, bb::k_index_build, div_up(c->cfg.capacity, 256), 256, s, c->table, c->cfg.capacity, f, ix.pcol);
+  return BB_OK;
+}
+
+// both scans of one query; `hits` (device or null), counters land in c->d_counters
+int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, uint64_t cap, cudaStream_t s) {
+  using namespace bb;
+  if (field >= c->cfg.n_fields || !c->index[field].live)
+    return fail(c, BB_ERR_STATE, "no index on this field (bb_index_create first)");
+  if (c->cfg.capacity >= (1ull << 30)) return fail(c, BB_ERR_ARG, "queries support up to 2^30 rows per shard");
+  const bb_ctx::IndexDev& ix = c->index[field];
+  const uint64_t n0 = (c->cfg.capacity + 1) & ~1ull, n1 = ix.xslots;
+  const uint32_t t0 = div_up(n0, SC_TILE), t1 = div_up(n1, SC_TILE);
+  BB_CUDA(c, c->scan_zero.ensure(2 + (size_t)t0 + t1));
+  mark(c, EV_Q0, s);
+  BB_CUDA(c, cudaMemsetAsync(c->scan_zero.p, 0, (2 + (size_t)t0 + t1) * sizeof(uint32_t), s));
+  BB_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  ScanArgs a;
+  a.out = hits;
+  a.cap = cap;
+  a.counters = c->d_counters;
+  a.err = c->d_err;
+  a.p = pred;
+  a.keys = ix.pcol; a.nodes = nullptr; a.n = n0; a.which = 0;
+  a.ticket = c->scan_zero.p; a.tile_state = c->scan_zero.p + 2; a.num_tiles = t0;
+  BB_LAUNCH(c, k_index_scan, t0, SC_THREADS, s, a);
+  a.keys = ix.xkey; a.nodes = ix.xnode; a.n = n1; a.which = 1;
+  a.ticket = c->scan_zero.p + 1; a.tile_state = c->scan_zero.p + 2 + t0; a.num_tiles = t1;
+  BB_LAUNCH(c, k_index_scan, t1, SC_THREADS, s, a);
+  mark(c, EV_Q1, s);
+  return BB_OK;
+}
+
+bb::Pred range_pred(const bb_bound* lo, const bb_bound* hi) {
+  bb::Pred p{};
+  p.mode = 1;
+  p.lo = lo->num; p.hi = hi->num;
+  p.lo_rank = lo->rank; p.hi_rank = hi->rank;
+  p.lo_flags = lo->flags; p.hi_flags = hi->flags;
+  return p;
+}
+
+int query_host(bb_ctx* c, uint32_t field, const bb::Pred& pred, bb_hits* out) {
+  if (!out || !out->n_dense || !out->n_extra || (out->cap && !out->node)) return fail(c, BB_ERR_ARG, "null argument");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  BB_CUDA(c, c->io_hits.ensure(out->cap ? out->cap : 1));
+  begin_call(c);
+  int rc = scan_dev(c, field, pred, c->io_hits.p, out->cap, s);
+  if (rc) return rc;
+  BB_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  rc = collect_device_error(c, s);  // synchronises
+  if (rc) return rc;
+  const uint64_t k = c->h_counters[0] + c->h_counters[1];
+  if (k) BB_CUDA(c, cudaMemcpyAsync(out->node, c->io_hits.p, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaStreamSynchronize(s));
+  *out->n_dense = c->h_counters[0];
+  *out->n_extra = c->h_counters[1];
+  return BB_OK;
+}
+
+int query_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, bb_hits* out, void* stream) {
+  if (!out || !out->n_dense || !out->n_extra || !out->node) return fail(c, BB_ERR_ARG, "null argument");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  begin_call(c);
+  int rc = scan_dev(c, field, pred, out->node, out->cap, s);
+  if (rc) return rc;
+  BB_CUDA(c, cudaMemcpyAsync(out->n_dense, c->d_counters, 8, cudaMemcpyDeviceToDevice, s));
+  BB_CUDA(c, cudaMemcpyAsync(out->n_extra, c->d_counters + 1, 8, cudaMemcpyDeviceToDevice, s));
   return BB_OK;
 }
 
@@ -280,6 +389,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_xused, BB_MAX_FIELDS * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->d_xused, 0, BB_MAX_FIELDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost((void**)&c->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_err, sizeof(uint32_t)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_nchanges, sizeof(uint64_t)) == cudaSuccess;
   for (int r = 0; ok && r < EV_RING; ++r)
@@ -303,6 +416,15 @@ int bb_destroy(bb_ctx* c) {
   c->io_path.release(); c->io_head.release(); c->io_clk.release(); c->io_val.release();
   c->io_out_head.release(); c->io_out_clk.release(); c->io_out_val.release(); c->io_rows.release();
   c->io_verdict.release(); c->io_out_idx.release();
+  c->scan_zero.release(); c->io_hits.release();
+  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+    if (c->index[f].pcol) cudaFree(c->index[f].pcol);
+    if (c->index[f].xkey) cudaFree(c->index[f].xkey);
+    if (c->index[f].xnode) cudaFree(c->index[f].xnode);
+  }
+  if (c->d_xused) cudaFree(c->d_xused);
+  if (c->d_counters) cudaFree(c->d_counters);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_nchanges) cudaFree(c->d_nchanges);
@@ -320,6 +442,11 @@ int bb_table_clear(bb_ctx* c) {
   if (!c) return BB_ERR_ARG;
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   BB_CUDA(c, cudaMemsetAsync(c->table, 0, c->cfg.capacity * sizeof(bb_row), c->stream));
+  for (int f = 0; f < BB_MAX_FIELDS; ++f)
+    if (c->index[f].live) {
+      int rc = index_fill(c, f, c->stream);
+      if (rc) return rc;
+    }
   BB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->seq = 0;
   return BB_OK;
@@ -328,6 +455,7 @@ int bb_table_clear(bb_ctx* c) {
 int bb_table_load(bb_ctx* c, uint64_t n, const uint64_t* path_id, const bb_row* rows) {
   if (!c || (n && (!path_id || !rows))) return fail(c, BB_ERR_ARG, "null argument");
   if (n == 0) return BB_OK;
+  if (c->index_mask) return fail(c, BB_ERR_STATE, "load the table before creating indices");
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   BB_CUDA(c, c->io_path.ensure(n));
@@ -430,6 +558,101 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   return BB_OK;
 }
 
+int bb_index_create(bb_ctx* c, uint32_t field, uint64_t extra_capacity) {
+  if (!c) return BB_ERR_ARG;
+  if (field >= c->cfg.n_fields) return fail(c, BB_ERR_ARG, "field slot out of range");
+  if (c->index[field].live) return BB_OK;  // query:33-35
+  if (!(c->cfg.flags & BB_CFG_POST_GETDATA))
+    return fail(c, BB_ERR_STATE, "indices need a ctx created with BB_CFG_POST_GETDATA");
+  if (extra_capacity >= (1ull << 31)) return fail(c, BB_ERR_ARG, "extra_capacity too large");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  bb_ctx::IndexDev& ix = c->index[field];
+  uint64_t slots = 1024;
+  while (slots - (slots >> 3) <= extra_capacity + 1) slots <<= 1;
+  const uint64_t cap2 = (c->cfg.capacity + 1) & ~1ull;
+  if (cudaMalloc((void**)&ix.pcol, cap2 * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMalloc((void**)&ix.xkey, slots * sizeof(uint64_t)) != cudaSuccess ||
+      cudaMalloc((void**)&ix.xnode, slots * sizeof(uint32_t)) != cudaSuccess) {
+    if (ix.pcol) cudaFree(ix.pcol);
+    if (ix.xkey) cudaFree(ix.xkey);
+    if (ix.xnode) cudaFree(ix.xnode);
+    ix = bb_ctx::IndexDev();
+    return fail(c, BB_ERR_CUDA, "index allocation failed", cudaGetLastError());
+  }
+  ix.xslots = slots;
+  begin_call(c);
+  mark(c, EV_Q0, c->stream);
+  int rc = index_fill(c, (int)field, c->stream);
+  if (rc) return rc;
+  mark(c, EV_Q1, c->stream);
+  BB_CUDA(c, cudaStreamSynchronize(c->stream));
+  ix.live = true;
+  c->index_mask |= 1u << field;
+  return BB_OK;
+}
+
+int bb_query_equals(bb_ctx* c, uint32_t field, uint64_t key, bb_hits* out) {
+  if (!c) return BB_ERR_ARG;
+  bb::Pred p{};
+  p.mode = 0;
+  p.eq = key;
+  return query_host(c, field, p, out);
+}
+
+int bb_query_range(bb_ctx* c, uint32_t field, const bb_bound* lo, const bb_bound* hi, bb_hits* out) {
+  if (!c) return BB_ERR_ARG;
+  if (!lo || !hi) return fail(c, BB_ERR_ARG, "null argument");
+  return query_host(c, field, range_pred(lo, hi), out);
+}
+
+int bb_query_equals_dev(bb_ctx* c, uint32_t field, uint64_t key, bb_hits* out, void* stream) {
+  if (!c) return BB_ERR_ARG;
+  bb::Pred p{};
+  p.mode = 0;
+  p.eq = key;
+  return query_dev(c, field, p, out, stream);
+}
+
+int bb_query_range_dev(bb_ctx* c, uint32_t field, const bb_bound* lo, const bb_bound* hi, bb_hits* out,
+                       void* stream) {
+  if (!c) return BB_ERR_ARG;
+  if (!lo || !hi) return fail(c, BB_ERR_ARG, "null argument");
+  return query_dev(c, field, range_pred(lo, hi), out, stream);
+}
+
+int bb_query_count(bb_ctx* c, uint32_t field, uint64_t key, uint64_t* count) {
+  if (!c) return BB_ERR_ARG;
+  if (!count) return fail(c, BB_ERR_ARG, "null argument");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  bb::Pred p{};
+  p.mode = 0;
+  p.eq = key;
+  begin_call(c);
+  int rc = scan_dev(c, field, p, nullptr, 0, c->stream);
+  if (rc) return rc;
+  BB_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  BB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *count = c->h_counters[0] + c->h_counters[1];
+  return BB_OK;
+}
+
+int bb_index_stats(bb_ctx* c, uint32_t field, uint64_t* n_dense, uint64_t* n_extra) {
+  if (!c) return BB_ERR_ARG;
+  if (!n_dense || !n_extra) return fail(c, BB_ERR_ARG, "null argument");
+  if (field >= c->cfg.n_fields || !c->index[field].live) return fail(c, BB_ERR_STATE, "no index on this field");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  const bb_ctx::IndexDev& ix = c->index[field];
+  BB_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  BB_LAUNCH(c, bb::k_count_live, 1184, 256, s, ix.pcol, c->cfg.capacity, c->d_counters);
+  BB_LAUNCH(c, bb::k_count_live, 1184, 256, s, ix.xkey, ix.xslots, c->d_counters + 1);
+  BB_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaStreamSynchronize(s));
+  *n_dense = c->h_counters[0];
+  *n_extra = c->h_counters[1];
+  return BB_OK;
+}
+
 uint64_t bb_launch_count(const bb_ctx* c) { return c ? c->launches : 0; }
 
 double bb_last_phase_ms(bb_ctx* c, const char* phase) { return bb_phase_ms(c, phase, 0); }
@@ -444,6 +667,7 @@ double bb_phase_ms(bb_ctx* c, const char* phase, uint32_t calls_ago) {
   else if (!strcmp(phase, "d2h")) { a = EV_MERGE; b = EV_D2H; }
   else if (!strcmp(phase, "device")) { a = EV_START; b = EV_MERGE; }
   else if (!strcmp(phase, "total")) { a = EV_H2D0; b = EV_D2H; }
+  else if (!strcmp(phase, "scan")) { a = EV_Q0; b = EV_Q1; }
   if (a < 0 || !c->ev_valid[slot][a] || !c->ev_valid[slot][b]) return -1.0;
   cudaSetDevice(c->cfg.device);
   if (cudaEventSynchronize(c->ev[slot][b]) != cudaSuccess) return -1.0;

@@ -87,6 +87,40 @@ class Engine:
     def sync(self, stream: int = 0):
         self._check(self.lib.bb_sync(self._h, C.c_void_p(stream)))
 
+    # ---- indices and queries (src/bullet-query.js)
+    def index_create(self, field: int, extra_capacity: int | None = None):
+        if extra_capacity is None:
+            extra_capacity = max(4 * self.capacity, 1 << 16)
+        self._check(self.lib.bb_index_create(self._h, field, int(extra_capacity)))
+
+    def _hits(self, out):
+        return out or capi.HitBuffers(2 * self.capacity + 1024)
+
+    def query_equals(self, field: int, key: int, out: capi.HitBuffers | None = None) -> np.ndarray:
+        """Node ids whose index entry has this key (codec.Schema.index_key)."""
+        out = self._hits(out)
+        hs = out.struct()
+        self._check(self.lib.bb_query_equals(self._h, field, int(key), C.byref(hs)))
+        return out.result()
+
+    def query_range(self, field: int, lo, hi, out: capi.HitBuffers | None = None) -> np.ndarray:
+        """lo / hi: codec.Schema.bound() records."""
+        out = self._hits(out)
+        hs = out.struct()
+        bl, bh = capi.bound_struct(lo), capi.bound_struct(hi)
+        self._check(self.lib.bb_query_range(self._h, field, C.byref(bl), C.byref(bh), C.byref(hs)))
+        return out.result()
+
+    def query_count(self, field: int, key: int) -> int:
+        n = C.c_uint64(0)
+        self._check(self.lib.bb_query_count(self._h, field, int(key), C.byref(n)))
+        return int(n.value)
+
+    def index_stats(self, field: int):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.bb_index_stats(self._h, field, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # ---- telemetry
     def launch_count(self) -> int:
         return int(self.lib.bb_launch_count(self._h))

@@ -178,3 +178,11 @@ def synth_ranks(n_records: int) -> dict:
     """rank_* of bb_config for the synthetic dictionary: in UTF-16 order
     "NaN" < "[object Object]" < "admin" < "editor" < "false" < "name..." < "true" < "user"."""
     return dict(rank_object=0, rank_nan=0, rank_false=2, rank_true=2 + n_records)
+
+
+def synth_schema(n_records: int) -> codec.Schema:
+    """The codec.Schema of the synthetic collection (materialises the dictionary: use for
+    tests and small tables; the bench builds keys and bounds from the id layout directly)."""
+    strings = ["admin", "editor", "user"] + ["name%07d" % i for i in range(n_records)]
+    return codec.Schema(["age", "score", "role", "name"], ["p%d" % i for i in range(P)],
+                        codec.StringDict(strings), "p0")

@@ -106,7 +106,8 @@ typedef struct bb_row {
   uint32_t v_order;              /* 100 */
   uint64_t hdr;                  /* 104: kind, tags, key order (flavour bit unused) */
   uint32_t flags;                /* 112: BB_ROW_* */
-  uint32_t reserved;             /* 116 */
+  uint32_t xcnt;                 /* 116: byte f = entries this node has in the overflow set of
+                                         the index on field f (saturates at 255 = unknown) */
   uint64_t cseq;                 /* 120: 1 + global sequence of the update that first
                                          touched the row (== key order of the parent
                                          collection object, query:61); 0 = never */
@@ -220,6 +221,77 @@ int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* s
  * change buffer was too small. */
 int bb_sync(bb_ctx* ctx, void* stream);
 
+/* ---- indices and queries: BulletQuery (src/bullet-query.js) --------------------
+ * One bb_ctx holds the children of ONE base path (`users/<id>` rows), so an index
+ * is named by its field slot alone.  An index is the reference's
+ * Map<String(value), Set<path>> seen as the set of (node, key) pairs it contains:
+ * `key` is the 64-bit canonical form of String(value), so that key equality ==
+ * bucket equality (25 == "25" is settled by the host, which passes the canonical
+ * number; -0 -> 0; every NaN -> one key):
+ *     number x   -> bits(x)                  (after -0 -> +0, NaN -> BB_KEY_NAN)
+ *     string id  -> BB_KEY_STR  | id         (dictionary strings are non-numeric)
+ *     boolean b  -> BB_KEY_BOOL | b
+ * Because the post-write hook never removes the pre-update value's entry
+ * (query:151-167), a node can sit in any number of buckets; the device keeps one
+ * entry per node in a dense column (8 bytes per row, what range/equals stream) and
+ * the rest in an open-addressing overflow set of `extra_capacity` slots.
+ * Results: node ids; first the matches of the dense column in ascending node id,
+ * then the matches of the overflow set.  A node with entries in two matching
+ * buckets appears twice, as in the reference (query:237-258).  The reference's
+ * (Map order, Set order) result order is not reproduced: compare as multisets. */
+#define BB_KEY_NAN 0x7FF8000000000000ull
+#define BB_KEY_STR 0xFFF9000000000000ull
+#define BB_KEY_BOOL 0xFFFA000000000000ull
+#define BB_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+/* BulletQuery.index(path, field) + _buildIndex (query:30-73): entries for every
+ * stored record that has the field with a value other than null (0, "" and false
+ * ARE indexed here, unlike in the hook).  From then on every merge call also runs
+ * _updateIndices (query:139-176) after each update, accepted or not; the ctx must
+ * have been created with BB_CFG_POST_GETDATA (the hook's _getData re-read).
+ * Creating an index that exists is a no-op (query:33-35).  There is no drop, as in
+ * the reference.  BB_ERR_CAPACITY is reported (by the merge call or bb_sync) when
+ * the overflow set is full. */
+int bb_index_create(bb_ctx* ctx, uint32_t field, uint64_t extra_capacity);
+
+/* One side of range(): ToNumber(bound) for numeric keys (NaN never matches), and,
+ * when the bound is a JS string, its place in the dictionary order for string
+ * keys: `rank` = number of dictionary strings < bound for a lower bound, number of
+ * dictionary strings <= bound for an upper bound; BB_BOUND_TRUE/FALSE/NAN say
+ * whether the keys "true", "false", "NaN" pass this side. */
+#define BB_BOUND_IS_STRING 1u
+#define BB_BOUND_TRUE 2u
+#define BB_BOUND_FALSE 4u
+#define BB_BOUND_NAN 8u
+typedef struct bb_bound {
+  double num;
+  uint64_t rank;
+  uint32_t flags;
+  uint32_t reserved;
+} bb_bound;
+
+typedef struct bb_hits {
+  uint64_t cap;        /* capacity of `node` in entries */
+  uint32_t* node;      /* [cap] */
+  uint64_t* n_dense;   /* [1] matches from the dense column (ascending node id) */
+  uint64_t* n_extra;   /* [1] matches from the overflow set, stored after them */
+} bb_hits;
+
+/* equals (query:186-210) / count (query:293-313) / range (query:221-261, both
+ * ends inclusive, JS relational semantics).  BB_ERR_STATE if the index does not
+ * exist (the reference would create it; the host shim calls bb_index_create
+ * first).  Host buffers; the call synchronises.  count needs no node buffer. */
+int bb_query_equals(bb_ctx* ctx, uint32_t field, uint64_t key, bb_hits* out);
+int bb_query_count(bb_ctx* ctx, uint32_t field, uint64_t key, uint64_t* count);
+int bb_query_range(bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb_bound* hi, bb_hits* out);
+/* Same, device buffers (out->node, n_dense, n_extra on ctx's device), enqueued on
+ * `stream`, not synchronised; too-small buffers are reported by bb_sync. */
+int bb_query_equals_dev(bb_ctx* ctx, uint32_t field, uint64_t key, bb_hits* out, void* stream);
+int bb_query_range_dev(bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb_bound* hi, bb_hits* out,
+                       void* stream);
+/* Entries currently held by the index (dense + overflow); synchronises. */
+int bb_index_stats(bb_ctx* ctx, uint32_t field, uint64_t* n_dense, uint64_t* n_extra);
+
 /* ---- telemetry ---------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
 uint64_t bb_launch_count(const bb_ctx* ctx);
@@ -228,7 +300,7 @@ uint64_t bb_launch_count(const bb_ctx* ctx);
 double bb_last_phase_ms(bb_ctx* ctx, const char* phase);
 /* Same for the merge call issued `calls_ago` calls before the most recent one
  * (0 = most recent; the last 64 calls are kept).  Phases: "h2d", "sort", "merge",
- * "d2h", "device" (sort+merge), "total". */
+ * "d2h", "device" (sort+merge), "total"; the query calls record "scan". */
 double bb_phase_ms(bb_ctx* ctx, const char* phase, uint32_t calls_ago);
 
 #ifdef __cplusplus

@@ -468,3 +468,251 @@ void bo_materialise(bb_row* row, uint64_t seq) {
   cur.n = 0;
   row->hdr = value_pack(&cur, row->val);
 }
+
+/* ======================================================================== *
+ * BulletQuery (src/bullet-query.js) on typed values.  The index is kept in the
+ * reference's own shape - a Map (buckets in creation order) of Sets (node ids in
+ * insertion order) keyed by String(value) - so results come out in the
+ * reference's (Map order, Set order).  String(value) is represented by the
+ * 64-bit key of include/bullet_b200.h (BB_KEY_*): equal keys <=> equal strings.
+ *   index / _buildIndex / _addToIndex      query:30-94
+ *   _removeFromIndex                       query:103-118
+ *   _updateIndices (field index)           query:139-167
+ *   equals / range / count                 query:186-210, 221-261, 293-313
+ * ======================================================================== */
+typedef struct {
+  uint64_t key;
+  uint32_t n, cap;
+  uint32_t* nodes; /* Set<path>: insertion order */
+  int alive;       /* Map.delete() clears it; a re-created bucket is a new one at the end */
+} obucket;
+
+typedef struct bo_index {
+  int field;
+  obucket* b; /* Map entries in creation order (dead ones skipped) */
+  uint64_t nb, capb;
+  int64_t* slot; /* open-addressing map key -> bucket index + 1 (0 empty, -1 deleted) */
+  uint64_t nslot, nused;
+} bo_index;
+
+static uint64_t okey_of(int tag, uint64_t pay) {
+  if (tag == BB_TAG_NUM) {
+    double d = as_double(pay);
+    if (d != d) return BB_KEY_NAN; /* String(NaN) */
+    if (d == 0.0) return 0;        /* String(-0) === "0" */
+    return pay;
+  }
+  return (tag == BB_TAG_STR ? BB_KEY_STR : BB_KEY_BOOL) | pay;
+}
+
+static uint64_t okey_hash(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  return k;
+}
+
+static void omap_rehash(bo_index* ix, uint64_t nslot) {
+  free(ix->slot);
+  ix->slot = (int64_t*)calloc(nslot, sizeof(int64_t));
+  ix->nslot = nslot;
+  ix->nused = 0;
+  for (uint64_t i = 0; i < ix->nb; ++i) {
+    if (!ix->b[i].alive) continue;
+    uint64_t h = okey_hash(ix->b[i].key) & (nslot - 1);
+    while (ix->slot[h]) h = (h + 1) & (nslot - 1);
+    ix->slot[h] = (int64_t)i + 1;
+    ++ix->nused;
+  }
+}
+
+/* index.has(key) ? bucket : NULL */
+static obucket* omap_get(bo_index* ix, uint64_t key, uint64_t* where) {
+  uint64_t h = okey_hash(key) & (ix->nslot - 1);
+  while (ix->slot[h]) {
+    if (ix->slot[h] > 0 && ix->b[ix->slot[h] - 1].key == key) {
+      if (where) *where = h;
+      return &ix->b[ix->slot[h] - 1];
+    }
+    h = (h + 1) & (ix->nslot - 1);
+  }
+  return 0;
+}
+
+bo_index* bo_index_new(int field) {
+  bo_index* ix = (bo_index*)calloc(1, sizeof(bo_index));
+  ix->field = field;
+  omap_rehash(ix, 1024);
+  return ix;
+}
+
+void bo_index_free(bo_index* ix) {
+  if (!ix) return;
+  for (uint64_t i = 0; i < ix->nb; ++i) free(ix->b[i].nodes);
+  free(ix->b);
+  free(ix->slot);
+  free(ix);
+}
+
+/* _addToIndex (query:82-94); the caller has dealt with null / undefined */
+static void oindex_add(bo_index* ix, uint64_t key, uint32_t node) {
+  obucket* b = omap_get(ix, key, 0);
+  if (!b) { /* index.set(indexValue, new Set()) - appended to the Map order */
+    if ((ix->nused + 1) * 2 > ix->nslot) omap_rehash(ix, ix->nslot * 2);
+    if (ix->nb == ix->capb) {
+      ix->capb = ix->capb ? ix->capb * 2 : 256;
+      ix->b = (obucket*)realloc(ix->b, ix->capb * sizeof(obucket));
+    }
+    b = &ix->b[ix->nb];
+    memset(b, 0, sizeof(*b));
+    b->key = key;
+    b->alive = 1;
+    uint64_t h = okey_hash(key) & (ix->nslot - 1);
+    while (ix->slot[h] > 0) h = (h + 1) & (ix->nslot - 1);
+    if (ix->slot[h] == 0) ++ix->nused;
+    ix->slot[h] = (int64_t)ix->nb + 1;
+    ++ix->nb;
+  }
+  for (uint32_t i = 0; i < b->n; ++i)
+    if (b->nodes[i] == node) return; /* Set.add of a member keeps its place */
+  if (b->n == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 4;
+    b->nodes = (uint32_t*)realloc(b->nodes, b->cap * sizeof(uint32_t));
+  }
+  b->nodes[b->n++] = node;
+}
+
+/* _removeFromIndex (query:103-118) */
+static void oindex_remove(bo_index* ix, uint64_t key, uint32_t node) {
+  uint64_t where = 0;
+  obucket* b = omap_get(ix, key, &where);
+  if (!b) return;
+  for (uint32_t i = 0; i < b->n; ++i) {
+    if (b->nodes[i] != node) continue;
+    memmove(b->nodes + i, b->nodes + i + 1, (b->n - i - 1) * sizeof(uint32_t));
+    --b->n;
+    break;
+  }
+  if (b->n == 0) { /* index.delete(indexValue) */
+    b->alive = 0;
+    ix->slot[where] = -1;
+  }
+}
+
+static int cmp_cseq(const void* a, const void* b) {
+  const uint64_t* x = (const uint64_t*)a;
+  const uint64_t* y = (const uint64_t*)b;
+  return x[0] < y[0] ? -1 : x[0] > y[0];
+}
+
+/* _buildIndex (query:53-73): Object.entries(store[path]) in own-key order == the order
+ * the children were first created in (row.cseq) */
+void bo_index_build(const bb_config* cfg, const bb_row* table, bo_index* ix) {
+  uint64_t n = 0;
+  uint64_t* ord = (uint64_t*)malloc(2 * sizeof(uint64_t) * (cfg->capacity ? cfg->capacity : 1));
+  for (uint64_t i = 0; i < cfg->capacity; ++i) {
+    if (!table[i].cseq) continue;
+    ord[2 * n] = table[i].cseq;
+    ord[2 * n + 1] = i;
+    ++n;
+  }
+  qsort(ord, n, 2 * sizeof(uint64_t), cmp_cseq);
+  for (uint64_t j = 0; j < n; ++j) {
+    const bb_row* row = &table[ord[2 * j + 1]];
+    ovalue v;
+    value_unpack(&v, row->hdr, row->val);
+    if (v.kind != BB_KIND_OBJ) continue; /* typeof value === "object" && value !== null */
+    int k = value_find(&v, ix->field);   /* field in value */
+    if (k < 0 || v.tag[k] == BB_TAG_NULL) continue;
+    oindex_add(ix, okey_of(v.tag[k], v.pay[k]), (uint32_t)ord[2 * j + 1]);
+  }
+  free(ord);
+}
+
+/* _updateIndices (query:139-167) for a path one segment below the indexed base */
+static void oindex_hook(bo_index* ix, uint32_t node, const bb_row* row_after, const bb_head* uh,
+                        const uint64_t* uval) {
+  ovalue old, x;
+  value_unpack(&old, row_after->hdr, row_after->val); /* _getData(indexedPath/part) after the write */
+  value_unpack(&x, uh->hdr, uval);                     /* the raw newData argument */
+  if (old.kind == BB_KIND_OBJ) {
+    int k = value_find(&old, ix->field);
+    if (k >= 0 && !prim_falsy(old.tag[k], old.pay[k])) oindex_remove(ix, okey_of(old.tag[k], old.pay[k]), node);
+  }
+  if (x.kind == BB_KIND_OBJ) {
+    int k = value_find(&x, ix->field);
+    if (k >= 0 && !prim_falsy(x.tag[k], x.pay[k])) oindex_add(ix, okey_of(x.tag[k], x.pay[k]), node);
+  }
+}
+
+/* setData with the query wrapper around it (query:16-20): merge, then the hook, per update */
+int bo_merge_batch_indexed(const bb_config* cfg, bb_row* table, uint64_t seq_base, const bb_batch* in,
+                           bb_changes* out, bo_index** idx, int n_idx) {
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < in->n; ++i) {
+    ovalue v;
+    oclock c;
+    int acc;
+    uint64_t pid = in->path_id[i];
+    if (pid >= cfg->capacity) return BB_ERR_CAPACITY;
+    int code = step(cfg, &table[pid], seq_base + i, &in->head[i], in->clk + i * BB_MAX_PEERS,
+                    in->val + i * BB_MAX_FIELDS, &v, &c, &acc);
+    out->verdict[i] = ((uint32_t)code << 29) | (acc ? (uint32_t)k : BB_NO_SLOT);
+    if (acc) {
+      if (k >= out->cap) return BB_ERR_CAPACITY;
+      emit(out, k++, i, &in->head[i], &v, &c);
+    }
+    for (int j = 0; j < n_idx; ++j)
+      oindex_hook(idx[j], (uint32_t)pid, &table[pid], &in->head[i], in->val + i * BB_MAX_FIELDS);
+  }
+  *out->n_changes = k;
+  return BB_OK;
+}
+
+/* equals (query:186-210): the bucket's paths in Set order. Returns the full count. */
+uint64_t bo_index_equals(bo_index* ix, uint64_t key, uint32_t* out, uint64_t cap) {
+  obucket* b = omap_get(ix, key, 0);
+  if (!b) return 0;
+  for (uint32_t i = 0; i < b->n && i < cap; ++i) out[i] = b->nodes[i];
+  return b->n;
+}
+
+uint64_t bo_index_count(bo_index* ix, uint64_t key) { /* query:293-313 */
+  obucket* b = omap_get(ix, key, 0);
+  return b ? b->n : 0;
+}
+
+/* `value >= min` / `value <= max` of query:246-251 for one bucket key.  value is
+ * Number(key) unless that is NaN, then the key string itself. */
+static int obound_ok(uint64_t key, const bb_bound* bd, int upper) {
+  uint64_t top = key >> 48;
+  if (top == (BB_KEY_STR >> 48)) { /* string vs string: UTF-16 order; vs anything else: NaN */
+    uint64_t id = key & 0xFFFFFFFFFFFFULL;
+    if (!(bd->flags & BB_BOUND_IS_STRING)) return 0;
+    return upper ? id < bd->rank : id >= bd->rank;
+  }
+  if (top == (BB_KEY_BOOL >> 48)) return (bd->flags & ((key & 1) ? BB_BOUND_TRUE : BB_BOUND_FALSE)) != 0;
+  if (key == BB_KEY_NAN) return (bd->flags & BB_BOUND_NAN) != 0;
+  double x = as_double(key);
+  return upper ? x <= bd->num : x >= bd->num;
+}
+
+/* range (query:221-261): every bucket in Map order, its paths in Set order */
+uint64_t bo_index_range(bo_index* ix, const bb_bound* lo, const bb_bound* hi, uint32_t* out, uint64_t cap) {
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < ix->nb; ++i) {
+    const obucket* b = &ix->b[i];
+    if (!b->alive) continue;
+    if (!(obound_ok(b->key, lo, 0) && obound_ok(b->key, hi, 1))) continue;
+    for (uint32_t j = 0; j < b->n; ++j, ++n)
+      if (n < cap) out[n] = b->nodes[j];
+  }
+  return n;
+}
+
+uint64_t bo_index_entries(const bo_index* ix) {
+  uint64_t n = 0;
+  for (uint64_t i = 0; i < ix->nb; ++i)
+    if (ix->b[i].alive) n += ix->b[i].n;
+  return n;
+}

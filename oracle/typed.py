@@ -39,6 +39,23 @@ def lib():
         _lib.bo_merge_batch_mt.restype = C.c_int
         _lib.bo_materialise.argtypes = [vp, C.c_uint64]
         _lib.bo_materialise.restype = None
+        u64 = C.c_uint64
+        _lib.bo_index_new.argtypes = [C.c_int]
+        _lib.bo_index_new.restype = vp
+        _lib.bo_index_free.argtypes = [vp]
+        _lib.bo_index_free.restype = None
+        _lib.bo_index_build.argtypes = [C.POINTER(capi.BBConfig), vp, vp]
+        _lib.bo_index_build.restype = None
+        _lib.bo_merge_batch_indexed.argtypes = _lib.bo_merge_batch.argtypes + [C.POINTER(vp), C.c_int]
+        _lib.bo_merge_batch_indexed.restype = C.c_int
+        _lib.bo_index_equals.argtypes = [vp, u64, vp, u64]
+        _lib.bo_index_equals.restype = u64
+        _lib.bo_index_count.argtypes = [vp, u64]
+        _lib.bo_index_count.restype = u64
+        _lib.bo_index_range.argtypes = [vp, C.POINTER(capi.BBBound), C.POINTER(capi.BBBound), vp, u64]
+        _lib.bo_index_range.restype = u64
+        _lib.bo_index_entries.argtypes = [vp]
+        _lib.bo_index_entries.restype = u64
     return _lib
 
 
@@ -49,6 +66,38 @@ class TypedOracle:
         self.cfg = cfg
         self.table = np.zeros(int(cfg.capacity), codec.ROW_DTYPE)
         self.seq = 0
+        self.indices: dict[int, int] = {}  # field slot -> bo_index*
+
+    def __del__(self):
+        for h in getattr(self, "indices", {}).values():
+            lib().bo_index_free(h)
+
+    # ---- BulletQuery (results in the reference's Map / Set order)
+    def index_create(self, field: int):
+        if field in self.indices:
+            return
+        h = lib().bo_index_new(field)
+        lib().bo_index_build(C.byref(self.cfg), self.table.ctypes.data, h)
+        self.indices[field] = h
+
+    def query_equals(self, field: int, key: int) -> np.ndarray:
+        n = int(lib().bo_index_count(self.indices[field], key))
+        out = np.zeros(max(n, 1), np.uint32)
+        lib().bo_index_equals(self.indices[field], key, out.ctypes.data, n)
+        return out[:n]
+
+    def query_count(self, field: int, key: int) -> int:
+        return int(lib().bo_index_count(self.indices[field], key))
+
+    def query_range(self, field: int, lo, hi) -> np.ndarray:
+        bl, bh = capi.bound_struct(lo), capi.bound_struct(hi)
+        n = int(lib().bo_index_range(self.indices[field], C.byref(bl), C.byref(bh), None, 0))
+        out = np.zeros(max(n, 1), np.uint32)
+        lib().bo_index_range(self.indices[field], C.byref(bl), C.byref(bh), out.ctypes.data, n)
+        return out[:n]
+
+    def index_entries(self, field: int) -> int:
+        return int(lib().bo_index_entries(self.indices[field]))
 
     def load(self, path_id, rows):
         self.table[np.asarray(path_id, np.int64)] = rows
@@ -56,7 +105,11 @@ class TypedOracle:
     def merge(self, batch: codec.Batch, threads: int = 1, out: capi.ChangeBuffers | None = None):
         out = out or capi.ChangeBuffers(batch.n)
         bs, cs = capi.batch_struct(batch), out.struct()
-        if threads > 1:
+        if self.indices:
+            hs = (C.c_void_p * len(self.indices))(*self.indices.values())
+            rc = lib().bo_merge_batch_indexed(C.byref(self.cfg), self.table.ctypes.data, self.seq,
+                                              C.byref(bs), C.byref(cs), hs, len(self.indices))
+        elif threads > 1:
             rc = lib().bo_merge_batch_mt(C.byref(self.cfg), self.table.ctypes.data, self.seq,
                                          C.byref(bs), C.byref(cs), threads)
         else:

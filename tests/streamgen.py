@@ -78,14 +78,19 @@ def relative_clock(rng, cur, mode):
 MODES = ["identical", "permuted", "dominating", "historical", "concurrent", "random"]
 
 
-def generate(seed, n_ops, n_paths, local_peer="p0", index_fields=(), p_local=0.3, p_prim=0.2):
-    """-> (ops, literal RefBullet after replay). ops = [(path, value, clock|None)]."""
+def generate(seed, n_ops, n_paths, local_peer="p0", index_fields=(), p_local=0.3, p_prim=0.2, late_index=None):
+    """-> (ops, literal RefBullet after replay). ops = [(path, value, clock|None)].
+    late_index: {field: op number} - index("users", field) is called just before that op."""
     rng = random.Random(seed)
-    ref = RefBullet(local_peer, enable_indexing=bool(index_fields))
+    late_index = late_index or {}
+    ref = RefBullet(local_peer, enable_indexing=bool(index_fields) or bool(late_index))
     for f in index_fields:
         ref.index("users", f)
     ops = []
-    for _ in range(n_ops):
+    for k in range(n_ops):
+        for f, at in late_index.items():
+            if at == k:
+                ref.index("users", f)
         path = f"users/u{rng.randrange(n_paths)}"
         is_prim = rng.random() < p_prim
         value = rand_prim(rng) if is_prim else rand_record(rng)

@@ -1,0 +1,140 @@
+"""GPU parity for BulletQuery: index build, the post-write hook fused into the merge kernel, and
+the equals / range / count scans, through the C ABI, against the typed oracle (multiset equality:
+the device returns hits in node order, the reference in Map / Set order)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from bullet_js_b200 import capi, codec, synth
+from oracle.typed import TypedOracle
+from tests import streamgen
+from tests.test_oracle_query import BOUNDS, EQ_VALUES
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(schema, capacity, **kw):
+    from bullet_js_b200.engine import Engine
+
+    if schema is not None:
+        eng = Engine.for_schema(schema, capacity, post_getdata=True, **kw)
+    else:
+        eng = Engine(capacity, post_getdata=True, **kw)
+    return eng, TypedOracle(eng.cfg)
+
+
+def same_rows(eng, orc, n):
+    ids = np.arange(n, dtype=np.uint64)
+    got, want = eng.table_read(ids), orc.read(ids)
+    got["xcnt"] = 0  # device-private: entries the node has in the index overflow sets
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (bad[:5], got[bad[:2]], want[bad[:2]])
+
+
+def check_queries(schema, eng, orc, fields, bounds=BOUNDS):
+    for f in fields:
+        nd, nx = eng.index_stats(f)
+        assert nd + nx == orc.index_entries(f)
+        for v in EQ_VALUES:
+            key = schema.index_key(v)
+            if key is None:
+                continue
+            got, want = eng.query_equals(f, key), orc.query_equals(f, key)
+            assert np.array_equal(np.sort(got), np.sort(want)), (f, v)
+            assert eng.query_count(f, key) == len(want)
+        for lo, hi in itertools.product(bounds, bounds):
+            bl, bh = schema.bound(lo, False), schema.bound(hi, True)
+            got, want = eng.query_range(f, bl, bh), orc.query_range(f, bl, bh)
+            assert np.array_equal(np.sort(got), np.sort(want)), (f, lo, hi)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_js_streams_with_indices(seed):
+    ops, _ref = streamgen.generate(300 + seed, 4000, 37, index_fields=("age", "role"), late_index={"score": 1500})
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    eng, orc = pair(schema, 64)
+    for x in (eng, orc):
+        x.index_create(0)
+        x.index_create(2)
+    for lo, hi, late in ((0, 1, False), (1, 1500, False), (1500, 1501, True), (1501, 4000, False)):
+        if late:
+            eng.index_create(1)
+            orc.index_create(1)
+        got, want = eng.merge(batch.slice(lo, hi)), orc.merge(batch.slice(lo, hi))
+        assert got.same_as(want), (seed, lo, hi)
+    same_rows(eng, orc, 64)
+    check_queries(schema, eng, orc, (0, 1, 2))
+    eng.close()
+
+
+@pytest.mark.parametrize("keys", ["uniform", "zipf"])
+def test_synthetic_schema_with_indices(keys):
+    n_rec = 50_000
+    rng = synth.rng_for(4, salt=2)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = pair(None, n_rec, **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    schema = synth.synth_schema(n_rec)
+    for x in (eng, orc):
+        x.index_create(0)  # age
+        x.index_create(2)  # role
+    small = [20.0, 30.0, 0.0, 99.0, "admin", "user", "a", "zzz", "20", None]
+    check_queries(schema, eng, orc, (0, 2), small)  # build path
+    for _ in range(2):
+        b = synth.make_batch(table, 200_000, rng, keys=keys)
+        got, want = eng.merge(b), orc.merge(b)
+        assert got.same_as(want)
+    same_rows(eng, orc, n_rec)
+    check_queries(schema, eng, orc, (0, 2), small)  # build + hook
+    nd, nx = eng.index_stats(0)
+    assert nx > 0  # stale entries piled up in the overflow set, as in the reference
+    eng.close()
+
+
+def test_query_errors():
+    from bullet_js_b200.engine import Engine
+
+    schema = streamgen.make_schema()
+    eng = Engine.for_schema(schema, 64, post_getdata=True)
+    with pytest.raises(capi.BulletB200Error) as e:
+        eng.query_count(0, 5)
+    assert e.value.code == capi.ERR_STATE
+    plain = Engine.for_schema(schema, 64)
+    with pytest.raises(capi.BulletB200Error) as e:
+        plain.index_create(0)
+    assert e.value.code == capi.ERR_STATE
+    # hit buffer too small
+    ops = [(f"users/u{i}", {"age": 30.0}, None) for i in range(10)]
+    eng.merge(codec.encode_updates(schema, ops))
+    eng.index_create(0)
+    with pytest.raises(capi.BulletB200Error) as e:
+        eng.query_equals(0, schema.index_key(30.0), capi.HitBuffers(4))
+    assert e.value.code == capi.ERR_CAPACITY
+    assert len(eng.query_equals(0, schema.index_key(30.0))) == 10
+    # overflow set too small: 2000 distinct stale values for one node
+    tiny = Engine.for_schema(schema, 64, post_getdata=True)
+    tiny.index_create(0, extra_capacity=16)
+    ops = [("users/u1", {"age": float(i + 1)}, None) for i in range(2000)]
+    with pytest.raises(capi.BulletB200Error) as e:
+        tiny.merge(codec.encode_updates(schema, ops))
+    assert e.value.code == capi.ERR_CAPACITY
+    for x in (eng, plain, tiny):
+        x.close()
+
+
+def test_kat_h_on_gpu():
+    """SURVEY 8c KAT-H: hook staleness - u1 sits in buckets "30" and "31", {age:0} changes nothing."""
+    from bullet_js_b200.engine import Engine
+
+    schema = codec.Schema(["age", "role"], ["A", "B"], codec.StringDict(["admin", "user"]), "B")
+    eng = Engine.for_schema(schema, 8, post_getdata=True)
+    eng.index_create(0)
+    ops = [("users/u1", {"age": 30.0}, None), ("users/u1", {"age": 31.0}, None), ("users/u1", {"age": 0.0}, None)]
+    eng.merge(codec.encode_updates(schema, ops))
+    assert eng.query_range(0, schema.bound(30.0, False), schema.bound(31.0, True)).tolist() == [0, 0]
+    assert eng.index_stats(0) == (1, 1)
+    eng.close()
