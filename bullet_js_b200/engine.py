@@ -93,19 +93,19 @@ class Engine:
             extra_capacity = max(4 * self.capacity, 1 << 16)
         self._check(self.lib.bb_index_create(self._h, field, int(extra_capacity)))
 
-    def _hits(self, out):
-        return out or capi.HitBuffers(2 * self.capacity + 1024)
+    def _hits(self, out, field):
+        return out or capi.HitBuffers(sum(self.index_stats(field)))  # every entry could match
 
     def query_equals(self, field: int, key: int, out: capi.HitBuffers | None = None) -> np.ndarray:
         """Node ids whose index entry has this key (codec.Schema.index_key)."""
-        out = self._hits(out)
+        out = self._hits(out, field)
         hs = out.struct()
         self._check(self.lib.bb_query_equals(self._h, field, int(key), C.byref(hs)))
         return out.result()
 
     def query_range(self, field: int, lo, hi, out: capi.HitBuffers | None = None) -> np.ndarray:
         """lo / hi: codec.Schema.bound() records."""
-        out = self._hits(out)
+        out = self._hits(out, field)
         hs = out.struct()
         bl, bh = capi.bound_struct(lo), capi.bound_struct(hi)
         self._check(self.lib.bb_query_range(self._h, field, C.byref(bl), C.byref(bh), C.byref(hs)))
