@@ -152,6 +152,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_keys_hist(const uint64_t* __re
   }
 }
 
+// whole-batch bounds check ahead of a chunked host call: one bad id rejects every chunk
+__global__ void __launch_bounds__(256) k_check_range(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                     uint64_t capacity, uint32_t* __restrict__ err) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  for (; i < n; i += (uint64_t)gridDim.x * blockDim.x) bad |= path_id[i] >= capacity;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(err, 1u);
+}
+
 // one CTA per pass: exclusive scan of its 256-bin histogram, in place
 __global__ void __launch_bounds__(RADIX) k_hist_scan(uint32_t* __restrict__ ghist) {
   uint32_t* h = ghist + blockIdx.x * RADIX;
@@ -266,6 +275,8 @@ struct MergeArgs {
   uint32_t* ticket;        // zeroed per launch
   uint32_t num_tiles;
   uint64_t seq_base;
+  uint32_t idx_base;       // added to the arrival indices this launch reports (chunked host calls)
+  const uint64_t* chg_base;  // ORDERED: entries already in the change set when the launch began
   uint32_t* err;           // bit0 in: batch rejected by K0; bit1 out: cap too small
   Params p;
   IndexArgs ix;
@@ -492,8 +503,9 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
     if (w == 0) {
       const uint32_t ex = tile_prefix(a.tile_state, tile, in_cnt + over_cnt);
       if (lane == 0) {
-        s_ex = ex;
-        if (tile == a.num_tiles - 1) *a.n_changes = (uint64_t)ex + in_cnt + over_cnt;
+        const uint64_t b0 = *a.chg_base;
+        s_ex = (uint32_t)b0 + ex;
+        if (tile == a.num_tiles - 1) *a.n_changes = b0 + ex + in_cnt + over_cnt;
       }
     }
   } else if (tid == 0) {  // tiles claim their slice of the change set as they finish
@@ -509,7 +521,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
   if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : NO_SLOT);
   if (acc) {
     if (dest < a.cap) {
-      a.out_idx[dest] = idx;
+      a.out_idx[dest] = a.idx_base + idx;
       a.out_head[dest] = s_upd[tid * UPD_Q];
     } else {
       overflow = true;
@@ -536,7 +548,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
     a.verdict[gi] = (packed & ~NO_SLOT) | (uint32_t)odest;
     if (odest < a.cap) {
       const uint4* q = a.st_ent + sp * UPD_Q;
-      a.out_idx[odest] = gi;
+      a.out_idx[odest] = a.idx_base + gi;
       a.out_head[odest] = q[0];
       a.out_clk[2 * odest] = q[1];
       a.out_clk[2 * odest + 1] = q[2];

@@ -19,6 +19,8 @@ thread_local std::string g_create_error;
 
 enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_D2H, EV_Q0, EV_Q1, EV_COUNT };
 constexpr int EV_RING = 64;  // merge calls whose phase timings can still be queried
+constexpr int MAX_CHUNKS = 8;          // a host call is pipelined as up to this many chunks
+constexpr uint64_t MIN_CHUNK = 1 << 16;  // updates
 
 template <class T>
 struct DevBuf {
@@ -66,7 +68,10 @@ struct bb_ctx {
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
   uint64_t* d_nchanges = nullptr;
-  uint64_t* h_nchanges = nullptr;  // pinned
+  uint64_t* d_chg_base = nullptr;
+  uint64_t* h_nchanges = nullptr;  // pinned [MAX_CHUNKS]: running total after each chunk of a host call
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[MAX_CHUNKS]{}, ev_done[MAX_CHUNKS]{}, ev_cnt[MAX_CHUNKS]{};
   // indices (bb_index.cuh): dense key column + overflow set per indexed field
   struct IndexDev {
     bool live = false;
@@ -167,15 +172,22 @@ int reserve_io(bb_ctx* c, uint64_t n) {
   return BB_OK;
 }
 
-int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
+// One batch (or one chunk of a host call: `idx_base` = arrival index of its first update,
+// `append` = keep adding to *out->n_changes instead of starting a new change set).
+int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, uint32_t idx_base = 0,
+              bool append = false) {
   using namespace bb;
   const uint64_t n = in->n;
   if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
-  mark(c, EV_START, s);
-  BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+  if (!append) {
+    mark(c, EV_START, s);
+    BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+  }
   if (n == 0) {
-    mark(c, EV_SORT, s);
-    mark(c, EV_MERGE, s);
+    if (!append) {
+      mark(c, EV_SORT, s);
+      mark(c, EV_MERGE, s);
+    }
     return BB_OK;
   }
   {
@@ -200,7 +212,9 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
     src = dst;
     dst = t;
   }
-  mark(c, EV_SORT, s);
+  if (!append) mark(c, EV_SORT, s);
+  if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
+    BB_CUDA(c, cudaMemcpyAsync(c->d_chg_base, out->n_changes, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
 
   // K2: per-path sequential replay against the table + change-set compaction
   MergeArgs ma;
@@ -223,6 +237,8 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
   ma.ticket = zp + z.tickets + MAX_PASSES;
   ma.num_tiles = z.merge_tiles;
   ma.seq_base = c->seq;
+  ma.idx_base = idx_base;
+  ma.chg_base = c->d_chg_base;
   ma.err = c->d_err;
   ma.p.rank_object = c->cfg.rank_object;
   ma.p.me = c->cfg.local_peer;
@@ -243,7 +259,7 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s) {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, false>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, false>), z.merge_tiles, MT, s, ma);
   }
-  mark(c, EV_MERGE, s);
+  if (!append) mark(c, EV_MERGE, s);
   c->seq += n;
   return BB_OK;
 }
@@ -389,12 +405,19 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_xused, BB_MAX_FIELDS * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_xused, 0, BB_MAX_FIELDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_err, sizeof(uint32_t)) == cudaSuccess &&
-            cudaMallocHost((void**)&c->h_nchanges, sizeof(uint64_t)) == cudaSuccess;
+            cudaMallocHost((void**)&c->h_nchanges, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess;
+  for (int i = 0; ok && i < MAX_CHUNKS; ++i)
+    ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming) == cudaSuccess;
   for (int r = 0; ok && r < EV_RING; ++r)
     for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&c->ev[r][i]) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -428,6 +451,14 @@ int bb_destroy(bb_ctx* c) {
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
   if (c->d_nchanges) cudaFree(c->d_nchanges);
+  if (c->d_chg_base) cudaFree(c->d_chg_base);
+  for (int i = 0; i < MAX_CHUNKS; ++i) {
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_cnt[i]) cudaEventDestroy(c->ev_cnt[i]);
+  }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->h_err) cudaFreeHost(c->h_err);
   if (c->h_nchanges) cudaFreeHost(c->h_nchanges);
   for (int r = 0; r < EV_RING; ++r)
@@ -508,11 +539,16 @@ int bb_sync(bb_ctx* c, void* stream) {
   return collect_device_error(c, stream ? (cudaStream_t)stream : c->stream);
 }
 
+// Host entry.  The batch is cut into up to MAX_CHUNKS chunks in arrival order and pipelined over
+// three streams - H2D of chunk i+1, sort + merge of chunk i and D2H of chunk i-1 overlap - so both
+// PCIe directions are busy at once.  Chunks are merged strictly in order on one stream, so the
+// per-path arrival order (and therefore every decision) is that of the unsplit batch.
 int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   if (!c || !in || !out || !out->n_changes) return fail(c, BB_ERR_ARG, "null argument");
   const uint64_t n = in->n;
   if (n && (!in->path_id || !in->head || !in->clk || !in->val || !out->verdict))
     return fail(c, BB_ERR_ARG, "null buffer");
+  if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   begin_call(c);
@@ -522,39 +558,83 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
     mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_D2H, s);
     return BB_OK;
   }
+  uint64_t chunk = (n + MAX_CHUNKS - 1) / MAX_CHUNKS;
+  if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
+  if (c->cfg.flags & BB_CFG_ORDERED_CHANGES) chunk = n;  // one path-major run, as promised
+  const int nchunks = (int)((n + chunk - 1) / chunk);
   {
     int rc = reserve_io(c, n);
     if (rc) return rc;
-    rc = reserve_dev(c, n);
+    rc = reserve_dev(c, chunk);
     if (rc) return rc;
   }
-  BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, in->path_id, n * 8, cudaMemcpyHostToDevice, s));
-  BB_CUDA(c, cudaMemcpyAsync(c->io_head.p, in->head, n * 16, cudaMemcpyHostToDevice, s));
-  BB_CUDA(c, cudaMemcpyAsync(c->io_clk.p, in->clk, n * 32, cudaMemcpyHostToDevice, s));
-  BB_CUDA(c, cudaMemcpyAsync(c->io_val.p, in->val, n * 32, cudaMemcpyHostToDevice, s));
-  bb_batch din{n, c->io_path.p, reinterpret_cast<const bb_head*>(c->io_head.p),
-               reinterpret_cast<const uint32_t*>(c->io_clk.p), reinterpret_cast<const uint64_t*>(c->io_val.p)};
+  BB_CUDA(c, cudaEventRecord(c->ev_in[0], s));  // the side streams start after what is queued on ours
+  BB_CUDA(c, cudaStreamWaitEvent(c->s_h2d, c->ev_in[0], 0));
+  BB_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_in[0], 0));
+  // every path id first: a bad one must reject the batch before any chunk touches the table
+  BB_CUDA(c, cudaMemcpyAsync(c->io_path.p, in->path_id, n * 8, cudaMemcpyHostToDevice, c->s_h2d));
+  for (int i = 0; i < nchunks; ++i) {
+    const uint64_t o = (uint64_t)i * chunk, m = (o + chunk <= n) ? chunk : n - o;
+    BB_CUDA(c, cudaMemcpyAsync(c->io_head.p + o, in->head + o, m * 16, cudaMemcpyHostToDevice, c->s_h2d));
+    BB_CUDA(c, cudaMemcpyAsync(c->io_clk.p + 2 * o, in->clk + 8 * o, m * 32, cudaMemcpyHostToDevice, c->s_h2d));
+    BB_CUDA(c, cudaMemcpyAsync(c->io_val.p + 2 * o, in->val + 4 * o, m * 32, cudaMemcpyHostToDevice, c->s_h2d));
+    BB_CUDA(c, cudaEventRecord(c->ev_in[i], c->s_h2d));
+  }
   bb_changes dout{n, c->io_verdict.p, c->d_nchanges, c->io_out_idx.p,
                   reinterpret_cast<bb_head*>(c->io_out_head.p), reinterpret_cast<uint32_t*>(c->io_out_clk.p),
                   reinterpret_cast<uint64_t*>(c->io_out_val.p)};
-  int rc = merge_dev(c, &din, &dout, s);
-  if (rc) return rc;
-  BB_CUDA(c, cudaMemcpyAsync(out->verdict, c->io_verdict.p, n * 4, cudaMemcpyDeviceToHost, s));
-  BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges, c->d_nchanges, 8, cudaMemcpyDeviceToHost, s));
-  rc = collect_device_error(c, s);  // synchronises
-  if (rc) return rc;
-  const uint64_t k = *c->h_nchanges;
-  if (k > out->cap) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
-  if (k && (!out->idx || !out->head || !out->clk || !out->val)) return fail(c, BB_ERR_ARG, "null buffer");
-  if (k) {
-    BB_CUDA(c, cudaMemcpyAsync(out->idx, c->io_out_idx.p, k * 4, cudaMemcpyDeviceToHost, s));
-    BB_CUDA(c, cudaMemcpyAsync(out->head, c->io_out_head.p, k * 16, cudaMemcpyDeviceToHost, s));
-    BB_CUDA(c, cudaMemcpyAsync(out->clk, c->io_out_clk.p, k * 32, cudaMemcpyDeviceToHost, s));
-    BB_CUDA(c, cudaMemcpyAsync(out->val, c->io_out_val.p, k * 32, cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_in[0], 0));
+  mark(c, EV_START, s);
+  BB_CUDA(c, cudaMemsetAsync(c->d_nchanges, 0, sizeof(uint64_t), s));
+  if (nchunks > 1) BB_LAUNCH(c, bb::k_check_range, 296, 256, s, c->io_path.p, n, c->cfg.capacity, c->d_err);
+  for (int i = 0; i < nchunks; ++i) {
+    const uint64_t o = (uint64_t)i * chunk, m = (o + chunk <= n) ? chunk : n - o;
+    bb_batch din{m, c->io_path.p + o, reinterpret_cast<const bb_head*>(c->io_head.p + o),
+                 reinterpret_cast<const uint32_t*>(c->io_clk.p + 2 * o),
+                 reinterpret_cast<const uint64_t*>(c->io_val.p + 2 * o)};
+    bb_changes dchunk = dout;
+    dchunk.verdict = c->io_verdict.p + o;
+    BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_in[i], 0));
+    int rc = merge_dev(c, &din, &dchunk, s, (uint32_t)o, true);
+    if (rc) return rc;
+    BB_CUDA(c, cudaEventRecord(c->ev_done[i], s));
   }
+  mark(c, EV_SORT, s);  // (phases of a chunked call: "sort" is 0, "merge" = sort + merge of every chunk)
+  mark(c, EV_MERGE, s);
+  uint64_t done = 0;
+  int rc = BB_OK;
+  for (int i = 0; i < nchunks; ++i) {  // a chunk's entries are final once its kernels are: ship them
+    const uint64_t o = (uint64_t)i * chunk, m = (o + chunk <= n) ? chunk : n - o;
+    BB_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_done[i], 0));
+    BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges + i, c->d_nchanges, 8, cudaMemcpyDeviceToHost, c->s_d2h));
+    BB_CUDA(c, cudaEventRecord(c->ev_cnt[i], c->s_d2h));
+    BB_CUDA(c, cudaMemcpyAsync(out->verdict + o, c->io_verdict.p + o, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    BB_CUDA(c, cudaEventSynchronize(c->ev_cnt[i]));
+    const uint64_t k = c->h_nchanges[i];
+    if (k > out->cap) {
+      rc = fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
+      break;
+    }
+    if (k > done && (!out->idx || !out->head || !out->clk || !out->val)) {
+      rc = fail(c, BB_ERR_ARG, "null buffer");
+      break;
+    }
+    if (k > done) {
+      const uint64_t cnt = k - done;
+      BB_CUDA(c, cudaMemcpyAsync(out->idx + done, c->io_out_idx.p + done, cnt * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_CUDA(c, cudaMemcpyAsync(out->head + done, c->io_out_head.p + done, cnt * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_CUDA(c, cudaMemcpyAsync(out->clk + 8 * done, c->io_out_clk.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_CUDA(c, cudaMemcpyAsync(out->val + 4 * done, c->io_out_val.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    done = k;
+  }
+  BB_CUDA(c, cudaEventRecord(c->ev_cnt[0], c->s_d2h));
+  BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_cnt[0], 0));  // our stream is "done" when the last copy is
   mark(c, EV_D2H, s);
-  BB_CUDA(c, cudaStreamSynchronize(s));
-  *out->n_changes = k;
+  const int drc = collect_device_error(c, s);  // synchronises everything
+  if (rc) return rc;
+  if (drc) return drc;
+  *out->n_changes = done;
   return BB_OK;
 }
 

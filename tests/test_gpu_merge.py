@@ -201,3 +201,25 @@ def test_device_pointer_entry_matches_host_entry():
     assert_same_table(eng, orc, n_rec)
     assert eng.launch_count() > 0 and eng.phase_ms("merge") > 0 and eng.phase_ms("sort") > 0
     eng.close()
+
+
+def test_chunked_host_call_rejects_whole_batch():
+    """bb_merge_batch pipelines big batches in chunks; one bad path id in the LAST chunk must still
+    leave the table untouched (include/bullet_b200.h: batch rejected whole)."""
+    n_rec = 1000
+    rng = synth.rng_for(2, salt=7)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec, **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    b = synth.make_batch(table, 300_000, rng)
+    b.path_id[-1] = n_rec
+    with pytest.raises(capi.BulletB200Error) as e:
+        eng.merge(b)
+    assert e.value.code == capi.ERR_CAPACITY
+    assert_same_table(eng, orc, n_rec)
+    b.path_id[-1] = 0
+    assert eng.merge(b).same_as(orc.merge(b))  # the ctx is still usable, and chunking changes nothing
+    assert_same_table(eng, orc, n_rec)
+    eng.close()
