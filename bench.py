@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--keys", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--query-records", type=int, default=100_000_000,
+                    help="nodes per GPU for the index build + range/equals scans (BASELINE config 4)")
+    ap.add_argument("--no-query", action="store_true")
     return ap.parse_args()
 
 
@@ -164,6 +167,118 @@ def run_reference(args, rank, world):
         "note": "reference is JavaScript; no JS engine on the box, so this is the C restatement (oracle/bullet_oracle.c)",
     }
     print(json.dumps(line))
+
+
+def run_queries(args, rank, world, local_rank, dev, table, dist):
+    """BASELINE config 4: index('users','age') build + range(20,30) + equals(role,'admin') over
+    --query-records nodes per GPU (the 2.5 M-record image tiled), every rank scanning its shard;
+    results all-gathered (counts, then padded payload) when world > 1."""
+    import torch
+
+    from bullet_js_b200 import capi, codec, synth
+    from bullet_js_b200.engine import Engine
+
+    nq = args.query_records
+    eng = Engine(nq, device=local_rank, post_getdata=True, **synth.synth_ranks(args.records))
+    base = np.arange(table.n, dtype=np.uint64)
+    for off in range(0, nq, table.n):
+        m = min(table.n, nq - off)
+        eng.table_load(base[:m] + np.uint64(off), table.rows[:m])
+    t0 = time.perf_counter()
+    eng.index_create(0, extra_capacity=1 << 16)
+    build_ms_age = eng.phase_ms("scan")
+    eng.index_create(2, extra_capacity=1 << 16)
+    build_ms_role = eng.phase_ms("scan")
+    build_wall = time.perf_counter() - t0
+    side = torch.cuda.current_stream(dev)
+    stream = side.cuda_stream
+    cap = nq
+    hits = torch.zeros(cap, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    hs = capi.BBHits(cap=cap, node=hits.data_ptr(), n_dense=cnt.data_ptr(), n_extra=cnt[1:].data_ptr())
+    import ctypes as C
+
+    lo = capi.BBBound(num=20.0, rank=0, flags=0, reserved=0)
+    hi = capi.BBBound(num=30.0, rank=0, flags=0, reserved=0)
+    admin = codec.KEY_STR | 0
+
+    def range_dev():
+        eng._check(eng.lib.bb_query_range_dev(eng._h, 0, C.byref(lo), C.byref(hi), C.byref(hs), C.c_void_p(stream)))
+
+    def equals_dev():
+        eng._check(eng.lib.bb_query_equals_dev(eng._h, 2, admin, C.byref(hs), C.c_void_p(stream)))
+
+    out = {}
+    reps = 10
+    for name, fn in (("range", range_dev), ("equals", equals_dev)):
+        for _ in range(3):
+            fn()
+        eng.sync(stream)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        kernel_ms = float(np.mean([eng.phase_ms("scan", j) for j in range(reps)]))
+        nh = int(cnt.sum().item())
+        out[name] = {"ms": ms, "scan_ms": kernel_ms, "hits": nh}
+    # e2e through the host entry points (pinned output, D2H of the hits inside the timed region)
+    hn = out["range"]["hits"] + 16
+    h_node = torch.zeros(hn, dtype=torch.int32).pin_memory()
+    h_cnt = torch.zeros(2, dtype=torch.int64).pin_memory()
+    hhs = capi.BBHits(cap=hn, node=h_node.data_ptr(), n_dense=h_cnt.data_ptr(), n_extra=h_cnt[1:].data_ptr())
+    eng.query_range_raw(0, lo, hi, hhs)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.query_range_raw(0, lo, hi, hhs)
+    e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
+    assert int(h_cnt.sum()) == out["range"]["hits"]
+    if dist is not None:  # all-gather(v) of the result ids: counts first, then the padded payload
+        t = torch.tensor([out["range"]["ms"], out["equals"]["ms"], e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["range"]["ms"], out["equals"]["ms"], e2e_ms = (float(x) for x in t)
+        n_local = torch.tensor([out["range"]["hits"]], device=dev, dtype=torch.int64)
+        counts = torch.zeros(world, device=dev, dtype=torch.int64)
+        dist.all_gather_into_tensor(counts, n_local)
+        mx = int(counts.max().item())
+        range_dev()
+        gids = hits[:mx].to(torch.int64) * world + rank  # local row -> global path id
+        allh = torch.zeros(world * mx, device=dev, dtype=torch.int64)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(allh, gids)
+        g1.record()
+        torch.cuda.synchronize()
+        out["allgather_ms"] = g0.elapsed_time(g1)
+        out["allgather_bytes"] = int(world * mx * 8)
+    peak, _ = peaks()
+    res = {
+        "workload": f"config4: index(age)+index(role) build, range(age,20,30), equals(role,'admin') over {nq} nodes/GPU",
+        "nodes_per_gpu": nq, "n_gpus": world,
+        "range_rows_per_sec": nq * world / (out["range"]["ms"] * 1e-3),
+        "equals_rows_per_sec": nq * world / (out["equals"]["ms"] * 1e-3),
+        "range_hits": out["range"]["hits"], "equals_hits": out["equals"]["hits"],
+        "range_ms": out["range"]["ms"], "equals_ms": out["equals"]["ms"],
+        "index_build_ms": {"age": build_ms_age, "role": build_ms_role, "wall_both": build_wall * 1e3},
+        "index_build_rows_per_sec": nq * world / (build_ms_age * 1e-3),
+        "e2e_range": {"rows_per_sec": nq * world / (e2e_ms * 1e-3), "ms": e2e_ms, "d2h_bytes": out["range"]["hits"] * 4 + 16,
+                      "api": "bb_query_range (host hit buffer, synchronous)"},
+        "roofline": {"bound": "hbm", "kernel": "k_index_scan", "unit": "GB/s", "peak": peak,
+                     "achieved": (8.0 * nq + 4.0 * out["range"]["hits"]) / (out["range"]["scan_ms"] * 1e-3) / 1e9,
+                     "bytes_per_row": 8.0 + 4.0 * out["range"]["hits"] / nq, "kernel_ms": out["range"]["scan_ms"]},
+    }
+    res["roofline"]["frac"] = res["roofline"]["achieved"] / peak
+    for k in ("allgather_ms", "allgather_bytes"):
+        if k in out:
+            res[k] = out[k]
+    eng.close()
+    return res
 
 
 def workload_config(args, world):
@@ -346,6 +461,13 @@ def main():
                "sample": f"{done} x {n}-update batches of the same workload on the same table, "
                          f"oracle/bullet_oracle.c single thread, {dtc:.1f} s"}
 
+    for e in engines:
+        e.close()
+    engines = []
+    query = None
+    if not args.no_query:
+        query = run_queries(args, rank, world, local_rank, dev, table, dist)
+
     if rank == 0:
         line = {
             "metric": "crdt_field_merges_per_sec", "value": merged_total * F / (dev_ms * 1e-3),
@@ -360,7 +482,7 @@ def main():
                          "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],
                          "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
                          "phase_ms": ph},
-            "cpu_baseline": cpu, "clocks": clocks,
+            "cpu_baseline": cpu, "clocks": clocks, "query": query,
         }
         print(json.dumps(line))
     for e in engines:

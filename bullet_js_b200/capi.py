@@ -70,6 +70,7 @@ EXPORTS = [
     "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
     "bb_index_create", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
+    "bb_route_pack_dev",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
 ]
 
@@ -124,6 +125,8 @@ def load():
     lib.bb_query_range_dev.restype = i32
     lib.bb_index_stats.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64)]
     lib.bb_index_stats.restype = i32
+    lib.bb_route_pack_dev.argtypes = [vp, u32, C.POINTER(BBBatch), C.POINTER(BBBatch), vp, vp]
+    lib.bb_route_pack_dev.restype = i32
     lib.bb_launch_count.argtypes = [vp]
     lib.bb_launch_count.restype = u64
     lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]

@@ -212,13 +212,20 @@ struct ScanArgs {
 // predicate, ranks the hits in entry order (ballots inside a warp, a 64-entry scan across the
 // warps and rounds of the tile, a decoupled look-back across tiles) and writes their node ids
 // as one dense run per tile.  Count-only calls skip the ranking and the chain.
+// ORDERED (BB_CFG_ORDERED_CHANGES): tiles are chained with a decoupled look-back, so the hits of
+// the whole column come out in ascending entry order; otherwise a tile claims its run with one
+// atomicAdd when it is done (ascending inside the run, runs in completion order) and never waits.
+template <bool ORDERED>
 __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
   __shared__ uint32_t s_cnt[SC_ROUNDS * SC_WARPS];
-  __shared__ uint32_t s_tile, s_base_lo;
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  if (ORDERED) {
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+  }
+  const uint32_t tile = ORDERED ? s_tile : blockIdx.x;
   const uint64_t base = (uint64_t)tile * SC_TILE;
   const uint4* k4 = reinterpret_cast<const uint4*>(a.keys);
   uint4 v[SC_ROUNDS];
@@ -250,17 +257,19 @@ __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
     const uint32_t tile_total = __shfl_sync(0xffffffffu, inc, 31);
     if (a.out == nullptr) {
       if (lane == 0 && tile_total) atomicAdd(a.counters + a.which, (unsigned long long)tile_total);
-    } else {
+    } else if (ORDERED) {
       const uint32_t ex = tile_prefix(a.tile_state, tile, tile_total);
       if (lane == 0) {
-        s_base_lo = ex;
+        s_base = ex;
         if (tile == a.num_tiles - 1) a.counters[a.which] = (unsigned long long)ex + tile_total;
       }
+    } else if (lane == 0) {
+      s_base = tile_total ? atomicAdd(a.counters + a.which, (unsigned long long)tile_total) : 0ull;
     }
   }
   __syncthreads();
   if (a.out == nullptr || flags == 0) return;
-  const uint64_t obase = (a.which ? a.counters[0] : 0ull) + s_base_lo;
+  const uint64_t obase = (a.which ? a.counters[0] : 0ull) + s_base;
   bool overflow = false;
 #pragma unroll
   for (int j = 0; j < SC_ROUNDS; ++j) {

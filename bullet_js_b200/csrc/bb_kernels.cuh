@@ -601,4 +601,83 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
   for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[q];
 }
 
+// ---------------------------------------------------------------- K6: shard routing pack
+// A sharded table: path id p lives on rank p % world as local row p / world.  The pack
+// is a STABLE partition of the batch by owner - updates for rank 0 first, arrival order kept
+// inside every destination - so that the owner, which concatenates what it receives in source-rank
+// order, replays each path in (source rank, arrival index) order.  Three small launches: per-tile
+// destination counts, one CTA scanning them (tile-major inside destination-major), the scatter.
+constexpr int RT_THREADS = 256;
+constexpr int RT_MAX_WORLD = 16;
+
+__global__ void __launch_bounds__(RT_THREADS) k_route_count(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                            uint32_t world, uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t s_cnt[RT_MAX_WORLD];
+  if (threadIdx.x < RT_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+  const uint32_t d = i < n ? (uint32_t)(path_id[i] % world) : world;
+  for (uint32_t r = 0; r < world; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, d == r);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[r], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < world) tile_cnt[(uint64_t)blockIdx.x * world + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// one CTA: tile_cnt[tile][r] -> exclusive offsets in the packed order; counts[r] = updates for rank r
+__global__ void __launch_bounds__(RT_THREADS) k_route_scan(uint32_t* __restrict__ tile_cnt, uint32_t tiles,
+                                                           uint32_t world, uint64_t* __restrict__ counts) {
+  __shared__ uint32_t s_run;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (uint32_t r = 0; r < world; ++r) {
+    const uint32_t start = s_run;
+    for (uint32_t t0 = 0; t0 < tiles; t0 += RT_THREADS) {
+      const uint32_t t = t0 + threadIdx.x;
+      const uint32_t v = t < tiles ? tile_cnt[(uint64_t)t * world + r] : 0;
+      uint32_t total;
+      const uint32_t ex = block_exclusive_scan<RT_THREADS>(v, &total);
+      if (t < tiles) tile_cnt[(uint64_t)t * world + r] = s_run + ex;
+      __syncthreads();
+      if (threadIdx.x == 0) s_run += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[r] = s_run - start;
+    __syncthreads();
+  }
+}
+
+struct RouteArgs {
+  const uint64_t* path_id; const uint4* head; const uint4* clk; const uint4* val;  // [n] in
+  uint64_t* o_path; uint4* o_head; uint4* o_clk; uint4* o_val;                      // [n] packed out
+  uint64_t n;
+  uint32_t world;
+  const uint32_t* tile_off;  // [tiles][world] from k_route_scan
+};
+
+__global__ void __launch_bounds__(RT_THREADS) k_route_scatter(const RouteArgs a) {
+  __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
+  const uint64_t p = i < a.n ? a.path_id[i] : 0;
+  const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
+  uint32_t below = 0;
+  for (uint32_t r = 0; r < a.world; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, d == r);
+    if (d == r) below = __popc(m & lanemask_lt());
+    if (lane == 0) s_w[w][r] = __popc(m);
+  }
+  __syncthreads();
+  if (i >= a.n) return;
+  uint32_t dst = a.tile_off[(uint64_t)blockIdx.x * a.world + d] + below;
+  for (int ww = 0; ww < w; ++ww) dst += s_w[ww][d];
+  a.o_path[dst] = p / a.world;
+  a.o_head[dst] = a.head[i];
+  a.o_clk[2 * (uint64_t)dst] = a.clk[2 * i];
+  a.o_clk[2 * (uint64_t)dst + 1] = a.clk[2 * i + 1];
+  a.o_val[2 * (uint64_t)dst] = a.val[2 * i];
+  a.o_val[2 * (uint64_t)dst + 1] = a.val[2 * i + 1];
+}
+
 }  // namespace bb

@@ -84,6 +84,7 @@ struct bb_ctx {
   uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
   unsigned long long* d_counters = nullptr;  // [2] dense / overflow matches of the running query
   unsigned long long* h_counters = nullptr;  // pinned [2]
+  DevBuf<uint32_t> route_tiles;            // [tiles][world] of bb_route_pack_dev
   DevBuf<uint32_t> scan_zero;              // [ticket x 2 | tile states of both scans]
   DevBuf<uint32_t> io_hits;
 };
@@ -310,10 +311,13 @@ int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, ui
   a.p = pred;
   a.keys = ix.pcol; a.nodes = nullptr; a.n = n0; a.which = 0;
   a.ticket = c->scan_zero.p; a.tile_state = c->scan_zero.p + 2; a.num_tiles = t0;
-  BB_LAUNCH(c, k_index_scan, t0, SC_THREADS, s, a);
+  const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
+  if (ordered) BB_LAUNCH(c, k_index_scan<true>, t0, SC_THREADS, s, a);
+  else BB_LAUNCH(c, k_index_scan<false>, t0, SC_THREADS, s, a);
   a.keys = ix.xkey; a.nodes = ix.xnode; a.n = n1; a.which = 1;
   a.ticket = c->scan_zero.p + 1; a.tile_state = c->scan_zero.p + 2 + t0; a.num_tiles = t1;
-  BB_LAUNCH(c, k_index_scan, t1, SC_THREADS, s, a);
+  if (ordered) BB_LAUNCH(c, k_index_scan<true>, t1, SC_THREADS, s, a);
+  else BB_LAUNCH(c, k_index_scan<false>, t1, SC_THREADS, s, a);
   mark(c, EV_Q1, s);
   return BB_OK;
 }
@@ -439,7 +443,7 @@ int bb_destroy(bb_ctx* c) {
   c->io_path.release(); c->io_head.release(); c->io_clk.release(); c->io_val.release();
   c->io_out_head.release(); c->io_out_clk.release(); c->io_out_val.release(); c->io_rows.release();
   c->io_verdict.release(); c->io_out_idx.release();
-  c->scan_zero.release(); c->io_hits.release();
+  c->scan_zero.release(); c->io_hits.release(); c->route_tiles.release();
   for (int f = 0; f < BB_MAX_FIELDS; ++f) {
     if (c->index[f].pcol) cudaFree(c->index[f].pcol);
     if (c->index[f].xkey) cudaFree(c->index[f].xkey);
@@ -635,6 +639,40 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   if (rc) return rc;
   if (drc) return drc;
   *out->n_changes = done;
+  return BB_OK;
+}
+
+int bb_route_pack_dev(bb_ctx* c, uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts, void* stream) {
+  using namespace bb;
+  if (!c || !in || !out || !counts) return fail(c, BB_ERR_ARG, "null argument");
+  if (world < 1 || world > RT_MAX_WORLD) return fail(c, BB_ERR_ARG, "world must be 1..16");
+  const uint64_t n = in->n;
+  if (n >= 0xFFFFFFFFull) return fail(c, BB_ERR_ARG, "batch too large");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (n == 0) {
+    BB_CUDA(c, cudaMemsetAsync(counts, 0, world * sizeof(uint64_t), s));
+    return BB_OK;
+  }
+  if (!in->path_id || !in->head || !in->clk || !in->val || !out->path_id || !out->head || !out->clk || !out->val)
+    return fail(c, BB_ERR_ARG, "null buffer");
+  const uint32_t tiles = div_up(n, RT_THREADS);
+  BB_CUDA(c, c->route_tiles.ensure((size_t)tiles * world));
+  BB_LAUNCH(c, k_route_count, tiles, RT_THREADS, s, in->path_id, n, world, c->route_tiles.p);
+  BB_LAUNCH(c, k_route_scan, 1, RT_THREADS, s, c->route_tiles.p, tiles, world, counts);
+  RouteArgs a;
+  a.path_id = in->path_id;
+  a.head = reinterpret_cast<const uint4*>(in->head);
+  a.clk = reinterpret_cast<const uint4*>(in->clk);
+  a.val = reinterpret_cast<const uint4*>(in->val);
+  a.o_path = const_cast<uint64_t*>(out->path_id);
+  a.o_head = reinterpret_cast<uint4*>(const_cast<bb_head*>(out->head));
+  a.o_clk = reinterpret_cast<uint4*>(const_cast<uint32_t*>(out->clk));
+  a.o_val = reinterpret_cast<uint4*>(const_cast<uint64_t*>(out->val));
+  a.n = n;
+  a.world = world;
+  a.tile_off = c->route_tiles.p;
+  BB_LAUNCH(c, k_route_scatter, tiles, RT_THREADS, s, a);
   return BB_OK;
 }
 

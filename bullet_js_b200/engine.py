@@ -84,6 +84,11 @@ class Engine:
     def merge_dev(self, bs: capi.BBBatch, cs: capi.BBChanges, stream: int = 0):
         self._check(self.lib.bb_merge_batch_dev(self._h, C.byref(bs), C.byref(cs), C.c_void_p(stream)))
 
+    def route_pack_dev(self, world: int, bs: capi.BBBatch, out: capi.BBBatch, counts_ptr: int, stream: int = 0):
+        """Stable partition of a device batch by owner rank (bullet_js_b200/shard.py)."""
+        self._check(self.lib.bb_route_pack_dev(self._h, world, C.byref(bs), C.byref(out), C.c_void_p(counts_ptr),
+                                               C.c_void_p(stream)))
+
     def sync(self, stream: int = 0):
         self._check(self.lib.bb_sync(self._h, C.c_void_p(stream)))
 
@@ -110,6 +115,10 @@ class Engine:
         bl, bh = capi.bound_struct(lo), capi.bound_struct(hi)
         self._check(self.lib.bb_query_range(self._h, field, C.byref(bl), C.byref(bh), C.byref(hs)))
         return out.result()
+
+    def query_range_raw(self, field: int, bl: capi.BBBound, bh: capi.BBBound, hs: capi.BBHits):
+        """bb_query_range on prebuilt structs (pinned hit buffer, no numpy copies)."""
+        self._check(self.lib.bb_query_range(self._h, field, C.byref(bl), C.byref(bh), C.byref(hs)))
 
     def query_count(self, field: int, key: int) -> int:
         n = C.c_uint64(0)

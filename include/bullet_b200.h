@@ -145,7 +145,7 @@ typedef struct bb_config {
  * primitive into `{}` right after the write instead of at the next update. */
 #define BB_CFG_POST_GETDATA 1u
 /* Lay the change set out in path-major order (ascending path id, arrival order
- * within a path), bit-identical from run to run.  Without it tiles of 128 sorted
+ * within a path) and query hits in ascending node id, bit-identical from run to run.  Without it tiles of 128 sorted
  * updates claim their slice of the change set as they finish: the same entries,
  * each still found through verdict[], but the tiles' order in the buffers is not
  * fixed - and no tile ever waits for another one. */
@@ -235,7 +235,8 @@ int bb_sync(bb_ctx* ctx, void* stream);
  * (query:151-167), a node can sit in any number of buckets; the device keeps one
  * entry per node in a dense column (8 bytes per row, what range/equals stream) and
  * the rest in an open-addressing overflow set of `extra_capacity` slots.
- * Results: node ids; first the matches of the dense column in ascending node id,
+ * Results: node ids; first the matches of the dense column (runs of ascending node
+ * id, one per 4096-row tile; the whole column ascending with BB_CFG_ORDERED_CHANGES),
  * then the matches of the overflow set.  A node with entries in two matching
  * buckets appears twice, as in the reference (query:237-258).  The reference's
  * (Map order, Set order) result order is not reproduced: compare as multisets. */
@@ -273,7 +274,7 @@ typedef struct bb_bound {
 typedef struct bb_hits {
   uint64_t cap;        /* capacity of `node` in entries */
   uint32_t* node;      /* [cap] */
-  uint64_t* n_dense;   /* [1] matches from the dense column (ascending node id) */
+  uint64_t* n_dense;   /* [1] matches from the dense column */
   uint64_t* n_extra;   /* [1] matches from the overflow set, stored after them */
 } bb_hits;
 
@@ -291,6 +292,16 @@ int bb_query_range_dev(bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb
                        void* stream);
 /* Entries currently held by the index (dense + overflow); synchronises. */
 int bb_index_stats(bb_ctx* ctx, uint32_t field, uint64_t* n_dense, uint64_t* n_extra);
+
+/* ---- sharding: the table is split over `world` ranks, path id p lives on
+ *      rank p % world as local row p / world.  bb_route_pack_dev is the send side of the update
+ *      routing: a stable partition of a device-resident batch by owner rank (arrival order kept
+ *      inside every destination), path ids rewritten to local rows, counts[r] = updates for rank
+ *      r (device, [world]).  The caller exchanges counts and the four packed arrays with an
+ *      all-to-all (NCCL over NVLink in bullet_js_b200/shard.py) and hands what it received,
+ *      concatenated in source-rank order, to bb_merge_batch_dev.  world <= 16. */
+int bb_route_pack_dev(bb_ctx* ctx, uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts,
+                      void* stream);
 
 /* ---- telemetry ---------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */

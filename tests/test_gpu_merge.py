@@ -223,3 +223,38 @@ def test_chunked_host_call_rejects_whole_batch():
     assert eng.merge(b).same_as(orc.merge(b))  # the ctx is still usable, and chunking changes nothing
     assert_same_table(eng, orc, n_rec)
     eng.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_route_pack_is_a_stable_partition(world):
+    """bb_route_pack_dev (send side of the shard routing) == numpy stable partition by id % world."""
+    import ctypes as C
+
+    import torch
+
+    from bullet_js_b200.engine import Engine
+
+    n_rec, n = 4000, 70_001
+    rng = synth.rng_for(2, salt=9)
+    table = synth.make_table(n_rec, rng)
+    b = synth.make_batch(table, n, rng, keys="zipf")
+    eng = Engine(n_rec, **synth.synth_ranks(n_rec))
+    dev = torch.device("cuda", 0)
+    to_dev = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
+    src = [to_dev(x) for x in (b.path_id, b.head, b.clk, b.val)]
+    dst = [torch.zeros_like(t) for t in src]
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mk = lambda ts: capi.BBBatch(n=n, path_id=ts[0].data_ptr(), head=ts[1].data_ptr(), clk=ts[2].data_ptr(),
+                                 val=ts[3].data_ptr())
+    torch.cuda.synchronize()
+    eng.route_pack_dev(world, mk(src), mk(dst), counts.data_ptr())
+    eng.sync()
+    owner = (b.path_id % np.uint64(world)).astype(np.int64)
+    order = np.argsort(owner, kind="stable")
+    assert counts.cpu().tolist() == np.bincount(owner, minlength=world).tolist()
+    got = [t.cpu().numpy() for t in dst]
+    assert np.array_equal(got[0].view(np.uint64), b.path_id[order] // np.uint64(world))
+    assert np.array_equal(got[1].view(codec.HEAD_DTYPE), b.head[order])
+    assert np.array_equal(got[2].view(np.uint32).reshape(n, 8), b.clk[order])
+    assert np.array_equal(got[3].view(np.uint64).reshape(n, 4), b.val[order])
+    eng.close()

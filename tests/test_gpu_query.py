@@ -138,3 +138,23 @@ def test_kat_h_on_gpu():
     assert eng.query_range(0, schema.bound(30.0, False), schema.bound(31.0, True)).tolist() == [0, 0]
     assert eng.index_stats(0) == (1, 1)
     eng.close()
+
+
+def test_ordered_hits():
+    """BB_CFG_ORDERED_CHANGES: the dense column's hits come out in ascending node id."""
+    from bullet_js_b200.engine import Engine
+
+    n_rec = 300_000
+    rng = synth.rng_for(4, salt=5)
+    table = synth.make_table(n_rec, rng)
+    eng = Engine(n_rec, post_getdata=True, ordered_changes=True, **synth.synth_ranks(n_rec))
+    eng.table_load(np.arange(n_rec, dtype=np.uint64), table.rows)
+    eng.index_create(0, extra_capacity=1 << 12)
+    lo, hi = np.zeros((), codec.BOUND_DTYPE), np.zeros((), codec.BOUND_DTYPE)
+    lo["num"], hi["num"] = 20.0, 30.0
+    hb = capi.HitBuffers(n_rec)
+    got = eng.query_range(0, lo, hi, hb)
+    ages = table.rows["val"][:, 0].view(np.float64)
+    want = np.nonzero((ages >= 20) & (ages <= 30))[0]
+    assert int(hb.n_extra[0]) == 0 and np.array_equal(got, want.astype(np.uint32))
+    eng.close()
