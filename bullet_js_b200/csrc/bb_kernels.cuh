@@ -248,6 +248,196 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const uint64_t* _
   }
 }
 
+// ---------------------------------------------------------------- K1': counting sort on dense path ids
+// The table is direct-indexed, so when the batch is not tiny next to it the sort is a counting sort
+// keyed by the row index itself: count (one RED per update) -> exclusive scan over the rows ->
+// place (cnt counts back down to zero, so the array is clean for the next batch).  Placement order
+// inside a path is whatever the atomics gave; k_cs_fix restores arrival order: segments of up to
+// 8 updates in registers, longer ones (hot keys) by a CTA-wide LSD radix sort on the arrival index.
+constexpr int CS_THREADS = 256;
+constexpr int CS_SCAN_CTAS = 296;      // all co-resident: the scan's look-back never waits on an unscheduled CTA
+constexpr int CS_SHORT = 8;            // longest segment fixed in registers
+constexpr int CS_LONG_CTAS = 592;
+
+__global__ void __launch_bounds__(CS_THREADS) k_cs_count(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                         uint64_t capacity, uint32_t* __restrict__ cnt,
+                                                         uint32_t* __restrict__ err) {
+  const uint64_t i = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t pid = path_id[i];
+  if (pid >= capacity) atomicOr(err, 1u);  // batch rejected: k_cs_place only undoes the counts
+  else atomicAdd(&cnt[pid], 1u);
+}
+
+// off[r] = number of updates whose row index is < r, off[capacity] = all of them.  Each CTA owns a
+// contiguous chunk: sum it, publish, look back over the CTAs before it, then scan it.
+__global__ void __launch_bounds__(CS_THREADS) k_cs_offsets(const uint32_t* __restrict__ cnt, uint64_t capacity,
+                                                           uint64_t chunk, uint32_t* __restrict__ off,
+                                                           uint32_t* __restrict__ state) {
+  __shared__ uint32_t s_red[CS_THREADS / 32];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = min(capacity, lo + chunk);
+  uint32_t sum = 0;
+  for (uint64_t i = lo + 4 * tid; i < hi; i += 4 * CS_THREADS) {  // chunk and capacity padding keep this in bounds
+    const uint4 v = *reinterpret_cast<const uint4*>(cnt + i);
+    sum += v.x + v.y + v.z + v.w;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[w] = sum;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = lane < CS_THREADS / 32 ? s_red[lane] : 0u;
+    t = warp_sum(t);
+    const uint32_t ex = tile_prefix(state, blockIdx.x, t);
+    if (lane == 0) {
+      s_base = ex;
+      if (blockIdx.x == gridDim.x - 1) off[capacity] = ex + t;
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_base;
+  for (uint64_t i0 = lo; i0 < hi; i0 += 4 * CS_THREADS) {
+    const uint64_t i = i0 + 4 * tid;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < hi) v = *reinterpret_cast<const uint4*>(cnt + i);
+    uint32_t total;
+    const uint32_t ex = run + block_exclusive_scan<CS_THREADS>(v.x + v.y + v.z + v.w, &total);
+    if (i < hi) *reinterpret_cast<uint4*>(off + i) = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    run += total;
+  }
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_cs_place(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                         uint64_t capacity, uint32_t* __restrict__ cnt,
+                                                         const uint32_t* __restrict__ off, uint64_t* __restrict__ items,
+                                                         const uint32_t* __restrict__ err) {
+  const uint64_t i = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t pid = path_id[i];
+  if (pid >= capacity) return;
+  const uint32_t r = atomicSub(&cnt[pid], 1u) - 1u;
+  if (!(*err & 1u)) items[off[pid] + r] = (pid << 32) | i;
+}
+
+// one thread per sorted position; the thread on a segment's first position puts the segment in
+// arrival order (<= CS_SHORT updates) or queues it for k_cs_fix_long
+__global__ void __launch_bounds__(CS_THREADS) k_cs_fix(uint64_t* __restrict__ items, uint64_t n,
+                                                       const uint32_t* __restrict__ off, uint2* __restrict__ long_list,
+                                                       uint32_t* __restrict__ n_long, const uint32_t* __restrict__ err) {
+  const uint64_t p = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
+  if (p >= n || (*err & 1u)) return;
+  const uint64_t it = items[p];
+  const uint32_t key = (uint32_t)(it >> 32);
+  const uint32_t start = off[key];
+  if (start != (uint32_t)p) return;
+  const uint32_t len = off[key + 1] - start;
+  if (len < 2) return;
+  if (len > CS_SHORT) {
+    long_list[atomicAdd(n_long, 1u)] = make_uint2(start, len);
+    return;
+  }
+  uint32_t v[CS_SHORT];
+#pragma unroll
+  for (int k = 0; k < CS_SHORT; ++k) v[k] = k < (int)len ? (uint32_t)items[p + k] : 0xFFFFFFFFu;
+#pragma unroll
+  for (int a = 1; a < CS_SHORT; ++a) {  // insertion sort as a fixed compare-exchange network (registers only)
+#pragma unroll
+    for (int b = a; b > 0; --b) {
+      const uint32_t x = min(v[b - 1], v[b]), y = max(v[b - 1], v[b]);
+      v[b - 1] = x;
+      v[b] = y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CS_SHORT; ++k)
+    if (k < (int)len) items[p + k] = ((uint64_t)key << 32) | v[k];
+}
+
+// hot keys: each queued segment is sorted on its arrival index by one CTA, LSD radix, 8-bit digits,
+// ping-ponging between the item buffer and the scratch buffer at the same offsets
+__global__ void __launch_bounds__(CS_THREADS) k_cs_fix_long(uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
+                                                            const uint2* __restrict__ long_list,
+                                                            const uint32_t* __restrict__ n_long, uint32_t* __restrict__ next) {
+  __shared__ uint32_t hist[RADIX];
+  __shared__ uint32_t whist[CS_THREADS / 32][RADIX];
+  __shared__ uint32_t s_seg;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t lt = lanemask_lt();
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_seg = atomicAdd(next, 1u);
+    __syncthreads();
+    if (s_seg >= *n_long) return;
+    const uint2 seg = long_list[s_seg];
+    const uint32_t len = seg.y;
+    uint64_t* cur = items + seg.x;
+    uint64_t* oth = scratch + seg.x;
+    for (int shift = 0; shift < 32; shift += 8) {
+      hist[tid] = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < len; i += CS_THREADS) atomicAdd(&hist[((uint32_t)cur[i] >> shift) & 0xFFu], 1u);
+      __syncthreads();
+      const uint32_t mine = hist[tid];
+      const bool trivial = __syncthreads_or(mine == len);  // every index has the same digit: nothing to do
+      if (trivial) continue;
+      uint32_t total;
+      const uint32_t ex = block_exclusive_scan<CS_THREADS>(mine, &total);
+      hist[tid] = ex;  // running base of digit `tid`
+      __syncthreads();
+      for (uint32_t c0 = 0; c0 < len; c0 += CS_THREADS * 8) {  // chunks in order, warps own contiguous runs
+        for (int d = lane; d < RADIX; d += 32) whist[w][d] = 0;
+        __syncwarp();
+        const uint32_t wb = c0 + w * 256;
+        uint64_t kv[8];
+        uint32_t rank[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t i = wb + k * 32 + lane;
+          const bool valid = i < len;
+          kv[k] = valid ? cur[i] : 0;
+          const uint32_t d = valid ? (((uint32_t)kv[k] >> shift) & 0xFFu) : RADIX;
+          const uint32_t peers = __match_any_sync(0xffffffffu, d);
+          const int leader = __ffs(peers) - 1;
+          uint32_t old = 0;
+          if (lane == leader && valid) {
+            old = whist[w][d];
+            whist[w][d] = old + __popc(peers);
+          }
+          old = __shfl_sync(0xffffffffu, old, leader);
+          rank[k] = old + __popc(peers & lt);
+          __syncwarp();
+        }
+        __syncthreads();
+        {  // digit `tid`: offsets of the warps' runs, then advance the running base
+          uint32_t run = hist[tid];
+#pragma unroll
+          for (int ww = 0; ww < CS_THREADS / 32; ++ww) {
+            const uint32_t t = whist[ww][tid];
+            whist[ww][tid] = run;
+            run += t;
+          }
+          hist[tid] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t i = wb + k * 32 + lane;
+          if (i < len) oth[whist[w][((uint32_t)kv[k] >> shift) & 0xFFu] + rank[k]] = kv[k];
+        }
+        __syncthreads();
+      }
+      uint64_t* t = cur;
+      cur = oth;
+      oth = t;
+    }
+    if (cur != items + seg.x) {
+      __syncthreads();
+      for (uint32_t i = tid; i < len; i += CS_THREADS) oth[i] = cur[i];
+    }
+  }
+}
+
 }  // namespace bb
 
 #include "bb_index.cuh"  // needs the warp / look-back helpers above

@@ -67,6 +67,9 @@ struct bb_ctx {
   DevBuf<uint64_t> io_path;
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
+  uint32_t* cs_cnt = nullptr;  // counting sort: per-row update counts (all zero between calls)
+  uint32_t* cs_off = nullptr;  // and their exclusive scan, [capacity + 1] (both padded to 1024)
+  DevBuf<uint2> cs_long;       // segments longer than CS_SHORT, queued for k_cs_fix_long
   uint64_t* d_nchanges = nullptr;
   uint64_t* d_chg_base = nullptr;
   uint64_t* h_nchanges = nullptr;  // pinned [MAX_CHUNKS]: running total after each chunk of a host call
@@ -132,8 +135,14 @@ void mark(bb_ctx* c, int which, cudaStream_t s) {
 
 struct ZeroLayout {
   uint32_t passes, sort_tiles, merge_tiles;
-  size_t hist, tickets, sort_state, merge_state, total;  // offsets in uint32_t units
+  size_t hist, tickets, sort_state, merge_state, cs_state, cs_ctr, total;  // offsets in uint32_t units
 };
+
+// counting sort when the scan over the rows is cheap next to the batch, radix sort otherwise
+bool use_counting_sort(const bb_ctx* c, uint64_t n) {
+  if (c->cfg.flags & BB_CFG_RADIX_SORT) return false;
+  return c->cfg.capacity <= 64 * (n < 4096 ? 4096 : n);
+}
 
 ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   using namespace bb;
@@ -144,8 +153,11 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   z.hist = 0;
   z.tickets = z.hist + (size_t)MAX_PASSES * RADIX;
   z.sort_state = z.tickets + 8;
+  if (use_counting_sort(c, n)) z.passes = 0;
   z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
-  z.total = z.merge_state + z.merge_tiles;
+  z.cs_state = z.merge_state + z.merge_tiles;
+  z.cs_ctr = z.cs_state + CS_SCAN_CTAS;
+  z.total = z.cs_ctr + 2;
   return z;
 }
 
@@ -157,6 +169,7 @@ int reserve_dev(bb_ctx* c, uint64_t n) {
   BB_CUDA(c, c->zero.ensure(z.total));
   BB_CUDA(c, c->st_idx.ensure(n));
   BB_CUDA(c, c->st_ent.ensure(5 * n));
+  BB_CUDA(c, c->cs_long.ensure(n / 8 + 1));
   return BB_OK;
 }
 
@@ -199,19 +212,34 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   uint32_t* zp = c->zero.p;
   BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
 
-  // K0 + K1: stable sort of (path id, arrival index) by path id
-  BB_LAUNCH(c, k_keys_hist, z.sort_tiles, SORT_THREADS, s, in->path_id, n, c->cfg.capacity, (int)z.passes,
-            c->items_a.p, zp + z.hist, c->d_err);
-  BB_LAUNCH(c, k_hist_scan, z.passes, RADIX, s, zp + z.hist);
   uint64_t* src = c->items_a.p;
-  uint64_t* dst = c->items_b.p;
-  for (uint32_t pass = 0; pass < z.passes; ++pass) {
-    BB_LAUNCH(c, k_sort_pass, z.sort_tiles, SORT_THREADS, s, src, dst, n, (int)(8 * pass),
-              zp + z.hist + (size_t)pass * RADIX, zp + z.sort_state + (size_t)pass * z.sort_tiles * RADIX,
-              zp + z.tickets + pass);
-    uint64_t* t = src;
-    src = dst;
-    dst = t;
+  if (use_counting_sort(c, n)) {
+    // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
+    const uint32_t g = div_up(n, CS_THREADS);
+    const uint64_t cap = c->cfg.capacity;
+    uint32_t scan_ctas = div_up(cap, 4 * CS_THREADS);
+    if (scan_ctas > CS_SCAN_CTAS) scan_ctas = CS_SCAN_CTAS;
+    const uint64_t chunk = ((cap + scan_ctas - 1) / scan_ctas + 4 * CS_THREADS - 1) / (4 * CS_THREADS) * (4 * CS_THREADS);
+    BB_LAUNCH(c, k_cs_count, g, CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->d_err);
+    BB_LAUNCH(c, k_cs_offsets, scan_ctas, CS_THREADS, s, c->cs_cnt, cap, chunk, c->cs_off, zp + z.cs_state);
+    BB_LAUNCH(c, k_cs_place, g, CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->cs_off, src, c->d_err);
+    BB_LAUNCH(c, k_cs_fix, g, CS_THREADS, s, src, n, c->cs_off, c->cs_long.p, zp + z.cs_ctr, c->d_err);
+    BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, zp + z.cs_ctr,
+              zp + z.cs_ctr + 1);
+  } else {
+    // K0 + K1: stable LSD radix sort of (path id, arrival index) by path id
+    BB_LAUNCH(c, k_keys_hist, z.sort_tiles, SORT_THREADS, s, in->path_id, n, c->cfg.capacity, (int)z.passes,
+              c->items_a.p, zp + z.hist, c->d_err);
+    BB_LAUNCH(c, k_hist_scan, z.passes, RADIX, s, zp + z.hist);
+    uint64_t* dst = c->items_b.p;
+    for (uint32_t pass = 0; pass < z.passes; ++pass) {
+      BB_LAUNCH(c, k_sort_pass, z.sort_tiles, SORT_THREADS, s, src, dst, n, (int)(8 * pass),
+                zp + z.hist + (size_t)pass * RADIX, zp + z.sort_state + (size_t)pass * z.sort_tiles * RADIX,
+                zp + z.tickets + pass);
+      uint64_t* t = src;
+      src = dst;
+      dst = t;
+    }
   }
   if (!append) mark(c, EV_SORT, s);
   if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
@@ -402,12 +430,17 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
   c->key_bits = bits;
+  const size_t cs_words = ((size_t)cfg->capacity + 1 + 1023) / 1024 * 1024 + 1024;
   bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->table, cfg->capacity * sizeof(bb_row)) == cudaSuccess &&
             cudaMemsetAsync(c->table, 0, cfg->capacity * sizeof(bb_row), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->cs_cnt, cs_words * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->cs_cnt, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
@@ -454,6 +487,9 @@ int bb_destroy(bb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
+  if (c->cs_cnt) cudaFree(c->cs_cnt);
+  if (c->cs_off) cudaFree(c->cs_off);
+  c->cs_long.release();
   if (c->d_nchanges) cudaFree(c->d_nchanges);
   if (c->d_chg_base) cudaFree(c->d_chg_base);
   for (int i = 0; i < MAX_CHUNKS; ++i) {

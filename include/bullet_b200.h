@@ -150,6 +150,9 @@ typedef struct bb_config {
  * each still found through verdict[], but the tiles' order in the buffers is not
  * fixed - and no tile ever waits for another one. */
 #define BB_CFG_ORDERED_CHANGES 2u
+/* Always group a batch by path with the stable LSD radix sort.  By default the library uses a
+ * counting sort over the row indices whenever capacity <= 64 x batch size (same result). */
+#define BB_CFG_RADIX_SORT 4u
 
 typedef struct bb_ctx bb_ctx;
 

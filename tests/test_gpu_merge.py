@@ -9,13 +9,14 @@ from tests import streamgen
 pytestmark = pytest.mark.gpu
 
 
-def engine_and_oracle(schema=None, capacity=256, post_getdata=False, ordered=False, **kw):
+def engine_and_oracle(schema=None, capacity=256, post_getdata=False, ordered=False, radix=False, **kw):
     from bullet_js_b200.engine import Engine
 
     if schema is not None:
-        eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata, ordered_changes=ordered)
+        eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata, ordered_changes=ordered,
+                                radix_sort=radix)
     else:
-        eng = Engine(capacity, post_getdata=post_getdata, ordered_changes=ordered, **kw)
+        eng = Engine(capacity, post_getdata=post_getdata, ordered_changes=ordered, radix_sort=radix, **kw)
     return eng, TypedOracle(eng.cfg)
 
 
@@ -28,11 +29,12 @@ def assert_same_table(eng, orc, n):
 
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("indexed", [False, True])
-def test_random_js_streams(seed, indexed):
+@pytest.mark.parametrize("radix", [False, True])
+def test_random_js_streams(seed, indexed, radix):
     ops, _ref = streamgen.generate(100 + seed, 4000, 37, index_fields=("age",) if indexed else ())
     schema = streamgen.make_schema()
     batch = codec.encode_updates(schema, ops)
-    eng, orc = engine_and_oracle(schema, 64, post_getdata=indexed)
+    eng, orc = engine_and_oracle(schema, 64, post_getdata=indexed, radix=radix)
     cuts = [0, 1, 2, 35, 36, 1000, 1001, 3000, len(ops)]
     seen = set()
     for lo, hi in zip(cuts, cuts[1:]):
@@ -57,14 +59,15 @@ def test_kat_l_on_gpu():
     eng.close()
 
 
-@pytest.mark.parametrize("ordered", [False, True])
+@pytest.mark.parametrize("mode", ["default", "ordered", "radix"])
 @pytest.mark.parametrize("keys", ["uniform", "zipf"])
-def test_synthetic_schema_stream(keys, ordered):
+def test_synthetic_schema_stream(keys, mode):
     """SURVEY 8d schema at a size the oracle replays in a second: 50k records, 3 x 200k updates."""
     n_rec = 50_000
     rng = synth.rng_for(2, salt=1)
     table = synth.make_table(n_rec, rng)
-    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, **synth.synth_ranks(n_rec))
+    ordered = mode == "ordered"
+    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, radix=mode == "radix", **synth.synth_ranks(n_rec))
     ids = np.arange(n_rec, dtype=np.uint64)
     eng.table_load(ids, table.rows)
     orc.load(ids, table.rows)
