@@ -165,18 +165,27 @@ __global__ void __launch_bounds__(256) k_count_live(const uint64_t* __restrict__
 
 // ---------------------------------------------------------------- K5: equals / range / count scan
 struct Pred {
-  uint32_t mode;  // 0 equals, 1 range
+  uint32_t mode;  // 0 equals, 1 range with numeric bounds, 2 range with a string bound
   uint32_t lo_flags, hi_flags;
-  uint64_t eq;
+  uint64_t eq;           // mode 0: the key; mode 1: ordered image of the lower bound
+  uint64_t width;        // mode 1: ordered image of the upper bound minus that of the lower
   double lo, hi;
   uint64_t lo_rank, hi_rank;
 };
 
+// order-preserving image of f64 bits in u64: numbers keep their order, every NaN pattern (that is
+// every non-numeric key, BB_KEY_NAN and BB_KEY_NONE) lands outside [image(-inf), image(+inf)]
+__host__ __device__ __forceinline__ uint64_t ordered_image(uint64_t bits) {
+  return bits ^ ((uint64_t)((int64_t)bits >> 63) | 0x8000000000000000ull);
+}
+
 // equals: same String(value) (query:200-203).  range (query:238-252): v = Number(key), or the key
 // itself when that is NaN; v >= min && v <= max with JS relational semantics.
+template <int MODE>
 __device__ __forceinline__ bool pred_match(const Pred& p, uint64_t k) {
+  if (MODE == 0) return k == p.eq;                             // never BB_KEY_NONE
+  if (MODE == 1) return ordered_image(k) - p.eq <= p.width;    // one subtract, one compare
   if (k == BB_KEY_NONE) return false;
-  if (p.mode == 0) return k == p.eq;
   const uint32_t top = (uint32_t)(k >> 48);
   if (top == (uint32_t)(BB_KEY_STR >> 48)) {
     const uint64_t id = k & 0xFFFFFFFFFFFFull;
@@ -215,7 +224,7 @@ struct ScanArgs {
 // ORDERED (BB_CFG_ORDERED_CHANGES): tiles are chained with a decoupled look-back, so the hits of
 // the whole column come out in ascending entry order; otherwise a tile claims its run with one
 // atomicAdd when it is done (ascending inside the run, runs in completion order) and never waits.
-template <bool ORDERED>
+template <bool ORDERED, int MODE>
 __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
   __shared__ uint32_t s_cnt[SC_ROUNDS * SC_WARPS];
   __shared__ uint32_t s_tile;
@@ -239,8 +248,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
   const uint32_t lt = lanemask_lt();
 #pragma unroll
   for (int j = 0; j < SC_ROUNDS; ++j) {
-    const bool h0 = pred_match(a.p, (uint64_t)v[j].x | ((uint64_t)v[j].y << 32));
-    const bool h1 = pred_match(a.p, (uint64_t)v[j].z | ((uint64_t)v[j].w << 32));
+    const bool h0 = pred_match<MODE>(a.p, (uint64_t)v[j].x | ((uint64_t)v[j].y << 32));
+    const bool h1 = pred_match<MODE>(a.p, (uint64_t)v[j].z | ((uint64_t)v[j].w << 32));
     const uint32_t b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
     flags |= ((uint32_t)h0 | ((uint32_t)h1 << 1)) << (2 * j);
     const uint32_t below = __popc(b0 & lt) + __popc(b1 & lt);

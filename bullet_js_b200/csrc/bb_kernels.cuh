@@ -250,74 +250,99 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const uint64_t* _
 
 // ---------------------------------------------------------------- K1': counting sort on dense path ids
 // The table is direct-indexed, so when the batch is not tiny next to it the sort is a counting sort
-// keyed by the row index itself: count (one RED per update) -> exclusive scan over the rows ->
-// place (cnt counts back down to zero, so the array is clean for the next batch).  Placement order
-// inside a path is whatever the atomics gave; k_cs_fix restores arrival order: segments of up to
+// keyed by the row index itself: count (one atomic per update, its return value is the update's
+// rank inside its path) -> exclusive scan over the rows -> place.  The rank order inside a path
+// is whatever the atomics gave; k_cs_fix restores arrival order: segments of up to
 // 8 updates in registers, longer ones (hot keys) by a CTA-wide LSD radix sort on the arrival index.
 constexpr int CS_THREADS = 256;
-constexpr int CS_SCAN_CTAS = 296;      // all co-resident: the scan's look-back never waits on an unscheduled CTA
 constexpr int CS_SHORT = 8;            // longest segment fixed in registers
 constexpr int CS_LONG_CTAS = 592;
 
+constexpr int CS_ILP = 4;  // independent atomics / gathers in flight per thread
+
 __global__ void __launch_bounds__(CS_THREADS) k_cs_count(const uint64_t* __restrict__ path_id, uint64_t n,
                                                          uint64_t capacity, uint32_t* __restrict__ cnt,
-                                                         uint32_t* __restrict__ err) {
-  const uint64_t i = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t pid = path_id[i];
-  if (pid >= capacity) atomicOr(err, 1u);  // batch rejected: k_cs_place only undoes the counts
-  else atomicAdd(&cnt[pid], 1u);
+                                                         uint32_t* __restrict__ rank, uint32_t* __restrict__ err) {
+  const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + threadIdx.x;
+  uint64_t pid[CS_ILP];
+  uint32_t r[CS_ILP];
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) pid[k] = i0 + k * CS_THREADS < n ? path_id[i0 + k * CS_THREADS] : 0;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) {
+    const bool in = i0 + k * CS_THREADS < n;
+    bad |= in && pid[k] >= capacity;
+    r[k] = (in && pid[k] < capacity) ? atomicAdd(&cnt[pid[k]], 1u) : 0u;  // some order inside the path
+  }
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k)
+    if (i0 + k * CS_THREADS < n) rank[i0 + k * CS_THREADS] = r[k];
+  if (bad) atomicOr(err, 1u);  // batch rejected; the scan still runs and clears the counts
 }
 
-// off[r] = number of updates whose row index is < r, off[capacity] = all of them.  Each CTA owns a
-// contiguous chunk: sum it, publish, look back over the CTAs before it, then scan it.
-__global__ void __launch_bounds__(CS_THREADS) k_cs_offsets(const uint32_t* __restrict__ cnt, uint64_t capacity,
-                                                           uint64_t chunk, uint32_t* __restrict__ off,
-                                                           uint32_t* __restrict__ state) {
-  __shared__ uint32_t s_red[CS_THREADS / 32];
-  __shared__ uint32_t s_base;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint64_t lo = (uint64_t)blockIdx.x * chunk, hi = min(capacity, lo + chunk);
+// Exclusive scan of the counts over the rows, in two launches without any waiting between CTAs:
+// per-tile sums, then every tile sums the tiles before it (they are few) and scans its own 4096
+// rows.  The second pass also clears the counts, so the array is clean for the next batch.
+constexpr int CS_TILE = CS_THREADS * 16;
+
+__device__ __forceinline__ uint32_t cs_load16(const uint32_t* __restrict__ cnt, uint64_t i, uint4 (&v)[4]) {
   uint32_t sum = 0;
-  for (uint64_t i = lo + 4 * tid; i < hi; i += 4 * CS_THREADS) {  // chunk and capacity padding keep this in bounds
-    const uint4 v = *reinterpret_cast<const uint4*>(cnt + i);
-    sum += v.x + v.y + v.z + v.w;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = *reinterpret_cast<const uint4*>(cnt + i + 4 * k);  // arrays are padded to whole tiles
+    sum += v[k].x + v[k].y + v[k].z + v[k].w;
   }
-  sum = warp_sum(sum);
-  if (lane == 0) s_red[w] = sum;
-  __syncthreads();
-  if (w == 0) {
-    uint32_t t = lane < CS_THREADS / 32 ? s_red[lane] : 0u;
-    t = warp_sum(t);
-    const uint32_t ex = tile_prefix(state, blockIdx.x, t);
-    if (lane == 0) {
-      s_base = ex;
-      if (blockIdx.x == gridDim.x - 1) off[capacity] = ex + t;
-    }
-  }
-  __syncthreads();
-  uint32_t run = s_base;
-  for (uint64_t i0 = lo; i0 < hi; i0 += 4 * CS_THREADS) {
-    const uint64_t i = i0 + 4 * tid;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (i < hi) v = *reinterpret_cast<const uint4*>(cnt + i);
-    uint32_t total;
-    const uint32_t ex = run + block_exclusive_scan<CS_THREADS>(v.x + v.y + v.z + v.w, &total);
-    if (i < hi) *reinterpret_cast<uint4*>(off + i) = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
-    run += total;
+  return sum;
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_cs_tile_sums(const uint32_t* __restrict__ cnt,
+                                                             uint32_t* __restrict__ tile_sum) {
+  uint4 v[4];
+  uint32_t total;
+  const uint32_t sum = cs_load16(cnt, (uint64_t)blockIdx.x * CS_TILE + 16 * threadIdx.x, v);
+  block_exclusive_scan<CS_THREADS>(sum, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_cs_offsets(uint32_t* __restrict__ cnt, const uint32_t* __restrict__ tile_sum,
+                                                           uint32_t* __restrict__ off) {
+  uint32_t before = 0;
+  for (uint32_t t = threadIdx.x; t < blockIdx.x; t += CS_THREADS) before += tile_sum[t];
+  uint32_t base;
+  block_exclusive_scan<CS_THREADS>(before, &base);
+  const uint64_t i = (uint64_t)blockIdx.x * CS_TILE + 16 * threadIdx.x;
+  uint4 v[4];
+  uint32_t total;
+  uint32_t run = base + block_exclusive_scan<CS_THREADS>(cs_load16(cnt, i, v), &total);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 o;
+    o.x = run; run += v[k].x;
+    o.y = run; run += v[k].y;
+    o.z = run; run += v[k].z;
+    o.w = run; run += v[k].w;
+    *reinterpret_cast<uint4*>(off + i + 4 * k) = o;
+    *reinterpret_cast<uint4*>(cnt + i + 4 * k) = make_uint4(0, 0, 0, 0);
   }
 }
 
 __global__ void __launch_bounds__(CS_THREADS) k_cs_place(const uint64_t* __restrict__ path_id, uint64_t n,
-                                                         uint64_t capacity, uint32_t* __restrict__ cnt,
+                                                         uint64_t capacity, const uint32_t* __restrict__ rank,
                                                          const uint32_t* __restrict__ off, uint64_t* __restrict__ items,
                                                          const uint32_t* __restrict__ err) {
-  const uint64_t i = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t pid = path_id[i];
-  if (pid >= capacity) return;
-  const uint32_t r = atomicSub(&cnt[pid], 1u) - 1u;
-  if (!(*err & 1u)) items[off[pid] + r] = (pid << 32) | i;
+  if (*err & 1u) return;
+  const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + threadIdx.x;
+  uint64_t pid[CS_ILP];
+  uint32_t dst[CS_ILP];
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) pid[k] = i0 + k * CS_THREADS < n ? path_id[i0 + k * CS_THREADS] : 0;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k)
+    dst[k] = i0 + k * CS_THREADS < n ? off[pid[k]] + rank[i0 + k * CS_THREADS] : 0u;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k)
+    if (i0 + k * CS_THREADS < n) items[dst[k]] = (pid[k] << 32) | (i0 + k * CS_THREADS);
 }
 
 // one thread per sorted position; the thread on a segment's first position puts the segment in

@@ -70,6 +70,7 @@ struct bb_ctx {
   uint32_t* cs_cnt = nullptr;  // counting sort: per-row update counts (all zero between calls)
   uint32_t* cs_off = nullptr;  // and their exclusive scan, [capacity + 1] (both padded to 1024)
   DevBuf<uint2> cs_long;       // segments longer than CS_SHORT, queued for k_cs_fix_long
+  DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
   uint64_t* d_nchanges = nullptr;
   uint64_t* d_chg_base = nullptr;
   uint64_t* h_nchanges = nullptr;  // pinned [MAX_CHUNKS]: running total after each chunk of a host call
@@ -156,7 +157,7 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   if (use_counting_sort(c, n)) z.passes = 0;
   z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
   z.cs_state = z.merge_state + z.merge_tiles;
-  z.cs_ctr = z.cs_state + CS_SCAN_CTAS;
+  z.cs_ctr = z.cs_state;
   z.total = z.cs_ctr + 2;
   return z;
 }
@@ -217,12 +218,11 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
     const uint32_t g = div_up(n, CS_THREADS);
     const uint64_t cap = c->cfg.capacity;
-    uint32_t scan_ctas = div_up(cap, 4 * CS_THREADS);
-    if (scan_ctas > CS_SCAN_CTAS) scan_ctas = CS_SCAN_CTAS;
-    const uint64_t chunk = ((cap + scan_ctas - 1) / scan_ctas + 4 * CS_THREADS - 1) / (4 * CS_THREADS) * (4 * CS_THREADS);
-    BB_LAUNCH(c, k_cs_count, g, CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->d_err);
-    BB_LAUNCH(c, k_cs_offsets, scan_ctas, CS_THREADS, s, c->cs_cnt, cap, chunk, c->cs_off, zp + z.cs_state);
-    BB_LAUNCH(c, k_cs_place, g, CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->cs_off, src, c->d_err);
+    const uint32_t tiles = div_up(cap + 1, CS_TILE);  // + 1: off[capacity] = the batch size
+    BB_LAUNCH(c, k_cs_count, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->st_idx.p, c->d_err);
+    BB_LAUNCH(c, k_cs_tile_sums, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p);
+    BB_LAUNCH(c, k_cs_offsets, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p, c->cs_off);
+    BB_LAUNCH(c, k_cs_place, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->st_idx.p, c->cs_off, src, c->d_err);
     BB_LAUNCH(c, k_cs_fix, g, CS_THREADS, s, src, n, c->cs_off, c->cs_long.p, zp + z.cs_ctr, c->d_err);
     BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, zp + z.cs_ctr,
               zp + z.cs_ctr + 1);
@@ -318,6 +318,19 @@ int index_fill(bb_ctx* c, int f, cudaStream_t s) {
   return BB_OK;
 }
 
+int launch_scan(bb_ctx* c, const bb::ScanArgs& a, uint32_t tiles, bool ordered, cudaStream_t s) {
+  using namespace bb;
+  switch (a.p.mode * 2 + (ordered ? 1 : 0)) {
+    case 0: BB_LAUNCH(c, (k_index_scan<false, 0>), tiles, SC_THREADS, s, a); break;
+    case 1: BB_LAUNCH(c, (k_index_scan<true, 0>), tiles, SC_THREADS, s, a); break;
+    case 2: BB_LAUNCH(c, (k_index_scan<false, 1>), tiles, SC_THREADS, s, a); break;
+    case 3: BB_LAUNCH(c, (k_index_scan<true, 1>), tiles, SC_THREADS, s, a); break;
+    case 4: BB_LAUNCH(c, (k_index_scan<false, 2>), tiles, SC_THREADS, s, a); break;
+    default: BB_LAUNCH(c, (k_index_scan<true, 2>), tiles, SC_THREADS, s, a); break;
+  }
+  return BB_OK;
+}
+
 // both scans of one query; `hits` (device or null), counters land in c->d_counters
 int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, uint64_t cap, cudaStream_t s) {
   using namespace bb;
@@ -340,22 +353,41 @@ int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, ui
   a.keys = ix.pcol; a.nodes = nullptr; a.n = n0; a.which = 0;
   a.ticket = c->scan_zero.p; a.tile_state = c->scan_zero.p + 2; a.num_tiles = t0;
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
-  if (ordered) BB_LAUNCH(c, k_index_scan<true>, t0, SC_THREADS, s, a);
-  else BB_LAUNCH(c, k_index_scan<false>, t0, SC_THREADS, s, a);
+  {
+    int rc = launch_scan(c, a, t0, ordered, s);
+    if (rc) return rc;
+  }
   a.keys = ix.xkey; a.nodes = ix.xnode; a.n = n1; a.which = 1;
   a.ticket = c->scan_zero.p + 1; a.tile_state = c->scan_zero.p + 2 + t0; a.num_tiles = t1;
-  if (ordered) BB_LAUNCH(c, k_index_scan<true>, t1, SC_THREADS, s, a);
-  else BB_LAUNCH(c, k_index_scan<false>, t1, SC_THREADS, s, a);
+  {
+    int rc = launch_scan(c, a, t1, ordered, s);
+    if (rc) return rc;
+  }
   mark(c, EV_Q1, s);
   return BB_OK;
 }
 
 bb::Pred range_pred(const bb_bound* lo, const bb_bound* hi) {
   bb::Pred p{};
-  p.mode = 1;
   p.lo = lo->num; p.hi = hi->num;
   p.lo_rank = lo->rank; p.hi_rank = hi->rank;
   p.lo_flags = lo->flags; p.hi_flags = hi->flags;
+  if ((lo->flags | hi->flags) & BB_BOUND_IS_STRING) {
+    p.mode = 2;  // string keys can match: the general predicate
+    return p;
+  }
+  // numeric bounds only: x >= lo && x <= hi on the ordered images of the bits (keys hold no -0)
+  p.mode = 1;
+  p.eq = 1;     // an empty range: image 1 belongs to an unused NaN pattern
+  p.width = 0;
+  if (lo->num == lo->num && hi->num == hi->num && lo->num <= hi->num) {
+    double l = lo->num == 0.0 ? 0.0 : lo->num, h = hi->num == 0.0 ? 0.0 : hi->num;  // -0 -> +0
+    uint64_t lb, hb;
+    memcpy(&lb, &l, 8);
+    memcpy(&hb, &h, 8);
+    p.eq = bb::ordered_image(lb);
+    p.width = bb::ordered_image(hb) - p.eq;
+  }
   return p;
 }
 
@@ -430,7 +462,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
   c->key_bits = bits;
-  const size_t cs_words = ((size_t)cfg->capacity + 1 + 1023) / 1024 * 1024 + 1024;
+  const size_t cs_words = ((size_t)cfg->capacity + 1 + bb::CS_TILE - 1) / bb::CS_TILE * bb::CS_TILE;
   bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->table, cfg->capacity * sizeof(bb_row)) == cudaSuccess &&
@@ -441,6 +473,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->cs_cnt, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            c->cs_tile.ensure(cs_words / bb::CS_TILE) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
@@ -489,7 +522,7 @@ int bb_destroy(bb_ctx* c) {
   if (c->d_err) cudaFree(c->d_err);
   if (c->cs_cnt) cudaFree(c->cs_cnt);
   if (c->cs_off) cudaFree(c->cs_off);
-  c->cs_long.release();
+  c->cs_long.release(); c->cs_tile.release();
   if (c->d_nchanges) cudaFree(c->d_nchanges);
   if (c->d_chg_base) cudaFree(c->d_chg_base);
   for (int i = 0; i < MAX_CHUNKS; ++i) {
