@@ -35,6 +35,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE line
 
 N_RECORDS = 2_500_000   # per GPU: 10 M fields
 BATCH = 1_000_000       # updates per step per GPU
@@ -359,34 +360,45 @@ def main():
     if world > 1:
         from bullet_js_b200.shard import Router
 
-        router = Router(eng, world, rank, n, dev)
+        router = Router(world, rank, n, local_rank)
+        r_in = [capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
+                for p, h, c, v in d_in]
 
-    def step_dev(i):
+    def step_dev(i, last):
+        """One step.  Sharded: merge batch i (already routed into slot i % 2), then route batch
+        i + 1 while that merge runs - the routing never depends on the table."""
         p, h, c, v = d_in[i % N_BATCHES]
         if router is None:
             bs = capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
             engines[i].merge_dev(bs, cs, stream)
             return n
-        return router.route_and_merge(engines[i], p, h, c, v, cs, stream)
+        m = router.merge(engines[i], i % 2, cs, stream)
+        if not last:
+            router.route(r_in[(i + 1) % N_BATCHES], (i + 1) % 2)
+        return m
 
     sampler = ClockSampler(local_rank)
+    if router is not None:
+        router.route(r_in[0], 0)
     for i in range(W):
-        step_dev(i)
+        step_dev(i, False)
     eng.sync(stream)
     barrier()
     sampler.start()
-    launches0 = sum(e.launch_count() for e in engines)
+    launches0 = sum(e.launch_count() for e in engines) + (router.launches if router else 0)
+    sent0 = router.sent_bytes if router else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     merged = 0
     for i in range(K):
-        merged += step_dev(W + i)
+        merged += step_dev(W + i, i == K - 1)
     e1.record()
     barrier()
-    launches = sum(e.launch_count() for e in engines) - launches0
+    launches = sum(e.launch_count() for e in engines) - launches0 + (router.launches if router else 0)
     for e in engines:
         e.sync(stream)
     dev_ms = e0.elapsed_time(e1)
+    sent = (router.sent_bytes - sent0) if router else 0
     # phase timings of the timed steps (events recorded inside the library on the same stream)
     ph = {name: float(np.mean([engines[W + j].phase_ms(name) for j in range(K)]))
           for name in ("sort", "merge", "device")}
@@ -484,6 +496,11 @@ def main():
                          "phase_ms": ph},
             "cpu_baseline": cpu, "clocks": clocks, "query": query,
         }
+        if world > 1:  # the all-to-all of rank 0, against the measured NVLink peer-copy rate (B200_PROFILING.md)
+            gbs = sent / (dev_ms * 1e-3) / 1e9
+            line["alltoall"] = {"sent_bytes_per_step": sent // K, "gb_per_s_per_gpu": gbs, "nvlink_peak": 770.0,
+                                "frac": gbs / 770.0, "overlapped_with_merge": True, "last_route_ms": router.last_ms(),
+                                "api": "bb_router_route_dev (counts all-gather over NCCL, then one pack kernel storing rows straight into the owners' receive slots over NVLink)"}
         print(json.dumps(line))
     for e in engines:
         e.close()

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libbulletb200.so")
 
 ABI_VERSION = 1
 NO_SLOT = 0x1FFFFFFF
+NCCL_ID_BYTES = 128
 
 OK, ERR_ARG, ERR_CUDA, ERR_DOMAIN, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4, -5
 _ERR_NAMES = {
@@ -70,7 +71,9 @@ EXPORTS = [
     "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
     "bb_index_create", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
-    "bb_route_pack_dev",
+    "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
+    "bb_router_last_error", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
+    "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
 ]
 
@@ -127,6 +130,26 @@ def load():
     lib.bb_index_stats.restype = i32
     lib.bb_route_pack_dev.argtypes = [vp, u32, C.POINTER(BBBatch), C.POINTER(BBBatch), vp, vp]
     lib.bb_route_pack_dev.restype = i32
+    lib.bb_router_unique_id.argtypes = [C.c_char_p]
+    lib.bb_router_unique_id.restype = i32
+    lib.bb_router_create.argtypes = [C.c_int32, u32, u32, C.c_char_p, u64, u64, C.POINTER(vp)]
+    lib.bb_router_create.restype = i32
+    lib.bb_router_destroy.argtypes = [vp]
+    lib.bb_router_destroy.restype = i32
+    lib.bb_router_last_error.argtypes = [vp]
+    lib.bb_router_last_error.restype = C.c_char_p
+    lib.bb_router_route_dev.argtypes = [vp, C.POINTER(BBBatch), u32, C.POINTER(u64), vp]
+    lib.bb_router_route_dev.restype = i32
+    lib.bb_router_acquire.argtypes = [vp, u32, vp, C.POINTER(BBBatch)]
+    lib.bb_router_acquire.restype = i32
+    lib.bb_router_release.argtypes = [vp, u32, vp]
+    lib.bb_router_release.restype = i32
+    lib.bb_router_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.bb_router_last_ms.restype = i32
+    lib.bb_router_sent_bytes.argtypes = [vp]
+    lib.bb_router_sent_bytes.restype = u64
+    lib.bb_router_launch_count.argtypes = [vp]
+    lib.bb_router_launch_count.restype = u64
     lib.bb_launch_count.argtypes = [vp]
     lib.bb_launch_count.restype = u64
     lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]

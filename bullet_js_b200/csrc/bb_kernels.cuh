@@ -822,7 +822,8 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
 // inside every destination - so that the owner, which concatenates what it receives in source-rank
 // order, replays each path in (source rank, arrival index) order.  Three small launches: per-tile
 // destination counts, one CTA scanning them (tile-major inside destination-major), the scatter.
-constexpr int RT_THREADS = 256;
+constexpr int RT_THREADS = 1024;   // updates per tile of the count / scatter kernels
+constexpr int RS_THREADS = 256;    // threads of the single scan CTA
 constexpr int RT_MAX_WORLD = 16;
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_count(const uint64_t* __restrict__ path_id, uint64_t n,
@@ -841,18 +842,18 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_count(const uint64_t* __re
 }
 
 // one CTA: tile_cnt[tile][r] -> exclusive offsets in the packed order; counts[r] = updates for rank r
-__global__ void __launch_bounds__(RT_THREADS) k_route_scan(uint32_t* __restrict__ tile_cnt, uint32_t tiles,
+__global__ void __launch_bounds__(RS_THREADS) k_route_scan(uint32_t* __restrict__ tile_cnt, uint32_t tiles,
                                                            uint32_t world, uint64_t* __restrict__ counts) {
   __shared__ uint32_t s_run;
   if (threadIdx.x == 0) s_run = 0;
   __syncthreads();
   for (uint32_t r = 0; r < world; ++r) {
     const uint32_t start = s_run;
-    for (uint32_t t0 = 0; t0 < tiles; t0 += RT_THREADS) {
+    for (uint32_t t0 = 0; t0 < tiles; t0 += RS_THREADS) {
       const uint32_t t = t0 + threadIdx.x;
       const uint32_t v = t < tiles ? tile_cnt[(uint64_t)t * world + r] : 0;
       uint32_t total;
-      const uint32_t ex = block_exclusive_scan<RT_THREADS>(v, &total);
+      const uint32_t ex = block_exclusive_scan<RS_THREADS>(v, &total);
       if (t < tiles) tile_cnt[(uint64_t)t * world + r] = s_run + ex;
       __syncthreads();
       if (threadIdx.x == 0) s_run += total;
@@ -870,6 +871,95 @@ struct RouteArgs {
   uint32_t world;
   const uint32_t* tile_off;  // [tiles][world] from k_route_scan
 };
+
+// Fused pack + all-to-all: the same stable partition, but every row is stored straight into the
+// receive slot of its owner - peer memory mapped over NVLink (cudaIpc) - at the place the owner's
+// concatenation in source-rank order gives it.  No send buffer, no separate exchange launch.
+struct RouteP2PArgs {
+  const uint64_t* path_id; const uint4* head; const uint4* clk; const uint4* val;  // [n] in
+  uint64_t* d_path[RT_MAX_WORLD]; uint4* d_head[RT_MAX_WORLD]; uint4* d_clk[RT_MAX_WORLD]; uint4* d_val[RT_MAX_WORLD];
+  int64_t adj[RT_MAX_WORLD];  // row in the owner's slot = packed position + adj[owner]
+  uint64_t n;
+  uint32_t world;
+  const uint32_t* tile_off;
+};
+
+// Each CTA partitions its 1024 rows by owner in shared memory (88 KB), then streams every owner's
+// run out with fully coalesced 16-byte stores: one contiguous run per (tile, owner, array).
+constexpr int RT_SMEM = RT_THREADS * 88;
+
+__global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2PArgs a) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint4* s_head = reinterpret_cast<uint4*>(s_raw);                   // [1024]
+  uint4* s_clk = s_head + RT_THREADS;                                 // [2048]
+  uint4* s_val = s_clk + 2 * RT_THREADS;                              // [2048]
+  uint64_t* s_path = reinterpret_cast<uint64_t*>(s_val + 2 * RT_THREADS);  // [1024]
+  __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];
+  __shared__ uint32_t s_start[RT_MAX_WORLD + 1];
+  __shared__ int64_t s_dst[RT_MAX_WORLD];  // destination row of the owner's run minus its start in the tile
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + tid;
+  const uint64_t p = i < a.n ? a.path_id[i] : 0;
+  const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
+  uint4 h, c0, c1, v0, v1;
+  if (i < a.n) {
+    h = a.head[i];
+    c0 = a.clk[2 * i];
+    c1 = a.clk[2 * i + 1];
+    v0 = a.val[2 * i];
+    v1 = a.val[2 * i + 1];
+  }
+  uint32_t below = 0;
+  for (uint32_t r = 0; r < a.world; ++r) {
+    const uint32_t m = __ballot_sync(0xffffffffu, d == r);
+    if (d == r) below = __popc(m & lanemask_lt());
+    if (lane == 0) s_w[w][r] = __popc(m);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (uint32_t r = 0; r < a.world; ++r) {
+      s_start[r] = run;
+      s_dst[r] = (int64_t)a.tile_off[(uint64_t)blockIdx.x * a.world + r] + a.adj[r] - (int64_t)run;
+      for (int ww = 0; ww < RT_THREADS / 32; ++ww) run += s_w[ww][r];
+    }
+    s_start[a.world] = run;
+  }
+  __syncthreads();
+  if (i < a.n) {
+    uint32_t lp = s_start[d] + below;
+    for (int ww = 0; ww < w; ++ww) lp += s_w[ww][d];
+    s_path[lp] = p / a.world;
+    s_head[lp] = h;
+    s_clk[2 * lp] = c0;
+    s_clk[2 * lp + 1] = c1;
+    s_val[2 * lp] = v0;
+    s_val[2 * lp + 1] = v1;
+  }
+  __syncthreads();
+  const uint32_t rows = s_start[a.world];
+  {  // rows of the tile in partitioned order: thread j moves row j
+    const uint32_t j = tid;
+    if (j < rows) {
+      uint32_t r = 0;
+      while (j >= s_start[r + 1]) ++r;
+      const uint64_t dst = (uint64_t)(s_dst[r] + (int64_t)j);
+      a.d_path[r][dst] = s_path[j];
+      a.d_head[r][dst] = s_head[j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // the 32-byte columns as 2048 16-byte pieces
+    const uint32_t e = tid + k * RT_THREADS, j = e >> 1;
+    if (j < rows) {
+      uint32_t r = 0;
+      while (j >= s_start[r + 1]) ++r;
+      const uint64_t dst = 2 * (uint64_t)(s_dst[r] + (int64_t)j) + (e & 1u);
+      a.d_clk[r][dst] = s_clk[e];
+      a.d_val[r][dst] = s_val[e];
+    }
+  }
+}
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_scatter(const RouteArgs a) {
   __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];

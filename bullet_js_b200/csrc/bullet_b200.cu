@@ -2,7 +2,10 @@
 // One bb_ctx == one GPU-resident shard of the graph table (rows of 128 bytes,
 // row index == interned path id) plus the scratch the pipeline needs.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: libnccl.so.2 is opened at run time
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -711,6 +714,30 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   return BB_OK;
 }
 
+// the three pack launches; `tiles_buf` holds [tiles][world] words
+static cudaError_t launch_pack(uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts, uint32_t* tiles_buf,
+                        cudaStream_t s) {
+  using namespace bb;
+  const uint64_t n = in->n;
+  const uint32_t tiles = div_up(n, RT_THREADS);
+  k_route_count<<<tiles, RT_THREADS, 0, s>>>(in->path_id, n, world, tiles_buf);
+  k_route_scan<<<1, RS_THREADS, 0, s>>>(tiles_buf, tiles, world, counts);
+  RouteArgs a;
+  a.path_id = in->path_id;
+  a.head = reinterpret_cast<const uint4*>(in->head);
+  a.clk = reinterpret_cast<const uint4*>(in->clk);
+  a.val = reinterpret_cast<const uint4*>(in->val);
+  a.o_path = const_cast<uint64_t*>(out->path_id);
+  a.o_head = reinterpret_cast<uint4*>(const_cast<bb_head*>(out->head));
+  a.o_clk = reinterpret_cast<uint4*>(const_cast<uint32_t*>(out->clk));
+  a.o_val = reinterpret_cast<uint4*>(const_cast<uint64_t*>(out->val));
+  a.n = n;
+  a.world = world;
+  a.tile_off = tiles_buf;
+  k_route_scatter<<<tiles, RT_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 int bb_route_pack_dev(bb_ctx* c, uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts, void* stream) {
   using namespace bb;
   if (!c || !in || !out || !counts) return fail(c, BB_ERR_ARG, "null argument");
@@ -725,23 +752,9 @@ int bb_route_pack_dev(bb_ctx* c, uint32_t world, const bb_batch* in, bb_batch* o
   }
   if (!in->path_id || !in->head || !in->clk || !in->val || !out->path_id || !out->head || !out->clk || !out->val)
     return fail(c, BB_ERR_ARG, "null buffer");
-  const uint32_t tiles = div_up(n, RT_THREADS);
-  BB_CUDA(c, c->route_tiles.ensure((size_t)tiles * world));
-  BB_LAUNCH(c, k_route_count, tiles, RT_THREADS, s, in->path_id, n, world, c->route_tiles.p);
-  BB_LAUNCH(c, k_route_scan, 1, RT_THREADS, s, c->route_tiles.p, tiles, world, counts);
-  RouteArgs a;
-  a.path_id = in->path_id;
-  a.head = reinterpret_cast<const uint4*>(in->head);
-  a.clk = reinterpret_cast<const uint4*>(in->clk);
-  a.val = reinterpret_cast<const uint4*>(in->val);
-  a.o_path = const_cast<uint64_t*>(out->path_id);
-  a.o_head = reinterpret_cast<uint4*>(const_cast<bb_head*>(out->head));
-  a.o_clk = reinterpret_cast<uint4*>(const_cast<uint32_t*>(out->clk));
-  a.o_val = reinterpret_cast<uint4*>(const_cast<uint64_t*>(out->val));
-  a.n = n;
-  a.world = world;
-  a.tile_off = c->route_tiles.p;
-  BB_LAUNCH(c, k_route_scatter, tiles, RT_THREADS, s, a);
+  BB_CUDA(c, c->route_tiles.ensure((size_t)div_up(n, RT_THREADS) * world));
+  c->launches += 3;
+  BB_CUDA(c, launch_pack(world, in, out, counts, c->route_tiles.p, s));
   return BB_OK;
 }
 
@@ -862,5 +875,398 @@ double bb_phase_ms(bb_ctx* c, const char* phase, uint32_t calls_ago) {
   if (cudaEventElapsedTime(&ms, c->ev[slot][a], c->ev[slot][b]) != cudaSuccess) return -1.0;
   return (double)ms;
 }
+
+}  // extern "C"
+
+/* ======================================================================== *
+ * bb_router: update routing between the shards of one box.
+ * NCCL is reached through dlopen so that single-GPU users carry no dependency.
+ * ======================================================================== */
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+thread_local std::string g_router_error;
+
+bool nccl_load() {
+  if (g_nccl.lib) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the host process already uses, if any
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+  if (!h) return false;
+  NcclApi a;
+  a.lib = h;
+#define BB_SYM(field, name) *(void**)(&a.field) = dlsym(h, name)
+  BB_SYM(GetUniqueId, "ncclGetUniqueId");
+  BB_SYM(CommInitRank, "ncclCommInitRank");
+  BB_SYM(CommDestroy, "ncclCommDestroy");
+  BB_SYM(AllGather, "ncclAllGather");
+  BB_SYM(Send, "ncclSend");
+  BB_SYM(Recv, "ncclRecv");
+  BB_SYM(GroupStart, "ncclGroupStart");
+  BB_SYM(GroupEnd, "ncclGroupEnd");
+  BB_SYM(GetErrorString, "ncclGetErrorString");
+#undef BB_SYM
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.Send || !a.Recv || !a.GroupStart ||
+      !a.GroupEnd || !a.GetErrorString)
+    return false;
+  g_nccl = a;
+  return true;
+}
+
+constexpr size_t ROUTE_W[4] = {8, 16, 32, 32};  // bytes per update of path / head / clk / val
+
+}  // namespace
+
+struct bb_router {
+  int device = 0;
+  uint32_t world = 0, rank = 0;
+  uint64_t max_batch = 0, cap = 0;
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  char* send[4]{};
+  char* recv[2][4]{};
+  uint64_t n_recv[2]{};
+  cudaEvent_t ready[2]{}, merged[2]{}, ev_in = nullptr;
+  bool p2p = false;               // peers' receive slots are mapped here: rows are stored directly
+  char* peer[bb::RT_MAX_WORLD][2][4]{};  // [rank][slot][array]; our own entry = recv
+  uint64_t* d_bar = nullptr;      // [1 + world] barrier token + gather target
+  uint64_t* d_counts = nullptr;   // [world] this rank's send counts
+  uint64_t* d_matrix = nullptr;   // [world][world] everybody's
+  uint64_t* h_matrix = nullptr;   // pinned
+  uint32_t* tiles = nullptr;
+  uint64_t sent_bytes = 0, launches = 0;
+  cudaEvent_t tev[5]{};   // telemetry of the last route: start, packed, counts known, exchanged, own rows copied
+  double host_ms[2]{};    // host time of the last route: until the counts are known, whole call
+  std::string err;
+};
+
+namespace {
+
+int rfail(bb_router* r, int code, const std::string& what) {
+  if (r) r->err = what;
+  else g_router_error = what;
+  return code;
+}
+
+#define BB_RCUDA(r, call)                                                                           \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return rfail((r), BB_ERR_CUDA, std::string(#call ": ") + cudaGetErrorString(e_)); \
+  } while (0)
+#define BB_RNCCL(r, call)                                                                            \
+  do {                                                                                              \
+    ncclResult_t e_ = (call);                                                                       \
+    if (e_ != ncclSuccess) return rfail((r), BB_ERR_CUDA, std::string(#call ": ") + g_nccl.GetErrorString(e_)); \
+  } while (0)
+
+}  // namespace
+
+namespace {
+
+// Exchange cudaIpc handles of the receive slots over the communicator and map every peer's slots.
+void router_map_peers(bb_router* r) {
+  const uint32_t W = r->world, me = r->rank;
+  for (int sl = 0; sl < 2; ++sl)
+    for (int k = 0; k < 4; ++k) r->peer[me][sl][k] = r->recv[sl][k];
+  r->p2p = false;
+  if (getenv("BB_ROUTER_NO_P2P")) return;
+  if (W == 1) {
+    r->p2p = true;
+    return;
+  }
+  constexpr size_t HB = sizeof(cudaIpcMemHandle_t);
+  const size_t mine = 8 * HB;
+  std::string host(mine * W, '\0');
+  char* d_all = nullptr;
+  bool ok = cudaMalloc((void**)&d_all, mine * W) == cudaSuccess;
+  for (int sl = 0; ok && sl < 2; ++sl)
+    for (int k = 0; ok && k < 4; ++k) {
+      cudaIpcMemHandle_t h;
+      ok = cudaIpcGetMemHandle(&h, r->recv[sl][k]) == cudaSuccess;
+      memcpy(&host[mine * me + (sl * 4 + k) * HB], &h, HB);
+    }
+  ok = ok && cudaMemcpyAsync(d_all + mine * me, &host[mine * me], mine, cudaMemcpyHostToDevice, r->stream) == cudaSuccess;
+  // every rank must take part in the collective even if its own handles failed
+  const bool sent = g_nccl.AllGather(d_all ? d_all + mine * me : nullptr, d_all, mine, ncclUint8, r->comm, r->stream) == ncclSuccess;
+  ok = ok && sent && cudaMemcpyAsync(&host[0], d_all, mine * W, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+       cudaStreamSynchronize(r->stream) == cudaSuccess;
+  for (uint32_t q = 0; ok && q < W; ++q) {
+    if (q == me) continue;
+    for (int j = 0; ok && j < 8; ++j) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &host[mine * q + j * HB], HB);
+      void* p = nullptr;
+      ok = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      r->peer[q][j / 4][j % 4] = (char*)p;
+    }
+  }
+  if (d_all) cudaFree(d_all);
+  cudaGetLastError();
+  // all ranks must agree, or one would wait for rows that are sent the other way
+  uint64_t flag = ok ? 1 : 0;
+  if (cudaMemcpyAsync(r->d_bar, &flag, 8, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
+      g_nccl.AllGather(r->d_bar, r->d_bar + 1, 1, ncclUint64, r->comm, r->stream) == ncclSuccess) {
+    uint64_t flags[bb::RT_MAX_WORLD] = {0};
+    if (cudaMemcpyAsync(flags, r->d_bar + 1, W * 8, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+        cudaStreamSynchronize(r->stream) == cudaSuccess) {
+      bool all = true;
+      for (uint32_t q = 0; q < W; ++q) all = all && flags[q] == 1;
+      r->p2p = all;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int bb_router_unique_id(char id[BB_NCCL_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) <= BB_NCCL_ID_BYTES, "ncclUniqueId fits the id buffer");
+  if (!id) return rfail(nullptr, BB_ERR_ARG, "null argument");
+  if (!nccl_load()) return rfail(nullptr, BB_ERR_CUDA, "libnccl.so.2 not found");
+  ncclUniqueId u;
+  BB_RNCCL(nullptr, g_nccl.GetUniqueId(&u));
+  memset(id, 0, BB_NCCL_ID_BYTES);
+  memcpy(id, &u, sizeof(u));
+  return BB_OK;
+}
+
+const char* bb_router_last_error(const bb_router* r) { return r ? r->err.c_str() : g_router_error.c_str(); }
+
+int bb_router_destroy(bb_router* r) {
+  if (!r) return BB_ERR_ARG;
+  cudaSetDevice(r->device);
+  if (r->stream) cudaStreamSynchronize(r->stream);
+  if (r->comm) g_nccl.CommDestroy(r->comm);
+  for (int k = 0; k < 4; ++k) {
+    if (r->send[k]) cudaFree(r->send[k]);
+    for (int sl = 0; sl < 2; ++sl)
+      if (r->recv[sl][k]) cudaFree(r->recv[sl][k]);
+  }
+  for (int sl = 0; sl < 2; ++sl) {
+    if (r->ready[sl]) cudaEventDestroy(r->ready[sl]);
+    if (r->merged[sl]) cudaEventDestroy(r->merged[sl]);
+  }
+  if (r->ev_in) cudaEventDestroy(r->ev_in);
+  for (int i = 0; i < 5; ++i)
+    if (r->tev[i]) cudaEventDestroy(r->tev[i]);
+  for (uint32_t q = 0; q < r->world; ++q)
+    for (int j = 0; j < 8; ++j)
+      if (q != r->rank && r->peer[q][j / 4][j % 4]) cudaIpcCloseMemHandle(r->peer[q][j / 4][j % 4]);
+  if (r->d_bar) cudaFree(r->d_bar);
+  if (r->d_counts) cudaFree(r->d_counts);
+  if (r->d_matrix) cudaFree(r->d_matrix);
+  if (r->h_matrix) cudaFreeHost(r->h_matrix);
+  if (r->tiles) cudaFree(r->tiles);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  delete r;
+  return BB_OK;
+}
+
+int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char id[BB_NCCL_ID_BYTES],
+                     uint64_t max_batch, uint64_t recv_capacity, bb_router** out) {
+  if (!out || !id) return rfail(nullptr, BB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (world < 1 || world > bb::RT_MAX_WORLD || rank >= world || max_batch == 0 || max_batch >= 0xFFFFFFFFull)
+    return rfail(nullptr, BB_ERR_ARG, "bad world / rank / max_batch");
+  if (!nccl_load()) return rfail(nullptr, BB_ERR_CUDA, "libnccl.so.2 not found");
+  if (cudaSetDevice(device) != cudaSuccess) return rfail(nullptr, BB_ERR_CUDA, "cudaSetDevice failed");
+  bb_router* r = new (std::nothrow) bb_router();
+  if (!r) return rfail(nullptr, BB_ERR_ARG, "out of host memory");
+  r->device = device;
+  r->world = world;
+  r->rank = rank;
+  r->max_batch = max_batch;
+  r->cap = recv_capacity ? recv_capacity : max_batch * world;  // a rank may own every update of every batch
+  int prio_lo = 0, prio_hi = 0;  // routing runs beside a merge that fills the GPU: let its small kernels in first
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  bool ok = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+            cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+            cudaMalloc((void**)&r->d_counts, world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&r->d_bar, (1 + world) * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&r->d_matrix, (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&r->h_matrix, (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&r->tiles, (size_t)div_up(max_batch, bb::RT_THREADS) * world * sizeof(uint32_t)) == cudaSuccess;
+  for (int k = 0; ok && k < 4; ++k) {
+    ok = cudaMalloc((void**)&r->send[k], max_batch * ROUTE_W[k]) == cudaSuccess;
+    for (int sl = 0; ok && sl < 2; ++sl) ok = cudaMalloc((void**)&r->recv[sl][k], r->cap * ROUTE_W[k]) == cudaSuccess;
+  }
+  for (int i = 0; ok && i < 5; ++i) ok = cudaEventCreate(&r->tev[i]) == cudaSuccess;
+  for (int sl = 0; ok && sl < 2; ++sl)
+    ok = cudaEventCreateWithFlags(&r->ready[sl], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&r->merged[sl], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    g_router_error = std::string("router allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    bb_router_destroy(r);
+    return BB_ERR_CUDA;
+  }
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  ncclResult_t e = g_nccl.CommInitRank(&r->comm, (int)world, u, (int)rank);
+  if (e != ncclSuccess) {
+    g_router_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e);
+    r->comm = nullptr;
+    bb_router_destroy(r);
+    return BB_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(bb::k_route_scatter_p2p, cudaFuncAttributeMaxDynamicSharedMemorySize, bb::RT_SMEM);
+  router_map_peers(r);  // falls back to ncclSend/ncclRecv when the slots cannot be mapped
+  *out = r;
+  return BB_OK;
+}
+
+int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream) {
+  if (!r || !in || !n_recv || slot > 1) return rfail(r, BB_ERR_ARG, "bad argument");
+  const uint64_t n = in->n;
+  if (n > r->max_batch) return rfail(r, BB_ERR_CAPACITY, "batch larger than the router's max_batch");
+  if (n && (!in->path_id || !in->head || !in->clk || !in->val)) return rfail(r, BB_ERR_ARG, "null buffer");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  cudaStream_t s = r->stream;
+  const uint32_t W = r->world, me = r->rank;
+  if (in_stream) {
+    BB_RCUDA(r, cudaEventRecord(r->ev_in, (cudaStream_t)in_stream));
+    BB_RCUDA(r, cudaStreamWaitEvent(s, r->ev_in, 0));
+  }
+  BB_RCUDA(r, cudaStreamWaitEvent(s, r->merged[slot], 0));  // the merge that last read this slot is done
+  const auto h0 = std::chrono::steady_clock::now();
+  cudaEventRecord(r->tev[0], s);
+  const uint32_t tiles = div_up(n, bb::RT_THREADS);
+  if (n && r->p2p) {  // the scatter waits until every rank's counts are known
+    bb::k_route_count<<<tiles, bb::RT_THREADS, 0, s>>>(in->path_id, n, W, r->tiles);
+    bb::k_route_scan<<<1, bb::RS_THREADS, 0, s>>>(r->tiles, tiles, W, r->d_counts);
+    r->launches += 2;
+    BB_RCUDA(r, cudaGetLastError());
+  } else if (n) {
+    bb_batch packed{n, reinterpret_cast<uint64_t*>(r->send[0]), reinterpret_cast<bb_head*>(r->send[1]),
+                    reinterpret_cast<uint32_t*>(r->send[2]), reinterpret_cast<uint64_t*>(r->send[3])};
+    BB_RCUDA(r, launch_pack(W, in, &packed, r->d_counts, r->tiles, s));
+    r->launches += 3;
+  } else {
+    BB_RCUDA(r, cudaMemsetAsync(r->d_counts, 0, W * sizeof(uint64_t), s));
+  }
+  cudaEventRecord(r->tev[1], s);
+  // everybody's counts: row q = what rank q sends to each rank
+  BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
+  BB_RCUDA(r, cudaMemcpyAsync(r->h_matrix, r->d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(r->tev[2], s);
+  BB_RCUDA(r, cudaStreamSynchronize(s));  // the one host round trip of a step
+  r->host_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+  uint64_t so[bb::RT_MAX_WORLD + 1], ro[bb::RT_MAX_WORLD + 1];
+  so[0] = ro[0] = 0;
+  for (uint32_t q = 0; q < W; ++q) {
+    so[q + 1] = so[q] + r->h_matrix[(size_t)me * W + q];
+    ro[q + 1] = ro[q] + r->h_matrix[(size_t)q * W + me];
+  }
+  if (ro[W] > r->cap) return rfail(r, BB_ERR_CAPACITY, "receive slot too small for this batch");
+  if (r->p2p) {
+    // Fused pack + exchange.  Nobody stores into a slot before everyone has passed the counts
+    // all-gather above, i.e. before every owner has finished merging what the slot held.
+    if (n) {
+      bb::RouteP2PArgs a;
+      a.path_id = in->path_id;
+      a.head = reinterpret_cast<const uint4*>(in->head);
+      a.clk = reinterpret_cast<const uint4*>(in->clk);
+      a.val = reinterpret_cast<const uint4*>(in->val);
+      for (uint32_t q = 0; q < W; ++q) {
+        a.d_path[q] = reinterpret_cast<uint64_t*>(r->peer[q][slot][0]);
+        a.d_head[q] = reinterpret_cast<uint4*>(r->peer[q][slot][1]);
+        a.d_clk[q] = reinterpret_cast<uint4*>(r->peer[q][slot][2]);
+        a.d_val[q] = reinterpret_cast<uint4*>(r->peer[q][slot][3]);
+        uint64_t before = 0;  // rows ranks < me send to q: where my block starts in q's slot
+        for (uint32_t p = 0; p < me; ++p) before += r->h_matrix[(size_t)p * W + q];
+        a.adj[q] = (int64_t)before - (int64_t)so[q];
+      }
+      a.n = n;
+      a.world = W;
+      a.tile_off = r->tiles;
+      bb::k_route_scatter_p2p<<<tiles, bb::RT_THREADS, bb::RT_SMEM, s>>>(a);
+      r->launches += 1;
+      BB_RCUDA(r, cudaGetLastError());
+    }
+    cudaEventRecord(r->tev[3], s);
+    // every rank's stores are complete when its scatter kernel is: a tiny collective is the barrier
+    if (W > 1) BB_RNCCL(r, g_nccl.AllGather(r->d_bar, r->d_bar + 1, 1, ncclUint64, r->comm, s));
+    cudaEventRecord(r->tev[4], s);
+    BB_RCUDA(r, cudaEventRecord(r->ready[slot], s));
+    r->host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    r->sent_bytes += (so[W] - (so[me + 1] - so[me])) * 88;
+    r->n_recv[slot] = ro[W];
+    *n_recv = ro[W];
+    return BB_OK;
+  }
+  BB_RNCCL(r, g_nccl.GroupStart());
+  for (int k = 0; k < 4; ++k) {
+    const size_t w = ROUTE_W[k];
+    for (uint32_t q = 0; q < W; ++q) {
+      if (q == me) continue;
+      if (so[q + 1] > so[q])
+        BB_RNCCL(r, g_nccl.Send(r->send[k] + so[q] * w, (so[q + 1] - so[q]) * w, ncclUint8, (int)q, r->comm, s));
+      if (ro[q + 1] > ro[q])
+        BB_RNCCL(r, g_nccl.Recv(r->recv[slot][k] + ro[q] * w, (ro[q + 1] - ro[q]) * w, ncclUint8, (int)q, r->comm, s));
+    }
+  }
+  BB_RNCCL(r, g_nccl.GroupEnd());
+  cudaEventRecord(r->tev[3], s);
+  for (int k = 0; k < 4; ++k)  // this rank's own rows never leave the device
+    if (so[me + 1] > so[me])
+      BB_RCUDA(r, cudaMemcpyAsync(r->recv[slot][k] + ro[me] * ROUTE_W[k], r->send[k] + so[me] * ROUTE_W[k],
+                                  (so[me + 1] - so[me]) * ROUTE_W[k], cudaMemcpyDeviceToDevice, s));
+  cudaEventRecord(r->tev[4], s);
+  BB_RCUDA(r, cudaEventRecord(r->ready[slot], s));
+  r->host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+  r->sent_bytes += (so[W] - (so[me + 1] - so[me])) * 88;
+  r->n_recv[slot] = ro[W];
+  *n_recv = ro[W];
+  return BB_OK;
+}
+
+int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received) {
+  if (!r || !received || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
+  received->n = r->n_recv[slot];
+  received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);
+  received->head = reinterpret_cast<bb_head*>(r->recv[slot][1]);
+  received->clk = reinterpret_cast<uint32_t*>(r->recv[slot][2]);
+  received->val = reinterpret_cast<uint64_t*>(r->recv[slot][3]);
+  return BB_OK;
+}
+
+int bb_router_release(bb_router* r, uint32_t slot, void* stream) {
+  if (!r || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  BB_RCUDA(r, cudaEventRecord(r->merged[slot], (cudaStream_t)stream));
+  return BB_OK;
+}
+
+int bb_router_last_ms(bb_router* r, double out[6]) {
+  if (!r || !out) return BB_ERR_ARG;
+  cudaSetDevice(r->device);
+  if (cudaEventSynchronize(r->tev[4]) != cudaSuccess) return BB_ERR_STATE;
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r->tev[i], r->tev[i + 1]);
+    out[i] = ms;
+  }
+  out[4] = r->host_ms[0];
+  out[5] = r->host_ms[1];
+  return BB_OK;
+}
+
+uint64_t bb_router_sent_bytes(const bb_router* r) { return r ? r->sent_bytes : 0; }
+uint64_t bb_router_launch_count(const bb_router* r) { return r ? r->launches : 0; }
 
 }  // extern "C"

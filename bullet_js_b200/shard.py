@@ -5,8 +5,8 @@ lives on rank `p % world` as local row `p // world`.  A step:
 
   1. every rank packs its own batch by owner with the library's stable partition
      (bb_route_pack_dev: three small launches, 88 B per update moved once);
-  2. counts all-to-all (world x world int64), then one all-to-all per SoA array with
-     exact split sizes - (world-1)/world of every batch crosses NVLink;
+  2. counts all-to-all (world x world int64), then ONE grouped exchange of the four SoA arrays
+     with exact sizes - (world-1)/world of every batch crosses NVLink;
   3. every rank merges what it received, concatenated in source-rank order, into its
      shard (bb_merge_batch_dev).  The per-path replay order is therefore
      (source rank, arrival index): the same as one peer replaying rank 0's batch,
@@ -14,9 +14,11 @@ lives on rank `p % world` as local row `p // world`.  A step:
 
 The reference's transport is JSON over WebSocket between peers (src/bullet-network.js:
 404-418, sync chunks of 50 entries, src/bullet-network-sync.js:713-723); this module is
-its B200 equivalent for ONE logical peer whose table spans several GPUs.  The exchange
-itself (`Exchange`) is plumbing over torch.distributed so that the same routing logic
-runs under gloo on CPU in the tests, with the pack and the merge injected.
+its B200 equivalent for ONE logical peer whose table spans several GPUs.  The product
+path is `Router`, a thin wrapper over the library's native router (CUDA pack kernels +
+NCCL called from C).  `Exchange` / `route_on_host` restate the same routing over
+torch.distributed so that it runs under gloo on CPU in the tests, with numpy packing
+and the merge injected.
 """
 from __future__ import annotations
 
@@ -36,7 +38,8 @@ def local_row(path_id, world: int):
 
 
 class Exchange:
-    """counts all-to-all + four variable-size all-to-alls on byte tensors."""
+    """counts all-to-all + ONE grouped exchange of the four SoA arrays (every array's slice for
+    every peer is a send/recv of the same NCCL group, so it is a single launch on the wire)."""
 
     def __init__(self, dist, world: int, rank: int):
         self.dist, self.world, self.rank = dist, world, rank
@@ -49,56 +52,94 @@ class Exchange:
         self.dist.all_to_all_single(recv, send_counts)
         return recv
 
-    def payload(self, send, send_counts, recv, recv_counts, row_bytes: int):
-        """send / recv: uint8 tensors; counts: python lists of rows per peer."""
-        self.dist.all_to_all_single(
-            recv[: sum(recv_counts) * row_bytes], send[: sum(send_counts) * row_bytes],
-            output_split_sizes=[c * row_bytes for c in recv_counts],
-            input_split_sizes=[c * row_bytes for c in send_counts])
+    def payload(self, send: dict, send_counts, recv: dict, recv_counts):
+        """send / recv: {name: uint8 tensor}; rows for peer r start at sum(counts[:r]) in every array."""
+        dist = self.dist
+        so = np.concatenate([[0], np.cumsum(send_counts)]).tolist()
+        ro = np.concatenate([[0], np.cumsum(recv_counts)]).tolist()
+        ops = []
+        for k, w in ROW_BYTES.items():
+            me = self.rank
+            recv[k][ro[me] * w: ro[me + 1] * w].copy_(send[k][so[me] * w: so[me + 1] * w])  # own rows stay here
+            for r in range(self.world):
+                if r == me:
+                    continue
+                if recv_counts[r]:
+                    ops.append(dist.P2POp(dist.irecv, recv[k][ro[r] * w: ro[r + 1] * w], r))
+                if send_counts[r]:
+                    ops.append(dist.P2POp(dist.isend, send[k][so[r] * w: so[r + 1] * w], r))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
 
 
 class Router:
-    """Routes device-resident batches to their owner shard and merges them there."""
+    """The library's native router (bb_router_*: pack kernels, NCCL all-gather of the counts,
+    grouped ncclSend/ncclRecv, two receive slots on its own stream).  torch.distributed is only
+    used to hand rank 0's NCCL id to the other ranks.  `route` and `merge` are separate so that
+    routing batch i+1 overlaps merging batch i."""
 
-    def __init__(self, engine, world: int, rank: int, batch: int, device, dist=None, recv_factor: float = None):
-        import torch
+    def __init__(self, world: int, rank: int, batch: int, device_index: int, dist=None, recv_capacity: int = 0):
+        import ctypes as C
 
         if dist is None:
             import torch.distributed as dist
-        self.torch, self.world, self.rank, self.dev = torch, world, rank, device
-        self.ex = Exchange(dist, world, rank)
-        self.batch = batch
-        self.cap = batch * world if recv_factor is None else int(batch * recv_factor)  # a rank may own every update
+        self.lib = capi.load()
+        self.world, self.rank = world, rank
+        idbuf = C.create_string_buffer(capi.NCCL_ID_BYTES)
+        if rank == 0:
+            rc = self.lib.bb_router_unique_id(idbuf)
+            if rc:
+                raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(None) or b"").decode())
+        box = [idbuf.raw]
+        dist.broadcast_object_list(box, src=0)
+        h = C.c_void_p()
+        rc = self.lib.bb_router_create(device_index, world, rank, box[0], batch, recv_capacity, C.byref(h))
+        if rc:
+            raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(None) or b"").decode())
+        self._h = h
 
-        def buf(rows, width):
-            return torch.zeros(max(rows, 1) * width, dtype=torch.uint8, device=device)
+    def _check(self, rc):
+        if rc:
+            raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(self._h) or b"").decode())
 
-        self.send = {k: buf(batch, w) for k, w in ROW_BYTES.items()}
-        self.recv = {k: buf(self.cap, w) for k, w in ROW_BYTES.items()}
-        self.d_counts = torch.zeros(world, dtype=torch.int64, device=device)
-        self.nvlink_bytes = 0  # bytes this rank sent to other ranks so far
+    def route(self, bs: capi.BBBatch, slot: int, in_stream: int = 0) -> int:
+        """Collective: pack the device batch by owner and exchange it into receive slot `slot`."""
+        import ctypes as C
 
-    def route_and_merge(self, engine, p, h, c, v, cs: capi.BBChanges, stream: int) -> int:
-        """p/h/c/v: uint8 device tensors of one batch (bb_batch arrays). Returns updates merged here."""
-        torch = self.torch
-        n = p.numel() // 8
-        bs = capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
-        out = capi.BBBatch(n=n, path_id=self.send["path"].data_ptr(), head=self.send["head"].data_ptr(),
-                           clk=self.send["clk"].data_ptr(), val=self.send["val"].data_ptr())
-        engine.route_pack_dev(self.world, bs, out, self.d_counts.data_ptr(), stream)
-        recv_counts_t = self.ex.counts(self.d_counts)          # NCCL, on torch's current stream
-        both = torch.stack([self.d_counts, recv_counts_t]).cpu()  # the one host sync of the step
-        send_counts, recv_counts = both[0].tolist(), both[1].tolist()
-        n_recv = sum(recv_counts)
-        if n_recv > self.cap:
-            raise capi.BulletB200Error(capi.ERR_CAPACITY, f"rank {self.rank} received {n_recv} updates > {self.cap}")
-        for k, w in ROW_BYTES.items():
-            self.ex.payload(self.send[k], send_counts, self.recv[k], recv_counts, w)
-        self.nvlink_bytes += (n - send_counts[self.rank]) * sum(ROW_BYTES.values())
-        rb = capi.BBBatch(n=n_recv, path_id=self.recv["path"].data_ptr(), head=self.recv["head"].data_ptr(),
-                          clk=self.recv["clk"].data_ptr(), val=self.recv["val"].data_ptr())
+        n = C.c_uint64(0)
+        self._check(self.lib.bb_router_route_dev(self._h, C.byref(bs), slot, C.byref(n), C.c_void_p(in_stream)))
+        return int(n.value)
+
+    def merge(self, engine, slot: int, cs: capi.BBChanges, stream: int) -> int:
+        """Merge receive slot `slot` into this rank's shard on `stream` (a raw cudaStream_t)."""
+        import ctypes as C
+
+        rb = capi.BBBatch()
+        self._check(self.lib.bb_router_acquire(self._h, slot, C.c_void_p(stream), C.byref(rb)))
         engine.merge_dev(rb, cs, stream)
-        return n_recv
+        self._check(self.lib.bb_router_release(self._h, slot, C.c_void_p(stream)))
+        return int(rb.n)
+
+    def last_ms(self) -> dict:
+        import ctypes as C
+
+        out = (C.c_double * 6)()
+        self._check(self.lib.bb_router_last_ms(self._h, out))
+        return dict(zip(("pack", "counts", "exchange", "own_copy", "host_until_counts", "host_call"), out))
+
+    @property
+    def sent_bytes(self) -> int:
+        return int(self.lib.bb_router_sent_bytes(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.bb_router_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.bb_router_destroy(self._h)
+            self._h = None
 
 
 def route_on_host(world: int, rank: int, batch, dist, merge_fn):
@@ -119,10 +160,11 @@ def route_on_host(world: int, rank: int, batch, dist, merge_fn):
     sc = send_counts.tolist()
     n_recv = sum(rc)
     got = codec.Batch.empty(n_recv)
-    for name, arr_s, arr_r in (("path", packed.path_id, got.path_id), ("head", packed.head, got.head),
-                               ("clk", packed.clk, got.clk), ("val", packed.val, got.val)):
-        s = torch.from_numpy(np.ascontiguousarray(arr_s).view(np.uint8).reshape(-1).copy())
-        r = torch.zeros(max(n_recv, 1) * ROW_BYTES[name], dtype=torch.uint8)
-        ex.payload(s, sc, r, rc, ROW_BYTES[name])
-        arr_r.view(np.uint8).reshape(-1)[:] = r.numpy()[: n_recv * ROW_BYTES[name]]
+    arrays = {"path": (packed.path_id, got.path_id), "head": (packed.head, got.head),
+              "clk": (packed.clk, got.clk), "val": (packed.val, got.val)}
+    send = {k: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()) for k, (a, _) in arrays.items()}
+    recv = {k: torch.zeros(max(n_recv, 1) * w, dtype=torch.uint8) for k, w in ROW_BYTES.items()}
+    ex.payload(send, sc, recv, rc)
+    for k, (_, dst) in arrays.items():
+        dst.view(np.uint8).reshape(-1)[:] = recv[k].numpy()[: n_recv * ROW_BYTES[k]]
     return merge_fn(got), got

@@ -306,6 +306,34 @@ int bb_index_stats(bb_ctx* ctx, uint32_t field, uint64_t* n_dense, uint64_t* n_e
 int bb_route_pack_dev(bb_ctx* ctx, uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts,
                       void* stream);
 
+/* A router owns the exchange: send buffers, two receive slots, an NCCL communicator (libnccl.so.2
+ * is opened at run time; a process that never creates a router does not need it) and its own
+ * stream, so that routing batch i+1 overlaps merging batch i.  Lifecycle per batch:
+ *   bb_router_route_dev(r, batch, slot, &n)   pack by owner, all-gather the counts (one host
+ *                                             round trip), grouped ncclSend/ncclRecv of the four
+ *                                             arrays into receive slot `slot`; n = rows received
+ *   bb_router_acquire(r, slot, stream, &b)    `stream` waits for the slot; b = the received batch
+ *   bb_merge_batch_dev(ctx, &b, out, stream)  merge it into this rank's shard
+ *   bb_router_release(r, slot, stream)        the slot may be overwritten once `stream` gets here
+ * Every rank must call route in the same order (it is a collective). */
+typedef struct bb_router bb_router;
+#define BB_NCCL_ID_BYTES 128
+int bb_router_unique_id(char id[BB_NCCL_ID_BYTES]); /* rank 0; hand the bytes to every rank */
+int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char id[BB_NCCL_ID_BYTES],
+                     uint64_t max_batch, uint64_t recv_capacity, bb_router** out);
+int bb_router_destroy(bb_router* r);
+const char* bb_router_last_error(const bb_router* r);
+/* `in`: device batch; `in_stream`: stream the batch was produced on (0 = already complete). */
+int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
+int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
+int bb_router_release(bb_router* r, uint32_t slot, void* stream);
+/* Telemetry of the most recent route, ms: device time of [pack, counts all-gather + copy,
+ * exchange, own-rows copy], then host time until the counts were known and of the whole call. */
+int bb_router_last_ms(bb_router* r, double out[6]);
+/* bytes this rank has sent to other ranks, kernels it has launched */
+uint64_t bb_router_sent_bytes(const bb_router* r);
+uint64_t bb_router_launch_count(const bb_router* r);
+
 /* ---- telemetry ---------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
 uint64_t bb_launch_count(const bb_ctx* ctx);

@@ -261,3 +261,61 @@ def test_route_pack_is_a_stable_partition(world):
     assert np.array_equal(got[2].view(np.uint32).reshape(n, 8), b.clk[order])
     assert np.array_equal(got[3].view(np.uint64).reshape(n, 4), b.val[order])
     eng.close()
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+def test_native_router_single_rank(p2p, monkeypatch):
+    """bb_router_* with world == 1 (its own NCCL communicator): route -> acquire -> merge -> release
+    gives what a direct merge gives, for both receive slots; fused peer-store path and the
+    pack + ncclSend/ncclRecv path."""
+    import ctypes as C
+
+    if not p2p:
+        monkeypatch.setenv("BB_ROUTER_NO_P2P", "1")
+
+    import torch
+
+    from bullet_js_b200.engine import Engine
+
+    n_rec, n = 4000, 50_000
+    rng = synth.rng_for(2, salt=11)
+    table = synth.make_table(n_rec, rng)
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng, orc = engine_and_oracle(None, n_rec, **synth.synth_ranks(n_rec))
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    lib = capi.load()
+    idbuf = C.create_string_buffer(capi.NCCL_ID_BYTES)
+    assert lib.bb_router_unique_id(idbuf) == 0, lib.bb_router_last_error(None)
+    h = C.c_void_p()
+    assert lib.bb_router_create(0, 1, 0, idbuf.raw, n, 0, C.byref(h)) == 0, lib.bb_router_last_error(None)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    for step in range(3):
+        b = synth.make_batch(table, n, rng, keys="zipf")
+        t = [torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev) for a in (b.path_id, b.head, b.clk, b.val)]
+        torch.cuda.synchronize()
+        bs = capi.BBBatch(n=n, path_id=t[0].data_ptr(), head=t[1].data_ptr(), clk=t[2].data_ptr(), val=t[3].data_ptr())
+        got_n = C.c_uint64(0)
+        slot = step % 2
+        assert lib.bb_router_route_dev(h, C.byref(bs), slot, C.byref(got_n), None) == 0, lib.bb_router_last_error(h)
+        assert got_n.value == n
+        rb = capi.BBBatch()
+        assert lib.bb_router_acquire(h, slot, C.c_void_p(st.cuda_stream), C.byref(rb)) == 0
+        o = [torch.zeros(n * w, dtype=torch.uint8, device=dev) for w in (4, 8, 4, 16, 32, 32)]
+        cs = capi.BBChanges(cap=n, verdict=o[0].data_ptr(), n_changes=o[1].data_ptr(), idx=o[2].data_ptr(),
+                            head=o[3].data_ptr(), clk=o[4].data_ptr(), val=o[5].data_ptr())
+        eng.merge_dev(rb, cs, st.cuda_stream)
+        assert lib.bb_router_release(h, slot, C.c_void_p(st.cuda_stream)) == 0
+        eng.sync(st.cuda_stream)
+        want = orc.merge(b)
+        k = int(o[1].cpu().numpy().view(np.uint64)[0])
+        got = codec.Changes.from_verdicts(o[0].cpu().numpy().view(np.uint32), o[2].cpu().numpy().view(np.uint32)[:k],
+                                          o[3].cpu().numpy().view(codec.HEAD_DTYPE)[:k],
+                                          o[4].cpu().numpy().view(np.uint32).reshape(n, 8)[:k],
+                                          o[5].cpu().numpy().view(np.uint64).reshape(n, 4)[:k])
+        assert got.same_as(want)
+    assert_same_table(eng, orc, n_rec)
+    assert lib.bb_router_sent_bytes(h) == 0
+    lib.bb_router_destroy(h)
+    eng.close()
