@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's public API for this path: `Bullet`, `BulletNode`,
+`index / equals / range / count`, the batched sync ingress - same names, argument meaning
+and return shapes as the JavaScript, every decision taken on the GPU.
+
+    reference                                            here
+    new Bullet({storage:false, disableNetwork:true})     Bullet({"users": schema}, capacity=...)
+    bullet.get(path).put(data) / .value() / .on(cb)      src/bullet.js:681-759
+    bullet.setData(path, data, broadcast)                src/bullet.js:139-155
+    sync._processSyncEntries(entries)                    src/bullet-network-sync.js:551-569
+    bullet.index / equals / range / count                src/bullet.js:313-357 -> src/bullet-query.js
+    bullet.on(path, cb) + ancestor notification          src/bullet.js:227-266
+
+It is the Python twin of the JS shim in INTEGRATION.md: intern paths, pack SoA batches
+(codec), call the C ABI (engine), then replay the returned change set in arrival order
+through the host-side effects of `_applyUpdate` (log capped at 1000, listeners on the path
+and every ancestor).  One device table per collection (`users/*`, `products/*`): paths must
+be `<collection>/<key>`, one granularity per collection (SURVEY.md 8a restriction 2).
+There is no CPU fallback: values outside the typed domain raise `codec.DomainError`.
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable
+
+import numpy as np
+
+from . import codec
+from .engine import Engine
+
+
+class BulletNode:
+    """src/bullet.js:681-759 (value / put / on / get)."""
+
+    def __init__(self, bullet: "Bullet", path: str):
+        self.bullet, self.path = bullet, path
+
+    def value(self):
+        return self.bullet._get_data(self.path)
+
+    def put(self, data):
+        self.bullet.setData(self.path, data)
+        return self
+
+    def on(self, callback: Callable):
+        """src/bullet.js:710-720: subscribe, then call back at once with the current value."""
+        self.bullet.on(self.path, callback)
+        callback(self.value())
+        return self
+
+    def get(self, sub: str) -> "BulletNode":
+        return BulletNode(self.bullet, f"{self.path}/{sub}")
+
+    def __repr__(self):
+        return f"BulletNode({self.path!r})"
+
+    def __eq__(self, other):
+        return isinstance(other, BulletNode) and other.path == self.path
+
+    def __hash__(self):
+        return hash(self.path)
+
+
+class _Collection:
+    def __init__(self, name: str, schema: codec.Schema, capacity: int, device: int):
+        self.name, self.schema = name, schema
+        self.engine = Engine.for_schema(schema, capacity, device=device, post_getdata=True)
+        self.indexed: set[int] = set()
+
+    def slot(self, field: str) -> int:
+        return self.schema.fields.index(field)
+
+
+class Bullet:
+    def __init__(self, collections: dict[str, codec.Schema], capacity: int = 1 << 16, device: int = 0):
+        self._c = {name: _Collection(name, schema, capacity, device) for name, schema in collections.items()}
+        self.log: list[dict] = []          # src/bullet.js:206-215
+        self.listeners: dict[str, list] = {}
+        self.decisions: list[int] = []     # decision code of every setData, arrival order
+
+    # ---- src/bullet.js:104-108, 681-759
+    def get(self, path: str) -> BulletNode:
+        return BulletNode(self, path)
+
+    def on(self, path: str, callback: Callable):
+        self.listeners.setdefault(path, []).append(callback)
+        return self
+
+    def close(self):
+        for c in self._c.values():
+            c.engine.close()
+
+    # ---- writes
+    def _split(self, path: str):
+        parts = path.split("/")
+        if len(parts) != 2 or not all(parts) or parts[0] not in self._c:
+            raise codec.DomainError(f"path {path!r} is not <collection>/<key> of a configured collection")
+        return self._c[parts[0]]
+
+    def setData(self, path: str, data, broadcast: bool = True):
+        """One local put (src/bullet.js:139-155): a batch of one."""
+        self._merge([(path, data, None)])
+
+    def process_sync_entries(self, entries):
+        """BulletNetworkSync._processSyncEntries (sync:551-569): entries = [{path, data,
+        vectorClock}] applied in order; objects carry their clock, primitives do not (sync:560-563)."""
+        self._merge([(e["path"], e["data"], e.get("vectorClock") if isinstance(e["data"], dict) else None)
+                     for e in entries])
+
+    def _merge(self, updates):
+        # consecutive runs of the same collection keep the global arrival order of effects
+        i = 0
+        while i < len(updates):
+            col = self._split(updates[i][0])
+            j = i
+            while j < len(updates) and self._split(updates[j][0]) is col:
+                j += 1
+            run = updates[i:j]
+            batch = codec.encode_updates(col.schema, run)
+            ch = col.engine.merge(batch)
+            self.decisions.extend(ch.decision.tolist())
+            for entry in codec.decode_changes(col.schema, batch, ch):   # arrival order
+                self._apply_effects(entry["path"], entry["value"], entry["vectorClock"])
+            i = j
+
+    def _apply_effects(self, path, value, clock):
+        """The host-visible part of _applyUpdate + _notify (src/bullet.js:206-266)."""
+        self.log.append({"op": "set", "path": path, "data": value, "vectorClock": clock, "timestamp": time.time()})
+        if len(self.log) > 1000:
+            del self.log[: len(self.log) - 1000]
+        parts = path.split("/")
+        for cb in self.listeners.get(path, []):
+            cb(value)
+        for k in range(len(parts) - 1, -1, -1):  # every ancestor, root ("") last (src/bullet.js:238-255)
+            parent = "/".join(parts[:k])
+            for cb in self.listeners.get(parent, []):
+                cb(self._get_data(parent) if parent else {c: self._get_data(c) for c in self._c})
+
+    # ---- reads (src/bullet.js:115-129; materialising like the reference's _getData)
+    def _get_data(self, path: str):
+        parts = path.split("/")
+        if len(parts) == 1 and parts[0] in self._c:
+            col = self._c[parts[0]]
+            n = len(col.schema.paths)
+            rows = col.engine.table_read(np.arange(n, dtype=np.uint64)) if n else []
+            order = sorted(range(n), key=lambda i: int(rows[i]["cseq"]))
+            return {col.schema.paths.name(i).split("/")[1]: codec.decode_row(col.schema, rows[i])["value"]
+                    for i in order if int(rows[i]["cseq"])}
+        col = self._split(path)
+        row = col.engine.table_read([col.schema.paths.id(path)], materialise=True)[0]
+        return codec.decode_row(col.schema, row)["value"]
+
+    def meta(self, path: str):
+        """meta[path].vectorClock (src/bullet.js:198-203) or None."""
+        col = self._split(path)
+        return codec.decode_row(col.schema, col.engine.table_read([col.schema.paths.id(path)])[0])["M"]
+
+    # ---- queries (src/bullet.js:313-357 -> src/bullet-query.js)
+    def index(self, path: str, field: str):
+        col = self._c[path]
+        f = col.slot(field)
+        if f not in col.indexed:
+            col.engine.index_create(f)
+            col.indexed.add(f)
+        return self
+
+    def _nodes(self, col, ids):
+        return [BulletNode(self, col.schema.paths.name(i)) for i in ids]
+
+    def equals(self, path: str, field: str, value):
+        col = self._c[path]
+        self.index(path, field)  # query:194-196 creates the index on first use
+        key = col.schema.index_key(value)
+        return [] if key is None else self._nodes(col, col.engine.query_equals(col.slot(field), key))
+
+    def count(self, path: str, field: str, value) -> int:
+        col = self._c[path]
+        self.index(path, field)
+        key = col.schema.index_key(value)
+        return 0 if key is None else col.engine.query_count(col.slot(field), key)
+
+    def range(self, path: str, field: str, min=None, max=None, *, min_undefined=False, max_undefined=False):
+        """query:221-261.  Python has no `undefined`: pass min_undefined / max_undefined for it
+        (the reference then matches nothing); None is JS null."""
+        col = self._c[path]
+        self.index(path, field)
+        if min_undefined or max_undefined:
+            return []
+        return self._nodes(col, col.engine.query_range(col.slot(field), col.schema.bound(min, False),
+                                                       col.schema.bound(max, True)))

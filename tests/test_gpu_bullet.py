@@ -1,0 +1,107 @@
+"""The host mirror of the reference API (bullet_js_b200/bullet.py) on the GPU, driven with the
+reference's own example scripts and the known-answer traces of SURVEY.md 8c; every run is
+mirrored on the literal oracle and compared."""
+import pytest
+
+from bullet_js_b200 import codec
+from oracle.js_literal import RefBullet
+from tests.test_oracle_kat import PRODUCTS, USERS
+
+pytestmark = pytest.mark.gpu
+
+
+def js(v):
+    """Python ints of the fixtures -> JS numbers."""
+    if isinstance(v, dict):
+        return {k: js(x) for k, x in v.items()}
+    return float(v) if isinstance(v, int) and not isinstance(v, bool) else v
+
+
+def schemas(me="me"):
+    ustr = [u["name"] for u in USERS.values()] + ["admin", "user", "editor"]
+    pstr = [p["name"] for p in PRODUCTS.values()] + ["electronics", "accessories", "furniture"]
+    peers = [me, "peerA", "peerB"]
+    return {
+        "users": codec.Schema(["name", "age", "active", "role"], peers, codec.StringDict(ustr), me),
+        "products": codec.Schema(["name", "price", "stock", "category"], peers, codec.StringDict(pstr), me),
+    }
+
+
+def paths(nodes):
+    return sorted(n.path for n in nodes)
+
+
+def test_query_example_script():
+    """examples/bullet-query-example.js:17-139 (KAT-Q1), same calls on both sides."""
+    from bullet_js_b200.bullet import Bullet
+
+    db, ref = Bullet(schemas(), capacity=64), RefBullet("me")
+    for k, v in USERS.items():
+        db.get(f"users/{k}").put(js(v))
+        ref.put(f"users/{k}", js(v))
+    for k, v in PRODUCTS.items():
+        db.get(f"products/{k}").put(js(v))
+        ref.put(f"products/{k}", js(v))
+    db.index("users", "role").index("users", "age").index("users", "active")
+    db.index("products", "category").index("products", "price")
+    assert paths(db.equals("users", "role", "admin")) == ["users/user1", "users/user10", "users/user6"]
+    assert paths(db.range("users", "age", 30, 40)) == sorted(["users/user2", "users/user5", "users/user8", "users/user10"])
+    assert [db.count("users", "role", r) for r in ("admin", "user", "editor")] == [3, 5, 2]
+    assert paths(db.range("products", "price", 100, 300)) == sorted(
+        ["products/prod3", "products/prod6", "products/prod7", "products/prod9"])
+    for args in (("users", "active", True), ("users", "active", "true"), ("users", "age", "28"),
+                 ("products", "category", "furniture"), ("products", "stock", 5), ("users", "role", "nobody")):
+        assert paths(db.equals(*args)) == sorted(ref.equals(*[js(a) for a in args])), args
+    for args in (("users", "age", 0, 100), ("users", "age", "30", 40), ("users", "role", "a", "f"),
+                 ("products", "price", None, 100), ("users", "active", "a", "z"), ("users", "age", 40, 30)):
+        assert paths(db.range(*args)) == sorted(ref.range(*[js(a) for a in args])), args
+    assert db.get("users/user3").value() == js(USERS["user3"])
+    assert list(db._get_data("users").keys()) == list(USERS.keys())  # Object.entries order
+    db.close()
+
+
+def test_index_before_puts():
+    """docs/quick-start.md:183-209 (KAT-Q2): the index exists first, the hook fills it."""
+    from bullet_js_b200.bullet import Bullet
+
+    s = {"users": codec.Schema(["name", "email", "role"], ["me"],
+                               codec.StringDict(["Alice", "Bob", "alice@example.com", "bob@example.com", "admin", "user"]), "me")}
+    db = Bullet(s, capacity=16)
+    db.index("users", "role")
+    db.get("users/alice").put({"name": "Alice", "email": "alice@example.com", "role": "admin"})
+    db.get("users/bob").put({"name": "Bob", "email": "bob@example.com", "role": "user"})
+    assert paths(db.equals("users", "role", "admin")) == ["users/alice"]
+    db.close()
+
+
+def test_network_entries_and_listeners():
+    """KAT-N through process_sync_entries on peer "B", with listeners and the log."""
+    from bullet_js_b200.bullet import Bullet
+
+    s = {"users": codec.Schema(["age", "role"], ["A", "B"], codec.StringDict(["user", "admin"]), "B")}
+    db, ref = Bullet(s, capacity=8), RefBullet("B")
+    seen, seen_ref = [], []
+    db.get("users/u1").on(seen.append)      # called at once with {} (the read materialises the node)
+    ref.on("users/u1", seen_ref.append)
+    for x in (db, ref):
+        x.index("users", "age")
+        x.index("users", "role")
+    entries = [
+        {"path": "users/u1", "data": {"age": 30.0, "role": "user"}, "vectorClock": {"A": 3.0}},
+        {"path": "users/u1", "data": {"age": 25.0, "role": "admin"}, "vectorClock": {"A": 4.0}},
+        {"path": "users/u1", "data": {"age": 40.0}, "vectorClock": {"A": 5.0, "B": 2.0}},
+        {"path": "users/u1", "data": {"age": 10.0}, "vectorClock": {"A": 4.0, "B": 2.0}},
+        {"path": "users/u1", "data": {"age": 10.0}, "vectorClock": {"B": 2.0, "A": 5.0}},
+        {"path": "users/u1", "data": {"age": 10.0}, "vectorClock": {"B": 2.0, "A": 5.0}},
+    ]
+    db.process_sync_entries(entries)
+    ref.process_sync_entries(entries)
+    assert db.decisions == [0, 6, 4, 5, 6, 2] == [d["code"] for d in ref.decisions]
+    assert db.get("users/u1").value() == {"age": 10.0} == ref.store["users"]["u1"]
+    assert db.meta("users/u1") == {"B": 2.0, "A": 5.0} and list(db.meta("users/u1")) == ["B", "A"]
+    assert seen == seen_ref and len(seen) == 6          # 1 at subscription + 5 accepted; the rejected update notifies nobody
+    assert [e["data"] for e in db.log] == [c["value"] for c in ref.changes]
+    for v in (10.0, 25.0, 30.0, 40.0):
+        assert paths(db.equals("users", "age", v)) == sorted(ref.equals("users", "age", v)), v
+    assert paths(db.equals("users", "role", "admin")) == sorted(ref.equals("users", "role", "admin"))
+    db.close()
