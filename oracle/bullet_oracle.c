@@ -3,10 +3,16 @@
  * TEST INFRASTRUCTURE ONLY (checker + cpu_baseline); never linked into
  * libbulletb200.so and never called from the product path.
  *
- * PARITY UNPINNED BY THE REFERENCE: bullet-js has no tests or golden vectors
- * (SURVEY.md 8c).  This file is validated against oracle/js_literal.py (the
- * JS-object-level restatement, itself pinned by the KATs of SURVEY.md 8c) on
- * random streams by tests/test_oracle_typed.py.
+ * PARITY PIN: bullet-js ships no tests or golden vectors of its own (SURVEY.md
+ * 8c) and this image has no JS engine, so the reference's own sources are
+ * executed by oracle/minijs (an ECMAScript-subset interpreter written for this
+ * purpose) and their outputs are committed as tests/golden/*.json.gz
+ * (scripts/make_golden.py).  tests/test_golden.py checks this file against them:
+ * random JS-level streams (decisions, change set, final table, index contents and
+ * query results in the reference's exact Map/Set order) and BASELINE config 1 at
+ * full size (100 000 updates over 10 000 records).  Caveat: the interpreter is
+ * ours, not V8; its language semantics are unit-tested (tests/test_minijs.py) but
+ * have not been compared with node.
  *
  * It consumes the same typed struct-of-arrays format as the library
  * (include/bullet_b200.h describes the encoding) but shares no code with the CUDA

@@ -1,11 +1,16 @@
 """Literal oracle: a CPU restatement of the reference's hot path over JS-like
 Python values (TEST INFRASTRUCTURE ONLY - never imported by the product path).
 
-PARITY UNPINNED BY THE REFERENCE: KORandi/bullet-js ships no tests, fixtures or
-golden vectors and no JS engine exists in this image, so this
-restatement is pinned by the hand-derived known-answer traces of SURVEY.md 8c
-(tests/test_oracle_kat.py) and, where `oracle/minijs` can execute the reference's
-own source files, by traces generated from them (tests/golden/).
+PARITY PIN: KORandi/bullet-js ships no tests, fixtures or golden vectors
+and no JS engine exists in this image, so the reference's own source files are executed
+unmodified by `oracle/minijs` (an ECMAScript-subset interpreter written for the purpose,
+`oracle/ref_runner.py`) and the traces are committed under tests/golden/
+(scripts/make_golden.py).  tests/test_golden.py and tests/test_minijs.py hold this
+restatement to them: decisions, change sets, store, both clock maps and their aliasing,
+index Maps in exact (Map, Set) order and query results, on the SURVEY 8c scenarios and
+on random streams that take every branch of `resolve`.  Caveat: the interpreter is ours,
+not V8 (its semantics are unit-tested, not compared with node).  The hand-derived
+known-answer traces of SURVEY.md 8c remain in tests/test_oracle_kat.py.
 
 Every method names the reference lines it follows (paths relative to
 /root/reference).  Objects are Python dicts (insertion ordered == JS own-key
