@@ -57,6 +57,10 @@ def parse():
     ap.add_argument("--query-records", type=int, default=100_000_000,
                     help="nodes per GPU for the index build + range/equals scans (BASELINE config 4)")
     ap.add_argument("--no-query", action="store_true")
+    ap.add_argument("--merge-kernel", default="stage", choices=["stage", "pipe"],
+                    help="k_merge_stage (one CTA per 128-update tile; default) or k_merge_pipe (BB_CFG_CTA_PIPE)")
+    ap.add_argument("--front-end", default="group", choices=["group", "full", "radix"],
+                    help="how a batch is grouped by path: the library default, BB_CFG_FULL_SORT or BB_CFG_RADIX_SORT")
     return ap.parse_args()
 
 
@@ -287,7 +291,7 @@ def workload_config(args, world):
         "workload": f"config2: {args.records * F // 1_000_000}M-field table/GPU ({args.records} records x {F} fields, 128 B rows), "
                     f"{args.batch}-update conflicting batch/GPU/step, {args.keys} keys, clock mix 40/20/25/5/5/5",
         "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
-        "keys": args.keys, "sharding": f"path_id % {world}" if world > 1 else "none",
+        "keys": args.keys, "front_end": args.front_end, "merge_kernel": args.merge_kernel, "sharding": f"path_id % {world}" if world > 1 else "none",
         "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2",
     }
 
@@ -325,7 +329,8 @@ def main():
     ids = np.arange(args.records, dtype=np.uint64)
     engines = []
     for _ in range(W + K):
-        e = Engine(args.records, device=local_rank, **synth.synth_ranks(args.records))
+        e = Engine(args.records, device=local_rank, full_sort=args.front_end == "full",
+                   radix_sort=args.front_end == "radix", cta_pipe=args.merge_kernel == "pipe", **synth.synth_ranks(args.records))
         e.table_load(ids, table.rows)
         e.reserve(args.batch * world, host_entry=(world == 1))
         engines.append(e)

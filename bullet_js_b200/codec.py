@@ -29,6 +29,8 @@ ROW_M_PRESENT, ROW_V_PRESENT, ROW_ALIAS = 1, 2, 4
 CFG_POST_GETDATA = 1
 CFG_ORDERED_CHANGES = 2
 CFG_RADIX_SORT = 4
+CFG_FULL_SORT = 8
+CFG_CTA_PIPE = 32
 
 DEC_NO_CURRENT, DEC_IDENTICAL, DEC_TIE_INCOMING, DEC_TIE_CURRENT = 0, 1, 2, 3
 DEC_INCOMING, DEC_HISTORICAL, DEC_CONCURRENT = 4, 5, 6

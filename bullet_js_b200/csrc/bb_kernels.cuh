@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(CS_THREADS) k_cs_fix(uint64_t* __restrict__ it
 // ping-ponging between the item buffer and the scratch buffer at the same offsets
 __global__ void __launch_bounds__(CS_THREADS) k_cs_fix_long(uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
                                                             const uint2* __restrict__ long_list,
-                                                            const uint32_t* __restrict__ n_long, uint32_t* __restrict__ next) {
+                                                            const uint32_t* __restrict__ n_long, uint32_t* __restrict__ next,
+                                                            const uint32_t* __restrict__ region_base) {
   __shared__ uint32_t hist[RADIX];
   __shared__ uint32_t whist[CS_THREADS / 32][RADIX];
   __shared__ uint32_t s_seg;
@@ -396,8 +397,9 @@ __global__ void __launch_bounds__(CS_THREADS) k_cs_fix_long(uint64_t* __restrict
     if (s_seg >= *n_long) return;
     const uint2 seg = long_list[s_seg];
     const uint32_t len = seg.y;
-    uint64_t* cur = items + seg.x;
-    uint64_t* oth = scratch + seg.x;
+    const uint32_t seg0 = seg.x + (region_base ? *region_base : 0u);
+    uint64_t* cur = items + seg0;
+    uint64_t* oth = scratch + seg0;
     for (int shift = 0; shift < 32; shift += 8) {
       hist[tid] = 0;
       __syncthreads();
@@ -456,11 +458,154 @@ __global__ void __launch_bounds__(CS_THREADS) k_cs_fix_long(uint64_t* __restrict
       cur = oth;
       oth = t;
     }
-    if (cur != items + seg.x) {
+    if (cur != items + seg0) {
       __syncthreads();
       for (uint32_t i = tid; i < len; i += CS_THREADS) oth[i] = cur[i];
     }
   }
+}
+
+
+// ---------------------------------------------------------------- K1'': grouping front end (the default)
+// The merge kernel needs a path's updates adjacent and in arrival order; it does not need the paths
+// themselves in order.  So after the count (k_cs_count: one atomic per update) the batch is only GROUPED:
+//   singles  (the path has one update in the batch: ~2/3 of a uniform batch) keep their arrival order at
+//            the front of the item list.  Their payload gathers in the merge kernel then walk the batch
+//            arrays almost sequentially (full 64-byte DRAM accesses instead of 16/32-byte pieces of
+//            them) and only their 128-byte table rows are accessed at random;
+//   multis   the first-counted update of a path claims a run of cnt slots behind the singles with one
+//            atomic; k_cg_place drops the path's updates into it, k_cg_fix / k_cs_fix_long put each
+//            run in arrival order.
+// No pass over the capacity-sized arrays: every kernel is O(batch), and the counters are cleared by
+// the threads that used them.  Item-list order (hence change-set layout) is not deterministic;
+// BB_CFG_ORDERED_CHANGES keeps the full counting sort.
+constexpr uint32_t CG_MULTI = 0x80000000u;
+constexpr int CG_CTR_SINGLE = 0, CG_CTR_MULTI = 1, CG_CTR_LONG = 2, CG_CTR_NEXT = 3;
+
+__global__ void __launch_bounds__(CS_THREADS) k_cg_classify(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                            uint64_t capacity, uint32_t* __restrict__ cnt,
+                                                            uint32_t* __restrict__ rank, uint2* __restrict__ off,
+                                                            uint64_t* __restrict__ items, uint32_t* __restrict__ ctr,
+                                                            uint2* __restrict__ long_list) {
+  __shared__ uint32_t s_w[CS_ILP][CS_THREADS / 32];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + tid;
+  uint64_t pid[CS_ILP];
+  uint32_t r[CS_ILP], c[CS_ILP];
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) {
+    const uint64_t i = i0 + k * CS_THREADS;
+    pid[k] = i < n ? path_id[i] : ~0ull;
+    r[k] = i < n ? rank[i] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) c[k] = pid[k] < capacity ? cnt[pid[k]] : 0u;  // final: k_cs_count has completed
+  uint32_t before[CS_ILP];
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) {
+    const uint32_t m = __ballot_sync(0xffffffffu, c[k] == 1u);
+    before[k] = __popc(m & lanemask_lt());
+    if (lane == 0) s_w[k][w] = __popc(m);
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive scan of the 4 x 8 warp counts in (k, warp) order == arrival order inside the tile
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < CS_ILP; ++k)
+#pragma unroll
+      for (int ww = 0; ww < CS_THREADS / 32; ++ww) {
+        const uint32_t t = s_w[k][ww];
+        s_w[k][ww] = run;
+        run += t;
+      }
+    s_base = run ? atomicAdd(&ctr[CG_CTR_SINGLE], run) : 0u;
+  }
+  __syncthreads();
+  const uint32_t base = s_base;
+  // runs of the multi-update paths: one claim per CTA (a same-address atomic per path would serialise)
+  uint32_t claim = 0;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k)
+    if (c[k] > 1u && r[k] == 0u) claim += c[k];
+  uint32_t claimed;
+  uint32_t run = block_exclusive_scan<CS_THREADS>(claim, &claimed);
+  if (tid == 0) s_base = claimed ? atomicAdd(&ctr[CG_CTR_MULTI], claimed) : 0u;  // s_base was read above, before the scan's barriers
+  __syncthreads();
+  run += s_base;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) {
+    const uint64_t i = i0 + k * CS_THREADS;
+    const bool head = c[k] > 1u && r[k] == 0u;  // the path's first-counted update owns the run
+    const bool is_long = head && c[k] > (uint32_t)CS_SHORT;
+    const uint32_t lmask = __ballot_sync(0xffffffffu, is_long);
+    uint32_t lbase = 0;
+    if (lmask) {
+      if (lane == __ffs(lmask) - 1) lbase = atomicAdd(&ctr[CG_CTR_LONG], __popc(lmask));
+      lbase = __shfl_sync(0xffffffffu, lbase, __ffs(lmask) - 1);
+    }
+    if (i >= n) continue;
+    uint32_t tag = 0;
+    if (c[k] == 1u) {
+      items[base + s_w[k][w] + before[k]] = (pid[k] << 32) | i;
+      cnt[pid[k]] = 0;  // nobody else looks at this counter
+    } else if (c[k] > 1u) {
+      tag = r[k] | CG_MULTI;
+      if (head) {
+        off[pid[k]] = make_uint2(run, c[k]);
+        if (is_long) long_list[lbase + __popc(lmask & lanemask_lt())] = make_uint2(run, c[k]);
+        run += c[k];
+      }
+    }
+    rank[i] = tag;
+  }
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_cg_place(const uint64_t* __restrict__ path_id, uint64_t n,
+                                                         const uint32_t* __restrict__ rank, const uint2* __restrict__ off,
+                                                         uint32_t* __restrict__ cnt, uint64_t* __restrict__ items,
+                                                         const uint32_t* __restrict__ ctr) {
+  const uint32_t region = ctr[CG_CTR_SINGLE];  // the multi-update runs start behind the singles
+  const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + threadIdx.x;
+  uint32_t tag[CS_ILP];
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) tag[k] = i0 + k * CS_THREADS < n ? rank[i0 + k * CS_THREADS] : 0u;
+#pragma unroll
+  for (int k = 0; k < CS_ILP; ++k) {
+    if (!(tag[k] & CG_MULTI)) continue;
+    const uint64_t i = i0 + k * CS_THREADS;
+    const uint64_t pid = path_id[i];
+    const uint32_t r = tag[k] & ~CG_MULTI;
+    items[region + off[pid].x + r] = (pid << 32) | i;
+    if (r == 0u) cnt[pid] = 0;  // k_cg_classify was the last reader
+  }
+}
+
+// one thread per position of the multi-update region; the thread on a run's first slot sorts it (<= CS_SHORT)
+__global__ void __launch_bounds__(CS_THREADS) k_cg_fix(uint64_t* __restrict__ items, const uint2* __restrict__ off,
+                                                       const uint32_t* __restrict__ ctr) {
+  const uint32_t p = blockIdx.x * CS_THREADS + threadIdx.x;
+  if (p >= ctr[CG_CTR_MULTI]) return;
+  uint64_t* run = items + ctr[CG_CTR_SINGLE] + p;
+  const uint32_t key = (uint32_t)(run[0] >> 32);
+  const uint2 o = off[key];
+  if (o.x != p || o.y > (uint32_t)CS_SHORT) return;
+  const int len = (int)o.y;
+  uint32_t v[CS_SHORT];
+#pragma unroll
+  for (int k = 0; k < CS_SHORT; ++k) v[k] = k < len ? (uint32_t)run[k] : 0xFFFFFFFFu;
+#pragma unroll
+  for (int a = 1; a < CS_SHORT; ++a) {
+#pragma unroll
+    for (int b = a; b > 0; --b) {
+      const uint32_t x = min(v[b - 1], v[b]), y = max(v[b - 1], v[b]);
+      v[b - 1] = x;
+      v[b] = y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CS_SHORT; ++k)
+    if (k < len) run[k] = ((uint64_t)key << 32) | v[k];
 }
 
 }  // namespace bb
@@ -577,15 +722,16 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
   __shared__ __align__(16) uint4 s_row[MT * ROW_S];
   __shared__ uint32_t s_idx[MT], s_res[MT];
   __shared__ uint32_t s_hmask[MT_WARPS], s_wsum[MT_WARPS];
-  __shared__ uint32_t s_tile, s_over, s_ex;
+  __shared__ uint32_t s_tile, s_over, s_ex, s_nextk;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wbase = w * 32;
-  if (*a.err & 1u) return;
-  if (tid == 0) {
-    s_tile = atomicAdd(a.ticket, 1u);
-    s_over = 0;
+  const uint32_t err_in = *a.err;  // bit 0 was decided before this launch; looked at after the loads are on their way
+  uint32_t tile = blockIdx.x;
+  if (ORDERED) {  // the look-back chain needs tiles to start in order; otherwise any order will do
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    tile = s_tile;
   }
-  __syncthreads();
-  const uint32_t tile = s_tile;
+  if (tid == 0) s_over = 0;
   const uint64_t base = (uint64_t)tile * MT;
   const uint64_t pos = base + tid;
   const bool valid = pos < a.n;
@@ -598,6 +744,8 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
   const uint32_t hmask = __ballot_sync(0xffffffffu, is_head);
   if (lane == 0) s_hmask[w] = hmask;
   s_idx[tid] = idx;
+  // the key right behind the tile tells its last segment whether it goes on: fetched now, not in the resolver
+  if (tid == MT - 1) s_nextk = base + MT < a.n ? (uint32_t)(a.sorted[base + MT] >> 32) : ~0u;
 
   // ---- stage: lane pairs fetch whole 32-byte clocks / values, 8 lanes fetch one 128-byte row
   if (valid) cp_async16(&s_upd[tid * UPD_Q], a.head + idx);
@@ -617,6 +765,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
     if ((hmask >> e) & 1u) cp_async16(&s_row[(wbase + e) * ROW_S + chunk], a.table + (uint64_t)ekey * ROW_Q + chunk);
   }
   cp_async_wait_all();
+  if (err_in & 1u) return;  // batch rejected by the front end: nothing may be written
   __syncthreads();
 
   // ---- resolve: thread == segment head
@@ -655,7 +804,7 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
       if (BB_DEC_ACCEPTED(code)) pack_change(u, h.w, ov, oc);
       s_res[p] = code;
     }
-    if (last && nvalid == MT) {  // last segment of a full tile: it may run on into the next tiles
+    if (last && nvalid == MT && s_nextk == key) {  // the tile's last segment runs on into the next tiles
       uint32_t over = 0;
       for (uint64_t gp = base + MT; gp < a.n; ++gp) {
         const uint64_t it = a.sorted[gp];
@@ -774,6 +923,283 @@ __global__ void __launch_bounds__(MT, BB_MERGE_MIN_CTAS) k_merge_stage(const Mer
     }
   }
   if (overflow) atomicOr(a.err, 2u);
+}
+
+// ---------------------------------------------------------------- K2': the same merge, software-pipelined
+// k_merge_stage's CTAs spend about half of their life waiting for memory with nothing else to do:
+// ticket -> sorted items -> payloads and rows are three dependent DRAM round trips before the first
+// resolver instruction, and a tile is gone after ~12 us (ncu: 21 % of the stall samples on the
+// cp.async wait, 17 % on the loads in front of it).  Here a CTA is PERSISTENT (4 per SM, tiles dealt round-robin)
+// and works on three tiles at once:
+//     tile i      resolve + drain out of shared-memory stage i & 1
+//     tile i + 1  payloads and rows in flight (cp.async group) into stage (i + 1) & 1
+//     tile i + 2  its sorted items in flight into registers
+// so in steady state no warp waits for DRAM: loads have a whole iteration to land.  Rows are staged at a
+// 128-byte stride with the 16-byte chunk index XOR-swizzled by the row number (conflict-free both for the
+// 8-lanes-per-row copies and for the one-thread-per-row unpack), which makes two stages fit four times
+// into an SM.  Semantics, change-set layout (tiles claim their slice with one atomic) and the handling
+// of a segment that runs past its tile are those of k_merge_stage<false, *>.
+constexpr int MP_STAGES = 2;
+constexpr int MP_CTAS_PER_SM = 4;
+
+struct MergeStage {
+  uint4 upd[MT * UPD_Q];
+  uint4 row[MT * ROW_Q];
+  uint32_t idx[MT];
+  uint32_t key[MT];
+  uint32_t hmask[MT_WARPS];
+};
+
+struct MergePipeSmem {
+  MergeStage st[MP_STAGES];
+  uint32_t res[MT];
+  uint32_t wsum[MT_WARPS];
+  uint32_t over, ex;
+};
+
+__device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ (r & 7)); }
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool INDEXED>
+__global__ void __launch_bounds__(MT, MP_CTAS_PER_SM) k_merge_pipe(const MergeArgs a) {
+  extern __shared__ __align__(16) unsigned char mp_smem[];
+  MergePipeSmem& sm = *reinterpret_cast<MergePipeSmem*>(mp_smem);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wbase = w * 32;
+  if (*a.err & 1u) return;
+  const uint32_t G = gridDim.x, T = a.num_tiles;
+
+  // sorted items of a tile -> registers (plus the key in front of the tile, for lane 0 of warp 0 .. 3)
+  auto load_items = [&](uint32_t tile, uint64_t& item, uint32_t& prevk) {
+    item = ~0ull;
+    prevk = 0;
+    if (tile >= T) return;
+    const uint64_t pos = (uint64_t)tile * MT + tid;
+    if (pos < a.n) {
+      item = a.sorted[pos];
+      if (lane == 0 && pos > 0) prevk = (uint32_t)(a.sorted[pos - 1] >> 32);
+    }
+  };
+  // payloads + rows of a tile -> stage (one cp.async group)
+  auto issue = [&](uint32_t tile, MergeStage& st, uint64_t item, uint32_t prevk) {
+    if (tile < T) {
+      const uint64_t base = (uint64_t)tile * MT;
+      const uint64_t pos = base + tid;
+      const bool valid = pos < a.n;
+      const int nvalid = (int)min((uint64_t)MT, a.n - base);
+      const uint32_t key = (uint32_t)(item >> 32), idx = (uint32_t)item;
+      uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+      if (lane == 0) prev = (valid && pos > 0) ? prevk : ~key;
+      const bool is_head = valid && key != prev;
+      const uint32_t hmask = __ballot_sync(0xffffffffu, is_head);
+      if (lane == 0) st.hmask[w] = hmask;
+      st.idx[tid] = idx;
+      st.key[tid] = key;
+      if (valid) cp_async16(&st.upd[tid * UPD_Q], a.head + idx);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int e = j * 16 + (lane >> 1), half = lane & 1;
+        const uint32_t eidx = __shfl_sync(0xffffffffu, idx, e);
+        if (wbase + e < nvalid) {
+          cp_async16(&st.upd[(wbase + e) * UPD_Q + 1 + half], a.clk + 2 * (uint64_t)eidx + half);
+          cp_async16(&st.upd[(wbase + e) * UPD_Q + 3 + half], a.val + 2 * (uint64_t)eidx + half);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+        const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+        if ((hmask >> e) & 1u) cp_async16(&st.row[row_slot(wbase + e, chunk)], a.table + (uint64_t)ekey * ROW_Q + chunk);
+      }
+    }
+    cp_async_commit();  // an empty group keeps the wait_group arithmetic uniform
+  };
+
+  uint64_t item_n;
+  uint32_t prev_n;
+  {
+    uint64_t item0;
+    uint32_t prev0;
+    load_items(blockIdx.x, item0, prev0);
+    load_items(blockIdx.x + G, item_n, prev_n);
+    issue(blockIdx.x, sm.st[0], item0, prev0);
+  }
+
+  int buf = 0;
+  for (uint32_t tile = blockIdx.x; tile < T; tile += G, buf ^= 1) {
+    MergeStage& st = sm.st[buf];
+    // next tile's payloads and rows start now (its stage was drained before the barrier that ended the
+    // previous iteration); the tile after that sends for its sorted items
+    issue(tile + G, sm.st[buf ^ 1], item_n, prev_n);
+    load_items(tile + 2 * G, item_n, prev_n);
+    if (tid == 0) sm.over = 0;
+    cp_async_wait_group<1>();
+    __syncthreads();
+
+    const uint64_t base = (uint64_t)tile * MT;
+    const bool valid = base + tid < a.n;
+    const int nvalid = (int)min((uint64_t)MT, a.n - base);
+    const uint32_t key = st.key[tid], idx = st.idx[tid];
+    const uint32_t hmask = st.hmask[w];
+    const bool is_head = (hmask >> lane) & 1u;
+
+    // ---- resolve: thread == segment head
+    if (is_head) {
+      int end = nvalid;
+      bool last = true;
+      const uint32_t above = lane < 31 ? (hmask & ~((2u << lane) - 1u)) : 0u;
+      if (above) {
+        end = wbase + __ffs(above) - 1;
+        last = false;
+      } else {
+        for (int ww = w + 1; ww < MT_WARPS; ++ww) {
+          const uint32_t m = st.hmask[ww];
+          if (m) {
+            end = ww * 32 + __ffs(m) - 1;
+            last = false;
+            break;
+          }
+        }
+      }
+      uint64_t prim[F], prim0[F];
+      if (INDEXED) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) prim0[f] = prim[f] = ((a.ix.mask >> f) & 1u) ? a.ix.pcol[f][key] : BB_KEY_NONE;
+      }
+      RowState r;
+      {
+        uint4 q[ROW_Q];
+#pragma unroll
+        for (int c = 0; c < ROW_Q; ++c) q[c] = st.row[row_slot(tid, c)];
+        unpack_row(q, r);
+      }
+      for (int p = tid; p < end; ++p) {
+        uint4* u = &st.upd[p * UPD_Q];
+        const uint4 h = u[0];
+        Clock c, oc;
+        Value x, ov;
+        const bool net = unpack_update(h, u[1], u[2], u[3], u[4], c, x);
+        const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + st.idx[p], ov, oc);
+        if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
+        if (BB_DEC_ACCEPTED(code)) pack_change(u, h.w, ov, oc);
+        sm.res[p] = code;
+      }
+      if (last && nvalid == MT) {  // last segment of a full tile: it may run on into the next tiles
+        uint32_t over = 0;
+        for (uint64_t gp = base + MT; gp < a.n; ++gp) {
+          const uint64_t it = a.sorted[gp];
+          if ((uint32_t)(it >> 32) != key) break;
+          const uint32_t ui = (uint32_t)it;
+          const uint4 h = a.head[ui];
+          Clock c, oc;
+          Value x, ov;
+          const bool net = unpack_update(h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1],
+                                         a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
+          const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
+          if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
+          if (BB_DEC_ACCEPTED(code)) {
+            const uint64_t sp = base + MT + over;
+            pack_change(a.st_ent + sp * UPD_Q, h.w, ov, oc);
+            a.st_idx[sp] = ui | (code << 29);
+            ++over;
+          } else {
+            a.verdict[ui] = (code << 29) | NO_SLOT;
+          }
+        }
+        sm.over = over;
+      }
+      {
+        uint4 q[ROW_Q];
+        pack_row(q, r);
+#pragma unroll
+        for (int c = 0; c < ROW_Q; ++c) st.row[row_slot(tid, c)] = q[c];
+      }
+      if (INDEXED) {
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+          if (prim[f] != prim0[f]) a.ix.pcol[f][key] = prim[f];
+      }
+    }
+    __syncthreads();
+
+    // ---- drain
+    int first = MT;  // positions before the tile's first head continue a segment an earlier tile owns
+#pragma unroll
+    for (int ww = MT_WARPS - 1; ww >= 0; --ww)
+      if (st.hmask[ww]) first = ww * 32 + __ffs(st.hmask[ww]) - 1;
+    const bool owned = valid && tid >= first;
+    const uint32_t code = owned ? sm.res[tid] : 0xFFu;
+    const bool acc = owned && BB_DEC_ACCEPTED(code);
+    const uint32_t amask = __ballot_sync(0xffffffffu, acc);
+    if (lane == 0) sm.wsum[w] = __popc(amask);
+    __syncthreads();
+    uint32_t rank = __popc(amask & lanemask_lt()), in_cnt = 0, wex = 0;
+#pragma unroll
+    for (int ww = 0; ww < MT_WARPS; ++ww) {
+      const uint32_t c = sm.wsum[ww];
+      if (ww < w) wex += c;
+      in_cnt += c;
+    }
+    rank += wex;
+    const uint32_t over_cnt = sm.over;
+    if (tid == 0)  // the tile claims its slice of the change set
+      sm.ex = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes),
+                                  (unsigned long long)(in_cnt + over_cnt));
+    // rows go while the claim is in flight: nothing about them depends on where the entries land
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+      const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+      if ((hmask >> e) & 1u) a.table[(uint64_t)ekey * ROW_Q + chunk] = st.row[row_slot(wbase + e, chunk)];
+    }
+    __syncthreads();
+    const uint64_t obase = sm.ex;
+
+    bool overflow = false;
+    const uint64_t dest = obase + rank;
+    if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : NO_SLOT);
+    if (acc) {
+      if (dest < a.cap) {
+        a.out_idx[dest] = a.idx_base + idx;
+        a.out_head[dest] = st.upd[tid * UPD_Q];
+      } else {
+        overflow = true;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int e = j * 16 + (lane >> 1), half = lane & 1;
+      const uint64_t edest = obase + wex + __popc(amask & ((1u << e) - 1u));
+      if (((amask >> e) & 1u) && edest < a.cap) {
+        a.out_clk[2 * edest + half] = st.upd[(wbase + e) * UPD_Q + 1 + half];
+        a.out_val[2 * edest + half] = st.upd[(wbase + e) * UPD_Q + 3 + half];
+      }
+    }
+    for (uint32_t k = tid; k < over_cnt; k += MT) {
+      const uint64_t sp = base + MT + k, odest = obase + in_cnt + k;
+      const uint32_t packed = a.st_idx[sp];
+      const uint32_t gi = packed & NO_SLOT;
+      a.verdict[gi] = (packed & ~NO_SLOT) | (uint32_t)odest;
+      if (odest < a.cap) {
+        const uint4* q = a.st_ent + sp * UPD_Q;
+        a.out_idx[odest] = a.idx_base + gi;
+        a.out_head[odest] = q[0];
+        a.out_clk[2 * odest] = q[1];
+        a.out_clk[2 * odest + 1] = q[2];
+        a.out_val[2 * odest] = q[3];
+        a.out_val[2 * odest + 1] = q[4];
+      } else {
+        overflow = true;
+      }
+    }
+    if (overflow) atomicOr(a.err, 2u);
+    __syncthreads();  // the stage is free: the next iteration refills it
+  }
+  cp_async_wait_group<0>();
 }
 
 // ---------------------------------------------------------------- table import / export

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: libnccl.so.2 is opened at run time
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -54,6 +55,7 @@ struct bb_ctx {
   uint4* table = nullptr;
   uint64_t seq = 0;  // updates (and materialising reads) seen so far
   int key_bits = 0;
+  int n_sm = 148;
   uint64_t launches = 0;
   std::string err;
   cudaEvent_t ev[EV_RING][EV_COUNT]{};
@@ -71,7 +73,8 @@ struct bb_ctx {
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
   uint32_t* cs_cnt = nullptr;  // counting sort: per-row update counts (all zero between calls)
-  uint32_t* cs_off = nullptr;  // and their exclusive scan, [capacity + 1] (both padded to 1024)
+  uint32_t* cs_off = nullptr;  // full sort: their exclusive scan, u32[capacity + 1] (both padded to 1024);
+                               // grouping front end: uint2[capacity] = (start, length) of a path's run
   DevBuf<uint2> cs_long;       // segments longer than CS_SHORT, queued for k_cs_fix_long
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
   uint64_t* d_nchanges = nullptr;
@@ -125,6 +128,19 @@ int fail(bb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
+template <bool INDEXED>
+void kernel_pipe_launch(uint32_t grid, size_t smem, cudaStream_t s, const bb::MergeArgs& ma) {
+  static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16 && !configured[dev]) {
+    cudaFuncSetAttribute(bb::k_merge_pipe<INDEXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(bb::k_merge_pipe<INDEXED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured[dev] = true;
+  }
+  bb::k_merge_pipe<INDEXED><<<grid, bb::MT, smem, s>>>(ma);
+}
+
 void begin_call(bb_ctx* c) {
   ++c->calls;
   const int slot = (int)((c->calls - 1) % EV_RING);
@@ -142,9 +158,18 @@ struct ZeroLayout {
   size_t hist, tickets, sort_state, merge_state, cs_state, cs_ctr, total;  // offsets in uint32_t units
 };
 
-// counting sort when the scan over the rows is cheap next to the batch, radix sort otherwise
+// How a batch is brought into "a path's updates adjacent, in arrival order":
+//   grouping (default)  O(batch) passes, singles stay in arrival order (bb_kernels.cuh K1'')
+//   counting sort       BB_CFG_ORDERED_CHANGES / BB_CFG_FULL_SORT, when the scan over the rows is cheap
+//                       next to the batch: the item list is ascending in path id
+//   radix sort          otherwise, or with BB_CFG_RADIX_SORT
+bool use_grouping(const bb_ctx* c) {
+  return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT));
+}
+
 bool use_counting_sort(const bb_ctx* c, uint64_t n) {
   if (c->cfg.flags & BB_CFG_RADIX_SORT) return false;
+  if (use_grouping(c)) return true;  // no radix passes needed either
   return c->cfg.capacity <= 64 * (n < 4096 ? 4096 : n);
 }
 
@@ -161,7 +186,7 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
   z.cs_state = z.merge_state + z.merge_tiles;
   z.cs_ctr = z.cs_state;
-  z.total = z.cs_ctr + 2;
+  z.total = z.cs_ctr + 4;
   return z;
 }
 
@@ -217,7 +242,19 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
 
   uint64_t* src = c->items_a.p;
-  if (use_counting_sort(c, n)) {
+  if (use_grouping(c)) {
+    // K1'': count, then group (singles in arrival order, multi-update paths in claimed runs behind them)
+    const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
+    uint2* off2 = reinterpret_cast<uint2*>(c->cs_off);
+    uint32_t* ctr = zp + z.cs_ctr;
+    BB_LAUNCH(c, k_cs_count, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->d_err);
+    BB_LAUNCH(c, k_cg_classify, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, off2, src,
+              ctr, c->cs_long.p);
+    BB_LAUNCH(c, k_cg_place, g4, CS_THREADS, s, in->path_id, n, c->st_idx.p, off2, c->cs_cnt, src, ctr);
+    BB_LAUNCH(c, k_cg_fix, div_up(n, CS_THREADS), CS_THREADS, s, src, off2, ctr);
+    BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, ctr + CG_CTR_LONG,
+              ctr + CG_CTR_NEXT, ctr + CG_CTR_SINGLE);
+  } else if (use_counting_sort(c, n)) {
     // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
     const uint32_t g = div_up(n, CS_THREADS);
     const uint64_t cap = c->cfg.capacity;
@@ -228,7 +265,7 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     BB_LAUNCH(c, k_cs_place, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->st_idx.p, c->cs_off, src, c->d_err);
     BB_LAUNCH(c, k_cs_fix, g, CS_THREADS, s, src, n, c->cs_off, c->cs_long.p, zp + z.cs_ctr, c->d_err);
     BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, zp + z.cs_ctr,
-              zp + z.cs_ctr + 1);
+              zp + z.cs_ctr + 1, (const uint32_t*)nullptr);
   } else {
     // K0 + K1: stable LSD radix sort of (path id, arrival index) by path id
     BB_LAUNCH(c, k_keys_hist, z.sort_tiles, SORT_THREADS, s, in->path_id, n, c->cfg.capacity, (int)z.passes,
@@ -284,7 +321,16 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     ma.ix.xmask[f] = c->index[f].live ? (uint32_t)(c->index[f].xslots - 1) : 0u;
   }
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
-  if (c->index_mask) {
+  if (!ordered && (c->cfg.flags & BB_CFG_CTA_PIPE)) {
+    // K2': persistent, software-pipelined CTAs (4 per SM)
+    const uint32_t grid = std::min<uint32_t>(z.merge_tiles, (uint32_t)(c->n_sm * MP_CTAS_PER_SM));
+    const size_t smem = sizeof(MergePipeSmem);
+    if (c->index_mask) kernel_pipe_launch<true>(grid, smem, s, ma);
+    else kernel_pipe_launch<false>(grid, smem, s, ma);
+    ++c->launches;
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return fail(c, BB_ERR_CUDA, "k_merge_pipe", e_);
+  } else if (c->index_mask) {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
   } else {
@@ -465,6 +511,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
   c->key_bits = bits;
+  {
+    int n_sm = 0;
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
+  }
   const size_t cs_words = ((size_t)cfg->capacity + 1 + bb::CS_TILE - 1) / bb::CS_TILE * bb::CS_TILE;
   bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -473,7 +523,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->cs_cnt, cs_words * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint2)) == cudaSuccess &&
             cudaMemsetAsync(c->cs_cnt, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
             c->cs_tile.ensure(cs_words / bb::CS_TILE) == cudaSuccess &&

@@ -14,14 +14,17 @@ from . import capi, codec
 
 class Engine:
     def __init__(self, capacity: int, *, local_peer: int = 0, n_fields: int = codec.MAX_FIELDS,
-                 device: int = 0, post_getdata: bool = False, ordered_changes: bool = False, radix_sort: bool = False, rank_object: int = 0, rank_true: int = 0,
+                 device: int = 0, post_getdata: bool = False, ordered_changes: bool = False, radix_sort: bool = False,
+                 full_sort: bool = False, cta_pipe: bool = False, rank_object: int = 0, rank_true: int = 0,
                  rank_false: int = 0, rank_nan: int = 0):
         self.lib = capi.load()
         self.cfg = capi.make_config(
             capacity, n_fields=n_fields, local_peer=local_peer, device=device,
             flags=(codec.CFG_POST_GETDATA if post_getdata else 0)
             | (codec.CFG_ORDERED_CHANGES if ordered_changes else 0)
-            | (codec.CFG_RADIX_SORT if radix_sort else 0), rank_object=rank_object,
+            | (codec.CFG_RADIX_SORT if radix_sort else 0)
+            | (codec.CFG_FULL_SORT if full_sort else 0)
+            | (codec.CFG_CTA_PIPE if cta_pipe else 0), rank_object=rank_object,
             rank_true=rank_true, rank_false=rank_false, rank_nan=rank_nan)
         h = C.c_void_p()
         rc = self.lib.bb_create(C.byref(self.cfg), C.byref(h))

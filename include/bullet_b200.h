@@ -153,6 +153,15 @@ typedef struct bb_config {
 /* Always group a batch by path with the stable LSD radix sort.  By default the library uses a
  * counting sort over the row indices whenever capacity <= 64 x batch size (same result). */
 #define BB_CFG_RADIX_SORT 4u
+/* Always sort a batch by path id (counting sort over the row indices, or the radix sort when the table is
+ * much larger than the batch).  By default the library only GROUPS the batch: updates whose path occurs
+ * once keep their arrival order, the others are gathered into per-path runs (same decisions, table and
+ * change entries; only the layout of the change buffers differs, as described above). */
+#define BB_CFG_FULL_SORT 8u
+/* Merge with k_merge_pipe (persistent CTAs, 4 per SM, each software-pipelining three tiles) instead of
+ * k_merge_stage (one CTA per 128-update tile, 7 per SM).  Same results; measured slower on B200
+ * (0.113 vs 0.100 ms per 1 M updates: fewer resident warps for a latency-bound resolver), kept for A/B runs. */
+#define BB_CFG_CTA_PIPE 32u
 
 typedef struct bb_ctx bb_ctx;
 
