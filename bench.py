@@ -132,12 +132,20 @@ class ClockSampler:
         }
 
 
-def make_workload(args, rank):
+def make_workload(args, rank, world=1):
+    """Table image of one shard (every shard is loaded with the same image) and this rank's batches.
+    Sharded runs keep the per-GPU workload of the single-GPU run (weak scaling): the global table has
+    world x records rows, a batch row drawn for image row r goes to a uniformly drawn owner q as global
+    path id r * world + q (owner = id % world, local row = id // world = r), so every shard still sees
+    ~batch updates spread over all of its `records` rows, with clocks built against the row they hit."""
     from bullet_js_b200 import synth
 
     rng = synth.rng_for(2, salt=rank)
-    table = synth.make_table(args.records, rng)
+    table = synth.make_table(args.records, rng if world == 1 else synth.rng_for(2, salt=1000))
     batches = [synth.make_batch(table, args.batch, rng, keys=args.keys) for _ in range(N_BATCHES)]
+    if world > 1:
+        for b in batches:
+            b.path_id[:] = b.path_id * np.uint64(world) + rng.integers(0, world, b.n).astype(np.uint64)
     return table, batches
 
 
@@ -148,7 +156,7 @@ def run_reference(args, rank, world):
     from bullet_js_b200 import capi, synth
     from oracle.typed import TypedOracle
 
-    table, batches = make_workload(args, 0)
+    table, batches = make_workload(args, 0)  # one rank's share: the single-GPU workload
     cores = os.cpu_count() or 1
     cfg = capi.make_config(args.records, **synth.synth_ranks(args.records))
     orc = TypedOracle(cfg)
@@ -320,7 +328,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    table, batches = make_workload(args, rank)
+    table, batches = make_workload(args, rank, world)
     n, K, W = args.batch, args.steps, args.warmup
     # Every step merges into a PRISTINE copy of the table (one bb_ctx per step, all
     # loaded with the same image): the batches' clocks are built relative to that image,
@@ -440,6 +448,52 @@ def main():
         e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
                "d2h_bytes_per_step": d2h // Ke, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
                "api": "bb_merge_batch (pinned host buffers, synchronous)"}
+    elif world > 1:
+        # sharded e2e: every rank's batch starts in pinned HOST memory; H2D, route (all-to-all over NVLink),
+        # merge on the owning shards, then D2H of the decisions and the change set - all inside the timed region
+        h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
+        hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+        h_ver, h_idx, h_head, h_clk, h_val = hp(4 * cap), hp(4 * cap), hp(16 * cap), hp(32 * cap), hp(32 * cap)
+        stage = tuple(torch.empty_like(x) for x in d_in[0])  # device landing buffers of the H2D copies
+        r_stage = capi.BBBatch(n=n, path_id=stage[0].data_ptr(), head=stage[1].data_ptr(), clk=stage[2].data_ptr(),
+                               val=stage[3].data_ptr())
+        Ke = min(K, 10)
+        for e in engines[: W + Ke]:
+            e.table_load(ids, table.rows)  # pristine again
+
+        def step_e2e(i):
+            for dst, src in zip(stage, h_in[i % N_BATCHES]):
+                dst.copy_(src, non_blocking=True)
+            router.route(r_stage, i % 2, stream)
+            m = router.merge(engines[i], i % 2, cs, stream)
+            k = int(o_n.item())  # D2H of the count (synchronises the stream)
+            h_ver[: 4 * m].copy_(o_ver.view(torch.uint8)[: 4 * m], non_blocking=True)
+            h_idx[: 4 * k].copy_(o_idx.view(torch.uint8)[: 4 * k], non_blocking=True)
+            h_head[: 16 * k].copy_(o_head[: 16 * k], non_blocking=True)
+            h_clk[: 32 * k].copy_(o_clk[: 32 * k], non_blocking=True)
+            h_val[: 32 * k].copy_(o_val[: 32 * k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return m, 4 * m + 8 + 84 * k
+
+        for i in range(W):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = me = 0
+        for i in range(Ke):
+            m, b_ = step_e2e(W + i)
+            me += m
+            d2h += b_
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt, float(me), float(d2h)], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(t[1]) * F / float(tmax[0]), "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
+               "d2h_bytes_per_step": int(float(t[2]) / world / Ke), "ms_per_step": float(tmax[0]) / Ke * 1e3, "steps": Ke,
+               "api": "pinned host batch -> H2D -> bb_router_route_dev -> bb_merge_batch_dev -> D2H of verdicts + change set, "
+                      "per rank, max over ranks"}
     clocks = sampler.stop()
 
     # ---- max over ranks

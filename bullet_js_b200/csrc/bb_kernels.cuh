@@ -1304,9 +1304,12 @@ struct RouteArgs {
 struct RouteP2PArgs {
   const uint64_t* path_id; const uint4* head; const uint4* clk; const uint4* val;  // [n] in
   uint64_t* d_path[RT_MAX_WORLD]; uint4* d_head[RT_MAX_WORLD]; uint4* d_clk[RT_MAX_WORLD]; uint4* d_val[RT_MAX_WORLD];
-  int64_t adj[RT_MAX_WORLD];  // row in the owner's slot = packed position + adj[owner]
+  const uint64_t* matrix;     // [world][world] on the device: row p = what rank p sends to each rank
+  uint64_t slot_cap;          // rows a receive slot holds: nothing is stored if some owner would overflow
+  uint32_t me;
   uint64_t n;
   uint32_t world;
+  uint32_t bulk;  // 1: runs leave with cp.async.bulk (default); 0: with per-thread 16-byte stores
   const uint32_t* tile_off;
 };
 
@@ -1324,7 +1327,30 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
   __shared__ uint32_t s_start[RT_MAX_WORLD + 1];
   __shared__ int64_t s_dst[RT_MAX_WORLD];  // destination row of the owner's run minus its start in the tile
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + tid;
+  // where this rank's block starts in every owner's slot comes from the all-gathered counts ON THE DEVICE:
+  // the host never waits for them (row in the owner's slot = packed position + adj[owner])
+  __shared__ int64_t s_adj[RT_MAX_WORLD];
+  __shared__ uint32_t s_bad;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  if (tid < (int)a.world) {
+    uint64_t before = 0, so = 0, col = 0;
+    for (uint32_t p = 0; p < a.world; ++p) {
+      const uint64_t c = a.matrix[(uint64_t)p * a.world + tid];
+      col += c;
+      if (p < a.me) before += c;
+    }
+    for (int q = 0; q < tid; ++q) so += a.matrix[(uint64_t)a.me * a.world + q];
+    s_adj[tid] = (int64_t)before - (int64_t)so;
+    if (col > a.slot_cap) s_bad = 1;
+  }
+  __syncthreads();
+  if (s_bad) return;  // every rank sees the same matrix and skips; bb_router_acquire reports it
+  // PERSISTENT on a small grid (bb_router: 64 CTAs): the kernel is NVLink-bound and runs next to the
+  // merge of the previous batch; one CTA per tile would take every SM's thread slots away from it
+  const uint32_t tiles = (uint32_t)((a.n + RT_THREADS - 1) / RT_THREADS);
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
   const uint64_t p = i < a.n ? a.path_id[i] : 0;
   const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
   uint4 h, c0, c1, v0, v1;
@@ -1346,7 +1372,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
     uint32_t run = 0;
     for (uint32_t r = 0; r < a.world; ++r) {
       s_start[r] = run;
-      s_dst[r] = (int64_t)a.tile_off[(uint64_t)blockIdx.x * a.world + r] + a.adj[r] - (int64_t)run;
+      s_dst[r] = (int64_t)a.tile_off[(uint64_t)tile * a.world + r] + s_adj[r] - (int64_t)run;
       for (int ww = 0; ww < RT_THREADS / 32; ++ww) run += s_w[ww][r];
     }
     s_start[a.world] = run;
@@ -1364,6 +1390,40 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
   }
   __syncthreads();
   const uint32_t rows = s_start[a.world];
+  if (a.bulk) {
+    // Every (owner, array) run is contiguous in shared memory and in the owner's slot: ONE bulk copy each
+    // (cp.async.bulk shared -> global, to peer memory over NVLink).  The copy engine of the SM moves the
+    // bytes; no thread, register or LSU slot waits for the remote stores, so a handful of CTAs keeps
+    // NVLink busy and the merge kernel running next to them keeps its SMs to itself.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the partition above was written with st.shared
+    if (tid < (int)(3 * a.world)) {
+      const uint32_t r = tid / 3, arr = tid % 3;
+      const uint32_t first = s_start[r], cnt = s_start[r + 1] - first;
+      if (cnt) {
+        const uint64_t drow = (uint64_t)(s_dst[r] + (int64_t)first);
+        const void* src;
+        void* dst;
+        uint32_t bytes;
+        if (arr == 0) {
+          src = s_head + first, dst = a.d_head[r] + drow, bytes = cnt * 16u;
+        } else if (arr == 1) {
+          src = s_clk + 2 * first, dst = a.d_clk[r] + 2 * drow, bytes = cnt * 32u;
+        } else {
+          src = s_val + 2 * first, dst = a.d_val[r] + 2 * drow, bytes = cnt * 32u;
+        }
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                     "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(bytes)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (tid < (int)rows) {  // the 8-byte local row ids: runs are not 16-byte aligned, plain stores
+      uint32_t r = 0;
+      while ((uint32_t)tid >= s_start[r + 1]) ++r;
+      a.d_path[r][(uint64_t)(s_dst[r] + (int64_t)tid)] = s_path[tid];
+    }
+    if (tid < (int)(3 * a.world)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // sources read: reusable
+  } else {
   {  // rows of the tile in partitioned order: thread j moves row j
     const uint32_t j = tid;
     if (j < rows) {
@@ -1385,6 +1445,10 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
       a.d_val[r][dst] = s_val[e];
     }
   }
+  }
+  __syncthreads();  // shared memory is reused by the next tile
+  }
+  if (a.bulk && tid < (int)(3 * a.world)) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes done
 }
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_scatter(const RouteArgs a) {

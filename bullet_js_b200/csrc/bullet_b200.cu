@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -995,9 +996,14 @@ struct bb_router {
   uint64_t* d_bar = nullptr;      // [1 + world] barrier token + gather target
   uint64_t* d_counts = nullptr;   // [world] this rank's send counts
   uint64_t* d_matrix = nullptr;   // [world][world] everybody's
-  uint64_t* h_matrix = nullptr;   // pinned
+  uint64_t* h_matrix = nullptr;   // pinned [2][world][world]: one copy per receive slot
+  cudaEvent_t counts_ev[2]{};     // the slot's copy of the matrix has landed on the host
+  bool pending[2]{};              // n_recv[slot] still to be derived from it (bb_router_acquire)
+  uint64_t routed_n[2]{};
   uint32_t* tiles = nullptr;
   uint64_t sent_bytes = 0, launches = 0;
+  uint32_t scatter_ctas = 64;  // grid of the fused pack + exchange kernel (env BB_ROUTE_CTAS)
+  bool bulk = true;            // runs leave with cp.async.bulk (env BB_ROUTE_BULK=0: per-thread stores)
   cudaEvent_t tev[5]{};   // telemetry of the last route: start, packed, counts known, exchanged, own rows copied
   double host_ms[2]{};    // host time of the last route: until the counts are known, whole call
   std::string err;
@@ -1120,6 +1126,8 @@ int bb_router_destroy(bb_router* r) {
   if (r->d_counts) cudaFree(r->d_counts);
   if (r->d_matrix) cudaFree(r->d_matrix);
   if (r->h_matrix) cudaFreeHost(r->h_matrix);
+  for (int i = 0; i < 2; ++i)
+    if (r->counts_ev[i]) cudaEventDestroy(r->counts_ev[i]);
   if (r->tiles) cudaFree(r->tiles);
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
@@ -1137,6 +1145,11 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
   bb_router* r = new (std::nothrow) bb_router();
   if (!r) return rfail(nullptr, BB_ERR_ARG, "out of host memory");
   r->device = device;
+  if (const char* e = getenv("BB_ROUTE_CTAS")) {
+    const long v = strtol(e, nullptr, 10);
+    if (v > 0 && v < 65536) r->scatter_ctas = (uint32_t)v;
+  }
+  if (const char* e = getenv("BB_ROUTE_BULK")) r->bulk = e[0] != '0';
   r->world = world;
   r->rank = rank;
   r->max_batch = max_batch;
@@ -1148,7 +1161,9 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
             cudaMalloc((void**)&r->d_counts, world * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&r->d_bar, (1 + world) * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&r->d_matrix, (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
-            cudaMallocHost((void**)&r->h_matrix, (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&r->h_matrix, 2 * (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaEventCreateWithFlags(&r->counts_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&r->counts_ev[1], cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc((void**)&r->tiles, (size_t)div_up(max_batch, bb::RT_THREADS) * world * sizeof(uint32_t)) == cudaSuccess;
   for (int k = 0; ok && k < 4; ++k) {
     ok = cudaMalloc((void**)&r->send[k], max_batch * ROUTE_W[k]) == cudaSuccess;
@@ -1210,20 +1225,14 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
   cudaEventRecord(r->tev[1], s);
   // everybody's counts: row q = what rank q sends to each rank
   BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
-  BB_RCUDA(r, cudaMemcpyAsync(r->h_matrix, r->d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
+  BB_RCUDA(r, cudaMemcpyAsync(hm, r->d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   cudaEventRecord(r->tev[2], s);
-  BB_RCUDA(r, cudaStreamSynchronize(s));  // the one host round trip of a step
-  r->host_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-  uint64_t so[bb::RT_MAX_WORLD + 1], ro[bb::RT_MAX_WORLD + 1];
-  so[0] = ro[0] = 0;
-  for (uint32_t q = 0; q < W; ++q) {
-    so[q + 1] = so[q] + r->h_matrix[(size_t)me * W + q];
-    ro[q + 1] = ro[q] + r->h_matrix[(size_t)q * W + me];
-  }
-  if (ro[W] > r->cap) return rfail(r, BB_ERR_CAPACITY, "receive slot too small for this batch");
   if (r->p2p) {
-    // Fused pack + exchange.  Nobody stores into a slot before everyone has passed the counts
-    // all-gather above, i.e. before every owner has finished merging what the slot held.
+    // Fused pack + exchange, fully asynchronous: the scatter kernel reads the all-gathered counts on the
+    // device, the host picks its copy up in bb_router_acquire.  Nobody stores into a slot before everyone
+    // has passed the counts all-gather above, i.e. before every owner has finished merging what it held.
+    BB_RCUDA(r, cudaEventRecord(r->counts_ev[slot], s));
     if (n) {
       bb::RouteP2PArgs a;
       a.path_id = in->path_id;
@@ -1235,14 +1244,15 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
         a.d_head[q] = reinterpret_cast<uint4*>(r->peer[q][slot][1]);
         a.d_clk[q] = reinterpret_cast<uint4*>(r->peer[q][slot][2]);
         a.d_val[q] = reinterpret_cast<uint4*>(r->peer[q][slot][3]);
-        uint64_t before = 0;  // rows ranks < me send to q: where my block starts in q's slot
-        for (uint32_t p = 0; p < me; ++p) before += r->h_matrix[(size_t)p * W + q];
-        a.adj[q] = (int64_t)before - (int64_t)so[q];
       }
+      a.matrix = r->d_matrix;
+      a.slot_cap = r->cap;
+      a.me = me;
       a.n = n;
       a.world = W;
+      a.bulk = r->bulk ? 1u : 0u;
       a.tile_off = r->tiles;
-      bb::k_route_scatter_p2p<<<tiles, bb::RT_THREADS, bb::RT_SMEM, s>>>(a);
+      bb::k_route_scatter_p2p<<<std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s>>>(a);
       r->launches += 1;
       BB_RCUDA(r, cudaGetLastError());
     }
@@ -1251,12 +1261,21 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
     if (W > 1) BB_RNCCL(r, g_nccl.AllGather(r->d_bar, r->d_bar + 1, 1, ncclUint64, r->comm, s));
     cudaEventRecord(r->tev[4], s);
     BB_RCUDA(r, cudaEventRecord(r->ready[slot], s));
-    r->host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-    r->sent_bytes += (so[W] - (so[me + 1] - so[me])) * 88;
-    r->n_recv[slot] = ro[W];
-    *n_recv = ro[W];
+    r->host_ms[0] = r->host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    r->pending[slot] = true;
+    r->routed_n[slot] = n;
+    *n_recv = ~0ull;  // not known on the host yet: bb_router_acquire returns it
     return BB_OK;
   }
+  BB_RCUDA(r, cudaStreamSynchronize(s));  // NCCL send/recv path: the host needs the counts to post the exchange
+  r->host_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+  uint64_t so[bb::RT_MAX_WORLD + 1], ro[bb::RT_MAX_WORLD + 1];
+  so[0] = ro[0] = 0;
+  for (uint32_t q = 0; q < W; ++q) {
+    so[q + 1] = so[q] + hm[(size_t)me * W + q];
+    ro[q + 1] = ro[q] + hm[(size_t)q * W + me];
+  }
+  if (ro[W] > r->cap) return rfail(r, BB_ERR_CAPACITY, "receive slot too small for this batch");
   BB_RNCCL(r, g_nccl.GroupStart());
   for (int k = 0; k < 4; ++k) {
     const size_t w = ROUTE_W[k];
@@ -1286,6 +1305,24 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received) {
   if (!r || !received || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
   BB_RCUDA(r, cudaSetDevice(r->device));
+  if (r->pending[slot]) {  // the counts of this slot's route: long on the host by now
+    BB_RCUDA(r, cudaEventSynchronize(r->counts_ev[slot]));
+    const uint32_t W = r->world, me = r->rank;
+    const uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
+    uint64_t recv = 0, sent = 0;
+    bool fits = true;
+    for (uint32_t q = 0; q < W; ++q) {
+      recv += hm[(size_t)q * W + me];
+      if (q != me) sent += hm[(size_t)me * W + q];
+      uint64_t col = 0;
+      for (uint32_t p = 0; p < W; ++p) col += hm[(size_t)p * W + q];
+      fits = fits && col <= r->cap;
+    }
+    r->pending[slot] = false;
+    if (!fits) return rfail(r, BB_ERR_CAPACITY, "receive slot too small for this batch (nothing was exchanged)");
+    r->n_recv[slot] = recv;
+    r->sent_bytes += sent * 88;
+  }
   BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
   received->n = r->n_recv[slot];
   received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);

@@ -104,7 +104,8 @@ class Router:
             raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(self._h) or b"").decode())
 
     def route(self, bs: capi.BBBatch, slot: int, in_stream: int = 0) -> int:
-        """Collective: pack the device batch by owner and exchange it into receive slot `slot`."""
+        """Collective: pack the device batch by owner and exchange it into receive slot `slot`.  Asynchronous when
+        the peers' slots are mapped (P2P): the received count is then only known in `merge` (returns 2**64 - 1)."""
         import ctypes as C
 
         n = C.c_uint64(0)
