@@ -1315,6 +1315,75 @@ struct RouteP2PArgs {
 
 // Each CTA partitions its 1024 rows by owner in shared memory (88 KB), then streams every owner's
 // run out with fully coalesced 16-byte stores: one contiguous run per (tile, owner, array).
+// ---- signalling between the ranks' routers through peer-mapped memory (one RouteCtl per rank)
+// The two tiny collectives of a route (everybody's counts before the scatter, "all my stores have
+// landed" after it) cost 25-40 us each as NCCL all-gathers at 8 GPUs, on the critical path of the step.
+// Here a rank stores its words straight into every peer's control block, then a flag (after a
+// system-scope fence), and spins on its own flags: a few microseconds.  Flags carry the route's
+// epoch and only grow, so a peer that is already one route ahead never confuses a waiter.
+struct RouteCtl {
+  uint64_t matrix[2][RT_MAX_WORLD * RT_MAX_WORLD];  // [slot][source rank][destination rank]
+  uint64_t cflag[2][RT_MAX_WORLD];                  // [slot][source]: that source's counts row is in
+  uint64_t bflag[2][RT_MAX_WORLD];                  // [slot][source]: that source's rows have landed
+  uint64_t err;
+};
+
+struct RouteCtlPeers {
+  RouteCtl* ctl[RT_MAX_WORLD];  // [rank]; our own entry is local memory
+};
+
+constexpr long long RT_SPIN_LIMIT = 120000000000ll;  // ~60 s of SM clocks: a peer died; fail loudly instead of hanging
+
+__device__ __forceinline__ uint64_t ld_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until(const uint64_t* flag, uint64_t epoch, uint64_t* err) {
+  const long long t0 = clock64();
+  while (ld_sys(flag) < epoch) {
+    if (clock64() - t0 > RT_SPIN_LIMIT) {
+      st_sys(err, 1);
+      __trap();
+    }
+    __nanosleep(64);
+  }
+}
+
+// counts[W] of this rank -> row `me` of everybody's matrix, then wait for everybody's row
+__global__ void __launch_bounds__(RT_MAX_WORLD * RT_MAX_WORLD) k_route_publish(const uint64_t* __restrict__ counts,
+                                                                                RouteCtlPeers peers, uint32_t me, uint32_t world,
+                                                                                uint32_t slot, uint64_t epoch) {
+  const uint32_t t = threadIdx.x;
+  if (t < world * world) {
+    const uint32_t q = t / world, j = t % world;
+    st_sys(&peers.ctl[q]->matrix[slot][(uint64_t)me * world + j], counts[j]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < world) {
+    __threadfence_system();
+    st_sys(&peers.ctl[t]->cflag[slot][me], epoch);
+    spin_until(&peers.ctl[me]->cflag[slot][t], epoch, &peers.ctl[me]->err);
+  }
+  __threadfence_system();
+}
+
+// "every store of my scatter kernel has landed" to everybody, then wait for everybody's
+__global__ void __launch_bounds__(32) k_route_barrier(RouteCtlPeers peers, uint32_t me, uint32_t world, uint32_t slot,
+                                                      uint64_t epoch) {
+  const uint32_t t = threadIdx.x;
+  if (t < world) {
+    __threadfence_system();  // cumulative: the previous kernel's stores (visible to this thread) go first
+    st_sys(&peers.ctl[t]->bflag[slot][me], epoch);
+    spin_until(&peers.ctl[me]->bflag[slot][t], epoch, &peers.ctl[me]->err);
+  }
+  __threadfence_system();
+}
+
 constexpr int RT_SMEM = RT_THREADS * 88;
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2PArgs a) {

@@ -1004,6 +1004,15 @@ struct bb_router {
   uint64_t sent_bytes = 0, launches = 0;
   uint32_t scatter_ctas = 64;  // grid of the fused pack + exchange kernel (env BB_ROUTE_CTAS)
   bool bulk = true;            // runs leave with cp.async.bulk (env BB_ROUTE_BULK=0: per-thread stores)
+  bool flag_sync = true;       // counts / completion through peer-mapped flags (env BB_ROUTE_NCCL_SYNC=1: NCCL all-gathers)
+  bb::RouteCtl* ctl = nullptr; // this rank's control block (peer-mapped by everybody)
+  bb::RouteCtlPeers ctl_peers{};
+  uint64_t epoch = 0;
+  // two-stream route (flag_sync): `prep` counts + publishes the next batch while `stream` still exchanges
+  cudaStream_t prep = nullptr;
+  uint32_t* tiles2[2]{};          // per-slot tile offsets (the scatter of one batch and the count of the next overlap)
+  uint64_t* d_counts2[2]{};
+  cudaEvent_t prep_done[2]{};
   cudaEvent_t tev[5]{};   // telemetry of the last route: start, packed, counts known, exchanged, own rows copied
   double host_ms[2]{};    // host time of the last route: until the counts are known, whole call
   std::string err;
@@ -1039,12 +1048,13 @@ void router_map_peers(bb_router* r) {
     for (int k = 0; k < 4; ++k) r->peer[me][sl][k] = r->recv[sl][k];
   r->p2p = false;
   if (getenv("BB_ROUTER_NO_P2P")) return;
+  r->ctl_peers.ctl[me] = r->ctl;
   if (W == 1) {
     r->p2p = true;
     return;
   }
   constexpr size_t HB = sizeof(cudaIpcMemHandle_t);
-  const size_t mine = 8 * HB;
+  const size_t mine = 9 * HB;  // 2 slots x 4 arrays + the control block
   std::string host(mine * W, '\0');
   char* d_all = nullptr;
   bool ok = cudaMalloc((void**)&d_all, mine * W) == cudaSuccess;
@@ -1054,6 +1064,12 @@ void router_map_peers(bb_router* r) {
       ok = cudaIpcGetMemHandle(&h, r->recv[sl][k]) == cudaSuccess;
       memcpy(&host[mine * me + (sl * 4 + k) * HB], &h, HB);
     }
+  if (ok) {
+    cudaIpcMemHandle_t h;
+    ok = cudaIpcGetMemHandle(&h, r->ctl) == cudaSuccess;
+    memcpy(&host[mine * me + 8 * HB], &h, HB);
+  }
+  r->ctl_peers.ctl[me] = r->ctl;
   ok = ok && cudaMemcpyAsync(d_all + mine * me, &host[mine * me], mine, cudaMemcpyHostToDevice, r->stream) == cudaSuccess;
   // every rank must take part in the collective even if its own handles failed
   const bool sent = g_nccl.AllGather(d_all ? d_all + mine * me : nullptr, d_all, mine, ncclUint8, r->comm, r->stream) == ncclSuccess;
@@ -1061,12 +1077,13 @@ void router_map_peers(bb_router* r) {
        cudaStreamSynchronize(r->stream) == cudaSuccess;
   for (uint32_t q = 0; ok && q < W; ++q) {
     if (q == me) continue;
-    for (int j = 0; ok && j < 8; ++j) {
+    for (int j = 0; ok && j < 9; ++j) {
       cudaIpcMemHandle_t h;
       memcpy(&h, &host[mine * q + j * HB], HB);
       void* p = nullptr;
       ok = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-      r->peer[q][j / 4][j % 4] = (char*)p;
+      if (j < 8) r->peer[q][j / 4][j % 4] = (char*)p;
+      else r->ctl_peers.ctl[q] = reinterpret_cast<bb::RouteCtl*>(p);
     }
   }
   if (d_all) cudaFree(d_all);
@@ -1125,6 +1142,13 @@ int bb_router_destroy(bb_router* r) {
   if (r->d_bar) cudaFree(r->d_bar);
   if (r->d_counts) cudaFree(r->d_counts);
   if (r->d_matrix) cudaFree(r->d_matrix);
+  if (r->ctl) cudaFree(r->ctl);
+  if (r->prep) cudaStreamDestroy(r->prep);
+  for (int i = 0; i < 2; ++i) {
+    if (r->tiles2[i]) cudaFree(r->tiles2[i]);
+    if (r->d_counts2[i]) cudaFree(r->d_counts2[i]);
+    if (r->prep_done[i]) cudaEventDestroy(r->prep_done[i]);
+  }
   if (r->h_matrix) cudaFreeHost(r->h_matrix);
   for (int i = 0; i < 2; ++i)
     if (r->counts_ev[i]) cudaEventDestroy(r->counts_ev[i]);
@@ -1150,6 +1174,7 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
     if (v > 0 && v < 65536) r->scatter_ctas = (uint32_t)v;
   }
   if (const char* e = getenv("BB_ROUTE_BULK")) r->bulk = e[0] != '0';
+  if (const char* e = getenv("BB_ROUTE_NCCL_SYNC")) r->flag_sync = e[0] == '0';
   r->world = world;
   r->rank = rank;
   r->max_batch = max_batch;
@@ -1161,6 +1186,9 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
             cudaMalloc((void**)&r->d_counts, world * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&r->d_bar, (1 + world) * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&r->d_matrix, (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&r->ctl, sizeof(bb::RouteCtl)) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&r->prep, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+            cudaMemset(r->ctl, 0, sizeof(bb::RouteCtl)) == cudaSuccess &&
             cudaMallocHost((void**)&r->h_matrix, 2 * (size_t)world * world * sizeof(uint64_t)) == cudaSuccess &&
             cudaEventCreateWithFlags(&r->counts_ev[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&r->counts_ev[1], cudaEventDisableTiming) == cudaSuccess &&
@@ -1170,6 +1198,10 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
     for (int sl = 0; ok && sl < 2; ++sl) ok = cudaMalloc((void**)&r->recv[sl][k], r->cap * ROUTE_W[k]) == cudaSuccess;
   }
   for (int i = 0; ok && i < 5; ++i) ok = cudaEventCreate(&r->tev[i]) == cudaSuccess;
+  for (int sl = 0; ok && sl < 2; ++sl)
+    ok = cudaMalloc((void**)&r->tiles2[sl], (size_t)div_up(max_batch, bb::RT_THREADS) * world * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMalloc((void**)&r->d_counts2[sl], world * sizeof(uint64_t)) == cudaSuccess &&
+         cudaEventCreateWithFlags(&r->prep_done[sl], cudaEventDisableTiming) == cudaSuccess;
   for (int sl = 0; ok && sl < 2; ++sl)
     ok = cudaEventCreateWithFlags(&r->ready[sl], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&r->merged[sl], cudaEventDisableTiming) == cudaSuccess;
@@ -1201,17 +1233,26 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
   BB_RCUDA(r, cudaSetDevice(r->device));
   cudaStream_t s = r->stream;
   const uint32_t W = r->world, me = r->rank;
+  const bool flags = r->p2p && r->flag_sync && W > 1;
+  // flag-sync mode: counting and publishing this batch run on `prep`, concurrently with the exchange of the
+  // previous batch on `stream`; they may start once the previous route on this slot has finished EVERYWHERE
+  // (ready[slot] follows its barrier): until then some peer may still read that route's counts
+  cudaStream_t sp = flags ? r->prep : s;
+  uint32_t* tile_buf = flags ? r->tiles2[slot] : r->tiles;
+  uint64_t* cnt_buf = flags ? r->d_counts2[slot] : r->d_counts;
   if (in_stream) {
     BB_RCUDA(r, cudaEventRecord(r->ev_in, (cudaStream_t)in_stream));
-    BB_RCUDA(r, cudaStreamWaitEvent(s, r->ev_in, 0));
+    BB_RCUDA(r, cudaStreamWaitEvent(sp, r->ev_in, 0));
+    if (flags) BB_RCUDA(r, cudaStreamWaitEvent(s, r->ev_in, 0));
   }
+  if (flags) BB_RCUDA(r, cudaStreamWaitEvent(sp, r->ready[slot], 0));
   BB_RCUDA(r, cudaStreamWaitEvent(s, r->merged[slot], 0));  // the merge that last read this slot is done
   const auto h0 = std::chrono::steady_clock::now();
-  cudaEventRecord(r->tev[0], s);
+  cudaEventRecord(r->tev[0], sp);
   const uint32_t tiles = div_up(n, bb::RT_THREADS);
   if (n && r->p2p) {  // the scatter waits until every rank's counts are known
-    bb::k_route_count<<<tiles, bb::RT_THREADS, 0, s>>>(in->path_id, n, W, r->tiles);
-    bb::k_route_scan<<<1, bb::RS_THREADS, 0, s>>>(r->tiles, tiles, W, r->d_counts);
+    bb::k_route_count<<<tiles, bb::RT_THREADS, 0, sp>>>(in->path_id, n, W, tile_buf);
+    bb::k_route_scan<<<1, bb::RS_THREADS, 0, sp>>>(tile_buf, tiles, W, cnt_buf);
     r->launches += 2;
     BB_RCUDA(r, cudaGetLastError());
   } else if (n) {
@@ -1220,19 +1261,33 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
     BB_RCUDA(r, launch_pack(W, in, &packed, r->d_counts, r->tiles, s));
     r->launches += 3;
   } else {
-    BB_RCUDA(r, cudaMemsetAsync(r->d_counts, 0, W * sizeof(uint64_t), s));
+    BB_RCUDA(r, cudaMemsetAsync(cnt_buf, 0, W * sizeof(uint64_t), sp));
   }
-  cudaEventRecord(r->tev[1], s);
+  cudaEventRecord(r->tev[1], sp);
   // everybody's counts: row q = what rank q sends to each rank
-  BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
+  const uint64_t epoch = ++r->epoch;
+  const uint64_t* d_matrix = r->d_matrix;
+  if (flags) {
+    bb::k_route_publish<<<1, bb::RT_MAX_WORLD * bb::RT_MAX_WORLD, 0, sp>>>(cnt_buf, r->ctl_peers, me, W, slot, epoch);
+    r->launches += 1;
+    BB_RCUDA(r, cudaGetLastError());
+    d_matrix = r->ctl->matrix[slot];
+  } else {
+    BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
+  }
   uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
-  BB_RCUDA(r, cudaMemcpyAsync(hm, r->d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  BB_RCUDA(r, cudaMemcpyAsync(hm, d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, sp));
+  if (flags) {
+    BB_RCUDA(r, cudaEventRecord(r->counts_ev[slot], sp));
+    BB_RCUDA(r, cudaEventRecord(r->prep_done[slot], sp));
+    BB_RCUDA(r, cudaStreamWaitEvent(s, r->prep_done[slot], 0));
+  }
   cudaEventRecord(r->tev[2], s);
   if (r->p2p) {
     // Fused pack + exchange, fully asynchronous: the scatter kernel reads the all-gathered counts on the
     // device, the host picks its copy up in bb_router_acquire.  Nobody stores into a slot before everyone
     // has passed the counts all-gather above, i.e. before every owner has finished merging what it held.
-    BB_RCUDA(r, cudaEventRecord(r->counts_ev[slot], s));
+    if (!flags) BB_RCUDA(r, cudaEventRecord(r->counts_ev[slot], s));
     if (n) {
       bb::RouteP2PArgs a;
       a.path_id = in->path_id;
@@ -1245,20 +1300,26 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
         a.d_clk[q] = reinterpret_cast<uint4*>(r->peer[q][slot][2]);
         a.d_val[q] = reinterpret_cast<uint4*>(r->peer[q][slot][3]);
       }
-      a.matrix = r->d_matrix;
+      a.matrix = d_matrix;
       a.slot_cap = r->cap;
       a.me = me;
       a.n = n;
       a.world = W;
       a.bulk = r->bulk ? 1u : 0u;
-      a.tile_off = r->tiles;
+      a.tile_off = tile_buf;
       bb::k_route_scatter_p2p<<<std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s>>>(a);
       r->launches += 1;
       BB_RCUDA(r, cudaGetLastError());
     }
     cudaEventRecord(r->tev[3], s);
-    // every rank's stores are complete when its scatter kernel is: a tiny collective is the barrier
-    if (W > 1) BB_RNCCL(r, g_nccl.AllGather(r->d_bar, r->d_bar + 1, 1, ncclUint64, r->comm, s));
+    // every rank's stores are complete when its scatter kernel is: a barrier across the ranks follows
+    if (flags) {
+      bb::k_route_barrier<<<1, 32, 0, s>>>(r->ctl_peers, me, W, slot, epoch);
+      r->launches += 1;
+      BB_RCUDA(r, cudaGetLastError());
+    } else if (W > 1) {
+      BB_RNCCL(r, g_nccl.AllGather(r->d_bar, r->d_bar + 1, 1, ncclUint64, r->comm, s));
+    }
     cudaEventRecord(r->tev[4], s);
     BB_RCUDA(r, cudaEventRecord(r->ready[slot], s));
     r->host_ms[0] = r->host_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
