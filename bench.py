@@ -64,6 +64,18 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel, expect_default):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
+    (profiles/traffic.json, written by scripts/make_profiles.py); null when the run is not the captured workload."""
+    if not expect_default:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[kernel]["bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -284,7 +296,8 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
                       "api": "bb_query_range (host hit buffer, synchronous)"},
         "roofline": {"bound": "hbm", "kernel": "k_index_scan", "unit": "GB/s", "peak": peak,
                      "achieved": (8.0 * nq + 4.0 * out["range"]["hits"]) / (out["range"]["scan_ms"] * 1e-3) / 1e9,
-                     "bytes_per_row": 8.0 + 4.0 * out["range"]["hits"] / nq, "kernel_ms": out["range"]["scan_ms"]},
+                     "bytes_per_row": 8.0 + 4.0 * out["range"]["hits"] / nq, "kernel_ms": out["range"]["scan_ms"],
+                     "traffic": ncu_traffic("k_index_scan", world == 1 and nq == 100_000_000)},
     }
     res["roofline"]["frac"] = res["roofline"]["achieved"] / peak
     for k in ("allgather_ms", "allgather_bytes"):
@@ -548,7 +561,11 @@ def main():
             "updates_per_sec": merged_total / (dev_ms * 1e-3),
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_merge_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic("k_merge_stage", world == 1 and args.records == N_RECORDS and args.batch == BATCH
+                                                and args.keys == "uniform" and args.front_end == "group"
+                                                and args.merge_kernel == "stage"),
+                         "algorithmic_bytes_per_launch": bytes_per_update * per_launch_updates, "peak_source": peak_src,
                          "bytes_per_update": bytes_per_update, "accepted_frac": acc_frac,
                          "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],
                          "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
