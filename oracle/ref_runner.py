@@ -125,6 +125,12 @@ class JSRefBullet:
     def changes(self):
         return to_py(self._trace.get("changes"))
 
+    def n_changes(self) -> int:
+        return len(self._trace.get("changes").items)
+
+    def last_change(self):
+        return to_py(self._trace.get("changes").items[-1])
+
     @property
     def store(self):
         return to_py(self.bullet.get("store"))

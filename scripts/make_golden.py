@@ -10,6 +10,9 @@ Fixtures (all inputs are regenerated deterministically or stored alongside the o
                    `bullet.setData` / `BulletNetworkSync._processSyncEntries`: per-update decision,
                    ordered change set, final store / meta clocks / crt.vectorClocks / aliasing, the
                    index Maps in their exact (Map, Set) order, equals / count / range results.
+  mesh.json.gz     BASELINE config 5 in miniature: 4 peers in a full mesh (tests/meshsim.py), every peer an
+                   instance of the reference; per-peer logs (own puts interleaved with received broadcasts),
+                   decisions, change sets and final replicas.
   config1.json.gz  BASELINE config 1 at full size (10 000 records, 100 000 updates of the synthetic
                    typed schema, then equals(users, role, admin)): decisions, SHA-256 of the change
                    set and of the final table in a canonical text form, and the query results.
@@ -205,6 +208,24 @@ def stream_cases():
     return out
 
 
+# ----------------------------------------------------------------------------- config 5 in miniature: a mesh of peers
+def mesh_case(n_peers=4, n_ops=600, n_paths=10, seed=42):
+    from tests import meshsim
+    peers, logs = meshsim.run_mesh(lambda i: JSRefBullet(i, enable_indexing=False), n_peers, n_ops, n_paths, seed)
+    out = dict(n_peers=n_peers, n_ops=n_ops, n_paths=n_paths, seed=seed, peers=[])
+    for js, log in zip(peers, logs):
+        d = js.decisions
+        entry = dict(
+            id=js.id,
+            log=[[p, jsonable(v), None if c is None else list(map(list, c.items()))] for p, v, c in log],
+            codes="".join(str(x["code"]) for x in d),
+            changes=[[c["seq"], c["path"], jsonable(c["value"]), list(map(list, c["vectorClock"].items())),
+                      c["fromNetwork"]] for c in js.changes])
+        entry.update(snapshot_state(js, with_index=False))
+        out["peers"].append(entry)
+    return out
+
+
 # ----------------------------------------------------------------------------- config 1 (typed synthetic schema)
 def canonical_value(v):
     return json.dumps(jsonable(v), separators=(",", ":"), ensure_ascii=True)
@@ -293,7 +314,7 @@ def config1_case(n_records=10_000, n_updates=100_000, chunk=50):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["kat", "streams", "config1"])
+    ap.add_argument("--only", choices=["kat", "streams", "config1", "mesh"])
     ap.add_argument("--config1-updates", type=int, default=100_000)
     args = ap.parse_args()
     if not ref_runner.available():
@@ -303,6 +324,8 @@ def main():
         write("kat.json.gz", dict(reference=ident, cases=kat_cases()))
     if args.only in (None, "streams"):
         write("streams.json.gz", dict(reference=ident, cases=stream_cases()))
+    if args.only in (None, "mesh"):
+        write("mesh.json.gz", dict(reference=ident, case=mesh_case()))
     if args.only in (None, "config1"):
         write("config1.json.gz", dict(reference=ident, case=config1_case(n_updates=args.config1_updates)))
 
