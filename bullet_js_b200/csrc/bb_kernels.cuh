@@ -262,7 +262,11 @@ constexpr int CS_ILP = 4;  // independent atomics / gathers in flight per thread
 
 __global__ void __launch_bounds__(CS_THREADS) k_cs_count(const uint64_t* __restrict__ path_id, uint64_t n,
                                                          uint64_t capacity, uint32_t* __restrict__ cnt,
-                                                         uint32_t* __restrict__ rank, uint32_t* __restrict__ err) {
+                                                         uint32_t* __restrict__ rank, uint32_t* __restrict__ err,
+                                                         uint32_t* __restrict__ zero4, uint64_t* __restrict__ zero_n) {
+  // first kernel of a batch: it also resets the few words later kernels accumulate into (saves two memsets)
+  if (blockIdx.x == 0 && threadIdx.x < 4 && zero4) zero4[threadIdx.x] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && zero_n) *zero_n = 0;
   const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + threadIdx.x;
   uint64_t pid[CS_ILP];
   uint32_t r[CS_ILP];

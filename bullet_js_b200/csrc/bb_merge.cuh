@@ -201,13 +201,20 @@ __device__ __forceinline__ uint32_t resolve_step(const Params& p, RowState& r, b
     out_clk = r.v;
     code = BB_DEC_NO_CURRENT;
   } else {
-    bool d1 = false, d2 = false;
+    // compareVectorClocks (crt:68-95) and mergeVectorClocks (crt:103-114) in one pass over the slots; the
+    // key-order work of the merge is only needed when current has a key incoming lacks (rare)
+    bool d1 = false, d2 = false, fresh = false;
 #pragma unroll
     for (int s = 0; s < P; ++s) {
-      d1 |= inc.cnt[s] > r.m.cnt[s];
-      d2 |= r.m.cnt[s] > inc.cnt[s];
+      const uint32_t ci = inc.cnt[s], cm = r.m.cnt[s];
+      d1 |= ci > cm;
+      d2 |= cm > ci;
+      fresh |= (ci == 0u) & (cm != 0u);
+      out_clk.cnt[s] = max(ci, cm);
     }
-    clock_merge(inc, r.m, out_clk);
+    out_clk.order = inc.order;
+    out_clk.present = 1;
+    if (fresh) clock_merge(inc, r.m, out_clk);
     r.v = out_clk;  // crt:197
     r.alias = 0;
     if (d1 != d2) {

@@ -223,9 +223,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   using namespace bb;
   const uint64_t n = in->n;
   if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
+  const bool lean = use_grouping(c) && n > 0;  // k_cs_count resets the counters itself: no memsets
   if (!append) {
     mark(c, EV_START, s);
-    BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+    if (!lean) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
   }
   if (n == 0) {
     if (!append) {
@@ -240,7 +241,7 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   }
   const ZeroLayout z = zero_layout(c, n);
   uint32_t* zp = c->zero.p;
-  BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
+  if (!lean) BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
 
   uint64_t* src = c->items_a.p;
   if (use_grouping(c)) {
@@ -248,7 +249,8 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
     uint2* off2 = reinterpret_cast<uint2*>(c->cs_off);
     uint32_t* ctr = zp + z.cs_ctr;
-    BB_LAUNCH(c, k_cs_count, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->d_err);
+    BB_LAUNCH(c, k_cs_count, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->d_err, ctr,
+              append ? (uint64_t*)nullptr : out->n_changes);
     BB_LAUNCH(c, k_cg_classify, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, off2, src,
               ctr, c->cs_long.p);
     BB_LAUNCH(c, k_cg_place, g4, CS_THREADS, s, in->path_id, n, c->st_idx.p, off2, c->cs_cnt, src, ctr);
@@ -260,7 +262,8 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     const uint32_t g = div_up(n, CS_THREADS);
     const uint64_t cap = c->cfg.capacity;
     const uint32_t tiles = div_up(cap + 1, CS_TILE);  // + 1: off[capacity] = the batch size
-    BB_LAUNCH(c, k_cs_count, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->st_idx.p, c->d_err);
+    BB_LAUNCH(c, k_cs_count, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->st_idx.p, c->d_err,
+              (uint32_t*)nullptr, (uint64_t*)nullptr);
     BB_LAUNCH(c, k_cs_tile_sums, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p);
     BB_LAUNCH(c, k_cs_offsets, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p, c->cs_off);
     BB_LAUNCH(c, k_cs_place, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->st_idx.p, c->cs_off, src, c->d_err);

@@ -315,16 +315,25 @@ int bb_index_stats(bb_ctx* ctx, uint32_t field, uint64_t* n_dense, uint64_t* n_e
 int bb_route_pack_dev(bb_ctx* ctx, uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts,
                       void* stream);
 
-/* A router owns the exchange: send buffers, two receive slots, an NCCL communicator (libnccl.so.2
- * is opened at run time; a process that never creates a router does not need it) and its own
- * stream, so that routing batch i+1 overlaps merging batch i.  Lifecycle per batch:
- *   bb_router_route_dev(r, batch, slot, &n)   pack by owner, all-gather the counts (one host
- *                                             round trip), grouped ncclSend/ncclRecv of the four
- *                                             arrays into receive slot `slot`; n = rows received
- *   bb_router_acquire(r, slot, stream, &b)    `stream` waits for the slot; b = the received batch
+/* A router owns the exchange: two receive slots, its own streams (routing batch i+1 overlaps merging
+ * batch i) and an NCCL communicator used for bootstrap and as the fallback transport (libnccl.so.2 is
+ * opened at run time; a process that never creates a router does not need it).  When the ranks' slots can be
+ * mapped into each other (cudaIpc: same box, NVLink / NVSwitch) the exchange is ONE kernel per rank that
+ * partitions the batch in shared memory and stores every update straight into its owner's slot
+ * (cp.async.bulk to peer memory); counts and completion travel through peer-mapped epoch flags.
+ * Lifecycle per batch:
+ *   bb_router_route_dev(r, batch, slot, &n)   collective: count by owner, exchange the counts, pack +
+ *                                             store into receive slot `slot` everywhere.  Peer-store
+ *                                             path: returns without waiting, *n = 2^64 - 1 (not known
+ *                                             yet).  NCCL path (BB_ROUTER_NO_P2P): one host round trip,
+ *                                             grouped ncclSend/ncclRecv, *n = rows received
+ *   bb_router_acquire(r, slot, stream, &b)    `stream` waits for the slot; b = the received batch, in
+ *                                             (source rank, arrival index) order; BB_ERR_CAPACITY if
+ *                                             the slot was too small (then nothing was exchanged)
  *   bb_merge_batch_dev(ctx, &b, out, stream)  merge it into this rank's shard
  *   bb_router_release(r, slot, stream)        the slot may be overwritten once `stream` gets here
- * Every rank must call route in the same order (it is a collective). */
+ * Every rank must call route in the same order.  The batch passed to route must stay unchanged until
+ * the slot has been acquired. */
 typedef struct bb_router bb_router;
 #define BB_NCCL_ID_BYTES 128
 int bb_router_unique_id(char id[BB_NCCL_ID_BYTES]); /* rank 0; hand the bytes to every rank */
@@ -336,8 +345,8 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
-/* Telemetry of the most recent route, ms: device time of [pack, counts all-gather + copy,
- * exchange, own-rows copy], then host time until the counts were known and of the whole call. */
+/* Telemetry of the most recent route, ms: device time of [count by owner, counts exchange (+ wait for the
+ * exchange stream's turn), pack + exchange, completion barrier], then host time of the call (twice). */
 int bb_router_last_ms(bb_router* r, double out[6]);
 /* bytes this rank has sent to other ranks, kernels it has launched */
 uint64_t bb_router_sent_bytes(const bb_router* r);
