@@ -515,6 +515,11 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
   c->key_bits = bits;
+  // 8 x 27.7 KB of static shared memory per SM: ask for the full carve-out
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
@@ -1184,6 +1189,9 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
   r->cap = recv_capacity ? recv_capacity : max_batch * world;  // a rank may own every update of every batch
   int prio_lo = 0, prio_hi = 0;  // routing runs beside a merge that fills the GPU: let its small kernels in first
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char* e = getenv("BB_ROUTE_PRIO")) {  // 0: the router's streams at default priority
+    if (e[0] == '0') prio_hi = 0;
+  }
   bool ok = cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
             cudaEventCreateWithFlags(&r->ev_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc((void**)&r->d_counts, world * sizeof(uint64_t)) == cudaSuccess &&
