@@ -348,6 +348,9 @@ def main():
     # so re-merging into an already-merged table would turn the workload into "all
     # historical".  It also means no step ever finds its table in L2.
     ids = np.arange(args.records, dtype=np.uint64)
+    per_engine = args.records * (128 + 12) + args.batch * 120  # table + counters + per-batch scratch, bytes
+    if (W + K) * per_engine > 0.8 * torch.cuda.get_device_properties(dev).total_memory:
+        raise SystemExit(f"--steps {K}: {W + K} pristine tables of {per_engine >> 20} MiB do not fit this GPU; use fewer steps")
     engines = []
     for _ in range(W + K):
         e = Engine(args.records, device=local_rank, full_sort=args.front_end == "full",

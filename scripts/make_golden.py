@@ -160,10 +160,10 @@ def kat_cases():
 
 
 # ----------------------------------------------------------------------------- random JS-level streams
-def stream_case(seed, n_ops, n_paths, index_fields, late_index):
+def stream_case(seed, n_ops, n_paths, index_fields, late_index, **gen):
     from tests import streamgen
     from tests.test_oracle_query import BOUNDS, EQ_VALUES
-    ops, _ref = streamgen.generate(seed, n_ops, n_paths, index_fields=index_fields, late_index=late_index)
+    ops, _ref = streamgen.generate(seed, n_ops, n_paths, index_fields=index_fields, late_index=late_index, **gen)
     indexed = bool(index_fields) or bool(late_index)
     js = JSRefBullet("p0", enable_indexing=indexed)
     for f in index_fields:
@@ -205,6 +205,11 @@ def stream_cases():
         print(f"  stream seed {seed}: {time.time() - t:.1f} s")
     # one longer stream over more paths: what the GPU tests slice into uneven batches
     out.append(stream_case(3000, 4000, 37, ("age",), None))
+    # other mixes: mostly local puts (the M-alias / tie-by-value branches), mostly primitives written over records
+    # and back (kind changes, falsy materialisation, null = node.remove()), both with the index hook installed
+    out.append(stream_case(4000, 1500, 10, ("age", "name"), None, p_local=0.85))
+    out.append(stream_case(4001, 1500, 10, ("role",), {"age": 500}, p_prim=0.7))
+    out.append(stream_case(4002, 1500, 6, (), None, p_local=0.6, p_prim=0.5))
     return out
 
 
