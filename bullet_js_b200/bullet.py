@@ -135,6 +135,33 @@ class Bullet:
             for cb in self.listeners.get(parent, []):
                 cb(self._get_data(parent) if parent else {c: self._get_data(c) for c in self._c})
 
+    # ---- cold start / export (src/bullet-file-storage.js:96-210; bullet_js_b200/persist.py)
+    def load_reference_state(self, store: dict, meta: dict):
+        """What BulletFileStorage._loadData merges back at start: every configured collection of `store`
+        goes into its device table with M = meta[path].vectorClock and no crt clock (V absent)."""
+        from . import persist
+
+        for name, col in self._c.items():
+            if name in store:
+                ids, rows = persist.import_collection(col.schema, name, store, meta)
+                if len(ids):
+                    col.engine.table_load(ids, rows)
+        return self
+
+    def export_reference_state(self):
+        """-> (store, meta) as BulletFileStorage._saveData would stringify them (without source / lastModified)."""
+        from . import persist
+
+        store, meta = {}, {}
+        for name, col in self._c.items():
+            n = len(col.schema.paths)
+            ids = np.arange(n, dtype=np.uint64)
+            records, m = persist.export_collection(col.schema, name, ids, col.engine.table_read(ids) if n else [])
+            if records:
+                store[name] = records
+            meta.update(m)
+        return store, meta
+
     # ---- reads (src/bullet.js:115-129; materialising like the reference's _getData)
     def _get_data(self, path: str):
         parts = path.split("/")

@@ -1458,8 +1458,10 @@ def _setup_regexp_promise(g, rt):
 class Runtime:
     """One JS realm.  `require(path)` runs CommonJS modules from disk; Node built-ins are stubs."""
 
-    def __init__(self, console=None, start_ms=1_700_000_000_000.0, seed=0x9E3779B9):
+    def __init__(self, console=None, start_ms=1_700_000_000_000.0, seed=0x9E3779B9, files=None):
         self.console = console  # list collecting (kind, text), or None to drop output
+        self.files = files if files is not None else {}  # the in-memory file system behind require("fs")
+        self.dirs = set()
         self._now = float(start_ms)
         self._seed = seed & 0xFFFFFFFF
         self.microtasks = []
@@ -1642,10 +1644,57 @@ class Runtime:
                 return o
             c.define("createHash", native("createHash", create_hash, 1))
             return c
-        if name in ("fs", "ws", "http", "https", "net", "os", "util", "zlib", "stream", "url", "child_process"):
+        if name == "fs":
+            return self._fs_module()
+        if name in ("ws", "http", "https", "net", "os", "util", "zlib", "stream", "url", "child_process"):
             # present but inert: any use on the measured path would surface as "x is not a function"
             return new_object()
         raise JSThrow(make_error("Error", f"Cannot find module '{name}'"))
+
+    def _fs_module(self):
+        """An in-memory file system (`self.files`: normalised path -> str), enough for the reference's
+        BulletFileStorage (existsSync / mkdirSync / readFileSync / writeFileSync / unlinkSync / readdirSync)."""
+        files, dirs = self.files, self.dirs
+        norm = lambda v: os.path.normpath(to_str(v))
+        fs = new_object()
+
+        def read(this, a):
+            p = norm(arg(a, 0))
+            if p not in files:
+                e = make_error("Error", f"ENOENT: no such file or directory, open '{p}'")
+                e.put_own("code", "ENOENT")
+                raise JSThrow(e)
+            return files[p]
+
+        def write(this, a):
+            files[norm(arg(a, 0))] = to_str(arg(a, 1))
+            return UNDEFINED
+
+        def exists(this, a):
+            p = norm(arg(a, 0))
+            return p in files or p in dirs or any(f.startswith(p + "/") for f in files)
+
+        def mkdir(this, a):
+            dirs.add(norm(arg(a, 0)))
+            return UNDEFINED
+
+        def unlink(this, a):
+            files.pop(norm(arg(a, 0)), None)
+            return UNDEFINED
+
+        def readdir(this, a):
+            p = norm(arg(a, 0))
+            return JSArray(sorted({f[len(p) + 1:].split("/")[0] for f in files if f.startswith(p + "/")}))
+
+        def rename(this, a):
+            src, dst = norm(arg(a, 0)), norm(arg(a, 1))
+            if src in files:
+                files[dst] = files.pop(src)
+            return UNDEFINED
+        for name, fn in (("readFileSync", read), ("writeFileSync", write), ("existsSync", exists), ("mkdirSync", mkdir),
+                         ("unlinkSync", unlink), ("readdirSync", readdir), ("renameSync", rename)):
+            fs.define(name, native(name, fn, 2))
+        return fs
 
     def _events_module(self):
         src = """

@@ -94,9 +94,12 @@ class _CrtView:
 class JSRefBullet:
     """The reference `Bullet`, driven from Python.  Attribute names follow js_literal.RefBullet."""
 
-    def __init__(self, peer_id: str, enable_middleware=True, enable_indexing=True, options=None, console=None):
+    def __init__(self, peer_id: str, enable_middleware=True, enable_indexing=True, options=None, console=None,
+                 files=None):
+        """files: dict shared between instances = the disk behind the reference's BulletFileStorage
+        (options={"storageType": "file", "storagePath": "/data", "saveInterval": 0})."""
         root = _reference_root()
-        self.rt = Runtime(console=console)
+        self.rt = Runtime(console=console, files=files)
         rt = self.rt
         Bullet = rt.require(os.path.join(root, "src", "bullet.js"))
         Sync = rt.require(os.path.join(root, "src", "bullet-network-sync.js"))
@@ -166,6 +169,10 @@ class JSRefBullet:
             idx = indices.get(k)
             out[k] = [[bk, [p for p, _ in s.data.values()]] for bk, s in idx.data.values()]
         return out
+
+    def save(self):
+        """bullet.storage.save() (src/bullet-storage.js:169-171 -> BulletFileStorage._saveData)."""
+        self.rt.method(self.bullet.get("storage"), "save")
 
     # ---- driving (every call goes through the reference's own public entry points)
     def setData(self, path, data, broadcast=True):

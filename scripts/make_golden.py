@@ -13,6 +13,8 @@ Fixtures (all inputs are regenerated deterministically or stored alongside the o
   mesh.json.gz     BASELINE config 5 in miniature: 4 peers in a full mesh (tests/meshsim.py), every peer an
                    instance of the reference; per-peer logs (own puts interleaved with received broadcasts),
                    decisions, change sets and final replicas.
+  restart.json.gz  a peer saves through the reference's BulletFileStorage (in-memory disk), a new instance loads
+                   the files and carries on: the files, the loaded state and the second half's results.
   config1.json.gz  BASELINE config 1 at full size (10 000 records, 100 000 updates of the synthetic
                    typed schema, then equals(users, role, admin)): decisions, SHA-256 of the change
                    set and of the final table in a canonical text form, and the query results.
@@ -231,6 +233,33 @@ def mesh_case(n_peers=4, n_ops=600, n_paths=10, seed=42):
     return out
 
 
+# ----------------------------------------------------------------------------- restart from the reference's own files
+def restart_case(seed=5000, n_ops=1400, cut=800, n_paths=12):
+    """Peer p0 (file storage on an in-memory disk) takes ops[:cut] and saves; a new instance with a fresh id
+    (p1, as src/bullet.js:33 gives every start) loads the files and takes ops[cut:]."""
+    from tests import streamgen
+    ops, _ref = streamgen.generate(seed, n_ops, n_paths)
+    files = {}
+    opt = {"storageType": "file", "storagePath": "/data", "saveInterval": 0}
+    a = JSRefBullet("p0", enable_indexing=False, options=opt, files=files)
+    for op in ops[:cut]:
+        streamgen.apply_op(a, op)
+    a.save()
+    saved = {k: files[k] for k in ("/data/store.json", "/data/meta.json")}
+    b = JSRefBullet("p1", enable_indexing=False, options=opt, files=files)
+    loaded = snapshot_state(b, with_index=False)
+    for op in ops[cut:]:
+        streamgen.apply_op(b, op)
+    case = dict(seed=seed, cut=cut, n_paths=n_paths, files=saved, loaded=loaded,
+                before=snapshot_state(a, with_index=False),
+                ops=[[p, jsonable(v), None if c is None else list(map(list, c.items()))] for p, v, c in ops],
+                codes="".join(str(d["code"]) for d in b.decisions),
+                changes=[[c["seq"], c["path"], jsonable(c["value"]), list(map(list, c["vectorClock"].items())),
+                          c["fromNetwork"]] for c in b.changes])
+    case.update(snapshot_state(b, with_index=False))
+    return case
+
+
 # ----------------------------------------------------------------------------- config 1 (typed synthetic schema)
 def canonical_value(v):
     return json.dumps(jsonable(v), separators=(",", ":"), ensure_ascii=True)
@@ -319,7 +348,7 @@ def config1_case(n_records=10_000, n_updates=100_000, chunk=50):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["kat", "streams", "config1", "mesh"])
+    ap.add_argument("--only", choices=["kat", "streams", "config1", "mesh", "restart"])
     ap.add_argument("--config1-updates", type=int, default=100_000)
     args = ap.parse_args()
     if not ref_runner.available():
@@ -329,6 +358,8 @@ def main():
         write("kat.json.gz", dict(reference=ident, cases=kat_cases()))
     if args.only in (None, "streams"):
         write("streams.json.gz", dict(reference=ident, cases=stream_cases()))
+    if args.only in (None, "restart"):
+        write("restart.json.gz", dict(reference=ident, case=restart_case()))
     if args.only in (None, "mesh"):
         write("mesh.json.gz", dict(reference=ident, case=mesh_case()))
     if args.only in (None, "config1"):
