@@ -247,9 +247,8 @@ int bb_sync(bb_ctx* ctx, void* stream);
  * (query:151-167), a node can sit in any number of buckets; the device keeps one
  * entry per node in a dense column (8 bytes per row, what range/equals stream) and
  * the rest in an open-addressing overflow set of `extra_capacity` slots.
- * Results: node ids; first the matches of the dense column (runs of ascending node
- * id, one per 4096-row tile; the whole column ascending with BB_CFG_ORDERED_CHANGES),
- * then the matches of the overflow set.  A node with entries in two matching
+ * Results: node ids; first the matches of the dense column (in no particular order; the
+ * whole column ascending with BB_CFG_ORDERED_CHANGES), then the matches of the overflow set.  A node with entries in two matching
  * buckets appears twice, as in the reference (query:237-258).  The reference's
  * (Map order, Set order) result order is not reproduced: compare as multisets. */
 #define BB_KEY_NAN 0x7FF8000000000000ull
