@@ -300,6 +300,9 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
                      "traffic": ncu_traffic("k_index_scan", world == 1 and nq == 100_000_000)},
     }
     res["roofline"]["frac"] = res["roofline"]["achieved"] / peak
+    # the measured peak is a COPY (half reads, half writes); this kernel is a pure read stream and can exceed it:
+    # also report it against the data-sheet HBM3e figure the profiling recipe quotes
+    res["roofline"]["frac_of_nominal_7700"] = res["roofline"]["achieved"] / 7700.0
     for k in ("allgather_ms", "allgather_bytes"):
         if k in out:
             res[k] = out[k]
