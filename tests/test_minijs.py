@@ -181,6 +181,57 @@ def test_literal_oracle_equals_live_reference(seed, indexed):
 
 
 @needs_reference
+@pytest.mark.parametrize("seed", [8101, 8102, 8103])
+def test_typed_oracle_equals_live_reference(seed):
+    """The typed C oracle against the reference run live on fresh seeds (decisions, change set, final rows,
+    exact-order query results) - the same checks test_golden.py makes against the committed traces."""
+    from bullet_js_b200 import codec
+    from oracle.typed import TypedOracle
+    from tests import streamgen
+    from tests.golden_io import clock_items, same_js
+    from tests.test_oracle_typed import make_cfg
+
+    ops, _ = streamgen.generate(seed, 500, 9, index_fields=("age",), late_index={"role": 200}, p_local=0.4, p_prim=0.3)
+    js = ref_runner.JSRefBullet("p0")
+    js.index("users", "age")
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    orc = TypedOracle(make_cfg(schema, 32, True))
+    orc.index_create(0)
+    for k, op in enumerate(ops):
+        if k == 200:
+            js.index("users", "role")
+        streamgen.apply_op(js, op)
+    a = orc.merge(batch.slice(0, 200))
+    orc.index_create(2)
+    b = orc.merge(batch.slice(200, len(ops)))
+    assert a.decision.tolist() + b.decision.tolist() == [d["code"] for d in js.decisions]
+    got = codec.decode_changes(schema, batch.slice(0, 200), a)
+    tail = codec.decode_changes(schema, batch.slice(200, len(ops)), b)
+    for c in tail:
+        c["seq"] += 200
+    want = js.changes
+    assert len(got) + len(tail) == len(want)
+    for g, w in zip(got + tail, want):
+        assert (g["seq"], g["path"]) == (w["seq"], w["path"]) and same_js(g["value"], w["value"])
+        assert clock_items(g["vectorClock"]) == clock_items(w["vectorClock"])
+    users, meta, vclocks = js.store.get("users", {}), js.meta, js.crt.vectorClocks
+    for i in range(len(schema.paths)):
+        path = schema.paths.name(i)
+        d = codec.decode_row(schema, orc.table[i])
+        assert same_js(users[path.split("/")[1]], d["value"])
+        assert clock_items(d["M"]) == clock_items(meta[path]["vectorClock"])
+        assert clock_items(d["V"]) == clock_items(vclocks.get(path)) and d["alias"] == js.alias(path)
+    paths = lambda ids: [schema.paths.name(i) for i in ids]  # noqa: E731
+    for f, name in ((0, "age"), (2, "role")):
+        for lo, hi in ((0.0, 99.0), (25.0, 40.0), ("a", "zzz"), (-1e300, 1e300)):
+            assert paths(orc.query_range(f, schema.bound(lo, False), schema.bound(hi, True))) == js.range("users", name, lo, hi)
+        for v in (25.0, 30.0, "admin", "user", True, "25"):
+            key = schema.index_key(v)
+            assert ([] if key is None else paths(orc.query_equals(f, key))) == js.equals("users", name, v)
+
+
+@needs_reference
 def test_committed_fixtures_are_reproducible_from_the_reference():
     import importlib.util
     import os
