@@ -315,7 +315,7 @@ def workload_config(args, world):
         "workload": f"config2: {args.records * F // 1_000_000}M-field table/GPU ({args.records} records x {F} fields, 128 B rows), "
                     f"{args.batch}-update conflicting batch/GPU/step, {args.keys} keys, clock mix 40/20/25/5/5/5",
         "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
-        "keys": args.keys, "front_end": args.front_end, "merge_kernel": args.merge_kernel, "sharding": f"path_id % {world}" if world > 1 else "none",
+        "keys": args.keys, "front_end": args.front_end, "merge_kernel": args.merge_kernel, "hot_keys": args.keys == "zipf", "sharding": f"path_id % {world}" if world > 1 else "none",
         "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2",
     }
 
@@ -357,7 +357,7 @@ def main():
     engines = []
     for _ in range(W + K):
         e = Engine(args.records, device=local_rank, full_sort=args.front_end == "full",
-                   radix_sort=args.front_end == "radix", cta_pipe=args.merge_kernel == "pipe", **synth.synth_ranks(args.records))
+                   radix_sort=args.front_end == "radix", cta_pipe=args.merge_kernel == "pipe", hot_keys=args.keys == "zipf", **synth.synth_ranks(args.records))
         e.table_load(ids, table.rows)
         e.reserve(args.batch * world, host_entry=(world == 1))
         engines.append(e)

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_cs_count(const uint64_t* __restr
                                                          uint32_t* __restrict__ rank, uint32_t* __restrict__ err,
                                                          uint32_t* __restrict__ zero4, uint64_t* __restrict__ zero_n) {
   // first kernel of a batch: it also resets the few words later kernels accumulate into (saves two memsets)
-  if (blockIdx.x == 0 && threadIdx.x < 4 && zero4) zero4[threadIdx.x] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 8 && zero4) zero4[threadIdx.x] = 0;  // ctr[0..3] of the grouping kernels, n_hot
   if (blockIdx.x == 0 && threadIdx.x == 0 && zero_n) *zero_n = 0;
   const uint64_t i0 = (uint64_t)blockIdx.x * (CS_THREADS * CS_ILP) + threadIdx.x;
   uint64_t pid[CS_ILP];
@@ -638,6 +638,9 @@ struct MergeArgs {
   uint32_t* tile_state;    // [num_tiles], zeroed per launch
   uint32_t* ticket;        // zeroed per launch
   uint32_t num_tiles;
+  uint4* hot_list;         // (key, next position lo, hi, 0) of segments handed to k_merge_hot
+  uint32_t* n_hot;         // zeroed per batch
+  uint32_t hot_cap;
   uint64_t seq_base;
   uint32_t idx_base;       // added to the arrival indices this launch reports (chunked host calls)
   const uint64_t* chg_base;  // ORDERED: entries already in the change set when the launch began
@@ -704,6 +707,8 @@ __device__ __forceinline__ void pack_change(uint4* q, uint32_t user, const Value
 constexpr uint32_t NO_SLOT = BB_NO_SLOT;
 constexpr int MT = 128;    // sorted positions per CTA tile == threads per CTA
 constexpr int MT_WARPS = MT / 32;
+constexpr int HOT_SERIAL = 8;  // updates of an overrunning segment its owner replays alone before k_merge_hot takes over
+constexpr int HOT_CTAS = 64;
 // Staged rows sit at their natural 128-byte stride with the 16-byte chunk index XOR-swizzled by the row
 // number: conflict-free both for the 8-lanes-per-row copies and for the one-thread-per-row unpack
 // (LDS.128 / STS.128 by 32 rows at once), and 2 KB smaller than a padded stride.
@@ -722,7 +727,7 @@ __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED>
+template <bool ORDERED, bool INDEXED, bool HOT = false>
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * ROW_Q];
@@ -820,6 +825,13 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       for (uint64_t gp = base + MT; gp < a.n; ++gp) {
         const uint64_t it = a.sorted[gp];
         if ((uint32_t)(it >> 32) != key) break;
+        if (HOT && gp - (base + MT) >= (uint64_t)HOT_SERIAL) {  // a hot key (BB_CFG_HOT_KEYS): k_merge_hot replays the rest
+          const uint32_t slot = atomicAdd(a.n_hot, 1u);
+          if (slot < a.hot_cap) {
+            a.hot_list[slot] = make_uint4(key, (uint32_t)gp, (uint32_t)(gp >> 32), 0u);
+            break;
+          }
+        }
         const uint32_t ui = (uint32_t)it;
         const uint4 h = a.head[ui];
         Clock c, oc;
@@ -939,6 +951,103 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
     }
   }
   if (overflow) atomicOr(a.err, 2u);
+}
+
+// ---------------------------------------------------------------- K2h: hot keys
+// A path that takes thousands of a batch's updates (Zipf) is a serial chain for the thread that owns it:
+// ~1 us per update.  But a network-flavour update is decided by (its clock, M, S) alone - V and the alias
+// flag, the only things a REJECTED update changes, do not enter - and M, S change only when an update is
+// accepted.  So one CTA per hot segment (handed over by k_merge_stage after HOT_SERIAL updates) evaluates the
+// next 128 updates in parallel against the row in shared memory; everything in front of the first
+// state-changing update (the first accepted one, or the first local put, whose clock IS V) is final, that
+// update's own result is exact, and its thread publishes the row for the next round.  Rounds retire ~20-128
+// updates instead of one.  Runs after k_merge_stage on the same stream; exits at once when nothing is hot.
+__global__ void __launch_bounds__(MT) k_merge_hot(const MergeArgs a) {
+  __shared__ __align__(16) uint4 s_row[ROW_Q];
+  __shared__ uint32_t s_cnt[MT_WARPS], s_stop[MT_WARPS], s_loc[MT_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (*a.err & 1u) return;
+  const uint32_t n_hot = min(*a.n_hot, a.hot_cap);
+  for (uint32_t hseg = blockIdx.x; hseg < n_hot; hseg += gridDim.x) {
+    const uint4 he = a.hot_list[hseg];
+    const uint32_t hkey = he.x;
+    uint64_t gp0 = (uint64_t)he.y | ((uint64_t)he.z << 32);
+    __syncthreads();
+    if (tid < ROW_Q) s_row[tid] = a.table[(uint64_t)hkey * ROW_Q + tid];
+    __syncthreads();
+    bool overflow = false;
+    while (true) {
+      const uint64_t gp = gp0 + tid;
+      const uint64_t it = gp < a.n ? a.sorted[gp] : ~0ull;
+      const bool mine = gp < a.n && (uint32_t)(it >> 32) == hkey;  // the segment's positions are a prefix of the window
+      const uint32_t ui = (uint32_t)it;
+      uint32_t code = 0;
+      bool net = true;
+      uint4 h = make_uint4(0, 0, 0, 0);
+      RowState r;
+      Clock oc;
+      Value ov;
+      if (mine) {
+        h = a.head[ui];
+        Clock c;
+        Value x;
+        net = unpack_update(h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1], a.val[2 * (uint64_t)ui],
+                            a.val[2 * (uint64_t)ui + 1], c, x);
+        unpack_row(s_row, r);
+        code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
+      }
+      const bool stop = mine && (BB_DEC_ACCEPTED(code) || !net);
+      const uint32_t bm = __ballot_sync(0xffffffffu, mine), bs = __ballot_sync(0xffffffffu, stop),
+                     bl = __ballot_sync(0xffffffffu, mine && !net);
+      if (lane == 0) {
+        s_cnt[w] = __popc(bm);
+        s_stop[w] = bs;
+        s_loc[w] = bl;
+      }
+      __syncthreads();  // also: every thread has unpacked the row
+      int nseg = 0, f = MT;
+      bool f_local = false;
+#pragma unroll
+      for (int ww = MT_WARPS - 1; ww >= 0; --ww) {
+        nseg += (int)s_cnt[ww];
+        if (s_stop[ww]) {
+          const int b = __ffs(s_stop[ww]) - 1;
+          f = ww * 32 + b;
+          f_local = (s_loc[ww] >> b) & 1u;
+        }
+      }
+      if (nseg == 0) break;
+      // retired this round: up to and including the first stop - unless that is a local put further in, whose
+      // clock depends on the V the updates in front of it leave: it waits for the next round's position 0
+      const int retired = f >= nseg ? nseg : ((f_local && f > 0) ? f : f + 1);
+      if (tid < retired) {
+        if (tid == retired - 1) pack_row(s_row, r);  // its copy is the exact state after the retired updates
+        if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
+          const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
+          a.verdict[ui] = (code << 29) | (uint32_t)dest;
+          if (dest < a.cap) {
+            uint4 q[UPD_Q];
+            pack_change(q, h.w, ov, oc);
+            a.out_idx[dest] = a.idx_base + ui;
+            a.out_head[dest] = q[0];
+            a.out_clk[2 * dest] = q[1];
+            a.out_clk[2 * dest + 1] = q[2];
+            a.out_val[2 * dest] = q[3];
+            a.out_val[2 * dest + 1] = q[4];
+          } else {
+            overflow = true;
+          }
+        } else {
+          a.verdict[ui] = (code << 29) | NO_SLOT;
+        }
+      }
+      gp0 += (uint64_t)retired;
+      __syncthreads();  // the published row is visible; s_cnt / s_stop / s_loc may be rewritten
+    }
+    if (overflow) atomicOr(a.err, 2u);
+    __syncthreads();
+    if (tid < ROW_Q) a.table[(uint64_t)hkey * ROW_Q + tid] = s_row[tid];
+  }
 }
 
 // ---------------------------------------------------------------- K2': the same merge, software-pipelined

@@ -77,6 +77,7 @@ struct bb_ctx {
   uint32_t* cs_off = nullptr;  // full sort: their exclusive scan, u32[capacity + 1] (both padded to 1024);
                                // grouping front end: uint2[capacity] = (start, length) of a path's run
   DevBuf<uint2> cs_long;       // segments longer than CS_SHORT, queued for k_cs_fix_long
+  DevBuf<uint4> hot_list;      // segments k_merge_stage hands to k_merge_hot
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
   uint64_t* d_nchanges = nullptr;
   uint64_t* d_chg_base = nullptr;
@@ -164,6 +165,8 @@ struct ZeroLayout {
 //   counting sort       BB_CFG_ORDERED_CHANGES / BB_CFG_FULL_SORT, when the scan over the rows is cheap
 //                       next to the batch: the item list is ascending in path id
 //   radix sort          otherwise, or with BB_CFG_RADIX_SORT
+bool ordered_cfg(const bb_ctx* c) { return (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0; }
+
 bool use_grouping(const bb_ctx* c) {
   return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT));
 }
@@ -187,7 +190,7 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
   z.cs_state = z.merge_state + z.merge_tiles;
   z.cs_ctr = z.cs_state;
-  z.total = z.cs_ctr + 4;
+  z.total = z.cs_ctr + 8;  // grouping counters [0..3], n_hot [4]
   return z;
 }
 
@@ -200,6 +203,7 @@ int reserve_dev(bb_ctx* c, uint64_t n) {
   BB_CUDA(c, c->st_idx.ensure(n));
   BB_CUDA(c, c->st_ent.ensure(5 * n));
   BB_CUDA(c, c->cs_long.ensure(n / 8 + 1));
+  BB_CUDA(c, c->hot_list.ensure(n / 64 + 16));
   return BB_OK;
 }
 
@@ -309,6 +313,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.tile_state = zp + z.merge_state;
   ma.ticket = zp + z.tickets + MAX_PASSES;
   ma.num_tiles = z.merge_tiles;
+  ma.hot_list = c->hot_list.p;
+  ma.n_hot = zp + z.cs_ctr + 4;
+  const bool hot = (c->cfg.flags & BB_CFG_HOT_KEYS) && !ordered_cfg(c) && !c->index_mask && !(c->cfg.flags & BB_CFG_CTA_PIPE);
+  ma.hot_cap = hot ? (uint32_t)std::min<uint64_t>(c->hot_list.cap, 0x7FFFFFFFull) : 0u;
   ma.seq_base = c->seq;
   ma.idx_base = idx_base;
   ma.chg_base = c->d_chg_base;
@@ -339,8 +347,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
   } else {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, false>), z.merge_tiles, MT, s, ma);
+    else if (hot) BB_LAUNCH(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, false>), z.merge_tiles, MT, s, ma);
   }
+  if (hot) BB_LAUNCH(c, k_merge_hot, HOT_CTAS, MT, s, ma);
   if (!append) mark(c, EV_MERGE, s);
   c->seq += n;
   return BB_OK;
@@ -520,6 +530,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
@@ -585,6 +596,7 @@ int bb_destroy(bb_ctx* c) {
   if (c->cs_cnt) cudaFree(c->cs_cnt);
   if (c->cs_off) cudaFree(c->cs_off);
   c->cs_long.release(); c->cs_tile.release();
+  c->hot_list.release();
   if (c->d_nchanges) cudaFree(c->d_nchanges);
   if (c->d_chg_base) cudaFree(c->d_chg_base);
   for (int i = 0; i < MAX_CHUNKS; ++i) {

@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 
 def engine_and_oracle(schema=None, capacity=256, post_getdata=False, ordered=False, radix=False, **kw):
     """radix: False (defaults: grouping front end + k_merge_pipe) | True (radix sort) | "full" (counting sort by
-    path id) | "pipe" (grouping + k_merge_pipe instead of k_merge_stage)."""
+    path id) | "pipe" (grouping + k_merge_pipe instead of k_merge_stage) | "hot" (BB_CFG_HOT_KEYS: k_merge_hot takes over hot segments)."""
     from bullet_js_b200.engine import Engine
 
-    sort = dict(radix_sort=radix is True, full_sort=radix == "full", cta_pipe=radix == "pipe")
+    sort = dict(radix_sort=radix is True, full_sort=radix == "full", cta_pipe=radix == "pipe", hot_keys=radix == "hot")
     if schema is not None:
         eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata, ordered_changes=ordered, **sort)
     else:
@@ -31,7 +31,7 @@ def assert_same_table(eng, orc, n):
 
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("indexed", [False, True])
-@pytest.mark.parametrize("radix", [False, True, "full", "pipe"])
+@pytest.mark.parametrize("radix", [False, True, "full", "pipe", "hot"])
 def test_random_js_streams(seed, indexed, radix):
     ops, _ref = streamgen.generate(100 + seed, 4000, 37, index_fields=("age",) if indexed else ())
     schema = streamgen.make_schema()
@@ -61,7 +61,7 @@ def test_kat_l_on_gpu():
     eng.close()
 
 
-@pytest.mark.parametrize("mode", ["default", "ordered", "radix", "full", "pipe"])
+@pytest.mark.parametrize("mode", ["default", "ordered", "radix", "full", "pipe", "hot"])
 @pytest.mark.parametrize("keys", ["uniform", "zipf"])
 def test_synthetic_schema_stream(keys, mode):
     """SURVEY 8d schema at a size the oracle replays in a second: 50k records, 3 x 200k updates."""
@@ -69,7 +69,7 @@ def test_synthetic_schema_stream(keys, mode):
     rng = synth.rng_for(2, salt=1)
     table = synth.make_table(n_rec, rng)
     ordered = mode == "ordered"
-    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, radix={"radix": True, "full": "full", "pipe": "pipe"}.get(mode, False), **synth.synth_ranks(n_rec))
+    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, radix={"radix": True, "full": "full", "pipe": "pipe", "hot": "hot"}.get(mode, False), **synth.synth_ranks(n_rec))
     ids = np.arange(n_rec, dtype=np.uint64)
     eng.table_load(ids, table.rows)
     orc.load(ids, table.rows)
@@ -205,6 +205,27 @@ def test_device_pointer_entry_matches_host_entry():
     assert got.same_as(want)
     assert_same_table(eng, orc, n_rec)
     assert eng.launch_count() > 0 and eng.phase_ms("merge") > 0 and eng.phase_ms("sort") > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("n_rec", [40, 3000])
+def test_hot_keys_kernel(n_rec):
+    """BB_CFG_HOT_KEYS: segments of thousands (n_rec = 40) or tens (3000) of updates, local puts in between,
+    replayed round by round by k_merge_hot - decisions, change set and rows as the sequential oracle."""
+    rng = synth.rng_for(2, salt=21)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec, radix="hot", **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    mix = dict(synth.MIX, local=0.15, dominating=0.3)
+    tot = sum(mix.values())
+    mix = {k: v / tot for k, v in mix.items()}
+    for keys in ("uniform", "zipf"):
+        b = synth.make_batch(table, 120_000, rng, keys=keys, mix=mix)
+        out = capi.ChangeBuffers(b.n)
+        assert eng.merge(b, out).same_as(orc.merge(b))
+    assert_same_table(eng, orc, n_rec)
     eng.close()
 
 
