@@ -1,0 +1,170 @@
+/**
+ * bullet-b200.js - the reference-side shim: plugs libbulletb200 in under an unchanged Bullet instance.
+ *
+ * Constructed like the reference's own plugins (a constructor that receives the Bullet instance and replaces
+ * public properties: src/bullet-query.js:13-21, src/bullet-middleware.js:23-135):
+ *
+ *     const Bullet = require("bullet-js");
+ *     const BulletB200 = require("./js/bullet-b200");
+ *     const bullet = new Bullet({ ... });
+ *     new BulletB200(bullet, native, { capacity: 1 << 20, collections: { users: ["age", "score", "role", "name"] } });
+ *
+ * `native` is the N-API addon over include/bullet_b200.h (native/bullet_b200_napi.c).  Its surface, as used here:
+ *     native.create(options) -> ctx
+ *     native.merge(ctx, entries) -> { codes: [0..6 per entry], changes: [{ i, value, vectorClock }] }
+ *         entries: [{ path, data, vectorClock | undefined, local: bool }] in arrival order; the addon interns paths,
+ *         packs the struct-of-arrays batch and calls bb_merge_batch; changes come back in arrival order
+ *     native.clocks(ctx, path) -> { meta, crt }      bb_table_read: the two clock maps of a path
+ *     native.indexCreate / equals / range / count    bb_index_create, bb_query_*
+ *
+ * What is replaced, and nothing else:
+ *   bullet.crt.handleUpdate(path, data, isFromNetwork)   src/bullet-crt.js:329-385 - one update, decided on the device;
+ *       setData (src/bullet.js:139-155), the middleware and query wrappers around it, _applyUpdate, listeners,
+ *       log and broadcast all stay the reference's own code and keep bullet.store / bullet.meta as before
+ *   bullet.network.sync._processSyncEntries(entries)     src/bullet-network-sync.js:551-569 - the batched ingress:
+ *       ONE native call per chunk, then the reference's own effects for every entry, in arrival order
+ *   bullet.crt.getVectorClock / vectorClocks              read through to the device (crt clocks live there)
+ * Values outside the typed domain (nested records, integer-like keys, setCompare; SURVEY.md 8a) make the addon
+ * throw: there is no CPU fallback, such collections keep the stock BulletCRT.
+ */
+const REASONS = [
+  "no current state",
+  "identical clocks and values",
+  "identical clocks, decided by value comparison",
+  "identical clocks, decided by value comparison",
+  "incoming vector clock dominates",
+  "current vector clock dominates (incoming is historical)",
+  "concurrent modifications, merged objects",
+];
+
+class BulletB200 {
+  constructor(bullet, native, options = {}) {
+    this.bullet = bullet;
+    this.native = native;
+    this.ctx = native.create({ localPeer: bullet.id, ...options });
+    this.calls = 0; // native merge calls (telemetry)
+    this._installCrt();
+    this._installSync();
+  }
+
+  /** the decision object of src/bullet-crt.js:164-279 for a device decision code */
+  _decision(code, value, vectorClock) {
+    const accepted = code === 0 || code === 2 || code === 4 || code === 6;
+    return {
+      defer: false,
+      historical: code === 5,
+      converge: code === 6,
+      incoming: accepted,
+      current: code === 1 || code === 3 || code === 5,
+      concurrent: code === 6,
+      vectorClock,
+      reason: REASONS[code],
+      value,
+    };
+  }
+
+  _entry(path, incomingData, isFromNetwork) {
+    // flavour: network-with-clock iff an object carrying a truthy __vectorClock arrives from the network
+    // (src/bullet-crt.js:339-353); everything else, primitives from the network included, is a local update
+    if (
+      isFromNetwork &&
+      incomingData &&
+      typeof incomingData === "object" &&
+      incomingData.__vectorClock
+    ) {
+      const { __vectorClock, ...data } = incomingData;
+      return { path, data, vectorClock: __vectorClock, local: false };
+    }
+    return { path, data: incomingData, vectorClock: undefined, local: true };
+  }
+
+  _result(entry, code, change) {
+    // a rejected update leaves the stored value in place and only moves the crt clock: read them back like the
+    // reference would (inside a batch the crt clock read here is the one after the whole batch; setData does
+    // not use the clock of a rejected update)
+    const value = change ? change.value : this.bullet._getData(entry.path);
+    const vectorClock = change
+      ? change.vectorClock
+      : this.native.clocks(this.ctx, entry.path).crt;
+    let broadcastData = value;
+    if (typeof broadcastData === "object" && broadcastData !== null) {
+      broadcastData = { ...broadcastData, __vectorClock: vectorClock }; // src/bullet-crt.js:371-376
+    }
+    const decision = this._decision(code, value, vectorClock);
+    return { value, vectorClock, broadcastData, decision, doUpdate: decision.incoming };
+  }
+
+  _installCrt() {
+    const crt = this.bullet.crt;
+    const self = this;
+    crt.handleUpdate = function (path, incomingData, isFromNetwork = false) {
+      self.bullet._getData(path); // src/bullet-crt.js:331: the read that turns a stored falsy value into {}
+      const entry = self._entry(path, incomingData, isFromNetwork);
+      const out = self.native.merge(self.ctx, [entry]);
+      self.calls++;
+      if (entry.local && !out.changes[0] && self.bullet.meta[path]) {
+        // a rejected LOCAL put still bumps the clock it was compared with: incrementVectorClock works in place on
+        // the object meta[path].vectorClock aliases after an accepted write (src/bullet-crt.js:56-60, 358;
+        // src/bullet.js:198-203).  The device keeps that aliasing; mirror what it holds.
+        const held = self.native.clocks(self.ctx, path).meta;
+        if (held) self.bullet.meta[path].vectorClock = held;
+      }
+      return self._result(entry, out.codes[0], out.changes[0]);
+    };
+    crt.getVectorClock = (key) => self.native.clocks(self.ctx, key).crt;
+  }
+
+  _installSync() {
+    const sync = this.bullet.network && this.bullet.network.sync;
+    if (sync) sync._processSyncEntries = (entries, peerId) => this.processSyncEntries(entries, peerId);
+  }
+
+  /**
+   * BulletNetworkSync._processSyncEntries (src/bullet-network-sync.js:551-569) with ONE device call per chunk.
+   * The reference's per-entry effects run afterwards in arrival order through its own setData: crt.handleUpdate
+   * is answered from the batch result instead of calling the device again.
+   */
+  processSyncEntries(entries) {
+    // what setData would hand to handleUpdate for each entry: __fromNetwork already stripped (src/bullet.js:161-178)
+    const packed = entries.map((e) =>
+      e.deleted
+        ? this._entry(e.path, null, false)
+        : this._entry(
+            e.path,
+            typeof e.data === "object" && e.data !== null
+              ? { ...e.data, __vectorClock: e.vectorClock }
+              : e.data,
+            typeof e.data === "object" && e.data !== null
+          )
+    );
+    const out = this.native.merge(this.ctx, packed);
+    this.calls++;
+    const byIndex = new Map(out.changes.map((c) => [c.i, c]));
+    const crt = this.bullet.crt;
+    const live = crt.handleUpdate;
+    let k = 0;
+    crt.handleUpdate = (path) => {
+      this.bullet._getData(path);
+      const i = k++;
+      return this._result(packed[i], out.codes[i], byIndex.get(i));
+    };
+    try {
+      for (const entry of entries) {
+        const { path, data, vectorClock, deleted } = entry;
+        if (deleted) {
+          this.bullet.setData(path, null, false);
+        } else {
+          const networkData =
+            typeof data === "object" && data !== null
+              ? { ...data, __fromNetwork: true, __vectorClock: vectorClock }
+              : data;
+          this.bullet.setData(path, networkData, false);
+        }
+      }
+    } finally {
+      crt.handleUpdate = live;
+    }
+  }
+}
+
+module.exports = BulletB200;
