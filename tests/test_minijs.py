@@ -151,6 +151,35 @@ def test_reference_example_script_runs_unmodified():
 
 
 @needs_reference
+def test_other_reference_examples_run_unmodified():
+    """Breadth check of the interpreter on code that is NOT on the hot path: the reference's validation and
+    serializer examples (schemas, regular expressions, CSV / XML writers, classes with custom types, Date,
+    async functions, an in-memory fs) run to completion with the output their source prescribes."""
+    import os
+
+    def run(name):
+        rt = Runtime(console=[])
+        rt.require(os.path.join(ref_runner._reference_root(), "examples", name))
+        rt.run_microtasks()
+        rt.run_timers(120000)
+        assert not [t for k, t in rt.console if k == "error"], name
+        return [t.strip() for _, t in rt.console], rt
+
+    out, _ = run("bullet-validation-example.js")
+    assert "Validation result: true" in out and out.count("This should not be displayed due to validation error") == 7
+    assert "Users: [ 'john_doe', 'missing_email', 'wrong_age', 'bad_email', 'bad_role', 'unverified_admin' ]" in out
+    assert "Product created successfully after schema removal" in out and out[-1] == "All validation examples completed."
+    out, rt = run("bullet-serializer-example.js")
+    assert "Position has x and y: true" in out and "Distance calculation: 22.360679774997898" in out  # Math.sqrt(500)
+    assert "Imported location: { name: 'Office', position: { x: 10, y: 20 }, active: true }" in out
+    written = sorted(os.path.basename(p) for p in rt.files)
+    assert written == ["all_data.json", "all_data.xml", "locations.json", "new_user.json", "products.csv", "products.xml",
+                       "users.csv", "users.json"]
+    users_csv = next(v for p, v in rt.files.items() if p.endswith("users.csv")).split("\n")
+    assert users_csv[0].startswith("id,") and len(users_csv) >= 3
+
+
+@needs_reference
 @pytest.mark.parametrize("seed,indexed", [(7001, False), (7002, True)])
 def test_literal_oracle_equals_live_reference(seed, indexed):
     from tests import streamgen
