@@ -18,9 +18,11 @@ updates (F=4 fields each => 4 M field-merges) merged into a resident table of
   --impl reference   the same oracle on every host thread (the reference itself is
                 JavaScript and there is no JS engine on the box: see DESIGN.md)
 
-N > 1 (torchrun, one rank per GPU): the table is sharded by path id, every rank
-submits its own 1 M batch, updates are routed to their owner with one NCCL
-all-to-all, merged there; weak scaling (per-GPU work fixed).
+N > 1 (torchrun, one rank per GPU): the table is sharded by path id (global table =
+N x the per-GPU table), every rank submits its own 1 M batch, updates are routed to
+their owner by the library's fused pack + all-to-all over NVLink peer memory and
+merged there, routing of batch i+1 overlapping the merge of batch i; weak scaling
+(per-GPU work fixed).
 """
 from __future__ import annotations
 

@@ -1,16 +1,21 @@
 """Key-sharded table across the GPUs of one box.
 
-One process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).  Path id `p`
-lives on rank `p % world` as local row `p // world`.  A step:
+One process per GPU.  Path id `p` lives on rank `p % world` as local row `p // world`.  A step of the product
+path (`Router` -> the library's native router, bb_router_* in include/bullet_b200.h):
 
-  1. every rank packs its own batch by owner with the library's stable partition
-     (bb_route_pack_dev: three small launches, 88 B per update moved once);
-  2. counts all-to-all (world x world int64), then ONE grouped exchange of the four SoA arrays
-     with exact sizes - (world-1)/world of every batch crosses NVLink;
-  3. every rank merges what it received, concatenated in source-rank order, into its
-     shard (bb_merge_batch_dev).  The per-path replay order is therefore
-     (source rank, arrival index): the same as one peer replaying rank 0's batch,
-     then rank 1's, ... - which is what the parity test checks.
+  1. every rank counts its batch by owner (k_route_count / k_route_scan) and publishes the counts straight into
+     every peer's control block (peer-mapped memory, epoch flags) - on its own stream, while the previous batch
+     is still being exchanged;
+  2. ONE persistent kernel per rank partitions the batch in shared memory and stores every update's four SoA
+     pieces into its owner's receive slot over NVLink (cp.async.bulk to peer memory): (world-1)/world of every
+     batch crosses NVLink, nothing is staged in between; an epoch-flag barrier tells the owners their rows are in;
+  3. every rank merges what it received, concatenated in source-rank order, into its shard (bb_merge_batch_dev)
+     while the next batch is being routed.  The per-path replay order is therefore (source rank, arrival index):
+     the same as one peer replaying rank 0's batch, then rank 1's, ... - which is what the parity runs check
+     (tests/test_shard_gloo.py on CPU, scripts/check_shard_gpu.py on 2 / 4 / 8 GPUs).
+
+torch.distributed is only used to hand rank 0's NCCL id to the other ranks (NCCL bootstraps the communicator that
+carries the IPC handles and is the fallback transport: BB_ROUTER_NO_P2P, BB_ROUTE_NCCL_SYNC).
 
 The reference's transport is JSON over WebSocket between peers (src/bullet-network.js:
 404-418, sync chunks of 50 entries, src/bullet-network-sync.js:713-723); this module is

@@ -8,8 +8,9 @@
  * The reference has NO FFI / addon / operator registry for this path
  * (SURVEY.md 8b), so there is nothing to mirror symbol-for-symbol; each entry
  * point names the reference function(s) whose batched equivalent it is.  The
- * reference-side binding (N-API addon + JS shim that swaps `bullet.crt`,
- * `bullet.query` and `sync._processSyncEntries`) is shown in INTEGRATION.md.
+ * reference-side binding is js/bullet-b200.js (the shim that answers
+ * `bullet.crt.handleUpdate` and `sync._processSyncEntries` from this library on an
+ * unmodified Bullet instance) over the N-API addon sketched in INTEGRATION.md.
  *
  * Conventions: plain pointers and sizes only; returns 0 or a negative BB_ERR_*;
  * never aborts, never calls back into the host; host buffers are caller-owned
@@ -150,8 +151,8 @@ typedef struct bb_config {
  * each still found through verdict[], but the tiles' order in the buffers is not
  * fixed - and no tile ever waits for another one. */
 #define BB_CFG_ORDERED_CHANGES 2u
-/* Always group a batch by path with the stable LSD radix sort.  By default the library uses a
- * counting sort over the row indices whenever capacity <= 64 x batch size (same result). */
+/* Always sort a batch by path id with the stable LSD radix sort (same decisions, table and change entries
+ * as the default grouping front end described under BB_CFG_FULL_SORT). */
 #define BB_CFG_RADIX_SORT 4u
 /* Always sort a batch by path id (counting sort over the row indices, or the radix sort when the table is
  * much larger than the batch).  By default the library only GROUPS the batch: updates whose path occurs
