@@ -150,6 +150,25 @@ def kat_cases():
     js.put("users/bob", {"name": "Bob", "email": "bob@example.com", "role": "user"})
     cases.append(dict(name="KAT-Q2", equals_role_admin=js.equals("users", "role", "admin"), index=js.index_dump()))
 
+    # docs/conflict-resolution.md:446-483 (the documented examples that agree with the code): two peers write
+    # concurrently and exchange their broadcasts; the documentation states the final values
+    import copy
+
+    def two_peers(path, va, vb):
+        a, b = JSRefBullet("peerA", enable_indexing=False), JSRefBullet("peerB", enable_indexing=False)
+        a.put(path, copy.deepcopy(va))
+        b.put(path, copy.deepcopy(vb))
+        ca, cb = a.last_change(), b.last_change()
+        for dst, ch in ((b, ca), (a, cb)):
+            v = copy.deepcopy(ch["value"])
+            dst.handle_put(path, {**v, "__vectorClock": dict(ch["vectorClock"])} if isinstance(v, dict) else v)
+        return dict(path=path, a=jsonable(va), b=jsonable(vb), store_a=jsonable(a.store), store_b=jsonable(b.store),
+                    reasons_a=[d["reason"] for d in a.decisions], reasons_b=[d["reason"] for d in b.decisions])
+    cases.append(dict(name="docs/conflict-resolution.md", runs=[
+        two_peers("settings/theme", "dark", "light"),
+        two_peers("users/bob", {"name": "Bob Smith", "age": 30.0, "preferences": {"theme": "dark"}},
+                  {"name": "Robert Smith", "location": "New York", "preferences": {"notifications": False}})]))
+
     # the reference's own example, run as a script
     from oracle.minijs.builtins import Runtime
     rt = Runtime(console=[])

@@ -131,6 +131,29 @@ def test_kat_traces_equal_reference():
     assert any(line.strip() == "All query examples completed." for line in lines)
 
 
+def test_documented_conflict_examples():
+    """docs/conflict-resolution.md:446-483: the reference does what its documentation says, and the literal
+    oracle (which models nested records too) does what the reference does."""
+    import copy
+
+    runs = {c["name"]: c for c in KAT["cases"]}["docs/conflict-resolution.md"]["runs"]
+    theme, bob = runs
+    assert unjsonable(theme["store_a"]) == unjsonable(theme["store_b"]) == {"settings": {"theme": "light"}}
+    final = unjsonable(bob["store_a"])["users"]["bob"]
+    assert final["name"] == "Robert Smith" and final["age"] == 30.0 and final["location"] == "New York"
+    assert final["preferences"] == {"theme": "dark", "notifications": False}
+    for run in runs:
+        a, b = RefBullet("peerA", enable_indexing=False), RefBullet("peerB", enable_indexing=False)
+        a.put(run["path"], copy.deepcopy(unjsonable(run["a"])))
+        b.put(run["path"], copy.deepcopy(unjsonable(run["b"])))
+        ca, cb = a.changes[-1], b.changes[-1]
+        for dst, ch in ((b, ca), (a, cb)):
+            v = copy.deepcopy(ch["value"])
+            dst.handle_put(run["path"], {**v, "__vectorClock": dict(ch["vectorClock"])} if isinstance(v, dict) else v)
+        assert same_js(a.store, unjsonable(run["store_a"])) and same_js(b.store, unjsonable(run["store_b"]))
+        assert [d["reason"] for d in a.decisions] == run["reasons_a"] and [d["reason"] for d in b.decisions] == run["reasons_b"]
+
+
 def test_kat_q1_literal_index_order():
     from tests.test_oracle_kat import PRODUCTS, USERS
     b = RefBullet("me")
