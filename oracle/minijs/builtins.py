@@ -1217,9 +1217,8 @@ def _setup_collections(g):
         if k.__class__ is float and k == 0:
             k = 0.0
         nk = map_key(k)
-        d = _m(this, "Map")
-        old = d.get(nk)
-        d[nk] = (old[0] if old is not None else k, arg(a, 1))
+        old = _m(this, "Map").get(nk)
+        this.insert(nk, (old[0] if old is not None else k, arg(a, 1)))
         return this
 
     @method(MP, "has", 1)
@@ -1228,11 +1227,13 @@ def _setup_collections(g):
 
     @method(MP, "delete", 1)
     def _(this, a):
-        return _m(this, "Map").pop(map_key(arg(a, 0)), None) is not None
+        _m(this, "Map")
+        return this.remove(map_key(arg(a, 0)))
 
     @method(MP, "clear")
     def _(this, a):
-        _m(this, "Map").clear()
+        _m(this, "Map")
+        this.clear()
         return UNDEFINED
 
     @method(MP, "forEach", 1)
@@ -1257,7 +1258,7 @@ def _setup_collections(g):
         d = _m(this, "Set")
         nk = map_key(k)
         if nk not in d:
-            d[nk] = (k, k)
+            this.insert(nk, (k, k))
         return this
 
     @method(SP, "has", 1)
@@ -1266,11 +1267,13 @@ def _setup_collections(g):
 
     @method(SP, "delete", 1)
     def _(this, a):
-        return _m(this, "Set").pop(map_key(arg(a, 0)), None) is not None
+        _m(this, "Set")
+        return this.remove(map_key(arg(a, 0)))
 
     @method(SP, "clear")
     def _(this, a):
-        _m(this, "Set").clear()
+        _m(this, "Set")
+        this.clear()
         return UNDEFINED
 
     @method(SP, "forEach", 1)

@@ -217,11 +217,28 @@ class JSFunction(JSObject):
 
 
 class JSMapObj(JSObject):
-    __slots__ = ("data",)  # normalised key -> (key, value)
+    __slots__ = ("data", "seqs", "counter")  # data: normalised key -> (key, value), in insertion order
 
     def __init__(self, proto, cls):
         JSObject.__init__(self, proto, cls)
         self.data = {}
+        self.seqs = {}     # normalised key -> insertion number (a delete + re-add gets a new one)
+        self.counter = 0
+
+    def insert(self, nk, pair):
+        """set / add: a new key goes to the end, an existing one keeps its place."""
+        if nk not in self.data:
+            self.counter += 1
+            self.seqs[nk] = self.counter
+        self.data[nk] = pair
+
+    def remove(self, nk) -> bool:
+        self.seqs.pop(nk, None)
+        return self.data.pop(nk, None) is not None
+
+    def clear(self):
+        self.data.clear()
+        self.seqs.clear()
 
 
 class Env:
@@ -787,21 +804,23 @@ def iterate(v):
 
 
 def _live_keys(m):
-    """Map/Set iteration is live: entries added during iteration are visited, deleted ones are not."""
-    seen = 0
+    """Map / Set iteration is live (ECMA-262 24.1.5.1): entries are visited in insertion order, an entry deleted
+    before it is reached is skipped, entries added during the iteration are visited, a deleted and re-added
+    entry is visited again at its new place."""
+    last = 0
     while True:
-        keys = list(m.data)
-        if seen >= len(keys):
-            return
-        progressed = False
-        for nk in keys[seen:]:
-            seen += 1
-            if nk in m.data:
-                progressed = True
-                yield nk
+        pending = []
+        for nk in reversed(m.data):  # the entries inserted after `last` are at the end
+            seq = m.seqs[nk]
+            if seq <= last:
                 break
-        if not progressed:
+            pending.append((nk, seq))
+        if not pending:
             return
+        for nk, seq in reversed(pending):
+            if m.seqs.get(nk) == seq:
+                last = seq
+                yield nk
 
 
 def py_iter_object(gen):

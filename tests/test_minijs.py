@@ -118,6 +118,35 @@ def test_string_array_builtins_used_by_the_reference():
                  [1.0, 2.0], ["a", 1.0], [1.0, 2.0, [3.0]], "00abc", ["h", "i"], True, True, [2.0, 3.0]]
 
 
+def test_more_semantics_the_reference_relies_on():
+    r = ev("""
+        function f(a, b) { return arguments.length; }
+        class Q { eq(path, field, value) { if (arguments.length === 2) { value = field; field = null; } return [field, value]; } }
+        const proto = { inherited: 1 };
+        const o = Object.create(proto); o.own = 2;
+        const seen = []; for (const k in o) seen.push(k);
+        class C { m() {} } const c = new C(); c.x = 1; const ck = []; for (const k in c) ck.push(k);
+        const m = new Map([["a", new Set([1])], ["b", new Set([2])]]);
+        for (const [k, s] of m) { s.delete(k === "a" ? 1 : 2); if (s.size === 0) m.delete(k); }
+        const d = { a: 1 }; delete d.a; d.a = 2; d.b = 3;
+        let sw = ""; switch (3) { case 1: sw += "1"; case 3: sw += "3"; case 4: sw += "4"; break; default: sw += "d"; }
+        const e = (() => { try { null.x; } catch (err) { return err instanceof TypeError; } })();
+        return [f(1), f(1, undefined), new Q().eq("p", "v"), new Q().eq("p", "f", 0), seen, ck, m.size,
+                Object.keys(d), sw, e, typeof null, typeof (() => 1), [1, 2, 3].indexOf(4), "x".localeCompare("y") < 0,
+                (1234.5678).toFixed(2), Number.isInteger(5.0), parseInt("42px"), parseFloat("3.5e2x"), 7 % -3, -7 % 3,
+                2 ** 10, 5 / 0, -5 / 0, 0 / 0, 1 / -0 === -Infinity, [10, 9, 1].sort(), String([1, [2, 3]]), String({}),
+                [..."ab"].map((ch) => ch.charCodeAt(0)), "a-b-c".replace("-", "+"), "a-b-c".split("-", 2),
+                Object.entries({ x: 1, y: 2 }).map(([k, v]) => k + v).join(","), JSON.stringify({ 2: "b", 1: "a", z: 0 })];
+    """)
+    assert r[:4] == [1.0, 2.0, [None, "v"], ["f", 0.0]]
+    assert r[4] == ["own", "inherited"] and r[5] == ["x"] and r[6] == 0.0 and r[7] == ["a", "b"] and r[8] == "34"
+    assert r[9] is True and r[10] == "object" and r[11] == "function" and r[12] == -1.0 and r[13] is True
+    assert r[14] == "1234.57" and r[15] is True and r[16] == 42.0 and r[17] == 350.0 and r[18] == 1.0 and r[19] == -1.0
+    assert r[20] == 1024.0 and r[21] == math.inf and r[22] == -math.inf and math.isnan(r[23]) and r[24] is True
+    assert r[25] == [1.0, 10.0, 9.0] and r[26] == "1,2,3" and r[27] == "[object Object]" and r[28] == [97.0, 98.0]
+    assert r[29] == "a+b-c" and r[30] == ["a", "b"] and r[31] == "x1,y2" and r[32] == '{"1":"a","2":"b","z":0}'
+
+
 def test_async_promises_and_timers_are_deterministic():
     rt = Runtime(console=[])
     out = rt.eval("""
