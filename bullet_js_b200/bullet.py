@@ -50,6 +50,22 @@ class BulletNode:
     def get(self, sub: str) -> "BulletNode":
         return BulletNode(self.bullet, f"{self.path}/{sub}")
 
+    def off(self, callback: Callable | None = None):
+        """src/bullet.js:733-746: drop one subscription, or all of this path's."""
+        subs = self.bullet.listeners.get(self.path)
+        if subs is not None:
+            if callback is not None:
+                if callback in subs:
+                    subs.remove(callback)
+            else:
+                self.bullet.listeners[self.path] = []
+        return self
+
+    def remove(self):
+        """src/bullet.js:752-755: a local put of null (the reference has no tombstones)."""
+        self.bullet.setData(self.path, None)
+        return self
+
     def __repr__(self):
         return f"BulletNode({self.path!r})"
 
@@ -161,6 +177,14 @@ class Bullet:
                 store[name] = records
             meta.update(m)
         return store, meta
+
+    def collect_sync_entries(self, since: float = 0):
+        """What a reference peer would be sent for a full sync request (src/bullet-network-sync.js:592-664),
+        in chunks of 50 (`:713-723`)."""
+        from . import persist
+
+        store, meta = self.export_reference_state()
+        return persist.chunk_sync_data(persist.collect_full_sync_data(store, meta, since))
 
     # ---- reads (src/bullet.js:115-129; materialising like the reference's _getData)
     def _get_data(self, path: str):

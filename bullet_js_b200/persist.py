@@ -12,6 +12,11 @@ restarted peer holds every path in the state "M present, V absent" (and has a fr
                        (`source` / `lastModified` are not kept on the device: callers that need them keep them
                        on the host)
 
+    collect_full_sync_data / chunk_sync_data   the sync PRODUCER side: what
+                       `BulletNetworkSync._collectFullSyncData` / `_chunkSyncData` (src/bullet-network-sync.js:592-664,
+                       713-723) would ship for the exported state, entry for entry, so a B200 peer can answer a
+                       reference peer's sync request
+
 JSON has already flattened what it cannot hold (NaN / +-Infinity -> null, -0 -> 0) when the reference wrote the
 files: the import takes the files as they are.  Paths outside `<collection>/<key>`, nested records and keys
 outside the schema raise `codec.DomainError` (no CPU fallback: such collections stay with the stock storage).
@@ -102,3 +107,39 @@ def json_value(v):
             return None
         return 0.0 if v == 0 else v
     return v
+
+
+def collect_full_sync_data(store: dict, meta: dict, since: float = 0):
+    """BulletNetworkSync._collectFullSyncData (src/bullet-network-sync.js:592-664) over (store, meta) dicts as
+    `export_collection` returns them.  The reference walks the store down to its LEAVES and looks the clock up in
+    `meta[<leaf path>]` - which only exists for paths that were written as such, so a collection written record
+    by record ships `users/u1/age`-style entries with `{}` clocks, while a primitive written at `users/u3`
+    carries its own.  Reproduced as is; `lastModified` is not kept on the device (0 here), and `meta.deleted`
+    is never set by the reference either, so there are no tombstone entries."""
+    entries = []
+
+    def leaf(path, data):
+        m = meta.get(path) or {}
+        last = m.get("lastModified") or 0
+        if since > 0 and last and last < since:
+            return
+        entries.append({"path": path, "data": data, "vectorClock": m.get("vectorClock") or {},
+                        "lastModified": last, "deleted": False})
+
+    def traverse(obj, path):
+        if not isinstance(obj, dict):
+            leaf(path[1:], obj)
+            return
+        for key, value in obj.items():
+            if isinstance(value, dict):
+                traverse(value, path + "/" + key)
+            else:
+                leaf((path + "/" + key)[1:], value)
+
+    traverse(store, "")
+    return entries
+
+
+def chunk_sync_data(entries, chunk_size: int = 50):
+    """BulletNetworkSync._chunkSyncData (src/bullet-network-sync.js:713-723)."""
+    return [entries[i:i + chunk_size] for i in range(0, len(entries), chunk_size)]

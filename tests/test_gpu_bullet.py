@@ -105,3 +105,40 @@ def test_network_entries_and_listeners():
         assert paths(db.equals("users", "age", v)) == sorted(ref.equals("users", "age", v)), v
     assert paths(db.equals("users", "role", "admin")) == sorted(ref.equals("users", "role", "admin"))
     db.close()
+
+
+def test_restart_export_sync_and_node_surface():
+    """Cold start from a reference data directory, BulletNode.off / remove, export and the sync producer side
+     through the mirror: mirrored on the literal oracle."""
+    from bullet_js_b200 import persist
+    from bullet_js_b200.bullet import Bullet
+
+    store = {"users": {k: js(v) for k, v in USERS.items()}}
+    meta = {f"users/{k}": {"source": "local", "vectorClock": {"peerA": float(i + 1)}} for i, k in enumerate(USERS)}
+    db, ref = Bullet(schemas(), capacity=64), RefBullet("me")
+    db.load_reference_state(store, meta)
+    ref.store = {"users": {k: js(v) for k, v in USERS.items()}}
+    ref.meta = {p: {"source": "local", "vectorClock": dict(m["vectorClock"])} for p, m in meta.items()}
+    # with an index on the collection the reference's post-write hook re-reads the node (query:151,169): the
+    # mirror's tables are created for that regime (a stored null becomes {} right after the write)
+    db.index("users", "age")
+    ref.index("users", "age")
+    heard = []
+    cb = heard.append
+    db.get("users/user2").on(cb)
+    for x in (db, ref):
+        x.get("users/user2").put({"age": 36.0}) if x is db else x.put("users/user2", {"age": 36.0})
+    db.get("users/user2").off(cb)
+    db.get("users/user3").remove()
+    ref.put("users/user3", None)
+    db.process_sync_entries([{"path": "users/user1", "data": {"age": 99.0}, "vectorClock": {"peerA": 5.0}}])
+    ref.process_sync_entries([{"path": "users/user1", "data": {"age": 99.0}, "vectorClock": {"peerA": 5.0}}])
+    assert db.decisions == [d["code"] for d in ref.decisions]
+    assert len(heard) == 2  # at subscription and for the put; nothing after off()
+    got_store, got_meta = db.export_reference_state()
+    assert got_store["users"] == ref.store["users"] and list(got_store["users"]) == list(ref.store["users"])
+    assert {p: m["vectorClock"] for p, m in got_meta.items()} == {p: m["vectorClock"] for p, m in ref.meta.items()}
+    chunks = db.collect_sync_entries()
+    want = persist.collect_full_sync_data(ref.store, ref.meta)
+    assert [e for c in chunks for e in c] == want and all(len(c) <= 50 for c in chunks)
+    db.close()

@@ -104,3 +104,27 @@ def test_gpu_restart():
 
     eng = run_typed(lambda schema: Engine.for_schema(schema, 32), lambda e, ids: e.table_read(ids))
     eng.close()
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_runner", fromlist=["x"]).available(), reason="reference sources not present")
+def test_sync_producer_equals_reference():
+    """persist.collect_full_sync_data / chunk_sync_data == BulletNetworkSync._collectFullSyncData(0) /
+    _chunkSyncData of a live reference instance (records, primitives and nulls in the store)."""
+    from oracle import ref_runner
+    from oracle.minijs.builtins import to_py
+
+    js = ref_runner.JSRefBullet("p0", enable_indexing=False)
+    for op in golden_io.ops_of(CASE)[:500]:
+        streamgen.apply_op(js, op)
+    js.put("settings/theme", "dark")
+    want = to_py(js.rt.method(js._sync, "_collectFullSyncData", 0.0))
+    for e in want:
+        e["lastModified"] = 0  # wall clock in the reference, not kept on the device
+    got = persist.collect_full_sync_data(js.store, js.meta)
+    assert len(got) == len(want) > 10
+    for g, w in zip(got, want):
+        assert g["path"] == w["path"] and same_js(g["data"], w["data"]) and g["deleted"] is w["deleted"] is False
+        assert clock_items(g["vectorClock"]) == clock_items(w["vectorClock"])
+    assert any(e["vectorClock"] for e in got) and any(not e["vectorClock"] and "/" in e["path"][6:] for e in got)
+    chunks = to_py(js.rt.method(js._sync, "_chunkSyncData", js.rt.method(js._sync, "_collectFullSyncData", 0.0)))
+    assert [len(c) for c in persist.chunk_sync_data(got)] == [len(c) for c in chunks]
