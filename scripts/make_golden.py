@@ -15,6 +15,7 @@ Fixtures (all inputs are regenerated deterministically or stored alongside the o
                    decisions, change sets and final replicas.
   restart.json.gz  a peer saves through the reference's BulletFileStorage (in-memory disk), a new instance loads
                    the files and carries on: the files, the loaded state and the second half's results.
+  config4.json.gz  BASELINE config 4 reduced to 20 000 nodes: index build from the store + range / equals / count.
   config1.json.gz  BASELINE config 1 at full size (10 000 records, 100 000 updates of the synthetic
                    typed schema, then equals(users, role, admin)): decisions, SHA-256 of the change
                    set and of the final table in a canonical text form, and the query results.
@@ -365,9 +366,38 @@ def config1_case(n_records=10_000, n_updates=100_000, chunk=50):
     )
 
 
+# ----------------------------------------------------------------------------- config 4 (index build + scans), reduced
+def config4_case(n_records=20_000):
+    """BASELINE config 4 at a size the interpreter finishes in seconds: the synthetic table is placed in the
+    reference's store, then index('users','age') / index('users','role') are BUILT from it (_buildIndex,
+    src/bullet-query.js:53-73) and range(20,30) / equals(role,'admin') / count run."""
+    from bullet_js_b200 import codec, synth
+    from oracle.minijs.builtins import from_py
+
+    table = synth.make_table(n_records, synth.rng_for(4))
+    schema = synth.synth_schema(n_records)
+    js = JSRefBullet("p0")
+    users = from_py({})
+    js.bullet.get("store").put_own("users", users)
+    for i in range(n_records):
+        users.put_own(f"u{i}", from_py(codec.decode_row(schema, table.rows[i])["value"]))
+    js.index("users", "age")
+    js.index("users", "role")
+
+    def ids(paths):
+        return [int(p.split("/u")[1]) for p in paths]
+    return dict(n_records=n_records, rng="synth.rng_for(4)",
+                range_age_20_30=ids(js.range("users", "age", 20.0, 30.0)),
+                range_age_0_1000=len(js.range("users", "age", 0.0, 1000.0)),
+                equals_role_admin=ids(js.equals("users", "role", "admin")),
+                equals_age_25=ids(js.equals("users", "age", 25.0)),
+                count_role=[js.count("users", "role", r) for r in ("admin", "editor", "user")],
+                buckets={k: len(v) for k, v in js.index_dump().items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", choices=["kat", "streams", "config1", "mesh", "restart"])
+    ap.add_argument("--only", choices=["kat", "streams", "config1", "mesh", "restart", "config4"])
     ap.add_argument("--config1-updates", type=int, default=100_000)
     args = ap.parse_args()
     if not ref_runner.available():
@@ -381,6 +411,8 @@ def main():
         write("restart.json.gz", dict(reference=ident, case=restart_case()))
     if args.only in (None, "mesh"):
         write("mesh.json.gz", dict(reference=ident, case=mesh_case()))
+    if args.only in (None, "config4"):
+        write("config4.json.gz", dict(reference=ident, case=config4_case()))
     if args.only in (None, "config1"):
         write("config1.json.gz", dict(reference=ident, case=config1_case(n_updates=args.config1_updates)))
 

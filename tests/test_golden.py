@@ -331,3 +331,47 @@ def test_gpu_config1_equals_reference():
     rows = eng.table_read(np.arange(c["n_records"], dtype=np.uint64))
     config1_check(c, schema, batch, ch, rows, eq.tolist(), rg.tolist(), counts, ordered_queries=False)
     eng.close()
+
+
+# ----------------------------------------------------------------------------- config 4 (index build + scans), reduced
+CONFIG4 = golden_io.load("config4.json.gz")["case"]
+
+
+def config4_run(eng):
+    c = CONFIG4
+    n = c["n_records"]
+    table = synth.make_table(n, synth.rng_for(4))
+    schema = synth.synth_schema(n)
+    ids = np.arange(n, dtype=np.uint64)
+    (eng.table_load if hasattr(eng, "table_load") else eng.load)(ids, table.rows)
+    eng.index_create(0)
+    eng.index_create(2)
+    b = lambda v, up: schema.bound(v, up)  # noqa: E731
+    return dict(
+        range_age_20_30=eng.query_range(0, b(20.0, False), b(30.0, True)).tolist(),
+        range_age_0_1000=len(eng.query_range(0, b(0.0, False), b(1000.0, True))),
+        equals_role_admin=eng.query_equals(2, schema.index_key("admin")).tolist(),
+        equals_age_25=eng.query_equals(0, schema.index_key(25.0)).tolist(),
+        count_role=[eng.query_count(2, schema.index_key(r)) for r in ("admin", "editor", "user")])
+
+
+def test_config4_typed_oracle_equals_reference():
+    """Index BUILD from the store (_buildIndex) + range / equals / count on 20 000 nodes, exact result order."""
+    cfg = capi.make_config(CONFIG4["n_records"], local_peer=0, flags=codec.CFG_POST_GETDATA,
+                           **synth.synth_ranks(CONFIG4["n_records"]))
+    got = config4_run(TypedOracle(cfg))
+    for k, v in got.items():
+        assert v == CONFIG4[k], k
+    assert len(CONFIG4["range_age_20_30"]) > 1500 and sum(CONFIG4["count_role"]) == CONFIG4["n_records"]
+
+
+@pytest.mark.gpu
+def test_gpu_config4_equals_reference():
+    from bullet_js_b200.engine import Engine
+
+    eng = Engine(CONFIG4["n_records"], post_getdata=True, **synth.synth_ranks(CONFIG4["n_records"]))
+    got = config4_run(eng)
+    for k, v in got.items():
+        want = CONFIG4[k]
+        assert (sorted(v) == sorted(want)) if isinstance(v, list) and k != "count_role" else v == want, k
+    eng.close()
