@@ -12,7 +12,7 @@ path (`Router` -> the library's native router, bb_router_* in include/bullet_b20
   3. every rank merges what it received, concatenated in source-rank order, into its shard (bb_merge_batch_dev)
      while the next batch is being routed.  The per-path replay order is therefore (source rank, arrival index):
      the same as one peer replaying rank 0's batch, then rank 1's, ... - which is what the parity runs check
-     (tests/test_shard_gloo.py on CPU, scripts/check_shard_gpu.py on 2 / 4 / 8 GPUs).
+     (tests/test_shard_gloo.py on CPU, tests/check_shard_gpu.py on 2 / 4 / 8 GPUs).
 
 torch.distributed is only used to hand rank 0's NCCL id to the other ranks (NCCL bootstraps the communicator that
 carries the IPC handles and is the fallback transport: BB_ROUTER_NO_P2P, BB_ROUTE_NCCL_SYNC).

@@ -1,8 +1,8 @@
 """CPU oracle for the bullet-js hot path - TEST INFRASTRUCTURE ONLY.
 
 Nothing under `bullet_js_b200/` imports this package.  Allowed importers:
-`tests/`, `__graft_entry__.smoke()`, bench.py's cpu_baseline / --impl reference legs, and
-`scripts/make_golden.py` (which writes the fixtures the tests read).
+`tests/` (including `tests/golden/make_golden.py`, which writes the fixtures the tests read, and
+`tests/check_shard_gpu.py`), `__graft_entry__.smoke()` and bench.py's cpu_baseline / --impl reference legs.
 
   js_literal.py / jsvalue.py   statement-level restatement over JS-like Python values
   bullet_oracle.c / typed.py   the same on the typed struct-of-arrays format (C, built by oracle/Makefile)

@@ -7,7 +7,7 @@
  * 8c) and this image has no JS engine, so the reference's own sources are
  * executed by oracle/minijs (an ECMAScript-subset interpreter written for this
  * purpose) and their outputs are committed as tests/golden/*.json.gz
- * (scripts/make_golden.py).  tests/test_golden.py checks this file against them:
+ * (tests/golden/make_golden.py).  tests/test_golden.py checks this file against them:
  * random JS-level streams (decisions, change set, final table, index contents and
  * query results in the reference's exact Map/Set order) and BASELINE config 1 at
  * full size (100 000 updates over 10 000 records).  Caveat: the interpreter is

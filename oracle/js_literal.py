@@ -5,7 +5,7 @@ PARITY PIN: KORandi/bullet-js ships no tests, fixtures or golden vectors (SURVEY
 and no JS engine exists in this image, so the reference's own source files are executed
 unmodified by `oracle/minijs` (an ECMAScript-subset interpreter written for the purpose,
 `oracle/ref_runner.py`) and the traces are committed under tests/golden/
-(scripts/make_golden.py).  tests/test_golden.py and tests/test_minijs.py hold this
+(tests/golden/make_golden.py).  tests/test_golden.py and tests/test_minijs.py hold this
 restatement to them: decisions, change sets, store, both clock maps and their aliasing,
 index Maps in exact (Map, Set) order and query results, on the SURVEY 8c scenarios and
 on random streams that take every branch of `resolve`.  Caveat: the interpreter is ours,

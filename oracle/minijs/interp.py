@@ -2,7 +2,7 @@
 bullet-query.js, bullet-middleware.js, ...) UNMODIFIED, because this image has no JS engine.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): it exists to pin `oracle/js_literal.py` and
-`oracle/bullet_oracle.c` to outputs of the reference itself (scripts/make_golden.py writes
+`oracle/bullet_oracle.c` to outputs of the reference itself (tests/golden/make_golden.py writes
 tests/golden/*.json from it).  Nothing under bullet_js_b200/ may import it.
 
 Design: the AST of parser.py is compiled once into Python closures `f(env) -> value`; statements

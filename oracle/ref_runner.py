@@ -14,7 +14,7 @@ What is the reference's and what is ours:
   * The network is disabled (`disableNetwork: true`); the sync driver is constructed on a stub
     EventEmitter because only its `_processSyncEntries` loop is on the path.
 
-`scripts/make_golden.py` uses this module to write tests/golden/*.json; the GPU box has no
+`tests/golden/make_golden.py` uses this module to write tests/golden/*.json; the GPU box has no
 /root/reference, so everything that runs there reads the committed fixtures instead.
 """
 from __future__ import annotations

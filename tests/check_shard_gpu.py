@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity of the sharded path (run under torchrun, one rank per GPU):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/check_shard_gpu.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/check_shard_gpu.py
 
 Every rank owns the rows `id % N == rank`, submits its own seeded batch through the library's native
 router (fused pack + all-to-all over NVLink) and merges what it receives on its GPU.  Each rank then

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Writes tests/golden/*.json.gz from the REFERENCE ITSELF: /root/reference/src/*.js executed,
 unmodified, by oracle/minijs (this image has no node).  Run here (the GPU box has no
-/root/reference):   python scripts/make_golden.py [--only kat|streams|config1]
+/root/reference):   python tests/golden/make_golden.py [--only kat|streams|config1]
 
 Fixtures (all inputs are regenerated deterministically or stored alongside the outputs):
   kat.json.gz      step-by-step traces of the SURVEY 8c scenarios (KAT-L/N/H/R/Q1/Q2) + the console
@@ -31,7 +31,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_runner  # noqa: E402

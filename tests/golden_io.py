@@ -1,7 +1,7 @@
 """Loading and comparing the committed golden fixtures (tests/golden/*.json.gz).
 
 The fixtures are OUTPUTS OF THE REFERENCE ITSELF (src/*.js executed by oracle/minijs,
-scripts/make_golden.py); nothing here touches /root/reference, so these helpers also run on the GPU box.
+tests/golden/make_golden.py); nothing here touches /root/reference, so these helpers also run on the GPU box.
 """
 from __future__ import annotations
 
@@ -47,7 +47,7 @@ def canonical_value(v):
 
 
 def changes_sha256(changes):
-    """changes: iterable of dict(seq, path, value, vectorClock) in change-set order (scripts/make_golden.py)."""
+    """changes: iterable of dict(seq, path, value, vectorClock) in change-set order (tests/golden/make_golden.py)."""
     h = hashlib.sha256()
     for c in changes:
         h.update(f"{int(c['seq'])}|{c['path']}|{canonical_value(c['value'])}|{canonical_value(c['vectorClock'])}\n".encode())

@@ -1,5 +1,5 @@
 """Parity pinned to the reference itself: tests/golden/*.json.gz hold outputs of /root/reference/src/*.js
-(executed unmodified by oracle/minijs, see scripts/make_golden.py).  Checked here against
+(executed unmodified by oracle/minijs, see tests/golden/make_golden.py).  Checked here against
   * the literal oracle (oracle/js_literal.py)            - CPU
   * the typed C oracle (oracle/bullet_oracle.c)          - CPU
   * libbulletb200.so through the C ABI                   - `-m gpu`

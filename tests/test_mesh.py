@@ -1,6 +1,6 @@
 """BASELINE config 5 (mesh-topology sync replay) at test size.
 
-tests/golden/mesh.json.gz: 4 instances of the reference in a full mesh (scripts/make_golden.py, tests/meshsim.py).
+tests/golden/mesh.json.gz: 4 instances of the reference in a full mesh (tests/golden/make_golden.py, tests/meshsim.py).
   * the literal oracle, run through the same mesh simulator, must produce the same per-peer logs, decisions,
     change sets and replicas (order-dependent rule: "converged" means "equals the reference replay")
   * the typed C oracle and (gpu) the CUDA path replay every peer's log in uneven batches

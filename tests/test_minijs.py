@@ -296,7 +296,7 @@ def test_committed_fixtures_are_reproducible_from_the_reference():
     from tests import golden_io
 
     spec = importlib.util.spec_from_file_location(
-        "make_golden", os.path.join(os.path.dirname(golden_io.GOLDEN), "..", "scripts", "make_golden.py"))
+        "make_golden", os.path.join(golden_io.GOLDEN, "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mg)
     assert mg.reference_identity() == golden_io.load("kat.json.gz")["reference"]
