@@ -9,13 +9,14 @@
  *     const bullet = new Bullet({ ... });
  *     new BulletB200(bullet, native, { capacity: 1 << 20, collections: { users: ["age", "score", "role", "name"] } });
  *
- * `native` is the N-API addon over include/bullet_b200.h (native/bullet_b200_napi.c).  Its surface, as used here:
- *     native.create(options) -> ctx
- *     native.merge(ctx, entries) -> { codes: [0..6 per entry], changes: [{ i, value, vectorClock }] }
- *         entries: [{ path, data, vectorClock | undefined, local: bool }] in arrival order; the addon interns paths,
- *         packs the struct-of-arrays batch and calls bb_merge_batch; changes come back in arrival order
- *     native.clocks(ctx, path) -> { meta, crt }      bb_table_read: the two clock maps of a path
- *     native.indexCreate / equals / range / count    bb_index_create, bb_query_*
+ * `native` is the N-API addon over include/bullet_b200.h (INTEGRATION.md): a thin pass-through of typed arrays.
+ *     native.create({ capacity, nFields, localPeer, flags, rankObject, rankTrue, rankFalse, rankNaN }) -> ctx   bb_create
+ *     native.mergeBatch(ctx, n, pathId, head, clk, val, out) -> number of change entries                       bb_merge_batch
+ *         in:  Uint32Array views of bb_batch (js/pack.js packs them: interned path ids, heads, clocks, values)
+ *         out: { verdict: Uint32Array(n), idx: Uint32Array(n), head: Uint32Array(4n), clk: Uint32Array(8n), val: Uint32Array(8n) }
+ *     native.tableRead(ctx, pathId) -> Uint32Array(32)   one 128-byte bb_row                                   bb_table_read
+ * All host-side logic - interning, dictionary, packing, decoding, the reference's result shapes - is JavaScript
+ * (this file and js/pack.js).
  *
  * What is replaced, and nothing else:
  *   bullet.crt.handleUpdate(path, data, isFromNetwork)   src/bullet-crt.js:329-385 - one update, decided on the device;
@@ -27,6 +28,11 @@
  * Values outside the typed domain (nested records, integer-like keys, setCompare; SURVEY.md 8a) make the addon
  * throw: there is no CPU fallback, such collections keep the stock BulletCRT.
  */
+const { Schema, packEntries, unpackChanges, decodeClock } = require("./pack");
+
+const BB_CFG_POST_GETDATA = 1;
+const ROW_M_PRESENT = 1, ROW_V_PRESENT = 2;
+
 const REASONS = [
   "no current state",
   "identical clocks and values",
@@ -41,10 +47,50 @@ class BulletB200 {
   constructor(bullet, native, options = {}) {
     this.bullet = bullet;
     this.native = native;
-    this.ctx = native.create({ localPeer: bullet.id, ...options });
+    this.schema = new Schema({
+      fields: options.fields,
+      peers: options.peers,
+      strings: options.strings || [],
+      localPeer: bullet.id,
+    });
+    this.ctx = native.create({
+      capacity: options.capacity,
+      nFields: options.fields.length,
+      localPeer: this.schema.pslot.get(bullet.id),
+      flags: options.postGetData ? BB_CFG_POST_GETDATA : 0, // set it when an index hook is installed (query:151,169)
+      ...this.schema.ranks(),
+    });
     this.calls = 0; // native merge calls (telemetry)
     this._installCrt();
     this._installSync();
+  }
+
+  /** one bb_merge_batch: pack, call, decode -> { codes, changes: [{ i, value, vectorClock }] } in arrival order */
+  merge(entries) {
+    const b = packEntries(this.schema, entries);
+    const n = b.n;
+    const out = {
+      verdict: new Uint32Array(n),
+      idx: new Uint32Array(n),
+      head: new Uint32Array(4 * n),
+      clk: new Uint32Array(8 * n),
+      val: new Uint32Array(8 * n),
+    };
+    this.native.mergeBatch(this.ctx, n, b.pathId, b.head, b.clk, b.val, out);
+    this.calls++;
+    return unpackChanges(this.schema, n, out);
+  }
+
+  /** the two clock maps the device holds for a path: { meta, crt } (undefined when absent) */
+  clocks(path) {
+    const id = this.schema.pid.get(path);
+    if (id === undefined) return { meta: undefined, crt: undefined };
+    const row = this.native.tableRead(this.ctx, id); // bb_row as 32 words: val 0-7, m_cnt 8-15, v_cnt 16-23, orders 24-25, flags 28
+    const flags = row[28];
+    return {
+      meta: flags & ROW_M_PRESENT ? decodeClock(this.schema, row, 8, row[24]) : undefined,
+      crt: flags & ROW_V_PRESENT ? decodeClock(this.schema, row, 16, row[25]) : undefined,
+    };
   }
 
   /** the decision object of src/bullet-crt.js:164-279 for a device decision code */
@@ -85,7 +131,7 @@ class BulletB200 {
     const value = change ? change.value : this.bullet._getData(entry.path);
     const vectorClock = change
       ? change.vectorClock
-      : this.native.clocks(this.ctx, entry.path).crt;
+      : this.clocks(entry.path).crt;
     let broadcastData = value;
     if (typeof broadcastData === "object" && broadcastData !== null) {
       broadcastData = { ...broadcastData, __vectorClock: vectorClock }; // src/bullet-crt.js:371-376
@@ -100,18 +146,17 @@ class BulletB200 {
     crt.handleUpdate = function (path, incomingData, isFromNetwork = false) {
       self.bullet._getData(path); // src/bullet-crt.js:331: the read that turns a stored falsy value into {}
       const entry = self._entry(path, incomingData, isFromNetwork);
-      const out = self.native.merge(self.ctx, [entry]);
-      self.calls++;
+      const out = self.merge([entry]);
       if (entry.local && !out.changes[0] && self.bullet.meta[path]) {
         // a rejected LOCAL put still bumps the clock it was compared with: incrementVectorClock works in place on
         // the object meta[path].vectorClock aliases after an accepted write (src/bullet-crt.js:56-60, 358;
         // src/bullet.js:198-203).  The device keeps that aliasing; mirror what it holds.
-        const held = self.native.clocks(self.ctx, path).meta;
+        const held = self.clocks(path).meta;
         if (held) self.bullet.meta[path].vectorClock = held;
       }
       return self._result(entry, out.codes[0], out.changes[0]);
     };
-    crt.getVectorClock = (key) => self.native.clocks(self.ctx, key).crt;
+    crt.getVectorClock = (key) => self.clocks(key).crt;
   }
 
   _installSync() {
@@ -137,8 +182,7 @@ class BulletB200 {
             typeof e.data === "object" && e.data !== null
           )
     );
-    const out = this.native.merge(this.ctx, packed);
-    this.calls++;
+    const out = this.merge(packed);
     const byIndex = new Map(out.changes.map((c) => [c.i, c]));
     const crt = this.bullet.crt;
     const live = crt.handleUpdate;

@@ -11,7 +11,7 @@ import math
 import os
 
 from . import interp as I
-from .interp import (UNDEFINED, JSObject, JSArray, JSFunction, JSMapObj, JSThrow, JSSymbol, Env, Accessor,
+from .interp import (UNDEFINED, JSObject, JSArray, JSFunction, JSMapObj, JSTypedArray, JSThrow, JSSymbol, Env, Accessor,
                      call, construct, to_str, to_num, to_key, to_int, truthy, typeof, strict_eq, same_value_zero,
                      map_key, iterate, py_iter_object, make_error, throw_type, number_to_string)
 
@@ -1332,6 +1332,100 @@ def _setup_collections(g):
     IP.define(I.SYM_ITERATOR, native("[Symbol.iterator]", lambda t, a: t))
 
 
+# ----------------------------------------------------------------------------- ArrayBuffer / typed arrays
+def _setup_typed_arrays(g):
+    BP, TP = I.BUFFER_PROTO, I.TYPED_PROTO
+
+    def buffer_ctor(a, nt):
+        b = JSObject(BP, "ArrayBuffer")
+        b.define("%bytes", bytearray(to_int(arg(a, 0))))
+        return b
+    B = native("ArrayBuffer", lambda t, a: (_ for _ in ()).throw(throw_type("Constructor ArrayBuffer requires 'new'")), 1)
+    B.define("%construct", buffer_ctor)
+    B.define("prototype", BP)
+    BP.define("constructor", B)
+    BP.define("byteLength", Accessor(native("byteLength", lambda t, a: float(len(t.props["%bytes"])))))
+    g["ArrayBuffer"] = B
+
+    def _ta(this):
+        if this.__class__ is not JSTypedArray:
+            raise throw_type("this is not a typed array")
+        return this
+
+    @method(TP, "set", 2)
+    def _(this, a):
+        t, off = _ta(this), to_int(arg(a, 1)) if len(a) > 1 else 0
+        for i, v in enumerate(iterate(arg(a, 0))):
+            t.put_own(str(off + i), v)
+        return UNDEFINED
+
+    @method(TP, "fill", 1)
+    def _(this, a):
+        t = _ta(this)
+        for i in range(_rel_index(arg(a, 1), t.n, 0), _rel_index(arg(a, 2), t.n, t.n)):
+            t.put_own(str(i), arg(a, 0))
+        return this
+
+    @method(TP, "subarray", 2)
+    def _(this, a):
+        t = _ta(this)
+        lo, hi = _rel_index(arg(a, 0), t.n, 0), _rel_index(arg(a, 1), t.n, t.n)
+        out = JSTypedArray(t.proto, t.cls, t.buf, t.fmt, t.size, t.off + lo * t.size, max(hi - lo, 0))
+        out.props["%buffer"] = t.props.get("%buffer", UNDEFINED)
+        return out
+
+    @method(TP, "slice", 2)
+    def _(this, a):
+        t = _ta(this)
+        lo, hi = _rel_index(arg(a, 0), t.n, 0), _rel_index(arg(a, 1), t.n, t.n)
+        n = max(hi - lo, 0)
+        buf = bytearray(t.buf[t.off + lo * t.size: t.off + (lo + n) * t.size])
+        return JSTypedArray(t.proto, t.cls, buf, t.fmt, t.size, 0, n)
+
+    TP.define("forEach", native("forEach", lambda t, a: [call(arg(a, 0), UNDEFINED, [v, float(i), t])
+                                                        for i, v in enumerate(iterate(_ta(t)))] and UNDEFINED, 1))
+    TP.define("join", native("join", lambda t, a: ("," if arg(a, 0) is UNDEFINED else to_str(a[0])).join(
+        to_str(v) for v in iterate(_ta(t))), 1))
+    TP.define(I.SYM_ITERATOR, native("[Symbol.iterator]", lambda t, a: py_iter_object(iterate(_ta(t)))))
+
+    def mk(name, fmt, size):
+        proto = JSObject(TP, name)
+
+        def ctor(a, nt):
+            x = arg(a, 0)
+            if isinstance(x, JSObject) and x.cls == "ArrayBuffer":
+                raw = x.props["%bytes"]
+                off = to_int(arg(a, 1)) if len(a) > 1 and a[1] is not UNDEFINED else 0
+                n = to_int(a[2]) if len(a) > 2 and a[2] is not UNDEFINED else (len(raw) - off) // size
+                if off % size or off + n * size > len(raw):
+                    raise JSThrow(make_error("RangeError", f"start offset of {name} should be a multiple of {size}"))
+                t = JSTypedArray(proto, name, raw, fmt, size, off, n)
+                t.props["%buffer"] = x
+                return t
+            if x.__class__ is float or x is UNDEFINED:
+                n = 0 if x is UNDEFINED else to_int(x)
+                vals = None
+            else:
+                vals = list(iterate(x))
+                n = len(vals)
+            b = buffer_ctor([float(n * size)], None)
+            t = JSTypedArray(proto, name, b.props["%bytes"], fmt, size, 0, n)
+            t.props["%buffer"] = b
+            if vals:
+                for i, v in enumerate(vals):
+                    t.put_own(str(i), v)
+            return t
+        f = native(name, lambda t, a: (_ for _ in ()).throw(throw_type(f"Constructor {name} requires 'new'")), 3)
+        f.define("%construct", ctor)
+        f.define("prototype", proto)
+        f.define("BYTES_PER_ELEMENT", float(size))
+        proto.define("constructor", f)
+        g[name] = f
+    for name, fmt, size in (("Uint8Array", "<B", 1), ("Int8Array", "<b", 1), ("Uint16Array", "<H", 2), ("Int16Array", "<h", 2),
+                            ("Uint32Array", "<I", 4), ("Int32Array", "<i", 4), ("Float32Array", "<f", 4), ("Float64Array", "<d", 8)):
+        mk(name, fmt, size)
+
+
 # ----------------------------------------------------------------------------- RegExp / Promise
 def _setup_regexp_promise(g, rt):
     RP = I.REGEXP_PROTO
@@ -1484,6 +1578,7 @@ class Runtime:
         _setup_errors(v)
         _setup_collections(v)
         _setup_regexp_promise(v, self)
+        _setup_typed_arrays(v)
         self._setup_timers(v)
         self._setup_node(v)
         gt = new_object()
@@ -1799,7 +1894,8 @@ class Runtime:
 def _reset_protos():
     """Every Runtime is a fresh realm: clear the shared prototype objects before refilling them."""
     for p in (I.OBJECT_PROTO, I.FUNCTION_PROTO, I.ARRAY_PROTO, I.STRING_PROTO, I.NUMBER_PROTO, I.BOOLEAN_PROTO,
-              I.SYMBOL_PROTO, I.REGEXP_PROTO, I.PROMISE_PROTO, I.MAP_PROTO, I.SET_PROTO, I.DATE_PROTO, I.ITER_PROTO):
+              I.SYMBOL_PROTO, I.REGEXP_PROTO, I.PROMISE_PROTO, I.MAP_PROTO, I.SET_PROTO, I.DATE_PROTO, I.ITER_PROTO,
+              I.TYPED_PROTO, I.BUFFER_PROTO):
         p.props.clear()
         p.nonenum = None
     I.ERROR_PROTOS.clear()

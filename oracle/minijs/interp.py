@@ -241,6 +241,70 @@ class JSMapObj(JSObject):
         self.seqs.clear()
 
 
+class JSTypedArray(JSObject):
+    """Uint8Array / Uint32Array / Int32Array / Float64Array ... over a (shared) bytearray: what js/pack.js fills."""
+    __slots__ = ("buf", "fmt", "size", "off", "n")
+
+    def __init__(self, proto, cls, buf, fmt, size, off, n):
+        JSObject.__init__(self, proto, cls)
+        self.buf, self.fmt, self.size, self.off, self.n = buf, fmt, size, off, n
+
+    def own_keys(self):
+        return [str(i) for i in range(self.n)] + list(self.props)
+
+    def enumerable_keys(self):
+        return self.own_keys()
+
+    def has_own(self, k):
+        if k in ("length", "byteLength", "byteOffset", "buffer", "BYTES_PER_ELEMENT"):
+            return True
+        if _is_index(k):
+            return int(k) < self.n
+        return k in self.props
+
+    def get_own(self, k):
+        if _is_index(k):
+            i = int(k)
+            if i >= self.n:
+                return UNDEFINED
+            import struct
+            return float(struct.unpack_from(self.fmt, self.buf, self.off + i * self.size)[0])
+        if k == "length":
+            return float(self.n)
+        if k == "byteLength":
+            return float(self.n * self.size)
+        if k == "byteOffset":
+            return float(self.off)
+        if k == "BYTES_PER_ELEMENT":
+            return float(self.size)
+        if k == "buffer":
+            return self.props.get("%buffer", UNDEFINED)
+        return self.props.get(k, UNDEFINED)
+
+    def put_own(self, k, v):
+        if _is_index(k):
+            i = int(k)
+            if i < self.n:
+                import struct
+                x = to_num(v)
+                if self.fmt == "<d":
+                    val = x
+                elif self.fmt == "<f":
+                    val = x
+                else:
+                    bits = self.size * 8
+                    iv = 0 if (x != x or x in (math.inf, -math.inf)) else int(x) & ((1 << bits) - 1)
+                    if self.fmt in ("<b", "<h", "<i") and iv >= 1 << (bits - 1):
+                        iv -= 1 << bits
+                    val = iv
+                struct.pack_into(self.fmt, self.buf, self.off + i * self.size, val)
+            return
+        self.props[k] = v
+
+    def raw(self) -> bytes:
+        return bytes(self.buf[self.off:self.off + self.n * self.size])
+
+
 class Env:
     __slots__ = ("vars", "parent", "fn")
 
@@ -777,6 +841,10 @@ def iterate(v):
         return
     if v.__class__ is str:
         yield from v
+        return
+    if v.__class__ is JSTypedArray:
+        for i in range(v.n):
+            yield v.get_own(str(i))
         return
     if v.__class__ is JSMapObj:
         if v.cls == "Map":
@@ -2062,6 +2130,8 @@ PROMISE_PROTO = JSObject(OBJECT_PROTO, "Promise")
 MAP_PROTO = JSObject(OBJECT_PROTO, "Map")
 SET_PROTO = JSObject(OBJECT_PROTO, "Set")
 DATE_PROTO = JSObject(OBJECT_PROTO, "Date")
+TYPED_PROTO = JSObject(OBJECT_PROTO, "TypedArray")
+BUFFER_PROTO = JSObject(OBJECT_PROTO, "ArrayBuffer")
 ITER_PROTO = JSObject(OBJECT_PROTO, "Iterator")
 ERROR_PROTOS = {}
 

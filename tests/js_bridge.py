@@ -1,54 +1,68 @@
-"""The `native` object of js/bullet-b200.js for tests: the N-API addon's surface (create / merge / clocks)
-implemented in Python over any typed engine with the TypedOracle / Engine interface, handed to the shim running
-inside oracle/minijs.  In production this is native/bullet_b200_napi.c over libbulletb200.so."""
+"""The `native` addon of js/bullet-b200.js for tests: its typed-array surface (create / mergeBatch / tableRead,
+see INTEGRATION.md) implemented in Python over any typed engine with the TypedOracle / Engine interface and handed
+to the shim running inside oracle/minijs.  The buffers cross exactly as they would cross N-API: the JS side packs
+(js/pack.js), this side only reinterprets bytes as bb_batch / bb_changes / bb_row."""
 from __future__ import annotations
 
 import numpy as np
 
-from bullet_js_b200 import codec
-from oracle.jsvalue import UNDEFINED
+from bullet_js_b200 import capi, codec
 from oracle.minijs import interp as I
-from oracle.minijs.builtins import from_py, to_py
-from tests import streamgen
+from oracle.minijs.builtins import to_py
 
 
 class NativeBridge:
-    def __init__(self, make_engine):
-        self.make_engine = make_engine
-        self.codes: list[int] = []   # every decision the engine took, in order
-        self.batches: list[int] = []  # size of every merge call
-        self.schema = None
+    def __init__(self, rt, make_engine):
+        self.rt, self.make_engine = rt, make_engine
+        self.codes: list[int] = []    # every decision the engine took, in order
+        self.batches: list[int] = []  # size of every mergeBatch call
+        self.last_batch = None        # codec.Batch view of the most recent call's input buffers
         self.engine = None
 
     def js_object(self):
         o = I.JSObject(I.OBJECT_PROTO)
-        for name, fn in (("create", self._create), ("merge", self._merge), ("clocks", self._clocks)):
+        for name, fn in (("create", self._create), ("mergeBatch", self._merge_batch), ("tableRead", self._table_read)):
             o.define(name, I.JSFunction(name, (lambda f: lambda this, a: f(*a))(fn)), enumerable=True)
         return o
 
     def _create(self, options):
         opt = to_py(options)
-        self.schema = codec.Schema(streamgen.FIELDS, streamgen.PEERS, codec.StringDict(streamgen.STRINGS), opt["localPeer"])
-        self.engine = self.make_engine(self.schema, int(opt.get("capacity", 64)), bool(opt.get("postGetData", False)))
+        cfg = capi.make_config(int(opt["capacity"]), n_fields=int(opt["nFields"]), local_peer=int(opt["localPeer"]),
+                               flags=int(opt["flags"]), rank_object=int(opt["rankObject"]), rank_true=int(opt["rankTrue"]),
+                               rank_false=int(opt["rankFalse"]), rank_nan=int(opt["rankNaN"]))
+        self.engine = self.make_engine(cfg)
         return 1.0
 
-    def _merge(self, ctx, entries):
-        ops = []
-        for e in to_py(entries):
-            clock = e.get("vectorClock", UNDEFINED)
-            local = e["local"] or clock is UNDEFINED or clock is None
-            ops.append((e["path"], e["data"], None if local else clock))
-        batch = codec.encode_updates(self.schema, ops)
+    @staticmethod
+    def batch_of(n, path_id, head, clk, val) -> codec.Batch:
+        return codec.Batch(np.frombuffer(path_id.raw(), np.uint64).copy(), np.frombuffer(head.raw(), codec.HEAD_DTYPE).copy(),
+                           np.frombuffer(clk.raw(), np.uint32).reshape(n, 8).copy(),
+                           np.frombuffer(val.raw(), np.uint64).reshape(n, 4).copy())
+
+    def _merge_batch(self, ctx, n, path_id, head, clk, val, out):
+        n = int(n)
+        batch = self.batch_of(n, path_id, head, clk, val)
+        self.last_batch = batch
         ch = self.engine.merge(batch)
         self.codes.extend(ch.decision.tolist())
-        self.batches.append(len(ops))
-        changes = [dict(i=float(c["seq"]), value=c["value"], vectorClock=c["vectorClock"])
-                   for c in codec.decode_changes(self.schema, batch, ch)]
-        return from_py(dict(codes=[float(x) for x in ch.decision.tolist()], changes=changes))
+        self.batches.append(n)
+        k = len(ch.idx)
+        verdict = (ch.decision.astype(np.uint32) << 29) | np.uint32(codec.NO_SLOT)
+        verdict[ch.idx.astype(np.int64)] = (ch.decision[ch.idx.astype(np.int64)].astype(np.uint32) << 29) | np.arange(k, dtype=np.uint32)
 
-    def _clocks(self, ctx, path):
-        i = self.schema.paths.id(path)
-        row = (self.engine.table_read(np.array([i], np.uint64)) if hasattr(self.engine, "table_read")
-               else self.engine.read(np.array([i], np.uint64)))[0]
-        d = codec.decode_row(self.schema, row)
-        return from_py(dict(meta=d["M"] if d["M"] is not None else UNDEFINED, crt=d["V"] if d["V"] is not None else UNDEFINED))
+        def fill(name, arr):
+            t = out.get(name)
+            raw = np.ascontiguousarray(arr).tobytes()
+            t.buf[t.off:t.off + len(raw)] = raw
+        fill("verdict", verdict)
+        fill("idx", ch.idx.astype(np.uint32))
+        fill("head", ch.head)
+        fill("clk", ch.clk)
+        fill("val", ch.val)
+        return float(k)
+
+    def _table_read(self, ctx, path_id):
+        ids = np.array([int(path_id)], np.uint64)
+        row = (self.engine.table_read(ids) if hasattr(self.engine, "table_read") else self.engine.read(ids))[0]
+        proto = self.rt.globals.vars["Uint32Array"].get("prototype")
+        return I.JSTypedArray(proto, "Uint32Array", bytearray(row.tobytes()), "<I", 4, 0, 32)

@@ -4,6 +4,7 @@ engine (tests/js_bridge.py).  Everything around the decision stays the reference
 query hook, _applyUpdate, listeners), so the JS-visible outcome must equal the pure reference's golden traces."""
 import os
 
+import numpy as np
 import pytest
 
 from oracle import ref_runner
@@ -11,10 +12,9 @@ from oracle.minijs import interp as I
 from oracle.minijs.builtins import Runtime, from_py, to_py
 from oracle.ref_runner import unjsonable
 from oracle.typed import TypedOracle
-from tests import golden_io
+from tests import golden_io, streamgen
 from tests.golden_io import clock_items, same_js
 from tests.js_bridge import NativeBridge
-from tests.test_oracle_typed import make_cfg
 
 pytestmark = pytest.mark.skipif(not ref_runner.available(), reason="reference sources not present")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +24,7 @@ HARNESS = r"""
 const bullet = new Bullet({ disableNetwork: true, server: false, storage: true, storageType: "memory",
                             enableIndexing: indexed });
 bullet.id = "p0";
-const shim = new BulletB200(bullet, native, { capacity: 64, postGetData: indexed });
+const shim = new BulletB200(bullet, native, { capacity: 64, postGetData: indexed, fields: fields, peers: peers, strings: strings });
 const changes = [];
 const origApply = bullet._applyUpdate;
 bullet._applyUpdate = function (path, value, vectorClock, fromNetwork) {
@@ -40,15 +40,16 @@ return { bullet: bullet, shim: shim, changes: changes, heard: heard };
 def boot(indexed, make_engine):
     rt = Runtime(console=[])
     ref = ref_runner._reference_root()
-    bridge = NativeBridge(make_engine)
+    bridge = NativeBridge(rt, make_engine)
     r = rt.eval(HARNESS, Bullet=rt.require(os.path.join(ref, "src", "bullet.js")),
                 BulletB200=rt.require(os.path.join(ROOT, "js", "bullet-b200.js")), native=bridge.js_object(),
-                indexed=indexed, snapshot=I.JSFunction("snapshot", lambda this, a: from_py(to_py(a[0]))))
+                indexed=indexed, fields=from_py(streamgen.FIELDS), peers=from_py(streamgen.PEERS),
+                strings=from_py(streamgen.STRINGS), snapshot=I.JSFunction("snapshot", lambda this, a: from_py(to_py(a[0]))))
     return rt, bridge, r
 
 
-def oracle_engine(schema, capacity, post_getdata):
-    return TypedOracle(make_cfg(schema, capacity, post_getdata))
+def oracle_engine(cfg):
+    return TypedOracle(cfg)
 
 
 @pytest.mark.parametrize("k", [0, 1, 10])
@@ -101,6 +102,38 @@ def test_reference_with_shim_equals_reference(k):
     assert len(to_py(r.get("heard"))) == len(changes) + 1  # the `users` listener: once at subscription, then per change
 
 
+@pytest.mark.parametrize("k", [1, 11])
+def test_js_packer_equals_python_codec(k):
+    """js/pack.js fills the bb_batch buffers byte for byte like bullet_js_b200/codec.py (values incl. NaN / -0 /
+    +-Infinity, key orders, clocks and their key order, flavours, interned path ids), and its bb_config ranks and
+    string dictionary are the codec's."""
+    from bullet_js_b200 import codec
+    from tests.js_bridge import NativeBridge
+
+    case = STREAMS[k]
+    ops = golden_io.ops_of(case)
+    rt = Runtime(console=[])
+    pack = rt.require(os.path.join(ROOT, "js", "pack.js"))
+    schema_js = rt.new(pack.get("Schema"), from_py(dict(fields=streamgen.FIELDS, peers=streamgen.PEERS, strings=streamgen.STRINGS,
+                                                        localPeer="p0")))
+    entries = [dict(path=p, data=v, vectorClock=c, local=not (c is not None and isinstance(v, dict))) if c is not None
+               else dict(path=p, data=v, local=True) for p, v, c in ops]
+    b = rt.call(pack.get("packEntries"), None, schema_js, from_py(entries))
+    got = NativeBridge.batch_of(len(ops), b.get("pathId"), b.get("head"), b.get("clk"), b.get("val"))
+    schema = streamgen.make_schema()
+    want = codec.encode_updates(schema, ops)
+    want.head["user"] = np.arange(len(ops), dtype=np.uint32)  # pack.js stamps the arrival index into `user`
+    assert np.array_equal(got.path_id, want.path_id) and np.array_equal(got.head, want.head)
+    assert np.array_equal(got.clk, want.clk) and np.array_equal(got.val, want.val)
+    assert to_py(schema_js.get("strings")) == schema.strings.strings
+    ranks = to_py(rt.method(schema_js, "ranks"))
+    assert {"rank_object": ranks["rankObject"], "rank_true": ranks["rankTrue"], "rank_false": ranks["rankFalse"],
+            "rank_nan": ranks["rankNaN"]} == schema.config_ranks()
+    with pytest.raises(Exception) as e:
+        rt.call(pack.get("packEntries"), None, schema_js, from_py([dict(path="users/x", data={"age": {"deep": 1.0}}, local=True)]))
+    assert "DomainError" in str(e.value)
+
+
 def test_shim_is_plain_commonjs():
     src = open(os.path.join(ROOT, "js", "bullet-b200.js")).read()
-    assert "module.exports = BulletB200" in src and "require(" not in src.split("*/", 1)[1]
+    assert "module.exports = BulletB200" in src and src.split("*/", 1)[1].count("require(") == 1  # only ./pack
