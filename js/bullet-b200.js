@@ -15,6 +15,9 @@
  *         in:  Uint32Array views of bb_batch (js/pack.js packs them: interned path ids, heads, clocks, values)
  *         out: { verdict: Uint32Array(n), idx: Uint32Array(n), head: Uint32Array(4n), clk: Uint32Array(8n), val: Uint32Array(8n) }
  *     native.tableRead(ctx, pathId) -> Uint32Array(32)   one 128-byte bb_row                                   bb_table_read
+ *     native.indexCreate(ctx, field) / queryEquals(ctx, field, keyLo, keyHi) -> Uint32Array of node ids /
+ *     queryCount(...) -> number / queryRange(ctx, field, loNum, loRank, loFlags, hiNum, hiRank, hiFlags) -> Uint32Array
+ *                                                        bb_index_create, bb_query_equals / count / range
  * All host-side logic - interning, dictionary, packing, decoding, the reference's result shapes - is JavaScript
  * (this file and js/pack.js).
  *
@@ -25,6 +28,7 @@
  *   bullet.network.sync._processSyncEntries(entries)     src/bullet-network-sync.js:551-569 - the batched ingress:
  *       ONE native call per chunk, then the reference's own effects for every entry, in arrival order
  *   bullet.crt.getVectorClock / vectorClocks              read through to the device (crt clocks live there)
+ *   bullet.query.index / equals / range / count           with options.deviceQueries = "<collection>": the device index
  * Values outside the typed domain (nested records, integer-like keys, setCompare; SURVEY.md 8a) make the addon
  * throw: there is no CPU fallback, such collections keep the stock BulletCRT.
  */
@@ -63,6 +67,7 @@ class BulletB200 {
     this.calls = 0; // native merge calls (telemetry)
     this._installCrt();
     this._installSync();
+    if (options.deviceQueries) this._installQueries(options.deviceQueries);
   }
 
   /** one bb_merge_batch: pack, call, decode -> { codes, changes: [{ i, value, vectorClock }] } in arrival order */
@@ -157,6 +162,56 @@ class BulletB200 {
       return self._result(entry, out.codes[0], out.changes[0]);
     };
     crt.getVectorClock = (key) => self.clocks(key).crt;
+  }
+
+  /**
+   * bullet.query.index / equals / range / count on the device (src/bullet-query.js:30-45, 186-261, 293-313) for ONE
+   * collection (`base`, e.g. "users").  The index hook then runs inside the merge kernel on the raw incoming value
+   * (stale entries kept, as in query:139-176); the stock hook finds no JS-side index and does nothing.  Results
+   * are BulletNode[] like the reference's; their order is the reference's (Map, Set) order only up to a
+   * permutation (multiset) - see include/bullet_b200.h.
+   */
+  _installQueries(base) {
+    const q = this.bullet.query, self = this;
+    const slot = (field) => {
+      const f = self.schema.fslot.get(field);
+      if (f === undefined) throw new Error(`field ${field} not in schema`);
+      return f;
+    };
+    const nodes = (ids) => Array.from(ids, (id) => new self.bullet.BulletNode(self.bullet, self.schema.paths[id]));
+    const indexed = new Set();
+    const ensure = (field) => {
+      if (!indexed.has(field)) {
+        self.native.indexCreate(self.ctx, slot(field));
+        indexed.add(field);
+      }
+    };
+    const own = (path) => path === base;
+    const stock = { index: q.index.bind(q), equals: q.equals.bind(q), range: q.range.bind(q), count: q.count.bind(q) };
+    q.index = (path, field = null) => {
+      if (!own(path) || !field) return stock.index(path, field);
+      ensure(field);
+      return q;
+    };
+    q.equals = (path, field, value) => {
+      if (!own(path)) return stock.equals(path, field, value);
+      ensure(field); // the reference creates the index on first use (query:194-196)
+      const key = self.schema.indexKey(value);
+      return key === null ? [] : nodes(self.native.queryEquals(self.ctx, slot(field), key[0], key[1]));
+    };
+    q.count = (path, field, value) => {
+      if (!own(path)) return stock.count(path, field, value);
+      ensure(field);
+      const key = self.schema.indexKey(value);
+      return key === null ? 0 : self.native.queryCount(self.ctx, slot(field), key[0], key[1]);
+    };
+    q.range = (path, field, min, max) => {
+      if (!own(path)) return stock.range(path, field, min, max);
+      ensure(field);
+      if (min === undefined || max === undefined) return []; // query:246-251: an undefined bound matches nothing
+      const lo = self.schema.bound(min, false), hi = self.schema.bound(max, true);
+      return nodes(self.native.queryRange(self.ctx, slot(field), lo.num, lo.rank, lo.flags, hi.num, hi.rank, hi.flags));
+    };
   }
 
   _installSync() {

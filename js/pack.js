@@ -15,6 +15,8 @@ const HDR_FLAVOUR_NET = 1, HDR_KIND_SHIFT = 1, HDR_TAG_SHIFT = 8;
 const NO_SLOT = 0x1fffffff;
 const MAX_PEERS = 8, MAX_FIELDS = 4;
 const FORBIDDEN = ["true", "false", "NaN", "[object Object]"];
+const KEY_NAN_HI = 0x7ff80000, KEY_STR_HI = 0xfff90000, KEY_BOOL_HI = 0xfffa0000; // high words of BB_KEY_*
+const BOUND_IS_STRING = 1, BOUND_TRUE = 2, BOUND_FALSE = 4, BOUND_NAN = 8;
 
 class DomainError extends Error {
   constructor(message) {
@@ -62,6 +64,47 @@ class Schema {
       this.pid.set(path, id);
     }
     return id;
+  }
+
+  /**
+   * The 64-bit key of String(value) as [lo, hi] (include/bullet_b200.h), or null when no stored value can have that
+   * string.  equals / count are type-blind: 25 and "25" name the same bucket (src/bullet-query.js:126-131).
+   */
+  indexKey(value) {
+    if (typeof value === "boolean") return [value ? 1 : 0, KEY_BOOL_HI];
+    if (typeof value === "number") return this._numberKey(value);
+    if (value === null) value = "null";
+    if (typeof value === "object" || value === undefined) return null; // JSON.stringify(object): outside the typed domain
+    if (typeof value !== "string") throw new DomainError(`unsupported query value ${String(value)}`);
+    if (value === "true" || value === "false") return [value === "true" ? 1 : 0, KEY_BOOL_HI];
+    if (value === "NaN") return [0, KEY_NAN_HI];
+    const x = Number(value);
+    if (!Number.isNaN(x) && String(x) === value) return this._numberKey(x);
+    const id = this.sid.get(value);
+    return id === undefined ? null : [id, KEY_STR_HI];
+  }
+
+  _numberKey(x) {
+    if (Number.isNaN(x)) return [0, KEY_NAN_HI];
+    if (x === 0) return [0, 0]; // String(-0) is "0"
+    f64[0] = x;
+    return [u32[0], u32[1]];
+  }
+
+  /** One side of range() as a bb_bound { num, rank, flags } (src/bullet-query.js:238-252: JS relational semantics). */
+  bound(value, upper) {
+    if (typeof value === "string") {
+      let flags = BOUND_IS_STRING;
+      for (const [name, bit] of [["true", BOUND_TRUE], ["false", BOUND_FALSE], ["NaN", BOUND_NAN]]) {
+        if (upper ? name <= value : name >= value) flags |= bit;
+      }
+      const rank = this.strings.filter((s) => (upper ? s <= value : s < value)).length;
+      return { num: Number(value), rank, flags };
+    }
+    if (typeof value === "boolean") return { num: value ? 1 : 0, rank: 0, flags: 0 };
+    if (value === null) return { num: 0, rank: 0, flags: 0 }; // ToNumber(null)
+    if (typeof value === "number") return { num: value, rank: 0, flags: 0 };
+    return { num: NaN, rank: 0, flags: 0 }; // objects: ToNumber("[object Object]")
   }
 
   /** -> [tag, lo, hi] */

@@ -8,6 +8,8 @@
  *       pathId Uint32Array(2n) | head Uint32Array(4n) | clk Uint32Array(8n) | val Uint32Array(8n)  == bb_batch
  *       out { verdict Uint32Array(n), idx Uint32Array(n), head Uint32Array(4n), clk Uint32Array(8n), val Uint32Array(8n) }
  *   native.tableRead(ctx, pathId) -> Uint32Array(32)      one 128-byte bb_row
+ *   native.indexCreate(ctx, field) | queryEquals(ctx, field, keyLo, keyHi) -> Uint32Array | queryCount(...) -> number |
+ *   queryRange(ctx, field, loNum, loRank, loFlags, hiNum, hiRank, hiFlags) -> Uint32Array   (keys / bounds: js/pack.js)
  *   native.destroy(ctx)
  *
  * Build (node-gyp or by hand):
@@ -150,6 +152,93 @@ static napi_value TableRead(napi_env env, napi_callback_info info) {
   return array;
 }
 
+/* ---- index + queries: bb_index_create, bb_query_equals / count / range ------------------------------- */
+static int args_ctx_numbers(napi_env env, napi_callback_info info, size_t want, bb_ctx** ctx, double* num) {
+  size_t argc = 9;
+  napi_value a[9];
+  if (napi_get_cb_info(env, info, &argc, a, NULL, NULL) != napi_ok || argc < want + 1) return 0;
+  if (napi_get_value_external(env, a[0], (void**)ctx) != napi_ok) return 0;
+  for (size_t k = 0; k < want; ++k)
+    if (napi_get_value_double(env, a[1 + k], &num[k]) != napi_ok) return 0;
+  return 1;
+}
+
+static napi_value hits_to_array(napi_env env, bb_ctx* ctx, uint32_t* node, uint64_t n) {
+  void* data = NULL;
+  napi_value buffer, array;
+  if (napi_create_arraybuffer(env, (size_t)n * 4, &data, &buffer) != napi_ok) {
+    free(node);
+    return fail(env, ctx, BB_ERR_ARG);
+  }
+  memcpy(data, node, (size_t)n * 4);
+  free(node);
+  NAPI_OK(napi_create_typedarray(env, napi_uint32_array, (size_t)n, buffer, 0, &array));
+  return array;
+}
+
+static napi_value IndexCreate(napi_env env, napi_callback_info info) {
+  bb_ctx* ctx = NULL;
+  double v[1];
+  if (!args_ctx_numbers(env, info, 1, &ctx, v)) return fail(env, NULL, BB_ERR_ARG);
+  const int rc = bb_index_create(ctx, (uint32_t)v[0], 0);
+  if (rc != BB_OK) return fail(env, ctx, rc);
+  napi_value u;
+  NAPI_OK(napi_get_undefined(env, &u));
+  return u;
+}
+
+static napi_value QueryCount(napi_env env, napi_callback_info info) {
+  bb_ctx* ctx = NULL;
+  double v[3];
+  if (!args_ctx_numbers(env, info, 3, &ctx, v)) return fail(env, NULL, BB_ERR_ARG);
+  uint64_t count = 0;
+  const uint64_t key = (uint64_t)(uint32_t)v[1] | ((uint64_t)(uint32_t)v[2] << 32);
+  const int rc = bb_query_count(ctx, (uint32_t)v[0], key, &count);
+  if (rc != BB_OK) return fail(env, ctx, rc);
+  napi_value r;
+  NAPI_OK(napi_create_double(env, (double)count, &r));
+  return r;
+}
+
+/* two passes: count the hits, then fetch them into a buffer of that size */
+static napi_value QueryEquals(napi_env env, napi_callback_info info) {
+  bb_ctx* ctx = NULL;
+  double v[3];
+  if (!args_ctx_numbers(env, info, 3, &ctx, v)) return fail(env, NULL, BB_ERR_ARG);
+  const uint64_t key = (uint64_t)(uint32_t)v[1] | ((uint64_t)(uint32_t)v[2] << 32);
+  uint64_t count = 0, n_dense = 0, n_extra = 0;
+  int rc = bb_query_count(ctx, (uint32_t)v[0], key, &count);
+  if (rc != BB_OK) return fail(env, ctx, rc);
+  uint32_t* node = (uint32_t*)malloc((size_t)(count ? count : 1) * 4);
+  bb_hits hits = {count ? count : 1, node, &n_dense, &n_extra};
+  rc = bb_query_equals(ctx, (uint32_t)v[0], key, &hits);
+  if (rc != BB_OK) {
+    free(node);
+    return fail(env, ctx, rc);
+  }
+  return hits_to_array(env, ctx, node, n_dense + n_extra);
+}
+
+/* range(field, lo{num, rank, flags}, hi{num, rank, flags}); the hit buffer is sized by the table (bb_index_stats) */
+static napi_value QueryRange(napi_env env, napi_callback_info info) {
+  bb_ctx* ctx = NULL;
+  double v[7];
+  if (!args_ctx_numbers(env, info, 7, &ctx, v)) return fail(env, NULL, BB_ERR_ARG);
+  const bb_bound lo = {v[1], (uint64_t)v[2], (uint32_t)v[3], 0}, hi = {v[4], (uint64_t)v[5], (uint32_t)v[6], 0};
+  uint64_t dense = 0, extra = 0, n_dense = 0, n_extra = 0;
+  int rc = bb_index_stats(ctx, (uint32_t)v[0], &dense, &extra);
+  if (rc != BB_OK) return fail(env, ctx, rc);
+  const uint64_t cap = dense + extra + 1;
+  uint32_t* node = (uint32_t*)malloc((size_t)cap * 4);
+  bb_hits hits = {cap, node, &n_dense, &n_extra};
+  rc = bb_query_range(ctx, (uint32_t)v[0], &lo, &hi, &hits);
+  if (rc != BB_OK) {
+    free(node);
+    return fail(env, ctx, rc);
+  }
+  return hits_to_array(env, ctx, node, n_dense + n_extra);
+}
+
 static napi_value Destroy(napi_env env, napi_callback_info info) {
   size_t argc = 1;
   napi_value a[1];
@@ -164,7 +253,9 @@ NAPI_MODULE_INIT() {
   static const struct {
     const char* name;
     napi_callback fn;
-  } fns[] = {{"create", Create}, {"mergeBatch", MergeBatch}, {"tableRead", TableRead}, {"destroy", Destroy}};
+  } fns[] = {{"create", Create},           {"mergeBatch", MergeBatch},   {"tableRead", TableRead},
+             {"indexCreate", IndexCreate}, {"queryEquals", QueryEquals}, {"queryCount", QueryCount},
+             {"queryRange", QueryRange},   {"destroy", Destroy}};
   for (size_t i = 0; i < sizeof fns / sizeof fns[0]; ++i) {
     napi_value f;
     if (napi_create_function(env, fns[i].name, NAPI_AUTO_LENGTH, fns[i].fn, NULL, &f) != napi_ok) return NULL;

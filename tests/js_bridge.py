@@ -21,7 +21,9 @@ class NativeBridge:
 
     def js_object(self):
         o = I.JSObject(I.OBJECT_PROTO)
-        for name, fn in (("create", self._create), ("mergeBatch", self._merge_batch), ("tableRead", self._table_read)):
+        for name, fn in (("create", self._create), ("mergeBatch", self._merge_batch), ("tableRead", self._table_read),
+                         ("indexCreate", self._index_create), ("queryEquals", self._query_equals),
+                         ("queryCount", self._query_count), ("queryRange", self._query_range)):
             o.define(name, I.JSFunction(name, (lambda f: lambda this, a: f(*a))(fn)), enumerable=True)
         return o
 
@@ -66,3 +68,26 @@ class NativeBridge:
         row = (self.engine.table_read(ids) if hasattr(self.engine, "table_read") else self.engine.read(ids))[0]
         proto = self.rt.globals.vars["Uint32Array"].get("prototype")
         return I.JSTypedArray(proto, "Uint32Array", bytearray(row.tobytes()), "<I", 4, 0, 32)
+
+    # ---- bb_index_create / bb_query_*
+    def _u32(self, ids):
+        proto = self.rt.globals.vars["Uint32Array"].get("prototype")
+        raw = np.ascontiguousarray(ids, np.uint32).tobytes()
+        return I.JSTypedArray(proto, "Uint32Array", bytearray(raw), "<I", 4, 0, len(raw) // 4)
+
+    def _index_create(self, ctx, field):
+        self.engine.index_create(int(field))
+        return 0.0
+
+    def _query_equals(self, ctx, field, key_lo, key_hi):
+        return self._u32(self.engine.query_equals(int(field), int(key_lo) | (int(key_hi) << 32)))
+
+    def _query_count(self, ctx, field, key_lo, key_hi):
+        return float(self.engine.query_count(int(field), int(key_lo) | (int(key_hi) << 32)))
+
+    def _query_range(self, ctx, field, lo_num, lo_rank, lo_flags, hi_num, hi_rank, hi_flags):
+        def rec(num, rank, flags):
+            b = np.zeros((), codec.BOUND_DTYPE)
+            b["num"], b["rank"], b["flags"] = float(num), int(rank), int(flags)
+            return b
+        return self._u32(self.engine.query_range(int(field), rec(lo_num, lo_rank, lo_flags), rec(hi_num, hi_rank, hi_flags)))

@@ -24,7 +24,8 @@ HARNESS = r"""
 const bullet = new Bullet({ disableNetwork: true, server: false, storage: true, storageType: "memory",
                             enableIndexing: indexed });
 bullet.id = "p0";
-const shim = new BulletB200(bullet, native, { capacity: 64, postGetData: indexed, fields: fields, peers: peers, strings: strings });
+const shim = new BulletB200(bullet, native, { capacity: 64, postGetData: indexed, fields: fields, peers: peers, strings: strings,
+                                                deviceQueries: deviceQueries ? "users" : null });
 const changes = [];
 const origApply = bullet._applyUpdate;
 bullet._applyUpdate = function (path, value, vectorClock, fromNetwork) {
@@ -37,13 +38,13 @@ return { bullet: bullet, shim: shim, changes: changes, heard: heard };
 """
 
 
-def boot(indexed, make_engine):
+def boot(indexed, make_engine, device_queries=False):
     rt = Runtime(console=[])
     ref = ref_runner._reference_root()
     bridge = NativeBridge(rt, make_engine)
     r = rt.eval(HARNESS, Bullet=rt.require(os.path.join(ref, "src", "bullet.js")),
                 BulletB200=rt.require(os.path.join(ROOT, "js", "bullet-b200.js")), native=bridge.js_object(),
-                indexed=indexed, fields=from_py(streamgen.FIELDS), peers=from_py(streamgen.PEERS),
+                indexed=indexed, deviceQueries=device_queries, fields=from_py(streamgen.FIELDS), peers=from_py(streamgen.PEERS),
                 strings=from_py(streamgen.STRINGS), snapshot=I.JSFunction("snapshot", lambda this, a: from_py(to_py(a[0]))))
     return rt, bridge, r
 
@@ -100,6 +101,61 @@ def test_reference_with_shim_equals_reference(k):
                 for key in q.get("indices").enumerable_keys()}
         assert dump == case["index"]
     assert len(to_py(r.get("heard"))) == len(changes) + 1  # the `users` listener: once at subscription, then per change
+
+
+def test_device_queries_through_the_shim():
+    """options.deviceQueries: bullet.index / equals / range / count answered by the library's index (built and kept
+    by the merge kernel's hook) - with the typed oracle behind the addon the results come in the reference's exact
+    (Map, Set) order, so they must equal the golden query results; keys and bounds are computed in JavaScript."""
+    import itertools
+
+    from tests.test_oracle_query import BOUNDS, EQ_VALUES
+
+    case = STREAMS[1]
+    rt, bridge, r = boot(True, oracle_engine, device_queries=True)
+    bullet, shim = r.get("bullet"), r.get("shim")
+    for f in case["index_fields"]:
+        rt.method(bullet, "index", "users", f)
+    ops = golden_io.ops_of(case)
+    for i, (path, value, clock) in enumerate(ops):
+        for f, at in case["late_index"].items():
+            if at == i:
+                rt.method(bullet, "index", "users", f)
+        if clock is not None and isinstance(value, dict):
+            rt.method(shim, "processSyncEntries", from_py([dict(path=path, data=value, vectorClock=clock)]))
+        else:
+            rt.method(rt.method(bullet, "get", path), "put", from_py(value))
+    assert "".join(map(str, bridge.codes)) == case["codes"]
+    assert not bullet.get("query").get("indices").enumerable_keys()  # no JS-side index was ever built
+    paths = lambda nodes: [n.get("path") for n in nodes.items]  # noqa: E731
+    for name, q in case["queries"].items():
+        for v, want, cnt in zip(EQ_VALUES, q["equals"], q["count"]):
+            assert paths(rt.method(bullet, "equals", "users", name, from_py(v))) == want, (name, v)
+            assert rt.method(bullet.get("query"), "count", "users", name, from_py(v)) == float(cnt)
+        for (lo, hi), want in zip(itertools.product(BOUNDS, BOUNDS), q["range"]):
+            assert paths(rt.method(bullet, "range", "users", name, from_py(lo), from_py(hi))) == want, (name, lo, hi)
+    assert paths(rt.method(bullet, "range", "users", "age", 0.0)) == []  # max undefined
+
+
+def test_js_keys_and_bounds_equal_python_codec():
+    from bullet_js_b200 import codec
+    from tests.test_oracle_query import BOUNDS, EQ_VALUES
+
+    rt = Runtime(console=[])
+    pack = rt.require(os.path.join(ROOT, "js", "pack.js"))
+    sj = rt.new(pack.get("Schema"), from_py(dict(fields=streamgen.FIELDS, peers=streamgen.PEERS, strings=streamgen.STRINGS,
+                                                 localPeer="p0")))
+    schema = streamgen.make_schema()
+    for v in EQ_VALUES + [{"a": 1.0}]:
+        got = to_py(rt.method(sj, "indexKey", from_py(v)))
+        want = schema.index_key(v)
+        assert (None if got is None else int(got[0]) | (int(got[1]) << 32)) == want, v
+    for v in BOUNDS:
+        for upper in (False, True):
+            got = to_py(rt.method(sj, "bound", from_py(v), upper))
+            want = schema.bound(v, upper)
+            same_num = got["num"] == float(want["num"]) or (got["num"] != got["num"] and float(want["num"]) != float(want["num"]))
+            assert same_num and got["rank"] == float(want["rank"]) and got["flags"] == float(want["flags"]), (v, upper, got, want)
 
 
 @pytest.mark.parametrize("k", [1, 11])
