@@ -71,15 +71,43 @@ def one(seed, n_ops):
     return f"paths={n_paths} p_local={p_local} p_prim={p_prim} fields={fields} late={late} codes={sorted(set(want))}"
 
 
+def one_mesh(seed, n_ops):
+    """A full mesh of reference instances against the same mesh of literal oracles (tests/meshsim.py), then every
+    peer's log replayed by the typed oracle."""
+    from oracle.js_literal import RefBullet
+    from tests import meshsim
+    rng = random.Random(seed)
+    n_peers, n_paths = rng.choice([2, 3, 5, 8]), rng.choice([2, 6, 15])
+    kw = dict(p_prim=rng.choice([0.0, 0.1, 0.4]), mean_delay=rng.choice([0.5, 3.0, 20.0]))
+    jp, jlogs = meshsim.run_mesh(lambda i: ref_runner.JSRefBullet(i, enable_indexing=False), n_peers, n_ops, n_paths, seed, **kw)
+    lp, llogs = meshsim.run_mesh(lambda i: RefBullet(i, enable_indexing=False), n_peers, n_ops, n_paths, seed, **kw)
+    for i, (a, b, la, lb) in enumerate(zip(jp, lp, jlogs, llogs)):
+        assert len(la) == len(lb) and all(x[0] == y[0] and same_js(x[1], y[1]) and x[2] == y[2] for x, y in zip(la, lb)), ("log", i)
+        want = [d["code"] for d in a.decisions]
+        assert [d["code"] for d in b.decisions] == want, ("literal decisions", i)
+        assert same_js(a.store, b.store), ("literal store", i)
+        schema = codec.Schema(streamgen.FIELDS, streamgen.PEERS, codec.StringDict(streamgen.STRINGS), f"p{i}")
+        orc = TypedOracle(make_cfg(schema, 32, False))
+        assert orc.merge(codec.encode_updates(schema, la)).decision.tolist() == want, ("typed decisions", i)
+        users = a.store.get("users", {})
+        for k in range(len(schema.paths)):
+            d = codec.decode_row(schema, orc.table[k])
+            path = schema.paths.name(k)
+            assert same_js(users[path.split("/")[1]], d["value"]), ("typed value", i, path)
+            assert clock_items(d["M"]) == clock_items(a.meta[path]["vectorClock"]), ("typed M", i, path)
+    return f"mesh peers={n_peers} paths={n_paths} {kw} log sizes={[len(l) for l in jlogs]}"
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mesh", action="store_true", help="fuzz the mesh replay (BASELINE config 5) instead of single streams")
     ap.add_argument("--seeds", type=int, default=40)
     ap.add_argument("--first", type=int, default=90_000)
     ap.add_argument("--ops", type=int, default=800)
     a = ap.parse_args()
     for seed in range(a.first, a.first + a.seeds):
         try:
-            print(seed, one(seed, a.ops), flush=True)
+            print(seed, (one_mesh if a.mesh else one)(seed, a.ops), flush=True)
         except AssertionError as e:
             print("DIVERGENCE at seed", seed, e.args, flush=True)
             sys.exit(1)
