@@ -96,3 +96,31 @@ def test_kat_l_typed():
     assert ch.idx.tolist() == [0, 2, 4, 5, 7, 8]
     d = codec.decode_row(schema, orc.table[0])
     assert d["value"] == 4.0 and d["M"] == {"A": 11.0} and d["alias"]
+
+
+def test_incoming_wins_entries_repeat_the_incoming_update():
+    """The invariant a compact change set would rest on: when a NETWORK update wins outright
+    (codes 2 and 4: identical clocks / incoming dominates) the emitted value and clock are the update's own, bit for
+    bit, key orders included (crt:103-114: merging a dominating clock adds no key), so only concurrent merges,
+    first writes and local puts need their entry shipped back to the host."""
+    from bullet_js_b200 import synth
+
+    n_rec = 5000
+    rng = synth.rng_for(1, salt=77)
+    table = synth.make_table(n_rec, rng)
+    orc = TypedOracle(capi.make_config(n_rec, **synth.synth_ranks(n_rec)))
+    orc.load(np.arange(n_rec, dtype=np.uint64), table.rows)
+    for keys in ("uniform", "zipf"):
+        b = synth.make_batch(table, 60_000, rng, keys=keys)
+        ch = orc.merge(b)
+        idx = ch.idx.astype(np.int64)
+        code = ch.decision[idx]
+        net = (b.head["hdr"][idx] & codec.HDR_FLAVOUR_NET).astype(bool)
+        outright = net & ((code == codec.DEC_TIE_INCOMING) | (code == codec.DEC_INCOMING))
+        assert outright.sum() > 5000
+        assert (ch.val[outright] == b.val[idx][outright]).all()
+        assert ((ch.head["hdr"][outright] | 1) == (b.head["hdr"][idx][outright] | 1)).all()
+        assert (ch.clk[outright] == b.clk[idx][outright]).all()
+        assert (ch.head["clk_order"][outright] == b.head["clk_order"][idx][outright]).all()
+        merged = code == codec.DEC_CONCURRENT
+        assert not (ch.clk[merged] == b.clk[idx][merged]).all(axis=1).all()  # those do need their entry
