@@ -108,9 +108,9 @@ def test_incoming_wins_entries_repeat_the_incoming_update():
     n_rec = 5000
     rng = synth.rng_for(1, salt=77)
     table = synth.make_table(n_rec, rng)
-    orc = TypedOracle(capi.make_config(n_rec, **synth.synth_ranks(n_rec)))
-    orc.load(np.arange(n_rec, dtype=np.uint64), table.rows)
     for keys in ("uniform", "zipf"):
+        orc = TypedOracle(capi.make_config(n_rec, **synth.synth_ranks(n_rec)))
+        orc.load(np.arange(n_rec, dtype=np.uint64), table.rows)  # the batch's clocks are relative to this image
         b = synth.make_batch(table, 60_000, rng, keys=keys)
         ch = orc.merge(b)
         idx = ch.idx.astype(np.int64)
