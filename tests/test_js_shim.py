@@ -193,3 +193,32 @@ def test_js_packer_equals_python_codec(k):
 def test_shim_is_plain_commonjs():
     src = open(os.path.join(ROOT, "js", "bullet-b200.js")).read()
     assert "module.exports = BulletB200" in src and src.split("*/", 1)[1].count("require(") == 1  # only ./pack
+
+
+def test_quick_start_flow_with_the_shim():
+    """docs/quick-start.md:183-209 (index first, then puts, then equals) on an unmodified Bullet with the shim and the
+    device index: the documented answer, plus listeners, node.value() and a whole-collection read from the
+    reference's own store mirror."""
+    rt = Runtime(console=[])
+    ref = ref_runner._reference_root()
+    bridge = NativeBridge(rt, oracle_engine)
+    out = rt.eval(r"""
+        const bullet = new Bullet({ disableNetwork: true, server: false, storageType: "memory" });
+        const shim = new BulletB200(bullet, native, {
+          capacity: 16, fields: ["name", "email", "role"], peers: [bullet.id], postGetData: true,
+          strings: ["Alice", "Bob", "alice@example.com", "bob@example.com", "admin", "user"], deviceQueries: "users" });
+        const seen = [];
+        bullet.get("users/alice").on((v) => seen.push(v && v.role));
+        bullet.index("users", "role");
+        bullet.get("users/alice").put({ name: "Alice", email: "alice@example.com", role: "admin" });
+        bullet.get("users/bob").put({ name: "Bob", email: "bob@example.com", role: "user" });
+        const admins = bullet.equals("users", "role", "admin");
+        return { admins: admins.map((n) => n.path), value: admins[0].value(), count: bullet.query.count("users", "role", "user"),
+                 all: Object.keys(bullet.get("users").value()), seen: seen, calls: shim.calls,
+                 clock: bullet.meta["users/alice"].vectorClock, crt: bullet.crt.getVectorClock("users/alice") };
+    """, Bullet=rt.require(os.path.join(ref, "src", "bullet.js")), BulletB200=rt.require(os.path.join(ROOT, "js", "bullet-b200.js")),
+        native=bridge.js_object())
+    r = to_py(out)
+    assert r["admins"] == ["users/alice"] and r["value"] == {"name": "Alice", "email": "alice@example.com", "role": "admin"}
+    assert r["count"] == 1.0 and r["all"] == ["alice", "bob"] and r["seen"][-1] == "admin" and r["calls"] == 2.0
+    assert list(r["clock"].values()) == [3.0] and r["clock"] == r["crt"]  # a first local write: {me: 3} (SURVEY 8a), aliased
