@@ -24,7 +24,6 @@
 namespace bb {
 
 constexpr uint32_t X_EMPTY = 0xFFFFFFFFu, X_TOMB = 0xFFFFFFFEu;
-constexpr uint32_t ERR_RANGE = 1u, ERR_CHANGES = 2u, ERR_XFULL = 4u, ERR_HITS = 8u;
 
 struct IndexArgs {
   uint32_t mask;       // bit f: the index on field f is live

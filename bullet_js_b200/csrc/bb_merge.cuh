@@ -24,6 +24,11 @@ namespace bb {
 constexpr int P = BB_MAX_PEERS;
 constexpr int F = BB_MAX_FIELDS;
 
+// deferred device errors: word 0 of the ctx's error block (sticky until bb_sync), word 1 = ordinal of the first
+// rejected batch.  A batch with an out-of-range path id is rejected WHOLE: its own reject word tells the
+// kernels of that batch (and only that batch) to touch nothing.
+constexpr uint32_t ERR_RANGE = 1u, ERR_CHANGES = 2u, ERR_XFULL = 4u, ERR_HITS = 8u;
+
 struct Clock {
   uint32_t cnt[P];
   uint32_t order;

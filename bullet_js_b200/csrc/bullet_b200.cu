@@ -13,7 +13,9 @@
 #include <new>
 #include <string>
 
+#include "bb_direct.cuh"
 #include "bb_kernels.cuh"
+#include "bb_route.cuh"
 
 static_assert(sizeof(bb_row) == 128, "table rows are one 128-byte line");
 static_assert(sizeof(bb_head) == 16, "heads are one 16-byte vector");
@@ -65,21 +67,30 @@ struct bb_ctx {
   // pipeline scratch
   DevBuf<uint64_t> items_a, items_b;
   DevBuf<uint32_t> zero;  // zeroed per call: [digit histograms | tickets | sort tile states | merge tile states]
-  DevBuf<uint32_t> st_idx;
+  DevBuf<uint32_t> st_idx;     // sorted path: staging of overrunning segments; direct path: an update's rank in its path
   DevBuf<uint4> st_ent;
-  uint32_t* d_err = nullptr;    // bit0: path id out of range, bit1: change buffer too small
-  uint32_t* h_err = nullptr;    // pinned
+  uint32_t* d_err = nullptr;    // sticky until bb_sync: [0] ERR_* bits, [1] ordinal of the first rejected batch
+  uint32_t* h_err = nullptr;    // pinned [2]
+  uint32_t* d_callrej = nullptr;  // bit0: the chunked host call in flight holds a path id >= capacity (every chunk is skipped)
+  uint32_t batches_since_sync = 0;
   // device mirrors of the host-call buffers
   DevBuf<uint64_t> io_path;
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
-  uint32_t* cs_cnt = nullptr;  // counting sort: per-row update counts (all zero between calls)
-  uint32_t* cs_off = nullptr;  // full sort: their exclusive scan, u32[capacity + 1] (both padded to 1024);
-                               // grouping front end: uint2[capacity] = (start, length) of a path's run
-  DevBuf<uint2> cs_long;       // segments longer than CS_SHORT, queued for k_cs_fix_long
-  DevBuf<uint4> hot_list;      // segments k_merge_stage hands to k_merge_hot
+  // per-row words of the front ends, all zero between calls.  Direct pipeline (bb_direct.cuh): cw u64[capacity]
+  // = (sum of arrival indices << 32 | count) per path.  Sorted paths: the same memory as cs_cnt u32[capacity].
+  unsigned long long* cw = nullptr;
+  uint32_t* cs_cnt = nullptr;  // alias of cw
+  uint32_t* cs_off = nullptr;  // u32[capacity + 1] (padded to whole tiles): sorted paths: exclusive scan of the counts;
+                               // direct pipeline: a multi-update path's slab / run start
+  DevBuf<uint2> cs_long;       // sorted paths: segments longer than CS_SHORT, queued for k_cs_fix_long
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
+  // direct pipeline scratch
+  DevBuf<uint32_t> dm_slab, dm_slab_pid, dm_long_pid, dm_litems, dm_lscratch;
+  uint32_t* dm_ctr = nullptr;  // [2][DC_WORDS] per-batch counters, sets used alternately
+  uint32_t dm_parity = 0;
   uint64_t* d_nchanges = nullptr;
+  uint64_t* d_chunk_total = nullptr;  // [MAX_CHUNKS] host calls: the change count as it stood when chunk i was done
   uint64_t* d_chg_base = nullptr;
   uint64_t* h_nchanges = nullptr;  // pinned [MAX_CHUNKS]: running total after each chunk of a host call
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -120,28 +131,23 @@ int fail(bb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #call, e_); \
   } while (0)
 
-#define BB_LAUNCH(c, kernel, grid, block, stream, ...)                  \
-  do {                                                                  \
-    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);              \
-    ++(c)->launches;                                                    \
-    cudaError_t e_ = cudaGetLastError();                                \
-    if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);  \
+#define BB_LAUNCH(c, kernel, grid, block, stream, ...)                                        \
+  do {                                                                                        \
+    cudaError_t e_ = bb_launch(kernel, (uint32_t)(grid), (uint32_t)(block), 0, (stream), false, __VA_ARGS__); \
+    ++(c)->launches;                                                                          \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                           \
+    if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);                        \
+  } while (0)
+// same, with programmatic stream serialisation: the kernel calls pdl_wait() before it touches its predecessor's output
+#define BB_LAUNCH_PDL(c, kernel, grid, block, stream, ...)                                    \
+  do {                                                                                        \
+    cudaError_t e_ = bb_launch(kernel, (uint32_t)(grid), (uint32_t)(block), 0, (stream), true, __VA_ARGS__); \
+    ++(c)->launches;                                                                          \
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();                                           \
+    if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);                        \
   } while (0)
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
-
-template <bool INDEXED>
-void kernel_pipe_launch(uint32_t grid, size_t smem, cudaStream_t s, const bb::MergeArgs& ma) {
-  static bool configured[16] = {};  // per device: opt in to > 48 KB of dynamic shared memory once
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 16 && !configured[dev]) {
-    cudaFuncSetAttribute(bb::k_merge_pipe<INDEXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(bb::k_merge_pipe<INDEXED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured[dev] = true;
-  }
-  bb::k_merge_pipe<INDEXED><<<grid, bb::MT, smem, s>>>(ma);
-}
 
 void begin_call(bb_ctx* c) {
   ++c->calls;
@@ -161,19 +167,18 @@ struct ZeroLayout {
 };
 
 // How a batch is brought into "a path's updates adjacent, in arrival order":
-//   grouping (default)  O(batch) passes, singles stay in arrival order (bb_kernels.cuh K1'')
+//   direct (default)    no sort: per-path counts, then the batch is merged where it lies (bb_direct.cuh)
 //   counting sort       BB_CFG_ORDERED_CHANGES / BB_CFG_FULL_SORT, when the scan over the rows is cheap
 //                       next to the batch: the item list is ascending in path id
 //   radix sort          otherwise, or with BB_CFG_RADIX_SORT
 bool ordered_cfg(const bb_ctx* c) { return (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0; }
 
-bool use_grouping(const bb_ctx* c) {
+bool use_direct(const bb_ctx* c) {
   return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT));
 }
 
 bool use_counting_sort(const bb_ctx* c, uint64_t n) {
   if (c->cfg.flags & BB_CFG_RADIX_SORT) return false;
-  if (use_grouping(c)) return true;  // no radix passes needed either
   return c->cfg.capacity <= 64 * (n < 4096 ? 4096 : n);
 }
 
@@ -190,20 +195,27 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
   z.merge_state = z.sort_state + (size_t)z.passes * z.sort_tiles * RADIX;
   z.cs_state = z.merge_state + z.merge_tiles;
   z.cs_ctr = z.cs_state;
-  z.total = z.cs_ctr + 8;  // grouping counters [0..3], n_hot [4]
+  z.total = z.cs_ctr + 8;  // k_cs_fix counters [0..1], this batch's reject word [5]
   return z;
 }
 
 // size every scratch buffer of the device pipeline for batches of up to n updates
 int reserve_dev(bb_ctx* c, uint64_t n) {
+  BB_CUDA(c, c->st_idx.ensure(n));
+  if (use_direct(c)) {
+    BB_CUDA(c, c->dm_slab.ensure((n / 3 + 1) * bb::DM_SHORT));
+    BB_CUDA(c, c->dm_slab_pid.ensure(n / 3 + 1));
+    BB_CUDA(c, c->dm_long_pid.ensure(n / 9 + 1));
+    BB_CUDA(c, c->dm_litems.ensure(n));
+    BB_CUDA(c, c->dm_lscratch.ensure(n));
+    return BB_OK;
+  }
   const ZeroLayout z = zero_layout(c, n);
   BB_CUDA(c, c->items_a.ensure(n));
   BB_CUDA(c, c->items_b.ensure(n));
   BB_CUDA(c, c->zero.ensure(z.total));
-  BB_CUDA(c, c->st_idx.ensure(n));
   BB_CUDA(c, c->st_ent.ensure(5 * n));
   BB_CUDA(c, c->cs_long.ensure(n / 8 + 1));
-  BB_CUDA(c, c->hot_list.ensure(n / 64 + 16));
   return BB_OK;
 }
 
@@ -220,17 +232,83 @@ int reserve_io(bb_ctx* c, uint64_t n) {
   return BB_OK;
 }
 
+void fill_params(const bb_ctx* c, bb::Params& p, bb::IndexArgs& ix) {
+  p.rank_object = c->cfg.rank_object;
+  p.me = c->cfg.local_peer;
+  p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
+  ix.mask = c->index_mask;
+  ix.xused = c->d_xused;
+  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+    ix.pcol[f] = c->index[f].pcol;
+    ix.xkey[f] = c->index[f].xkey;
+    ix.xnode[f] = c->index[f].xnode;
+    ix.xmask[f] = c->index[f].live ? (uint32_t)(c->index[f].xslots - 1) : 0u;
+  }
+}
+
+// The default pipeline (bb_direct.cuh): count -> merge where the batch lies -> multi-update paths.
+int merge_direct(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, uint32_t idx_base, bool append,
+                 const uint32_t* call_rej) {
+  using namespace bb;
+  const uint64_t n = in->n;
+  DmArgs a;
+  a.path_id = in->path_id;
+  a.n = n;
+  a.capacity = c->cfg.capacity;
+  a.table = c->table;
+  a.head = reinterpret_cast<const uint4*>(in->head);
+  a.clk = reinterpret_cast<const uint4*>(in->clk);
+  a.val = reinterpret_cast<const uint4*>(in->val);
+  a.cw = c->cw;
+  a.off = c->cs_off;
+  a.rank = c->st_idx.p;
+  a.slab = c->dm_slab.p;
+  a.slab_pid = c->dm_slab_pid.p;
+  a.long_pid = c->dm_long_pid.p;
+  a.litems = c->dm_litems.p;
+  a.lscratch = c->dm_lscratch.p;
+  a.ctr = c->dm_ctr + (size_t)c->dm_parity * DC_WORDS;
+  a.ctr_next = c->dm_ctr + (size_t)(c->dm_parity ^ 1u) * DC_WORDS;
+  c->dm_parity ^= 1u;
+  a.verdict = out->verdict;
+  a.n_changes = reinterpret_cast<unsigned long long*>(out->n_changes);
+  a.out_idx = out->idx;
+  a.out_head = reinterpret_cast<uint4*>(out->head);
+  a.out_clk = reinterpret_cast<uint4*>(out->clk);
+  a.out_val = reinterpret_cast<uint4*>(out->val);
+  a.cap = out->cap;
+  a.seq_base = c->seq;
+  a.idx_base = idx_base;
+  a.zero_changes = append ? 0u : 1u;
+  a.ordinal = c->batches_since_sync;
+  a.err = c->d_err;
+  a.rej = call_rej ? call_rej : a.ctr + DC_REJ;
+  fill_params(c, a.p, a.ix);
+  BB_LAUNCH(c, k_dm_count, div_up(n, 256 * DM_ILP), 256, s, a);
+  if (!append) mark(c, EV_SORT, s);
+  const uint32_t g3 = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(n, 3 * DM3_T), (uint32_t)c->n_sm * 2u));
+  if (c->index_mask) {
+    BB_LAUNCH_PDL(c, k_dm_merge<true>, div_up(n, DM_T), DM_T, s, a);
+    BB_LAUNCH_PDL(c, k_dm_multi<true>, g3, DM3_T, s, a);
+  } else {
+    BB_LAUNCH_PDL(c, k_dm_merge<false>, div_up(n, DM_T), DM_T, s, a);
+    BB_LAUNCH_PDL(c, k_dm_multi<false>, g3, DM3_T, s, a);
+  }
+  return BB_OK;
+}
+
 // One batch (or one chunk of a host call: `idx_base` = arrival index of its first update,
-// `append` = keep adding to *out->n_changes instead of starting a new change set).
+// `append` = keep adding to *out->n_changes instead of starting a new change set; `call_rej` = the word
+// that says the whole host call is rejected).
 int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, uint32_t idx_base = 0,
-              bool append = false) {
+              bool append = false, const uint32_t* call_rej = nullptr) {
   using namespace bb;
   const uint64_t n = in->n;
   if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
-  const bool lean = use_grouping(c) && n > 0;  // k_cs_count resets the counters itself: no memsets
+  const bool direct = use_direct(c);
   if (!append) {
     mark(c, EV_START, s);
-    if (!lean) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+    if (!direct || n == 0) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
   }
   if (n == 0) {
     if (!append) {
@@ -243,41 +321,38 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     int rc = reserve_dev(c, n);  // no-op once the scratch is large enough
     if (rc) return rc;
   }
+  ++c->batches_since_sync;
+  if (direct) {
+    int rc = merge_direct(c, in, out, s, idx_base, append, call_rej);
+    if (rc) return rc;
+    if (!append) mark(c, EV_MERGE, s);
+    c->seq += n;
+    return BB_OK;
+  }
   const ZeroLayout z = zero_layout(c, n);
   uint32_t* zp = c->zero.p;
-  if (!lean) BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
+  BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
+  uint32_t* rej = zp + z.cs_ctr + 5;  // this batch's reject word
+  const uint32_t ordinal = c->batches_since_sync;
 
   uint64_t* src = c->items_a.p;
-  if (use_grouping(c)) {
-    // K1'': count, then group (singles in arrival order, multi-update paths in claimed runs behind them)
-    const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
-    uint2* off2 = reinterpret_cast<uint2*>(c->cs_off);
-    uint32_t* ctr = zp + z.cs_ctr;
-    BB_LAUNCH(c, k_cs_count, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->d_err, ctr,
-              append ? (uint64_t*)nullptr : out->n_changes);
-    BB_LAUNCH(c, k_cg_classify, g4, CS_THREADS, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, off2, src,
-              ctr, c->cs_long.p);
-    BB_LAUNCH(c, k_cg_place, g4, CS_THREADS, s, in->path_id, n, c->st_idx.p, off2, c->cs_cnt, src, ctr);
-    BB_LAUNCH(c, k_cg_fix, div_up(n, CS_THREADS), CS_THREADS, s, src, off2, ctr);
-    BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, ctr + CG_CTR_LONG,
-              ctr + CG_CTR_NEXT, ctr + CG_CTR_SINGLE);
-  } else if (use_counting_sort(c, n)) {
+  if (use_counting_sort(c, n)) {
     // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
     const uint32_t g = div_up(n, CS_THREADS);
     const uint64_t cap = c->cfg.capacity;
     const uint32_t tiles = div_up(cap + 1, CS_TILE);  // + 1: off[capacity] = the batch size
-    BB_LAUNCH(c, k_cs_count, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->st_idx.p, c->d_err,
-              (uint32_t*)nullptr, (uint64_t*)nullptr);
+    BB_LAUNCH(c, k_cs_count, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->cs_cnt, c->st_idx.p, rej,
+              c->d_err, ordinal);
     BB_LAUNCH(c, k_cs_tile_sums, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p);
     BB_LAUNCH(c, k_cs_offsets, tiles, CS_THREADS, s, c->cs_cnt, c->cs_tile.p, c->cs_off);
-    BB_LAUNCH(c, k_cs_place, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->st_idx.p, c->cs_off, src, c->d_err);
-    BB_LAUNCH(c, k_cs_fix, g, CS_THREADS, s, src, n, c->cs_off, c->cs_long.p, zp + z.cs_ctr, c->d_err);
+    BB_LAUNCH(c, k_cs_place, div_up(n, CS_THREADS * CS_ILP), CS_THREADS, s, in->path_id, n, cap, c->st_idx.p, c->cs_off, src, rej);
+    BB_LAUNCH(c, k_cs_fix, g, CS_THREADS, s, src, n, c->cs_off, c->cs_long.p, zp + z.cs_ctr, rej);
     BB_LAUNCH(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, s, src, c->items_b.p, c->cs_long.p, zp + z.cs_ctr,
               zp + z.cs_ctr + 1, (const uint32_t*)nullptr);
   } else {
     // K0 + K1: stable LSD radix sort of (path id, arrival index) by path id
     BB_LAUNCH(c, k_keys_hist, z.sort_tiles, SORT_THREADS, s, in->path_id, n, c->cfg.capacity, (int)z.passes,
-              c->items_a.p, zp + z.hist, c->d_err);
+              c->items_a.p, zp + z.hist, rej, c->d_err, ordinal);
     BB_LAUNCH(c, k_hist_scan, z.passes, RADIX, s, zp + z.hist);
     uint64_t* dst = c->items_b.p;
     for (uint32_t pass = 0; pass < z.passes; ++pass) {
@@ -293,7 +368,7 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
     BB_CUDA(c, cudaMemcpyAsync(c->d_chg_base, out->n_changes, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
 
-  // K2: per-path sequential replay against the table + change-set compaction
+  // K2s: per-path sequential replay over the sorted item list + change-set compaction
   MergeArgs ma;
   ma.sorted = src;
   ma.n = n;
@@ -313,56 +388,38 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.tile_state = zp + z.merge_state;
   ma.ticket = zp + z.tickets + MAX_PASSES;
   ma.num_tiles = z.merge_tiles;
-  ma.hot_list = c->hot_list.p;
-  ma.n_hot = zp + z.cs_ctr + 4;
-  const bool hot = (c->cfg.flags & BB_CFG_HOT_KEYS) && !ordered_cfg(c) && !c->index_mask && !(c->cfg.flags & BB_CFG_CTA_PIPE);
-  ma.hot_cap = hot ? (uint32_t)std::min<uint64_t>(c->hot_list.cap, 0x7FFFFFFFull) : 0u;
   ma.seq_base = c->seq;
   ma.idx_base = idx_base;
   ma.chg_base = c->d_chg_base;
   ma.err = c->d_err;
-  ma.p.rank_object = c->cfg.rank_object;
-  ma.p.me = c->cfg.local_peer;
-  ma.p.post_getdata = (c->cfg.flags & BB_CFG_POST_GETDATA) != 0;
-  ma.ix.mask = c->index_mask;
-  ma.ix.xused = c->d_xused;
-  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
-    ma.ix.pcol[f] = c->index[f].pcol;
-    ma.ix.xkey[f] = c->index[f].xkey;
-    ma.ix.xnode[f] = c->index[f].xnode;
-    ma.ix.xmask[f] = c->index[f].live ? (uint32_t)(c->index[f].xslots - 1) : 0u;
-  }
+  ma.rej = call_rej ? call_rej : rej;
+  fill_params(c, ma.p, ma.ix);
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
-  if (!ordered && (c->cfg.flags & BB_CFG_CTA_PIPE)) {
-    // K2': persistent, software-pipelined CTAs (4 per SM)
-    const uint32_t grid = std::min<uint32_t>(z.merge_tiles, (uint32_t)(c->n_sm * MP_CTAS_PER_SM));
-    const size_t smem = sizeof(MergePipeSmem);
-    if (c->index_mask) kernel_pipe_launch<true>(grid, smem, s, ma);
-    else kernel_pipe_launch<false>(grid, smem, s, ma);
-    ++c->launches;
-    cudaError_t e_ = cudaGetLastError();
-    if (e_ != cudaSuccess) return fail(c, BB_ERR_CUDA, "k_merge_pipe", e_);
-  } else if (c->index_mask) {
+  if (c->index_mask) {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
   } else {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, false>), z.merge_tiles, MT, s, ma);
-    else if (hot) BB_LAUNCH(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, false>), z.merge_tiles, MT, s, ma);
   }
-  if (hot) BB_LAUNCH(c, k_merge_hot, HOT_CTAS, MT, s, ma);
   if (!append) mark(c, EV_MERGE, s);
   c->seq += n;
   return BB_OK;
 }
 
-// fetch + clear the deferred device error word; stream must be idle afterwards
+// fetch + clear the deferred device error words; stream must be idle afterwards
 int collect_device_error(bb_ctx* c, cudaStream_t s) {
-  BB_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  BB_CUDA(c, cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), s));
+  static const uint32_t clear[2] = {0u, 0xFFFFFFFFu};
+  BB_CUDA(c, cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  BB_CUDA(c, cudaMemcpyAsync(c->d_err, clear, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   BB_CUDA(c, cudaStreamSynchronize(s));
-  const uint32_t e = *c->h_err;
-  if (e & bb::ERR_RANGE) return fail(c, BB_ERR_CAPACITY, "path id >= capacity (batch rejected, table unchanged)");
+  const uint32_t e = c->h_err[0], first = c->h_err[1];
+  c->batches_since_sync = 0;
+  if (e & bb::ERR_RANGE) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "path id >= capacity: batch %u since the last sync was rejected whole, table unchanged (later batches were merged)", first);
+    return fail(c, BB_ERR_CAPACITY, msg);
+  }
   if (e & bb::ERR_CHANGES) return fail(c, BB_ERR_CAPACITY, "change-set buffer too small");
   if (e & bb::ERR_XFULL) return fail(c, BB_ERR_CAPACITY, "index overflow set is full (bb_index_create extra_capacity)");
   if (e & bb::ERR_HITS) return fail(c, BB_ERR_CAPACITY, "hit buffer too small");
@@ -525,29 +582,44 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   int bits = 1;
   while (bits < 32 && (1ull << bits) < cfg->capacity) ++bits;
   c->key_bits = bits;
-  // 8 x 27.7 KB of static shared memory per SM: ask for the full carve-out
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  // everything below (function attributes included) is per device: select it first
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed";
+    delete c;
+    return BB_ERR_CUDA;
+  }
+  // k_merge_stage: 7 x 27.7 KB, k_dm_merge: 3 x 41 KB of static shared memory per SM: ask for the full carve-out
   cudaFuncSetAttribute(bb::k_merge_stage<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_dm_merge<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_dm_merge<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
   }
   const size_t cs_words = ((size_t)cfg->capacity + 1 + bb::CS_TILE - 1) / bb::CS_TILE * bb::CS_TILE;
-  bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+  const size_t cw_bytes = std::max(cs_words * sizeof(uint32_t), (size_t)cfg->capacity * sizeof(unsigned long long));
+  static const uint32_t err_clear[2] = {0u, 0xFFFFFFFFu};
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->table, cfg->capacity * sizeof(bb_row)) == cudaSuccess &&
             cudaMemsetAsync(c->table, 0, cfg->capacity * sizeof(bb_row), c->stream) == cudaSuccess &&
-            cudaMalloc((void**)&c->d_err, sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemsetAsync(c->d_err, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
-            cudaMalloc((void**)&c->cs_cnt, cs_words * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint2)) == cudaSuccess &&
-            cudaMemsetAsync(c->cs_cnt, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_err, 2 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemcpyAsync(c->d_err, err_clear, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_callrej, sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->cw, cw_bytes) == cudaSuccess &&
+            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->cw, 0, cw_bytes, c->stream) == cudaSuccess &&
             cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->dm_ctr, 2 * bb::DC_WORDS * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->dm_ctr, 0, 2 * bb::DC_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             c->cs_tile.ensure(cs_words / bb::CS_TILE) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_chunk_total, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
@@ -555,8 +627,9 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMemsetAsync(c->d_xused, 0, BB_MAX_FIELDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMallocHost((void**)&c->h_err, sizeof(uint32_t)) == cudaSuccess &&
+            cudaMallocHost((void**)&c->h_err, 2 * sizeof(uint32_t)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_nchanges, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess;
+  c->cs_cnt = reinterpret_cast<uint32_t*>(c->cw);
   for (int i = 0; ok && i < MAX_CHUNKS; ++i)
     ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -567,8 +640,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   if (!ok) {
     g_create_error = std::string("CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     bb_destroy(c);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return BB_ERR_CUDA;
   }
+  if (prev_dev >= 0 && prev_dev != cfg->device) cudaSetDevice(prev_dev);  // every entry point selects the ctx's device itself
   *out = c;
   return BB_OK;
 }
@@ -593,10 +668,13 @@ int bb_destroy(bb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
-  if (c->cs_cnt) cudaFree(c->cs_cnt);
+  if (c->cw) cudaFree(c->cw);
   if (c->cs_off) cudaFree(c->cs_off);
+  if (c->dm_ctr) cudaFree(c->dm_ctr);
+  if (c->d_callrej) cudaFree(c->d_callrej);
+  if (c->d_chunk_total) cudaFree(c->d_chunk_total);
   c->cs_long.release(); c->cs_tile.release();
-  c->hot_list.release();
+  c->dm_slab.release(); c->dm_slab_pid.release(); c->dm_long_pid.release(); c->dm_litems.release(); c->dm_lscratch.release();
   if (c->d_nchanges) cudaFree(c->d_nchanges);
   if (c->d_chg_base) cudaFree(c->d_chg_base);
   for (int i = 0; i < MAX_CHUNKS; ++i) {
@@ -733,7 +811,13 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_in[0], 0));
   mark(c, EV_START, s);
   BB_CUDA(c, cudaMemsetAsync(c->d_nchanges, 0, sizeof(uint64_t), s));
-  if (nchunks > 1) BB_LAUNCH(c, bb::k_check_range, 296, 256, s, c->io_path.p, n, c->cfg.capacity, c->d_err);
+  const uint32_t* call_rej = nullptr;
+  if (nchunks > 1) {  // one bad id anywhere rejects every chunk before any of them touches the table
+    BB_CUDA(c, cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), s));
+    BB_LAUNCH(c, bb::k_check_range, 296, 256, s, c->io_path.p, n, c->cfg.capacity, c->d_callrej, c->d_err,
+              c->batches_since_sync + 1);
+    call_rej = c->d_callrej;
+  }
   for (int i = 0; i < nchunks; ++i) {
     const uint64_t o = (uint64_t)i * chunk, m = (o + chunk <= n) ? chunk : n - o;
     bb_batch din{m, c->io_path.p + o, reinterpret_cast<const bb_head*>(c->io_head.p + o),
@@ -742,8 +826,11 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
     bb_changes dchunk = dout;
     dchunk.verdict = c->io_verdict.p + o;
     BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_in[i], 0));
-    int rc = merge_dev(c, &din, &dchunk, s, (uint32_t)o, true);
+    int rc = merge_dev(c, &din, &dchunk, s, (uint32_t)o, true, call_rej);
     if (rc) return rc;
+    // the change count as it stands NOW: later chunks keep adding to d_nchanges, and entries past this snapshot
+    // are not written yet when the copy-out of chunk i runs
+    BB_CUDA(c, cudaMemcpyAsync(c->d_chunk_total + i, c->d_nchanges, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
     BB_CUDA(c, cudaEventRecord(c->ev_done[i], s));
   }
   mark(c, EV_SORT, s);  // (phases of a chunked call: "sort" is 0, "merge" = sort + merge of every chunk)
@@ -753,7 +840,7 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   for (int i = 0; i < nchunks; ++i) {  // a chunk's entries are final once its kernels are: ship them
     const uint64_t o = (uint64_t)i * chunk, m = (o + chunk <= n) ? chunk : n - o;
     BB_CUDA(c, cudaStreamWaitEvent(c->s_d2h, c->ev_done[i], 0));
-    BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges + i, c->d_nchanges, 8, cudaMemcpyDeviceToHost, c->s_d2h));
+    BB_CUDA(c, cudaMemcpyAsync(c->h_nchanges + i, c->d_chunk_total + i, 8, cudaMemcpyDeviceToHost, c->s_d2h));
     BB_CUDA(c, cudaEventRecord(c->ev_cnt[i], c->s_d2h));
     BB_CUDA(c, cudaMemcpyAsync(out->verdict + o, c->io_verdict.p + o, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
     BB_CUDA(c, cudaEventSynchronize(c->ev_cnt[i]));
@@ -791,8 +878,8 @@ static cudaError_t launch_pack(uint32_t world, const bb_batch* in, bb_batch* out
   using namespace bb;
   const uint64_t n = in->n;
   const uint32_t tiles = div_up(n, RT_THREADS);
-  k_route_count<<<tiles, RT_THREADS, 0, s>>>(in->path_id, n, world, tiles_buf);
-  k_route_scan<<<1, RS_THREADS, 0, s>>>(tiles_buf, tiles, world, counts);
+  bb_launch(k_route_count, tiles, RT_THREADS, 0, s, false, in->path_id, n, world, tiles_buf);
+  bb_launch(k_route_scan, 1, RS_THREADS, 0, s, false, tiles_buf, tiles, world, counts);
   RouteArgs a;
   a.path_id = in->path_id;
   a.head = reinterpret_cast<const uint4*>(in->head);
@@ -805,7 +892,7 @@ static cudaError_t launch_pack(uint32_t world, const bb_batch* in, bb_batch* out
   a.n = n;
   a.world = world;
   a.tile_off = tiles_buf;
-  k_route_scatter<<<tiles, RT_THREADS, 0, s>>>(a);
+  bb_launch(k_route_scatter, tiles, RT_THREADS, 0, s, false, a);
   return cudaGetLastError();
 }
 
@@ -1274,8 +1361,8 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
   cudaEventRecord(r->tev[0], sp);
   const uint32_t tiles = div_up(n, bb::RT_THREADS);
   if (n && r->p2p) {  // the scatter waits until every rank's counts are known
-    bb::k_route_count<<<tiles, bb::RT_THREADS, 0, sp>>>(in->path_id, n, W, tile_buf);
-    bb::k_route_scan<<<1, bb::RS_THREADS, 0, sp>>>(tile_buf, tiles, W, cnt_buf);
+    bb_launch(bb::k_route_count, tiles, bb::RT_THREADS, 0, sp, false, in->path_id, n, W, tile_buf);
+    bb_launch(bb::k_route_scan, 1, bb::RS_THREADS, 0, sp, false, tile_buf, tiles, W, cnt_buf);
     r->launches += 2;
     BB_RCUDA(r, cudaGetLastError());
   } else if (n) {
@@ -1291,7 +1378,7 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
   const uint64_t epoch = ++r->epoch;
   const uint64_t* d_matrix = r->d_matrix;
   if (flags) {
-    bb::k_route_publish<<<1, bb::RT_MAX_WORLD * bb::RT_MAX_WORLD, 0, sp>>>(cnt_buf, r->ctl_peers, me, W, slot, epoch);
+    bb_launch(bb::k_route_publish, 1, bb::RT_MAX_WORLD * bb::RT_MAX_WORLD, 0, sp, false, cnt_buf, r->ctl_peers, me, W, slot, epoch);
     r->launches += 1;
     BB_RCUDA(r, cudaGetLastError());
     d_matrix = r->ctl->matrix[slot];
@@ -1330,14 +1417,14 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
       a.world = W;
       a.bulk = r->bulk ? 1u : 0u;
       a.tile_off = tile_buf;
-      bb::k_route_scatter_p2p<<<std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s>>>(a);
+      bb_launch(bb::k_route_scatter_p2p, std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s, false, a);
       r->launches += 1;
       BB_RCUDA(r, cudaGetLastError());
     }
     cudaEventRecord(r->tev[3], s);
     // every rank's stores are complete when its scatter kernel is: a barrier across the ranks follows
     if (flags) {
-      bb::k_route_barrier<<<1, 32, 0, s>>>(r->ctl_peers, me, W, slot, epoch);
+      bb_launch(bb::k_route_barrier, 1, 32, 0, s, false, r->ctl_peers, me, W, slot, epoch);
       r->launches += 1;
       BB_RCUDA(r, cudaGetLastError());
     } else if (W > 1) {
