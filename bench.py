@@ -434,8 +434,23 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     sent = (router.sent_bytes - sent0) if router else 0
     # phase timings of the timed steps (events recorded inside the library on the same stream)
-    ph = {name: float(np.mean([engines[W + j].phase_ms(name) for j in range(K)]))
-          for name in ("sort", "merge", "device")}
+    ph = {"device": float(np.mean([engines[W + j].phase_ms("device") for j in range(K)]))}
+    if world == 1:  # per-kernel split: a few extra steps with the event between the front end and the merge recorded
+        Kp = min(K, 5)
+        for e in engines[:Kp]:
+            e.table_load(ids, table.rows)
+            e.phase_events(True)
+        for i in range(Kp):
+            step_dev(i, False)
+        eng.sync(stream)
+        torch.cuda.synchronize()
+        for name in ("sort", "merge"):
+            ph[name] = float(np.mean([engines[j].phase_ms(name) for j in range(Kp)]))
+        ph["device_with_phase_events"] = float(np.mean([engines[j].phase_ms("device") for j in range(Kp)]))
+        for e in engines[:Kp]:
+            e.phase_events(False)
+    else:
+        ph["sort"] = ph["merge"] = float("nan")
     acc_frac = float(o_n.item()) / max(1, (merged // K))
 
     # ---- e2e through bb_merge_batch with pinned host buffers

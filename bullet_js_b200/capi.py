@@ -74,7 +74,7 @@ EXPORTS = [
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
     "bb_router_last_error", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
     "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
-    "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms",
+    "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms", "bb_phase_events",
 ]
 
 _lib = None
@@ -154,6 +154,8 @@ def load():
     lib.bb_launch_count.restype = u64
     lib.bb_last_phase_ms.argtypes = [vp, C.c_char_p]
     lib.bb_last_phase_ms.restype = C.c_double
+    lib.bb_phase_events.argtypes = [vp, i32]
+    lib.bb_phase_events.restype = i32
     lib.bb_phase_ms.argtypes = [vp, C.c_char_p, C.c_uint32]
     lib.bb_phase_ms.restype = C.c_double
     _lib = lib

@@ -4,19 +4,25 @@
 // src/bullet.js:184-220, driven by src/bullet-network-sync.js:551-569) only needs a path's updates replayed
 // in arrival order; paths are independent.  In a batch most paths occur once, so:
 //
-//   K1 k_dm_count   one 64-bit atomicAdd per update on cw[path] adds (arrival index << 32 | 1): the low half
-//                   counts the path's updates (the returned value is this update's rank inside the path, in
-//                   atomic order), the high half sums their arrival indices mod 2^32.  The third arrival of a
-//                   path claims a slab of 8 index slots, the ninth queues the path as "long"; the last CTA to
-//                   finish lays the long paths' runs out.
-//   K2 k_dm_merge   one CTA per tile of 256 CONSECUTIVE updates (arrival order).  The tile's payloads
+//   K1 k_dm_count   one 64-bit atomicAdd per update ON THE PATH'S TABLE ROW: its last 16-byte chunk holds
+//                   flags | count << 3 and, next to it, the sum of the arrival indices mod 2^32 (both 0 between
+//                   batches).  The returned value is the update's rank inside its path (atomic order).  Random
+//                   row accesses are DRAM-activation-bound (~30 us per million, scripts/ubench/atomics.cu), so
+//                   this kernel is where the batch's rows are pulled into L2: persistent CTAs prefetch the row
+//                   lines of their next tile while the atomics of the current one run, and walk the tiles in
+//                   REVERSE, so that the rows K2 wants first are the freshest.  The second arrival of a path
+//                   notes the first one's index (its "partner": the sum so far IS that index) and prefetches
+//                   its payload, the third claims a slab of 8 index slots, the ninth queues the path as
+//                   "long"; the last CTA lays the long paths' runs out.
+//   K2 k_dm_merge   one CTA per tile of 128 CONSECUTIVE updates (arrival order).  The tile's payloads
 //                   (16 + 32 + 32 bytes per update) are staged in shared memory by three cp.async.bulk
-//                   copies (TMA engine, mbarrier completion) issued before anything else.  Per update:
-//                     count 1 (2/3 of a uniform batch)  row -> registers (8 x 16 B, the fastest way to move a
-//                                   random 128-byte row: scripts/ubench/row_gather.cu), resolve, row back,
-//                                   change entry ranked inside the tile (arrival order), one atomic per CTA
-//                     count 2       partner = index sum - own index: the LATER update owns the path, fetches the
-//                                   partner's payload (cp.async) next to the row and replays both in order
+//                   copies (TMA engine, mbarrier completion) issued before anything else; every update's row
+//                   follows with cp.async, 8 lanes per 128-byte row (a divergent 16-byte load per thread
+//                   costs 8x the L1 wavefronts: scripts/ubench/row_gather.cu), and carries the path's count:
+//                     count 1 (2/3 of a uniform batch)  resolve, row back (count cleared), change entry ranked
+//                                   inside the tile, one atomic per CTA
+//                     count 2       the SECOND arrival owns the path: it fetched the partner's payload next to
+//                                   the row (speculatively, from K1's note) and replays both in arrival order
 //                     count 3..8    drops its index into the path's slab; > 8: into the path's run
 //   K3 k_dm_multi   one thread per slab (sort <= 8 indices in registers, replay), then one CTA per long path:
 //                   radix sort of its run on the arrival index, then rounds of 256 speculative evaluations
@@ -25,14 +31,13 @@
 //
 // K2 and K3 are launched with programmatic stream serialisation: their CTAs become resident while the
 // previous kernel drains and wait (griddepcontrol.wait) before touching its output; K2 stages payloads first.
-// cw[] is all zero between batches: whoever replays a path clears its word.
 #pragma once
 #include "bb_kernels.cuh"
 
 namespace bb {
 
 constexpr int DM_SHORT = 8;    // longest path one thread replays out of a slab
-constexpr int DM_T = 256;      // K2: updates per tile == threads per CTA
+constexpr int DM_T = 128;      // K2: updates per tile == threads per CTA
 constexpr int DM_WARPS = DM_T / 32;
 constexpr int DM_ILP = 4;      // K1: atomics in flight per thread
 constexpr int DM3_T = 256;     // K3: threads per CTA == speculation window of a long path
@@ -47,9 +52,8 @@ struct DmArgs {
   const uint4* head;       // [n]
   const uint4* clk;        // [n][2]
   const uint4* val;        // [n][2]
-  unsigned long long* cw;  // [capacity] (sum of arrival indices mod 2^32) << 32 | updates of this path; 0 between batches
   uint32_t* off;           // [capacity] this batch only: slab of a path with 3..8 updates, start of its run if > 8
-  uint32_t* rank;          // [n]
+  uint32_t* rank;          // [n] rank of the update in its path (atomic order); second arrivals: RANK_PAIR | partner
   uint32_t* slab;          // [n / 3 + 1][8]
   uint32_t* slab_pid;      // [n / 3 + 1]
   uint32_t* long_pid;      // [n / 9 + 1]
@@ -70,38 +74,79 @@ struct DmArgs {
   uint32_t ordinal;        // number of this batch since the last bb_sync (error reporting)
   uint32_t* err;           // sticky until bb_sync: [0] bits ERR_*, [1] ordinal of the first rejected batch
   const uint32_t* rej;     // bit 0: this batch is rejected (ctr[DC_REJ], or the whole-call word of a chunked host call)
+  uint32_t tune;           // experiment switches (env BB_DM_TUNE): 1 walk the tiles in reverse, 2 K1 releases K2 late,
+                           // 4 second arrivals prefetch the partner's payload, 8 prefetch only the row's last sector
+  unsigned long long* tl;  // diagnostics (BB_TIMELINE=1): [k][2] first start / last end of kernel k in globaltimer ns, or null
   Params p;
   IndexArgs ix;
 };
 
+__device__ __forceinline__ void tl_start(const DmArgs& a, int k) {
+  if (a.tl && threadIdx.x == 0) atomicMin(a.tl + 2 * k, global_timer_ns());
+}
+__device__ __forceinline__ void tl_end(const DmArgs& a, int k) {
+  if (a.tl && threadIdx.x == 0) atomicMax(a.tl + 2 * k + 1, global_timer_ns());
+}
+
+constexpr uint32_t RANK_PAIR = 0x80000000u;
+constexpr unsigned long long CW_ONE = 1ull << ROW_CNT_SHIFT;  // one more update of this path
+
+// the row's batch word: low half flags | count << 3, high half sum of arrival indices (bb_kernels.cuh: unpack_row)
+__device__ __forceinline__ unsigned long long* row_word(uint4* table, uint64_t pid) {
+  return reinterpret_cast<unsigned long long*>(table + pid * ROW_Q + 7);
+}
+__device__ __forceinline__ uint32_t word_count(unsigned long long wv) { return (uint32_t)wv >> ROW_CNT_SHIFT; }
+
 // ---------------------------------------------------------------- K1
-__global__ void __launch_bounds__(256) k_dm_count(const DmArgs a) {
+constexpr int DM1_T = 256;
+constexpr int DM1_CTAS_PER_SM = 4;
+
+__global__ void __launch_bounds__(DM1_T) k_dm_count(const DmArgs a) {
   __shared__ uint32_t s_last;
   const int tid = threadIdx.x, lane = tid & 31;
+  tl_start(a, 0);
+  if (!(a.tune & 2u)) pdl_launch_dependents();  // K2 may start staging its payload tiles
+  const bool rev = (a.tune & 1u) != 0;
+  const uint32_t tiles = (uint32_t)((a.n + DM1_T - 1) / DM1_T), G = gridDim.x;
+  const uint32_t lt = lanemask_lt();
+  bool bad = false;
+  // iteration t of this CTA handles tile tiles - 1 - t: the batch is walked back to front
+  auto load_pid = [&](uint32_t t) -> uint64_t {
+    if (t >= tiles) return ~0ull;
+    const uint64_t i = (uint64_t)(rev ? tiles - 1 - t : t) * DM1_T + tid;
+    return i < a.n ? a.path_id[i] : ~0ull;
+  };
+  uint32_t keep = 0;
+  auto pull = [&](uint64_t pid) {
+    if (pid >= a.capacity) return;
+    if (a.tune & 8u) keep ^= touch_l2(a.table + pid * ROW_Q + 7);
+    else prefetch_l2(a.table + pid * ROW_Q);
+  };
+  uint64_t pid_cur = load_pid(blockIdx.x), pid_nxt = load_pid(blockIdx.x + G);
+  pdl_wait();  // the previous batch's last kernel is complete: its rows and counters may be touched
   if (blockIdx.x == 0) {
     if (tid < DC_WORDS) a.ctr_next[tid] = 0;
     if (tid == 0 && a.zero_changes) *a.n_changes = 0;
   }
-  pdl_launch_dependents();  // K2 may start staging its payload tiles
-  const uint64_t i0 = (uint64_t)blockIdx.x * (256 * DM_ILP) + tid;
-  uint64_t pid[DM_ILP];
-  uint32_t r[DM_ILP];
-  bool ok[DM_ILP];
-#pragma unroll
-  for (int k = 0; k < DM_ILP; ++k) pid[k] = i0 + k * 256 < a.n ? a.path_id[i0 + k * 256] : ~0ull;
-  bool bad = false;
-#pragma unroll
-  for (int k = 0; k < DM_ILP; ++k) {
-    const uint64_t i = i0 + k * 256;
-    ok[k] = i < a.n && pid[k] < a.capacity;
-    bad |= i < a.n && !ok[k];
-    r[k] = ok[k] ? (uint32_t)atomicAdd(&a.cw[pid[k]], ((unsigned long long)(uint32_t)i << 32) | 1ull) : 0u;
-  }
-  const uint32_t lt = lanemask_lt();
-#pragma unroll
-  for (int k = 0; k < DM_ILP; ++k) {
-    if (i0 + k * 256 < a.n) a.rank[i0 + k * 256] = r[k];
-    const bool third = ok[k] && r[k] == 2u, ninth = ok[k] && r[k] == (uint32_t)DM_SHORT;
+  pull(pid_cur);
+  for (uint32_t t = blockIdx.x; t < tiles; t += G) {
+    const uint64_t pid_nn = load_pid(t + 2 * G);
+    pull(pid_nxt);  // the whole 128-byte row: K2 finds it in L2
+    const uint64_t i = (uint64_t)(rev ? tiles - 1 - t : t) * DM1_T + tid;
+    const uint64_t pid = pid_cur;
+    const bool ok = i < a.n && pid < a.capacity;
+    bad |= i < a.n && !ok;
+    const unsigned long long old = ok ? atomicAdd(row_word(a.table, pid), ((unsigned long long)(uint32_t)i << 32) | CW_ONE) : 0ull;
+    const uint32_t r = word_count(old);
+    const bool second = ok && r == 1u;  // knows the first arrival's index: the sum so far IS that index
+    const uint32_t partner = (uint32_t)(old >> 32);
+    if (i < a.n) a.rank[i] = second ? (RANK_PAIR | partner) : r;
+    if (second && (a.tune & 4u)) {  // K2 will most likely replay both updates from this thread's slot: the partner's payload into L2
+      prefetch_l2(a.head + partner);
+      prefetch_l2(a.clk + 2 * (uint64_t)partner);
+      prefetch_l2(a.val + 2 * (uint64_t)partner);
+    }
+    const bool third = ok && r == 2u, ninth = ok && r == (uint32_t)DM_SHORT;
     const uint32_t m3 = __ballot_sync(0xffffffffu, third), m9 = __ballot_sync(0xffffffffu, ninth);
     if (m3) {
       uint32_t base = 0;
@@ -109,47 +154,52 @@ __global__ void __launch_bounds__(256) k_dm_count(const DmArgs a) {
       base = __shfl_sync(0xffffffffu, base, __ffs(m3) - 1);
       if (third) {
         const uint32_t s = base + __popc(m3 & lt);
-        a.off[pid[k]] = s;
-        a.slab_pid[s] = (uint32_t)pid[k];
+        a.off[pid] = s;
+        a.slab_pid[s] = (uint32_t)pid;
       }
     }
     if (m9) {
       uint32_t base = 0;
       if (lane == __ffs(m9) - 1) base = atomicAdd(&a.ctr[DC_NLONG], (uint32_t)__popc(m9));
       base = __shfl_sync(0xffffffffu, base, __ffs(m9) - 1);
-      if (ninth) a.long_pid[base + __popc(m9 & lt)] = (uint32_t)pid[k];
+      if (ninth) a.long_pid[base + __popc(m9 & lt)] = (uint32_t)pid;
     }
+    pid_cur = pid_nxt;
+    pid_nxt = pid_nn;
   }
   if (bad) flag_reject(a.ctr + DC_REJ, a.err, a.ordinal);
+  if (keep == 0xA5C3F00Fu && a.n == ~0ull) a.rank[0] = keep;  // never true: keeps the touch loads alive
+  if (a.tune & 2u) pdl_launch_dependents();
 
-  // the last CTA to get here lays out the runs of the long paths (usually there are none)
-  __threadfence();
+  // the last CTA to get here lays out the runs of the long paths (usually there are none).  The CTA barrier orders
+  // every thread's stores before thread 0's fence, and the fence (cumulative) before its ticket
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(&a.ctr[DC_TICKET], 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(&a.ctr[DC_TICKET], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) {
+    tl_end(a, 0);
+    return;
+  }
   __threadfence();
   const uint32_t nlong = ld_volatile(a.ctr + DC_NLONG);
   uint32_t run = 0;
   for (uint32_t k0 = 0; k0 < nlong; k0 += 256) {
     const uint32_t k = k0 + tid;
     const uint32_t p = k < nlong ? __ldcg(a.long_pid + k) : 0u;
-    const uint32_t c = k < nlong ? (uint32_t)__ldcg(a.cw + p) : 0u;
+    const uint32_t c = k < nlong ? word_count(__ldcg(row_word(a.table, p))) : 0u;
     uint32_t total;
     const uint32_t ex = block_exclusive_scan<256>(c, &total);
     if (k < nlong) a.off[p] = run + ex;  // replaces the slab index the path's third arrival stored
     run += total;
   }
   if (tid == 0) a.ctr[DC_LTOTAL] = run;
+  tl_end(a, 0);
 }
 
 // ---------------------------------------------------------------- K2
-__device__ __forceinline__ void load_row_regs(const uint4* row, RowState& r) {
-  uint4 q[ROW_Q];
-#pragma unroll
-  for (int c = 0; c < ROW_Q; ++c) q[c] = ld_stream16(row + c);
-  unpack_row(q, r);
-}
 __device__ __forceinline__ void store_row_regs(uint4* row, const RowState& r) {
   uint4 q[ROW_Q];
   pack_row(q, r);
@@ -157,159 +207,206 @@ __device__ __forceinline__ void store_row_regs(uint4* row, const RowState& r) {
   for (int c = 0; c < ROW_Q; ++c) row[c] = q[c];
 }
 
+// shared memory of one K2 CTA (36 KB, six CTAs per SM)
+struct DmSmem {
+  uint4 head[DM_T];          // the tile's payloads, staged by cp.async.bulk; an accepted update's slot is
+  uint4 clk[2 * DM_T];       // overwritten with its change entry
+  uint4 val[2 * DM_T];
+  uint4 pp[DM_T * UPD_Q];    // partner payload of a 2-update path (slot of its owner), then its change entry
+  uint4 row[DM_T * ROW_Q];   // every update's table row, 128-byte stride, chunk index XOR-swizzled
+  uint64_t bar;
+  unsigned long long base;
+  uint32_t wsum[DM_WARPS];
+};
+
 template <bool INDEXED>
-__global__ void __launch_bounds__(DM_T, 3) k_dm_merge(const DmArgs a) {
-  __shared__ __align__(128) uint4 s_head[DM_T];      // the tile's payloads; an accepted update's slot is
-  __shared__ __align__(128) uint4 s_clk[2 * DM_T];   // overwritten with its change entry
-  __shared__ __align__(128) uint4 s_val[2 * DM_T];
-  __shared__ __align__(16) uint4 s_pp[DM_T * UPD_Q];  // partner payload of a 2-update path (slot of its owner)
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_wsum[DM_WARPS];
-  __shared__ unsigned long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+__global__ void __launch_bounds__(DM_T, 6) k_dm_merge(const DmArgs a) {
+  BB_DYN_SMEM(dm_raw);
+  DmSmem& sm = *reinterpret_cast<DmSmem*>(dm_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wbase = w * 32;
   const uint64_t base = (uint64_t)blockIdx.x * DM_T;
   const uint64_t i = base + tid;
   const bool valid = i < a.n;
   const uint32_t nvalid = (uint32_t)min((uint64_t)DM_T, a.n - base);
+  tl_start(a, 1);
 
   // ---- stage: the tile's payloads, three bulk copies; nothing here depends on K1
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(&sm.bar, 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&s_bar, nvalid * 80u);
-    bulk_g2s(s_head, a.head + base, nvalid * 16u, &s_bar);
-    bulk_g2s(s_clk, a.clk + 2 * base, nvalid * 32u, &s_bar);
-    bulk_g2s(s_val, a.val + 2 * base, nvalid * 32u, &s_bar);
+    mbar_arrive_expect_tx(&sm.bar, nvalid * 80u);
+    bulk_g2s(sm.head, a.head + base, nvalid * 16u, &sm.bar);
+    bulk_g2s(sm.clk, a.clk + 2 * base, nvalid * 32u, &sm.bar);
+    bulk_g2s(sm.val, a.val + 2 * base, nvalid * 32u, &sm.bar);
   }
   const uint64_t pid = valid ? a.path_id[i] : ~0ull;
   pdl_launch_dependents();
   __syncthreads();  // the barrier word is initialised for everybody
-  pdl_wait();       // K1 is complete: counts, ranks, slabs, runs
-  if (*a.rej & 1u) {  // rejected batch: the table stays as it is; only K1's counts are undone
-    if (pid < a.capacity) a.cw[pid] = 0ull;
-    mbar_wait(&s_bar, 0);  // no copy may be in flight into this CTA's shared memory when it exits
-    return;
-  }
-  const unsigned long long cwv = valid ? __ldcg(a.cw + pid) : 0ull;
-  const uint32_t cnt = (uint32_t)cwv;
-  const uint32_t partner = (uint32_t)(cwv >> 32) - (uint32_t)i;  // meaningful when cnt == 2
-  const bool single = cnt == 1u;
-  const bool owner = cnt == 2u && (uint32_t)i > partner;
-  const bool replay = single || owner;  // this thread replays the path
+  pdl_wait();       // K1 is complete: counts (in the rows), ranks, slabs, runs
 
-  RowState r;
-  uint64_t prim[F], prim0[F];
-  if (replay) {
-    load_row_regs(a.table + pid * ROW_Q, r);
-    if (INDEXED) {
+  // ---- everything K1 left for this update, fetched at once: its row (8 lanes per 128-byte row), its rank word,
+  // the batch's reject flag; a second arrival also fetches its partner's payload, before it knows whether the
+  // path stayed at two updates
+  const uint32_t rej = *a.rej;
+  const bool inrange = pid < a.capacity;  // a batch with an id out of range is rejected: no row is fetched through it
+  const uint32_t rk = valid ? a.rank[i] : 0u;
+  const uint32_t vmask = __ballot_sync(0xffffffffu, inrange);
+  const uint32_t key = (uint32_t)pid;
 #pragma unroll
-      for (int f = 0; f < F; ++f) prim0[f] = prim[f] = ((a.ix.mask >> f) & 1u) ? a.ix.pcol[f][pid] : BB_KEY_NONE;
-    }
-    if (owner) {
-      uint4* pp = &s_pp[tid * UPD_Q];
-      cp_async16(pp, a.head + partner);
-      cp_async16(pp + 1, a.clk + 2 * (uint64_t)partner);
-      cp_async16(pp + 2, a.clk + 2 * (uint64_t)partner + 1);
-      cp_async16(pp + 3, a.val + 2 * (uint64_t)partner);
-      cp_async16(pp + 4, a.val + 2 * (uint64_t)partner + 1);
-    }
-  } else if (cnt > 2u) {  // 3..8: the path's slab; more: its run.  K3 replays it
-    const uint32_t rk = a.rank[i], o = a.off[pid];
-    if (cnt <= (uint32_t)DM_SHORT) a.slab[(uint64_t)o * DM_SHORT + rk] = (uint32_t)i;
-    else a.litems[o + rk] = (uint32_t)i;
+  for (int j = 0; j < 8; ++j) {
+    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+    if ((vmask >> e) & 1u) cp_async16(&sm.row[row_slot(wbase + e, chunk)], a.table + (uint64_t)ekey * ROW_Q + chunk);
+  }
+  const bool second = inrange && (rk & RANK_PAIR) != 0u;
+  const uint32_t partner = rk & ~RANK_PAIR;
+  if (second) {
+    uint4* pp = &sm.pp[tid * UPD_Q];
+    cp_async16(pp, a.head + partner);
+    cp_async16(pp + 1, a.clk + 2 * (uint64_t)partner);
+    cp_async16(pp + 2, a.clk + 2 * (uint64_t)partner + 1);
+    cp_async16(pp + 3, a.val + 2 * (uint64_t)partner);
+    cp_async16(pp + 4, a.val + 2 * (uint64_t)partner + 1);
+  }
+  uint64_t prim[F], prim0[F];
+  if (INDEXED && inrange) {
+#pragma unroll
+    for (int f = 0; f < F; ++f) prim0[f] = prim[f] = ((a.ix.mask >> f) & 1u) ? a.ix.pcol[f][pid] : BB_KEY_NONE;
   }
   cp_async_wait_all();
-  mbar_wait(&s_bar, 0);
+  __syncwarp();  // a row's chunks were fetched by eight lanes of this warp
+  mbar_wait(&sm.bar, 0);
+  if (rej & 1u) {  // rejected batch: the table stays as it is; K1's additions to the rows' batch words are undone
+    if (inrange) atomicAdd(row_word(a.table, pid), 0ull - (((unsigned long long)(uint32_t)i << 32) | CW_ONE));
+    return;
+  }
 
-  // ---- resolve: pass 0 = the partner (owners only), pass 1 = the thread's own update
+  uint32_t cnt = 0;
+  if (inrange) cnt = sm.row[row_slot(tid, 7)].x >> ROW_CNT_SHIFT;
+  const bool single = cnt == 1u;
+  const bool owner = cnt == 2u && second;
+  const bool replay = single || owner;  // this thread replays the path
+  uint32_t slot_off = 0;
+  if (cnt > 2u) slot_off = a.off[pid];  // consumed after the resolve: the load hides behind it
+
+  // ---- resolve: pass 0 = the earlier update of a 2-update path (owners only), pass 1 = the later / only one
   uint32_t code0 = 0xFFu, code1 = 0xFFu;
+  const bool own_first = owner && (uint32_t)i < partner;  // the second arrival (atomic order) may be the earlier update
   if (replay) {
+    RowState r;
+    {
+      uint4 q[ROW_Q];
+#pragma unroll
+      for (int c = 0; c < ROW_Q; ++c) q[c] = sm.row[row_slot(tid, c)];
+      unpack_row(q, r);
+    }
 #pragma unroll 1
     for (int pass = owner ? 0 : 1; pass < 2; ++pass) {
+      const bool from_pp = owner && ((pass == 0) != own_first);  // this pass replays the partner's update
       uint4 h, c0, c1, v0, v1;
-      if (pass == 0) {
-        const uint4* pp = &s_pp[tid * UPD_Q];
+      if (from_pp) {
+        const uint4* pp = &sm.pp[tid * UPD_Q];
         h = pp[0]; c0 = pp[1]; c1 = pp[2]; v0 = pp[3]; v1 = pp[4];
       } else {
-        h = s_head[tid]; c0 = s_clk[2 * tid]; c1 = s_clk[2 * tid + 1]; v0 = s_val[2 * tid]; v1 = s_val[2 * tid + 1];
+        h = sm.head[tid]; c0 = sm.clk[2 * tid]; c1 = sm.clk[2 * tid + 1]; v0 = sm.val[2 * tid]; v1 = sm.val[2 * tid + 1];
       }
       Clock c, oc;
       Value x, ov;
       const bool net = unpack_update(h, c0, c1, v0, v1, c, x);
-      const uint32_t ui = pass == 0 ? partner : (uint32_t)i;
+      const uint32_t ui = from_pp ? partner : (uint32_t)i;
       const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
-      if (INDEXED) index_hook(a.ix, (uint32_t)pid, r.s, x, prim, r.xcnt, a.err);
+      if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
       if (BB_DEC_ACCEPTED(code)) {
         uint4 q[UPD_Q];
         pack_change(q, h.w, ov, oc);
-        if (pass == 0) {
-          uint4* pp = &s_pp[tid * UPD_Q];
+        if (from_pp) {
+          uint4* pp = &sm.pp[tid * UPD_Q];
 #pragma unroll
           for (int k = 0; k < UPD_Q; ++k) pp[k] = q[k];
         } else {
-          s_head[tid] = q[0]; s_clk[2 * tid] = q[1]; s_clk[2 * tid + 1] = q[2]; s_val[2 * tid] = q[3]; s_val[2 * tid + 1] = q[4];
+          sm.head[tid] = q[0]; sm.clk[2 * tid] = q[1]; sm.clk[2 * tid + 1] = q[2]; sm.val[2 * tid] = q[3]; sm.val[2 * tid + 1] = q[4];
         }
       }
-      if (pass == 0) code0 = code;
+      if (from_pp) code0 = code;  // code0 / code1: the partner's / the thread's own update
       else code1 = code;
     }
-    store_row_regs(a.table + pid * ROW_Q, r);
-    a.cw[pid] = 0ull;
+    {
+      uint4 q[ROW_Q];
+      pack_row(q, r);  // count and index sum are written back as zero: the path's batch word is clean again
+#pragma unroll
+      for (int c = 0; c < ROW_Q; ++c) sm.row[row_slot(tid, c)] = q[c];
+    }
     if (INDEXED) {
 #pragma unroll
       for (int f = 0; f < F; ++f)
         if (prim[f] != prim0[f]) a.ix.pcol[f][pid] = prim[f];
     }
+  } else if (cnt > 2u) {  // 3..8: the path's slab; more: its run.  K3 replays it
+    const uint32_t r3 = (rk & RANK_PAIR) ? 1u : rk;
+    if (cnt <= (uint32_t)DM_SHORT) a.slab[(uint64_t)slot_off * DM_SHORT + r3] = (uint32_t)i;
+    else a.litems[slot_off + r3] = (uint32_t)i;
+  }
+  __syncwarp();
+  // rows back, eight lanes per row
+  const uint32_t rmask = __ballot_sync(0xffffffffu, replay);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+    if ((rmask >> e) & 1u) a.table[(uint64_t)ekey * ROW_Q + chunk] = sm.row[row_slot(wbase + e, chunk)];
   }
 
-  // ---- rank the tile's accepted entries (partner before owner: arrival order), one claim per CTA
+  // ---- rank the tile's accepted entries (a path's two in arrival order), one claim per CTA
   const uint32_t acc0 = (code0 != 0xFFu && BB_DEC_ACCEPTED(code0)) ? 1u : 0u;
   const uint32_t acc1 = (code1 != 0xFFu && BB_DEC_ACCEPTED(code1)) ? 1u : 0u;
   const uint32_t mine = acc0 + acc1;
   const uint32_t inc = warp_inclusive_scan(mine);
-  if (lane == 31) s_wsum[w] = inc;
+  if (lane == 31) sm.wsum[w] = inc;
   __syncthreads();
   uint32_t before = inc - mine, total = 0;
 #pragma unroll
   for (int ww = 0; ww < DM_WARPS; ++ww) {
-    const uint32_t c = s_wsum[ww];
+    const uint32_t c = sm.wsum[ww];
     if (ww < w) before += c;
     total += c;
   }
-  if (tid == 0) s_base = total ? atomicAdd(a.n_changes, (unsigned long long)total) : 0ull;
+  if (tid == 0) sm.base = total ? atomicAdd(a.n_changes, (unsigned long long)total) : 0ull;
   __syncthreads();
-  const uint64_t d0 = s_base + before, d1 = d0 + acc0;
+  // slots: the earlier update's entry first
+  const uint64_t dfirst = sm.base + before;
+  const uint64_t dpp = own_first ? dfirst + acc1 : dfirst, down = own_first ? dfirst : dfirst + acc0;
   bool overflow = false;
   if (replay) {
-    a.verdict[i] = (code1 << 29) | (acc1 ? (uint32_t)d1 : NO_SLOT);
-    if (owner) a.verdict[partner] = (code0 << 29) | (acc0 ? (uint32_t)d0 : NO_SLOT);
+    a.verdict[i] = (code1 << 29) | (acc1 ? (uint32_t)down : NO_SLOT);
+    if (owner) a.verdict[partner] = (code0 << 29) | (acc0 ? (uint32_t)dpp : NO_SLOT);
     if (acc0) {
-      if (d0 < a.cap) {
-        const uint4* pp = &s_pp[tid * UPD_Q];
-        a.out_idx[d0] = a.idx_base + partner;
-        a.out_head[d0] = pp[0];
-        a.out_clk[2 * d0] = pp[1];
-        a.out_clk[2 * d0 + 1] = pp[2];
-        a.out_val[2 * d0] = pp[3];
-        a.out_val[2 * d0 + 1] = pp[4];
+      if (dpp < a.cap) {
+        const uint4* pp = &sm.pp[tid * UPD_Q];
+        a.out_idx[dpp] = a.idx_base + partner;
+        a.out_head[dpp] = pp[0];
+        a.out_clk[2 * dpp] = pp[1];
+        a.out_clk[2 * dpp + 1] = pp[2];
+        a.out_val[2 * dpp] = pp[3];
+        a.out_val[2 * dpp + 1] = pp[4];
       } else {
         overflow = true;
       }
     }
     if (acc1) {
-      if (d1 < a.cap) {
-        a.out_idx[d1] = a.idx_base + (uint32_t)i;
-        a.out_head[d1] = s_head[tid];
-        a.out_clk[2 * d1] = s_clk[2 * tid];
-        a.out_clk[2 * d1 + 1] = s_clk[2 * tid + 1];
-        a.out_val[2 * d1] = s_val[2 * tid];
-        a.out_val[2 * d1 + 1] = s_val[2 * tid + 1];
+      if (down < a.cap) {
+        a.out_idx[down] = a.idx_base + (uint32_t)i;
+        a.out_head[down] = sm.head[tid];
+        a.out_clk[2 * down] = sm.clk[2 * tid];
+        a.out_clk[2 * down + 1] = sm.clk[2 * tid + 1];
+        a.out_val[2 * down] = sm.val[2 * tid];
+        a.out_val[2 * down + 1] = sm.val[2 * tid + 1];
       } else {
         overflow = true;
       }
     }
   }
   if (overflow) atomicOr(a.err, ERR_CHANGES);
+  tl_end(a, 1);
 }
 
 // ---------------------------------------------------------------- K3
@@ -417,6 +514,8 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
   __shared__ uint64_t s_prim[F];
   __shared__ uint32_t s_cnt[DM3_WARPS], s_stop[DM3_WARPS], s_loc[DM3_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  tl_start(a, 2);
+  pdl_launch_dependents();  // the next batch's K1 may load its path ids
   pdl_wait();  // K2 (and K1 before it) is complete
   if (*a.rej & 1u) return;
   const uint32_t lt = lanemask_lt();
@@ -428,14 +527,25 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
     const uint32_t s = s0 + tid;
     bool active = s < nslab;
     const uint32_t pid = active ? a.slab_pid[s] : 0u;
-    uint32_t cnt = active ? (uint32_t)__ldcg(a.cw + pid) : 0u;
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+    if (active) {  // unclaimed slots hold garbage: masked by the count below
+      const uint4* sl = reinterpret_cast<const uint4*>(a.slab + (uint64_t)s * DM_SHORT);
+      lo = sl[0];
+      hi = sl[1];
+    }
+    RowState r;
+    uint32_t cnt = 0;
+    if (active) {
+      uint4 q[ROW_Q];
+#pragma unroll
+      for (int c = 0; c < ROW_Q; ++c) q[c] = __ldcg(a.table + (uint64_t)pid * ROW_Q + c);
+      cnt = q[7].x >> ROW_CNT_SHIFT;
+      unpack_row(q, r);
+    }
     if (cnt > (uint32_t)DM_SHORT) active = false;  // became a long path: phase B
     if (!active) cnt = 0;
-    RowState r;
     uint64_t prim[F], prim0[F];
     if (active) {
-      const uint4* sl = reinterpret_cast<const uint4*>(a.slab + (uint64_t)s * DM_SHORT);
-      const uint4 lo = sl[0], hi = sl[1];
       uint32_t v[DM_SHORT] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
       for (int k = 0; k < DM_SHORT; ++k)
@@ -443,7 +553,6 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
       sort8(v);
 #pragma unroll
       for (int k = 0; k < DM_SHORT; ++k) s_idx[k][tid] = v[k];
-      load_row_regs(a.table + (uint64_t)pid * ROW_Q, r);
       if (INDEXED) {
 #pragma unroll
         for (int f = 0; f < F; ++f) prim0[f] = prim[f] = ((a.ix.mask >> f) & 1u) ? a.ix.pcol[f][pid] : BB_KEY_NONE;
@@ -492,8 +601,7 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
       }
     }
     if (active) {
-      store_row_regs(a.table + (uint64_t)pid * ROW_Q, r);
-      a.cw[pid] = 0ull;
+      store_row_regs(a.table + (uint64_t)pid * ROW_Q, r);  // batch word cleared
       if (INDEXED) {
 #pragma unroll
         for (int f = 0; f < F; ++f)
@@ -510,7 +618,7 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
   const uint32_t nlong = a.ctr[DC_NLONG];
   for (uint32_t hseg = blockIdx.x; hseg < nlong; hseg += gridDim.x) {
     const uint32_t pid = a.long_pid[hseg];
-    const uint32_t len = (uint32_t)__ldcg(a.cw + pid), start = a.off[pid];
+    const uint32_t len = word_count(__ldcg(row_word(a.table, pid))), start = a.off[pid];
     const uint32_t* run = cta_radix_sort_u32(a.litems + start, a.lscratch + start, len, (uint32_t)(a.n - 1));
     if (tid < ROW_Q) s_row[tid] = a.table[(uint64_t)pid * ROW_Q + tid];
     if (INDEXED && tid < F) s_prim[tid] = ((a.ix.mask >> tid) & 1u) ? a.ix.pcol[tid][pid] : BB_KEY_NONE;
@@ -604,12 +712,12 @@ __global__ void __launch_bounds__(DM3_T) k_dm_multi(const DmArgs a) {
       gp0 += (uint32_t)retired;
       __syncthreads();  // the published row is visible; the window and s_cnt / s_stop / s_loc may be rewritten
     }
-    if (tid < ROW_Q) a.table[(uint64_t)pid * ROW_Q + tid] = s_row[tid];
+    if (tid < ROW_Q) a.table[(uint64_t)pid * ROW_Q + tid] = s_row[tid];  // packed by a retiring thread: batch word cleared
     if (INDEXED && tid < F && ((a.ix.mask >> tid) & 1u)) a.ix.pcol[tid][pid] = s_prim[tid];
-    if (tid == 0) a.cw[pid] = 0ull;
     __syncthreads();
   }
   if (overflow) atomicOr(a.err, ERR_CHANGES);
+  tl_end(a, 2);
 }
 
 }  // namespace bb

@@ -490,6 +490,34 @@ struct MergeArgs {
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
+// DEVICE layout of a row's last 16-byte chunk (the public bb_row differs in these words only; bb_table_load /
+// bb_table_read convert):
+//   x  bits 0-2 BB_ROW_* flags, bits 3-31 updates of this path in the batch being merged (0 between batches)
+//   y  sum of those updates' arrival indices mod 2^32                                   (0 between batches)
+//   z  cseq, low 32 bits          w  bits 0-15 cseq bits 32-47, bits 16-31 index bookkeeping: 4 bits per field =
+//      entries the node has in that field's overflow set, 15 = "15 or more, always probe"
+// x | y << 32 is the word K1 (bb_direct.cuh) counts a batch's updates with, one atomicAdd per update: the count
+// arrives with the row and is cleared by the row's write-back.
+constexpr int ROW_CNT_SHIFT = 3;
+__device__ __forceinline__ uint32_t xcnt_expand(uint32_t n16) {  // nibble f -> byte f, 15 -> 255 (saturated)
+  uint32_t x = 0;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const uint32_t v = (n16 >> (4 * f)) & 0xFu;
+    x |= (v == 0xFu ? 0xFFu : v) << (8 * f);
+  }
+  return x;
+}
+__device__ __forceinline__ uint32_t xcnt_pack(uint32_t x) {
+  uint32_t n16 = 0;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const uint32_t v = (x >> (8 * f)) & 0xFFu;
+    n16 |= (v > 0xFu ? 0xFu : v) << (4 * f);
+  }
+  return n16;
+}
+
 __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
   const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
   r.s.val[0] = u64_of(q0.x, q0.y); r.s.val[1] = u64_of(q0.z, q0.w);
@@ -505,8 +533,8 @@ __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
   r.m.present = (q7.x & BB_ROW_M_PRESENT) != 0;
   r.v.present = (q7.x & BB_ROW_V_PRESENT) != 0;
   r.alias = (q7.x & BB_ROW_ALIAS) != 0;
-  r.xcnt = q7.y;
-  r.cseq = u64_of(q7.z, q7.w);
+  r.xcnt = xcnt_expand(q7.w >> 16);
+  r.cseq = u64_of(q7.z, q7.w & 0xFFFFu);
 }
 
 __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
@@ -519,7 +547,7 @@ __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
   q[6] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
   const uint32_t flags = (r.m.present ? BB_ROW_M_PRESENT : 0u) | (r.v.present ? BB_ROW_V_PRESENT : 0u) |
                          (r.alias ? BB_ROW_ALIAS : 0u);
-  q[7] = make_uint4(flags, r.xcnt, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
+  q[7] = make_uint4(flags, 0u, (uint32_t)r.cseq, ((uint32_t)(r.cseq >> 32) & 0xFFFFu) | (xcnt_pack(r.xcnt) << 16));
 }
 
 // update payload / change entry as 5 x uint4: [head][clk lo][clk hi][val lo][val hi]
@@ -796,7 +824,10 @@ __global__ void __launch_bounds__(256) k_table_scatter(uint4* __restrict__ table
     atomicOr(err, 1u);
     return;
   }
-  table[p * 8 + (t & 7)] = rows[t];
+  uint4 v = rows[t];
+  if ((t & 7) == 7)  // public bb_row {flags, xcnt, cseq} -> device layout
+    v = make_uint4(v.x & 7u, 0u, v.z, (v.w & 0xFFFFu) | (xcnt_pack(v.y) << 16));
+  table[p * 8 + (t & 7)] = v;
 }
 
 __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table, const uint64_t* __restrict__ ids,
@@ -821,7 +852,9 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
     }
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[q];
+  for (int q = 0; q < 7; ++q) rows[i * 8 + q] = row[q];
+  const uint4 v = row[7];  // device layout -> public bb_row {flags, xcnt, cseq}
+  rows[i * 8 + 7] = make_uint4(v.x & 7u, xcnt_expand(v.w >> 16), v.z, v.w & 0xFFFFu);
 }
 
 }  // namespace bb

@@ -70,6 +70,34 @@ __device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
 #endif
 }
 
+// bring a 128-byte line into L2 ahead of its use; a hint, never a correctness dependency
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef BB_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
+// read one word so that its 32-byte sector is in L2 when the atomic that follows a little later needs it (prefetch.L2
+// would fetch the whole 128-byte line); the value is handed back so that the caller can keep the load alive
+__device__ __forceinline__ uint32_t touch_l2(const void* p) {
+#ifdef BB_EMU
+  return 0;
+#else
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+#ifdef BB_EMU
+  return 0;
+#else
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
+
 // ---- cp.async (LDGSTS): 16 bytes global -> shared, no registers held
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
 #ifdef BB_EMU

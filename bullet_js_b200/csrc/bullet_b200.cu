@@ -77,18 +77,21 @@ struct bb_ctx {
   DevBuf<uint64_t> io_path;
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
-  // per-row words of the front ends, all zero between calls.  Direct pipeline (bb_direct.cuh): cw u64[capacity]
-  // = (sum of arrival indices << 32 | count) per path.  Sorted paths: the same memory as cs_cnt u32[capacity].
-  unsigned long long* cw = nullptr;
-  uint32_t* cs_cnt = nullptr;  // alias of cw
-  uint32_t* cs_off = nullptr;  // u32[capacity + 1] (padded to whole tiles): sorted paths: exclusive scan of the counts;
-                               // direct pipeline: a multi-update path's slab / run start
+  // per-row scratch of the front ends, allocated on first use.  Sorted paths: cs_cnt u32[capacity] (all zero between
+  // calls) and its exclusive scan cs_off u32[capacity + 1], both padded to whole tiles.  Direct pipeline: dm_off
+  // u32[capacity] = a multi-update path's slab / run start (the counts live in the table rows).
+  uint32_t* cs_cnt = nullptr;
+  uint32_t* cs_off = nullptr;
+  uint32_t* dm_off = nullptr;
   DevBuf<uint2> cs_long;       // sorted paths: segments longer than CS_SHORT, queued for k_cs_fix_long
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
   // direct pipeline scratch
   DevBuf<uint32_t> dm_slab, dm_slab_pid, dm_long_pid, dm_litems, dm_lscratch;
   uint32_t* dm_ctr = nullptr;  // [2][DC_WORDS] per-batch counters, sets used alternately
   uint32_t dm_parity = 0;
+  unsigned long long* d_tl = nullptr;  // BB_TIMELINE=1: device timestamps of the last direct merge's kernels
+  uint32_t dm_tune = 0, k1_ctas = bb::DM1_CTAS_PER_SM;  // env BB_DM_TUNE, BB_K1_CTAS (experiments)
+  bool phase_events = false;   // record the event between the count and the merge kernels (it serialises them)
   uint64_t* d_nchanges = nullptr;
   uint64_t* d_chunk_total = nullptr;  // [MAX_CHUNKS] host calls: the change count as it stood when chunk i was done
   uint64_t* d_chg_base = nullptr;
@@ -139,9 +142,9 @@ int fail(bb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);                        \
   } while (0)
 // same, with programmatic stream serialisation: the kernel calls pdl_wait() before it touches its predecessor's output
-#define BB_LAUNCH_PDL(c, kernel, grid, block, stream, ...)                                    \
+#define BB_LAUNCH_PDL(c, kernel, grid, block, smem, stream, ...)                              \
   do {                                                                                        \
-    cudaError_t e_ = bb_launch(kernel, (uint32_t)(grid), (uint32_t)(block), 0, (stream), true, __VA_ARGS__); \
+    cudaError_t e_ = bb_launch(kernel, (uint32_t)(grid), (uint32_t)(block), (smem), (stream), true, __VA_ARGS__); \
     ++(c)->launches;                                                                          \
     if (e_ == cudaSuccess) e_ = cudaGetLastError();                                           \
     if (e_ != cudaSuccess) return fail((c), BB_ERR_CUDA, #kernel, e_);                        \
@@ -203,12 +206,22 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
 int reserve_dev(bb_ctx* c, uint64_t n) {
   BB_CUDA(c, c->st_idx.ensure(n));
   if (use_direct(c)) {
+    if (!c->dm_off) BB_CUDA(c, cudaMalloc((void**)&c->dm_off, c->cfg.capacity * sizeof(uint32_t)));
     BB_CUDA(c, c->dm_slab.ensure((n / 3 + 1) * bb::DM_SHORT));
     BB_CUDA(c, c->dm_slab_pid.ensure(n / 3 + 1));
     BB_CUDA(c, c->dm_long_pid.ensure(n / 9 + 1));
     BB_CUDA(c, c->dm_litems.ensure(n));
     BB_CUDA(c, c->dm_lscratch.ensure(n));
     return BB_OK;
+  }
+  if (!c->cs_cnt) {
+    const size_t cs_words = ((size_t)c->cfg.capacity + 1 + bb::CS_TILE - 1) / bb::CS_TILE * bb::CS_TILE;
+    BB_CUDA(c, cudaMalloc((void**)&c->cs_cnt, cs_words * sizeof(uint32_t)));
+    BB_CUDA(c, cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)));
+    BB_CUDA(c, cudaMemsetAsync(c->cs_cnt, 0, cs_words * sizeof(uint32_t), c->stream));
+    BB_CUDA(c, cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream));
+    BB_CUDA(c, c->cs_tile.ensure(cs_words / bb::CS_TILE));
+    BB_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   const ZeroLayout z = zero_layout(c, n);
   BB_CUDA(c, c->items_a.ensure(n));
@@ -259,8 +272,7 @@ int merge_direct(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s,
   a.head = reinterpret_cast<const uint4*>(in->head);
   a.clk = reinterpret_cast<const uint4*>(in->clk);
   a.val = reinterpret_cast<const uint4*>(in->val);
-  a.cw = c->cw;
-  a.off = c->cs_off;
+  a.off = c->dm_off;
   a.rank = c->st_idx.p;
   a.slab = c->dm_slab.p;
   a.slab_pid = c->dm_slab_pid.p;
@@ -284,15 +296,21 @@ int merge_direct(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s,
   a.err = c->d_err;
   a.rej = call_rej ? call_rej : a.ctr + DC_REJ;
   fill_params(c, a.p, a.ix);
-  BB_LAUNCH(c, k_dm_count, div_up(n, 256 * DM_ILP), 256, s, a);
-  if (!append) mark(c, EV_SORT, s);
+  a.tl = c->d_tl;
+  a.tune = c->dm_tune;
+  if (c->d_tl) {
+    static const unsigned long long tl_init[6] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+    BB_CUDA(c, cudaMemcpyAsync(c->d_tl, tl_init, sizeof(tl_init), cudaMemcpyHostToDevice, s));
+  }
+  BB_LAUNCH_PDL(c, k_dm_count, std::min<uint32_t>(div_up(n, DM1_T), (uint32_t)c->n_sm * c->k1_ctas), DM1_T, 0, s, a);
+  if (!append && c->phase_events) mark(c, EV_SORT, s);  // an event here ends the overlap of K1's tail with K2's prologue
   const uint32_t g3 = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(n, 3 * DM3_T), (uint32_t)c->n_sm * 2u));
   if (c->index_mask) {
-    BB_LAUNCH_PDL(c, k_dm_merge<true>, div_up(n, DM_T), DM_T, s, a);
-    BB_LAUNCH_PDL(c, k_dm_multi<true>, g3, DM3_T, s, a);
+    BB_LAUNCH_PDL(c, k_dm_merge<true>, div_up(n, DM_T), DM_T, sizeof(DmSmem), s, a);
+    BB_LAUNCH_PDL(c, k_dm_multi<true>, g3, DM3_T, 0, s, a);
   } else {
-    BB_LAUNCH_PDL(c, k_dm_merge<false>, div_up(n, DM_T), DM_T, s, a);
-    BB_LAUNCH_PDL(c, k_dm_multi<false>, g3, DM3_T, s, a);
+    BB_LAUNCH_PDL(c, k_dm_merge<false>, div_up(n, DM_T), DM_T, sizeof(DmSmem), s, a);
+    BB_LAUNCH_PDL(c, k_dm_multi<false>, g3, DM3_T, 0, s, a);
   }
   return BB_OK;
 }
@@ -590,19 +608,19 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
     delete c;
     return BB_ERR_CUDA;
   }
-  // k_merge_stage: 7 x 27.7 KB, k_dm_merge: 3 x 41 KB of static shared memory per SM: ask for the full carve-out
+  // k_merge_stage: 7 x 27.7 KB, k_dm_merge: 6 x 36 KB of dynamic shared memory per SM: ask for the full carve-out
   cudaFuncSetAttribute(bb::k_merge_stage<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_dm_merge<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_dm_merge<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_dm_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bb::DmSmem));
+  cudaFuncSetAttribute(bb::k_dm_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bb::DmSmem));
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
   }
-  const size_t cs_words = ((size_t)cfg->capacity + 1 + bb::CS_TILE - 1) / bb::CS_TILE * bb::CS_TILE;
-  const size_t cw_bytes = std::max(cs_words * sizeof(uint32_t), (size_t)cfg->capacity * sizeof(unsigned long long));
   static const uint32_t err_clear[2] = {0u, 0xFFFFFFFFu};
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->table, cfg->capacity * sizeof(bb_row)) == cudaSuccess &&
@@ -611,13 +629,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMemcpyAsync(c->d_err, err_clear, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_callrej, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
-            cudaMalloc((void**)&c->cw, cw_bytes) == cudaSuccess &&
-            cudaMalloc((void**)&c->cs_off, cs_words * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemsetAsync(c->cw, 0, cw_bytes, c->stream) == cudaSuccess &&
-            cudaMemsetAsync(c->cs_off, 0, cs_words * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->dm_ctr, 2 * bb::DC_WORDS * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->dm_ctr, 0, 2 * bb::DC_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
-            c->cs_tile.ensure(cs_words / bb::CS_TILE) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chunk_total, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
@@ -629,7 +642,6 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMallocHost((void**)&c->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_err, 2 * sizeof(uint32_t)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_nchanges, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess;
-  c->cs_cnt = reinterpret_cast<uint32_t*>(c->cw);
   for (int i = 0; ok && i < MAX_CHUNKS; ++i)
     ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -643,6 +655,9 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return BB_ERR_CUDA;
   }
+  if (const char* e = getenv("BB_DM_TUNE")) c->dm_tune = (uint32_t)strtoul(e, nullptr, 10);
+  if (const char* e = getenv("BB_K1_CTAS")) c->k1_ctas = (uint32_t)std::max(1l, std::min(8l, strtol(e, nullptr, 10)));
+  if (getenv("BB_TIMELINE")) cudaMalloc((void**)&c->d_tl, 6 * sizeof(unsigned long long));
   if (prev_dev >= 0 && prev_dev != cfg->device) cudaSetDevice(prev_dev);  // every entry point selects the ctx's device itself
   *out = c;
   return BB_OK;
@@ -668,8 +683,10 @@ int bb_destroy(bb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
-  if (c->cw) cudaFree(c->cw);
+  if (c->cs_cnt) cudaFree(c->cs_cnt);
   if (c->cs_off) cudaFree(c->cs_off);
+  if (c->dm_off) cudaFree(c->dm_off);
+  if (c->d_tl) cudaFree(c->d_tl);
   if (c->dm_ctr) cudaFree(c->dm_ctr);
   if (c->d_callrej) cudaFree(c->d_callrej);
   if (c->d_chunk_total) cudaFree(c->d_chunk_total);
@@ -1012,6 +1029,22 @@ int bb_index_stats(bb_ctx* c, uint32_t field, uint64_t* n_dense, uint64_t* n_ext
 }
 
 uint64_t bb_launch_count(const bb_ctx* c) { return c ? c->launches : 0; }
+
+/* diagnostics, not part of the ABI header: out[6] = {K1 first start, last end, K2 ..., K3 ...} in ns of the last
+ * direct-pipeline merge, relative to K1's start (needs BB_TIMELINE=1 in the environment at bb_create) */
+int bb_debug_timeline(bb_ctx* c, double out[6]) {
+  if (!c || !c->d_tl) return BB_ERR_STATE;
+  unsigned long long h[6];
+  if (cudaMemcpy(h, c->d_tl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return BB_ERR_CUDA;
+  for (int i = 0; i < 6; ++i) out[i] = (double)(long long)(h[i] - h[0]);
+  return BB_OK;
+}
+
+int bb_phase_events(bb_ctx* c, int on) {
+  if (!c) return BB_ERR_ARG;
+  c->phase_events = on != 0;
+  return BB_OK;
+}
 
 double bb_last_phase_ms(bb_ctx* c, const char* phase) { return bb_phase_ms(c, phase, 0); }
 

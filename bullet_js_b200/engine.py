@@ -139,5 +139,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bb_launch_count(self._h))
 
+    def phase_events(self, on: bool = True):
+        """Record the event between the front end and the merge kernels (serialises them: measurement only)."""
+        self._check(self.lib.bb_phase_events(self._h, 1 if on else 0))
+
     def phase_ms(self, phase: str, calls_ago: int = 0) -> float:
         return float(self.lib.bb_phase_ms(self._h, phase.encode(), calls_ago))

@@ -145,30 +145,20 @@ typedef struct bb_config {
  * with `_getData` after every setData (query:151,169), which turns a falsy stored
  * primitive into `{}` right after the write instead of at the next update. */
 #define BB_CFG_POST_GETDATA 1u
-/* Lay the change set out in path-major order (ascending path id, arrival order
- * within a path) and query hits in ascending node id, bit-identical from run to run.  Without it tiles of 128 sorted
- * updates claim their slice of the change set as they finish: the same entries,
- * each still found through verdict[], but the tiles' order in the buffers is not
- * fixed - and no tile ever waits for another one. */
+/* Lay the change set out in path-major order (ascending path id, arrival order within a path) and query hits in
+ * ascending node id, bit-identical from run to run: the batch is sorted by path id first (counting sort, or the LSD
+ * radix sort when the table is much larger than the batch) and merged by k_merge_stage.  Without it (the default) the
+ * batch is not sorted at all: tiles of 256 consecutive updates merge where they lie and claim their slice of the
+ * change set as they finish - the same entries, each still found through verdict[], arrival order inside a tile, but
+ * the tiles' order in the buffers is not fixed and no tile ever waits for another one. */
 #define BB_CFG_ORDERED_CHANGES 2u
-/* Always sort a batch by path id with the stable LSD radix sort (same decisions, table and change entries
- * as the default grouping front end described under BB_CFG_FULL_SORT). */
+/* Sort every batch by path id with the stable LSD radix sort / with the counting sort over the row indices before
+ * merging (same decisions, table and change entries as the default; kept for A/B measurements). */
 #define BB_CFG_RADIX_SORT 4u
-/* Always sort a batch by path id (counting sort over the row indices, or the radix sort when the table is
- * much larger than the batch).  By default the library only GROUPS the batch: updates whose path occurs
- * once keep their arrival order, the others are gathered into per-path runs (same decisions, table and
- * change entries; only the layout of the change buffers differs, as described above). */
 #define BB_CFG_FULL_SORT 8u
-/* Merge with k_merge_pipe (persistent CTAs, 4 per SM, each software-pipelining three tiles) instead of
- * k_merge_stage (one CTA per 128-update tile, 7 per SM).  Same results; measured slower on B200
- * (0.113 vs 0.100 ms per 1 M updates: fewer resident warps for a latency-bound resolver), kept for A/B runs. */
-#define BB_CFG_CTA_PIPE 32u
-/* Hot keys: a path that takes thousands of a batch's updates is a serial chain for the thread that owns it
- * (~1 us per update).  With this flag k_merge_stage hands such a segment (after 8 updates past its tile) to
- * k_merge_hot, where a whole CTA evaluates 128 of its updates per round against the row and retires
- * everything up to the first state-changing one: a Zipf(0.8) batch of 1 M updates over 2.5 M paths merges in
- * 2.5 ms instead of 9.4 ms.  Costs one extra (usually empty) launch per batch, ~5 % on a uniform batch, hence
- * opt-in; ignored with BB_CFG_ORDERED_CHANGES, BB_CFG_CTA_PIPE and while an index exists. */
+/* Hot keys (a path that takes thousands of a batch's updates is a serial chain) are handled by the default pipeline:
+ * a whole CTA evaluates 256 of the path's updates per round against the row and retires everything up to the first
+ * state-changing one, indexed collections included.  The round-1 opt-in flag is accepted and ignored. */
 #define BB_CFG_HOT_KEYS 64u
 
 typedef struct bb_ctx bb_ctx;
@@ -190,8 +180,7 @@ typedef struct bb_batch {
  * update was rejected (doUpdate == false, src/bullet-crt.js:383).
  * The change set == the _applyUpdate calls (src/bullet.js:184-220), one entry per
  * accepted update.  Entries are stored in the order the device resolves them in
- * (runs of ascending path id, arrival order within a path; see
- * BB_CFG_ORDERED_CHANGES); the reference's arrival order is recovered without a
+ * (see BB_CFG_ORDERED_CHANGES); the reference's arrival order is recovered without a
  * sort by walking verdict[] and following the slots.  A batch is limited to
  * 2^29-2 updates. */
 #define BB_NO_SLOT 0x1FFFFFFFu
@@ -231,14 +220,15 @@ int bb_reserve(bb_ctx* ctx, uint64_t max_batch, int host_entry);
  *      -> Bullet._applyUpdate (src/bullet.js:184-220)] in arrival order per path.
  *      Host buffers; H2D / D2H copies are part of the call. ------------------- */
 int bb_merge_batch(bb_ctx* ctx, const bb_batch* in, bb_changes* out);
-/* Same, all pointers are device pointers on ctx's device, work is enqueued on
- * `stream` (a cudaStream_t; 0 = ctx's own stream - pass cudaStreamLegacy (0x1) to
- * name the legacy default stream) and NOT synchronised. */
+/* Same, all pointers are device pointers on ctx's device (head, clk, val, and the out arrays 16-byte aligned, as
+ * cudaMalloc gives them), work is enqueued on `stream` (a cudaStream_t; 0 = ctx's own stream - pass
+ * cudaStreamLegacy (0x1) to name the legacy default stream) and NOT synchronised. */
 int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* stream);
 /* Synchronise `stream` (0 = ctx's own) and return the deferred status of the
  * *_dev calls enqueued since the last bb_sync: BB_ERR_CAPACITY if a batch held a
- * path id >= capacity (that batch was rejected whole, table unchanged) or a
- * change buffer was too small. */
+ * path id >= capacity or a change buffer was too small.  A batch with a bad path id is rejected WHOLE (table
+ * unchanged, its verdicts and change count undefined); batches enqueued after it are merged normally, and
+ * bb_last_error names the first rejected batch by its ordinal since the previous bb_sync (1 = first). */
 int bb_sync(bb_ctx* ctx, void* stream);
 
 /* ---- indices and queries: BulletQuery (src/bullet-query.js) --------------------
@@ -362,12 +352,17 @@ uint64_t bb_router_launch_count(const bb_router* r);
 /* ---- telemetry ---------------------------------------------------------- */
 /* Kernels launched by this ctx since creation (for bench.py's gpu_launches). */
 uint64_t bb_launch_count(const bb_ctx* ctx);
+/* on != 0: also record the event between the front end and the merge kernels of every later merge call, so that
+ * the "sort" and "merge" phases below can be told apart.  Off by default: that event sits between two launches the
+ * library chains with programmatic dependent launch, and an event in between serialises them. */
+int bb_phase_events(bb_ctx* ctx, int on);
 /* Device time of the named phase of the most recent *_dev / host call, in ms,
  * from CUDA events on the launching stream; -1 if unknown. Synchronises. */
 double bb_last_phase_ms(bb_ctx* ctx, const char* phase);
 /* Same for the merge call issued `calls_ago` calls before the most recent one
  * (0 = most recent; the last 64 calls are kept).  Phases: "h2d", "sort", "merge",
- * "d2h", "device" (sort+merge), "total"; the query calls record "scan". */
+ * "d2h", "device" (sort+merge), "total"; the query calls record "scan".  "sort" and "merge" need
+ * bb_phase_events(ctx, 1) on the default (unsorted) pipeline. */
 double bb_phase_ms(bb_ctx* ctx, const char* phase, uint32_t calls_ago);
 
 #ifdef __cplusplus
