@@ -6,10 +6,11 @@
 //                      (chained-scan / decoupled look-back across tiles); only as many
 //                      passes as the table's row-index width needs; moves 8-byte items,
 //                      never payloads
-//   K2s k_merge_stage  the merge over a SORTED item list (BB_CFG_ORDERED_CHANGES / FULL_SORT / RADIX_SORT):
-//                      one CTA per tile of 128 sorted positions, payloads and rows staged in shared
-//                      memory with cp.async, one thread per path segment replays its updates in
-//                      arrival order.  The default pipeline (no sort at all) is bb_direct.cuh
+//   K2  k_merge_stage  one CTA per tile of 128 item-list positions: payloads and rows staged in shared
+//                      memory with cp.async, one thread per path segment replays its updates in arrival
+//                      order, accepted entries compacted into the change set, rows written back with
+//                      16-byte stores.  The default front end that builds the item list (grouping, not
+//                      sorting) is bb_group.cuh; hot keys go to k_merge_hot
 //   K4/K5               index build and the equals / range / count scans: bb_index.cuh
 //
 // All of it is integer / f64 compare-and-move work: HBM-bound, no tensor cores.
@@ -377,6 +378,8 @@ __global__ void __launch_bounds__(CS_THREADS) k_cs_fix_long(uint64_t* __restrict
   __shared__ uint32_t s_seg;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t lt = lanemask_lt();
+  pdl_launch_dependents();
+  pdl_wait();
   while (true) {
     __syncthreads();
     if (tid == 0) s_seg = atomicAdd(next, 1u);
@@ -479,6 +482,9 @@ struct MergeArgs {
   uint32_t* tile_state;    // [num_tiles], zeroed per launch
   uint32_t* ticket;        // zeroed per launch
   uint32_t num_tiles;
+  uint4* hot_list;         // (key, next position lo, hi, 0) of the segments handed to k_merge_hot
+  uint32_t* n_hot;         // zero when the batch begins
+  uint32_t hot_cap;
   uint64_t seq_base;
   uint32_t idx_base;       // added to the arrival indices this launch reports (chunked host calls)
   const uint64_t* chg_base;  // ORDERED: entries already in the change set when the launch began
@@ -489,34 +495,6 @@ struct MergeArgs {
 };
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
-
-// DEVICE layout of a row's last 16-byte chunk (the public bb_row differs in these words only; bb_table_load /
-// bb_table_read convert):
-//   x  bits 0-2 BB_ROW_* flags, bits 3-31 updates of this path in the batch being merged (0 between batches)
-//   y  sum of those updates' arrival indices mod 2^32                                   (0 between batches)
-//   z  cseq, low 32 bits          w  bits 0-15 cseq bits 32-47, bits 16-31 index bookkeeping: 4 bits per field =
-//      entries the node has in that field's overflow set, 15 = "15 or more, always probe"
-// x | y << 32 is the word K1 (bb_direct.cuh) counts a batch's updates with, one atomicAdd per update: the count
-// arrives with the row and is cleared by the row's write-back.
-constexpr int ROW_CNT_SHIFT = 3;
-__device__ __forceinline__ uint32_t xcnt_expand(uint32_t n16) {  // nibble f -> byte f, 15 -> 255 (saturated)
-  uint32_t x = 0;
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const uint32_t v = (n16 >> (4 * f)) & 0xFu;
-    x |= (v == 0xFu ? 0xFFu : v) << (8 * f);
-  }
-  return x;
-}
-__device__ __forceinline__ uint32_t xcnt_pack(uint32_t x) {
-  uint32_t n16 = 0;
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const uint32_t v = (x >> (8 * f)) & 0xFFu;
-    n16 |= (v > 0xFu ? 0xFu : v) << (4 * f);
-  }
-  return n16;
-}
 
 __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
   const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
@@ -533,8 +511,8 @@ __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
   r.m.present = (q7.x & BB_ROW_M_PRESENT) != 0;
   r.v.present = (q7.x & BB_ROW_V_PRESENT) != 0;
   r.alias = (q7.x & BB_ROW_ALIAS) != 0;
-  r.xcnt = xcnt_expand(q7.w >> 16);
-  r.cseq = u64_of(q7.z, q7.w & 0xFFFFu);
+  r.xcnt = q7.y;
+  r.cseq = u64_of(q7.z, q7.w);
 }
 
 __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
@@ -547,7 +525,7 @@ __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
   q[6] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
   const uint32_t flags = (r.m.present ? BB_ROW_M_PRESENT : 0u) | (r.v.present ? BB_ROW_V_PRESENT : 0u) |
                          (r.alias ? BB_ROW_ALIAS : 0u);
-  q[7] = make_uint4(flags, 0u, (uint32_t)r.cseq, ((uint32_t)(r.cseq >> 32) & 0xFFFFu) | (xcnt_pack(r.xcnt) << 16));
+  q[7] = make_uint4(flags, r.xcnt, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
 }
 
 // update payload / change entry as 5 x uint4: [head][clk lo][clk hi][val lo][val hi]
@@ -574,6 +552,12 @@ __device__ __forceinline__ void pack_change(uint4* q, uint32_t user, const Value
 constexpr uint32_t NO_SLOT = BB_NO_SLOT;
 constexpr int MT = 128;    // sorted positions per CTA tile == threads per CTA
 constexpr int MT_WARPS = MT / 32;
+constexpr int HOT_MIN = 24;    // a segment with this many updates inside one tile goes to k_merge_hot whole
+constexpr uint32_t RES_HANDED = 0xFEu;
+constexpr int HOT_SERIAL = 8;  // updates of a segment that overruns its tile replayed by the owner thread before k_merge_hot takes over
+constexpr int HOT_T = 256;     // threads of a k_merge_hot CTA == its speculation window
+constexpr int HOT_WARPS = HOT_T / 32;
+constexpr int HOT_CTAS = 148;
 // Staged rows sit at their natural 128-byte stride with the 16-byte chunk index XOR-swizzled by the row
 // number: conflict-free both for the 8-lanes-per-row copies and for the one-thread-per-row unpack
 // (LDS.128 / STS.128 by 32 rows at once), and 2 KB smaller than a padded stride.
@@ -592,7 +576,7 @@ __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED>
+template <bool ORDERED, bool INDEXED, bool HOT = false>
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * ROW_Q];
@@ -600,6 +584,8 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ uint32_t s_hmask[MT_WARPS], s_wsum[MT_WARPS];
   __shared__ uint32_t s_tile, s_over, s_ex, s_nextk;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, wbase = w * 32;
+  pdl_launch_dependents();
+  pdl_wait();  // the front end is complete
   // bit 0 was decided before this launch.  A rejected batch has no valid item list (out-of-range ids never reach it), so
   // nothing may be loaded through it: return before the first dependent access
   if (*a.rej & 1u) return;
@@ -663,6 +649,17 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
         }
       }
     }
+    // a hot key: a segment this long is a serial chain for its owner thread; k_merge_hot replays it, a CTA per segment
+    bool handed = false;
+    if (HOT && end - tid >= HOT_MIN) {
+      const uint32_t slot = atomicAdd(a.n_hot, 1u);
+      if (slot < a.hot_cap) {
+        a.hot_list[slot] = make_uint4(key, (uint32_t)pos, (uint32_t)(pos >> 32), 0u);
+        for (int p = tid; p < end; ++p) s_res[p] = RES_HANDED;  // not this tile's to report
+        handed = true;
+      }
+    }
+    if (!handed) {
     uint64_t prim[F], prim0[F];  // the node's entries in the dense index columns
     if (INDEXED) {
 #pragma unroll
@@ -691,6 +688,13 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       for (uint64_t gp = base + MT; gp < a.n; ++gp) {
         const uint64_t it = a.sorted[gp];
         if ((uint32_t)(it >> 32) != key) break;
+        if (HOT && gp - (base + MT) >= (uint64_t)HOT_SERIAL) {  // a hot key: k_merge_hot replays the rest, a CTA per segment
+          const uint32_t slot = atomicAdd(a.n_hot, 1u);
+          if (slot < a.hot_cap) {
+            a.hot_list[slot] = make_uint4(key, (uint32_t)gp, (uint32_t)(gp >> 32), 0u);
+            break;
+          }
+        }
         const uint32_t ui = (uint32_t)it;
         const uint4 h = a.head[ui];
         Clock c, oc;
@@ -721,6 +725,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       for (int f = 0; f < F; ++f)
         if (prim[f] != prim0[f]) a.ix.pcol[f][key] = prim[f];
     }
+    }  // !handed
   }
   __syncthreads();
 
@@ -729,7 +734,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
 #pragma unroll
   for (int ww = MT_WARPS - 1; ww >= 0; --ww)
     if (s_hmask[ww]) first = ww * 32 + __ffs(s_hmask[ww]) - 1;
-  const bool owned = valid && tid >= first;
+  const bool owned = valid && tid >= first && s_res[tid] != RES_HANDED;
   const uint32_t code = owned ? s_res[tid] : 0xFFu;
   const bool acc = owned && BB_DEC_ACCEPTED(code);
   const uint32_t amask = __ballot_sync(0xffffffffu, acc);
@@ -812,6 +817,157 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   if (overflow) atomicOr(a.err, 2u);
 }
 
+// ---------------------------------------------------------------- K2h: hot keys
+// A path that takes thousands of a batch's updates (Zipf) is a serial chain for the thread that owns it: ~1 us per
+// update.  But a network-flavour update is decided by (its clock, M, S) alone - V and the alias flag, the only things
+// a REJECTED update changes, do not enter - and M, S change only when an update is accepted.  So one CTA per hot
+// segment (handed over by k_merge_stage after HOT_SERIAL updates past its tile) evaluates the next 256 updates in
+// parallel against the row in shared memory; everything in front of the first state-changing update (the first
+// accepted one, or the first local put, whose clock IS V) is final, that update's own result is exact, and its
+// thread publishes the row for the next round.  The post-write index hook (query:139-176) runs for every retired
+// update, in order, on the publishing thread.  Runs after k_merge_stage; exits at once when nothing is hot.
+template <bool INDEXED>
+__global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
+  __shared__ __align__(16) uint4 s_row[ROW_Q];
+  __shared__ __align__(16) uint4 s_win[HOT_T * UPD_Q];  // payload window
+  __shared__ uint64_t s_prim[F];
+  __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_loc[HOT_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (*a.rej & 1u) return;
+  const uint32_t n_hot = min(*a.n_hot, a.hot_cap);
+  bool overflow = false;
+  for (uint32_t hseg = blockIdx.x; hseg < n_hot; hseg += gridDim.x) {
+    const uint4 he = a.hot_list[hseg];
+    const uint32_t hkey = he.x;
+    uint64_t gp0 = (uint64_t)he.y | ((uint64_t)he.z << 32);
+    __syncthreads();
+    if (tid < ROW_Q) s_row[tid] = a.table[(uint64_t)hkey * ROW_Q + tid];
+    if (INDEXED && tid < F) s_prim[tid] = ((a.ix.mask >> tid) & 1u) ? a.ix.pcol[tid][hkey] : BB_KEY_NONE;
+    __syncthreads();
+    // the window is a ring: position p lives in slot p % HOT_T, so a round only fetches the payloads that ENTER the
+    // window (as many as the previous round retired); the positions behind it are pulled into L2 a window ahead
+    uint64_t staged_end = gp0;
+    while (true) {
+      const uint64_t gp = gp0 + tid;
+      const uint64_t it = gp < a.n ? a.sorted[gp] : ~0ull;
+      const bool mine = gp < a.n && (uint32_t)(it >> 32) == hkey;  // the segment's positions are a prefix of the window
+      const uint32_t ui = (uint32_t)it;
+      uint4* slot = &s_win[(gp & (HOT_T - 1)) * UPD_Q];
+      if (gp >= staged_end) {
+        const uint64_t gq = gp + HOT_T;
+        if (gq < a.n) {
+          const uint64_t iq = a.sorted[gq];
+          if ((uint32_t)(iq >> 32) == hkey) {
+            const uint32_t uq = (uint32_t)iq;
+            prefetch_l2(a.head + uq);
+            prefetch_l2(a.clk + 2 * (uint64_t)uq);
+            prefetch_l2(a.val + 2 * (uint64_t)uq);
+          }
+        }
+      }
+      if (mine && gp >= staged_end) {
+        cp_async16(slot, a.head + ui);
+        cp_async16(slot + 1, a.clk + 2 * (uint64_t)ui);
+        cp_async16(slot + 2, a.clk + 2 * (uint64_t)ui + 1);
+        cp_async16(slot + 3, a.val + 2 * (uint64_t)ui);
+        cp_async16(slot + 4, a.val + 2 * (uint64_t)ui + 1);
+      }
+      cp_async_wait_all();
+      uint32_t code = 0;
+      bool net = true;
+      uint4 h = make_uint4(0, 0, 0, 0);
+      RowState r;
+      Clock oc;
+      Value ov;
+      if (mine) {
+        h = slot[0];
+        Clock c;
+        Value x;
+        net = unpack_update(h, slot[1], slot[2], slot[3], slot[4], c, x);
+        unpack_row(s_row, r);
+        code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
+      }
+      const bool stop = mine && (BB_DEC_ACCEPTED(code) || !net);
+      const uint32_t bm = __ballot_sync(0xffffffffu, mine), bs = __ballot_sync(0xffffffffu, stop),
+                     bl = __ballot_sync(0xffffffffu, mine && !net);
+      if (lane == 0) {
+        s_cnt[w] = __popc(bm);
+        s_stop[w] = bs;
+        s_loc[w] = bl;
+      }
+      __syncthreads();  // also: every thread has unpacked the row and its window slot is in shared memory
+      int nseg = 0, first = HOT_T;
+      bool f_local = false;
+#pragma unroll
+      for (int ww = HOT_WARPS - 1; ww >= 0; --ww) {
+        nseg += (int)s_cnt[ww];
+        if (s_stop[ww]) {
+          const int b = __ffs(s_stop[ww]) - 1;
+          first = ww * 32 + b;
+          f_local = (s_loc[ww] >> b) & 1u;
+        }
+      }
+      if (nseg == 0) break;
+      // retired this round: up to and including the first stop - unless that is a local put further in, whose
+      // clock depends on the V the updates in front of it leave: it waits for the next round's position 0
+      const int retired = first >= nseg ? nseg : ((f_local && first > 0) ? first : first + 1);
+      if (tid < retired) {
+        if (tid == retired - 1) {  // its copy is the exact state after the retired updates
+          if (INDEXED) {
+            // the retired updates in front of this one were rejected network updates, after which the node reads
+            // as the round's initial S
+            RowState r0;
+            unpack_row(s_row, r0);
+            if (kind_of(r0.s.meta) == BB_KIND_NONE || falsy_primitive(r0.s)) materialise_empty_object(r0.s);
+            uint64_t prim[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) prim[f] = s_prim[f];
+            uint32_t xcnt = r0.xcnt;
+            for (int j = 0; j < retired; ++j) {
+              const uint4* sj = &s_win[((gp0 + j) & (HOT_T - 1)) * UPD_Q];
+              Clock cj;
+              Value xj;
+              unpack_update(sj[0], sj[1], sj[2], sj[3], sj[4], cj, xj);
+              index_hook(a.ix, hkey, j == retired - 1 ? r.s : r0.s, xj, prim, xcnt, a.err);
+            }
+            r.xcnt = xcnt;
+#pragma unroll
+            for (int f = 0; f < F; ++f) s_prim[f] = prim[f];
+          }
+          pack_row(s_row, r);
+        }
+        if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
+          const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
+          a.verdict[ui] = (code << 29) | (uint32_t)dest;
+          if (dest < a.cap) {
+            uint4 q[UPD_Q];
+            pack_change(q, h.w, ov, oc);
+            a.out_idx[dest] = a.idx_base + ui;
+            a.out_head[dest] = q[0];
+            a.out_clk[2 * dest] = q[1];
+            a.out_clk[2 * dest + 1] = q[2];
+            a.out_val[2 * dest] = q[3];
+            a.out_val[2 * dest + 1] = q[4];
+          } else {
+            overflow = true;
+          }
+        } else {
+          a.verdict[ui] = (code << 29) | NO_SLOT;
+        }
+      }
+      staged_end = gp0 + HOT_T;
+      gp0 += (uint64_t)retired;
+      __syncthreads();  // the published row is visible; retired slots and s_cnt / s_stop / s_loc may be rewritten
+    }
+    __syncthreads();
+    if (tid < ROW_Q) a.table[(uint64_t)hkey * ROW_Q + tid] = s_row[tid];
+    if (INDEXED && tid < F && ((a.ix.mask >> tid) & 1u)) a.ix.pcol[tid][hkey] = s_prim[tid];
+  }
+  if (overflow) atomicOr(a.err, ERR_CHANGES);
+}
+
 // ---------------------------------------------------------------- table import / export
 __global__ void __launch_bounds__(256) k_table_scatter(uint4* __restrict__ table, const uint64_t* __restrict__ ids,
                                                        const uint4* __restrict__ rows, uint64_t n,
@@ -824,10 +980,7 @@ __global__ void __launch_bounds__(256) k_table_scatter(uint4* __restrict__ table
     atomicOr(err, 1u);
     return;
   }
-  uint4 v = rows[t];
-  if ((t & 7) == 7)  // public bb_row {flags, xcnt, cseq} -> device layout
-    v = make_uint4(v.x & 7u, 0u, v.z, (v.w & 0xFFFFu) | (xcnt_pack(v.y) << 16));
-  table[p * 8 + (t & 7)] = v;
+  table[p * 8 + (t & 7)] = rows[t];
 }
 
 __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table, const uint64_t* __restrict__ ids,
@@ -852,9 +1005,7 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
     }
   }
 #pragma unroll
-  for (int q = 0; q < 7; ++q) rows[i * 8 + q] = row[q];
-  const uint4 v = row[7];  // device layout -> public bb_row {flags, xcnt, cseq}
-  rows[i * 8 + 7] = make_uint4(v.x & 7u, xcnt_expand(v.w >> 16), v.z, v.w & 0xFFFFu);
+  for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[q];
 }
 
 }  // namespace bb

@@ -13,7 +13,7 @@
 #include <new>
 #include <string>
 
-#include "bb_direct.cuh"
+#include "bb_group.cuh"
 #include "bb_kernels.cuh"
 #include "bb_route.cuh"
 
@@ -67,7 +67,7 @@ struct bb_ctx {
   // pipeline scratch
   DevBuf<uint64_t> items_a, items_b;
   DevBuf<uint32_t> zero;  // zeroed per call: [digit histograms | tickets | sort tile states | merge tile states]
-  DevBuf<uint32_t> st_idx;     // sorted path: staging of overrunning segments; direct path: an update's rank in its path
+  DevBuf<uint32_t> st_idx;     // an update's rank in its path (count kernels), then staging of overrunning segments
   DevBuf<uint4> st_ent;
   uint32_t* d_err = nullptr;    // sticky until bb_sync: [0] ERR_* bits, [1] ordinal of the first rejected batch
   uint32_t* h_err = nullptr;    // pinned [2]
@@ -78,19 +78,17 @@ struct bb_ctx {
   DevBuf<uint4> io_head, io_clk, io_val, io_out_head, io_out_clk, io_out_val, io_rows;
   DevBuf<uint32_t> io_verdict, io_out_idx;
   // per-row scratch of the front ends, allocated on first use.  Sorted paths: cs_cnt u32[capacity] (all zero between
-  // calls) and its exclusive scan cs_off u32[capacity + 1], both padded to whole tiles.  Direct pipeline: dm_off
-  // u32[capacity] = a multi-update path's slab / run start (the counts live in the table rows).
+  // calls; the grouping front end uses only this one) and its exclusive scan cs_off u32[capacity + 1], both padded
+  // to whole tiles.
   uint32_t* cs_cnt = nullptr;
   uint32_t* cs_off = nullptr;
-  uint32_t* dm_off = nullptr;
+  uint2* cg_off = nullptr;     // grouping front end: (start, length) of a multi-update path's run, uint2[capacity]
+  uint32_t* cg_ctr = nullptr;  // [2][CG_CTR_WORDS] per-batch counters, sets used alternately
+  uint32_t cg_parity = 0;
+  DevBuf<uint4> hot_list;      // segments k_merge_stage hands to k_merge_hot
   DevBuf<uint2> cs_long;       // sorted paths: segments longer than CS_SHORT, queued for k_cs_fix_long
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
-  // direct pipeline scratch
-  DevBuf<uint32_t> dm_slab, dm_slab_pid, dm_long_pid, dm_litems, dm_lscratch;
-  uint32_t* dm_ctr = nullptr;  // [2][DC_WORDS] per-batch counters, sets used alternately
-  uint32_t dm_parity = 0;
-  unsigned long long* d_tl = nullptr;  // BB_TIMELINE=1: device timestamps of the last direct merge's kernels
-  uint32_t dm_tune = 0, k1_ctas = bb::DM1_CTAS_PER_SM;  // env BB_DM_TUNE, BB_K1_CTAS (experiments)
+  uint32_t tune = 0;  // env BB_TUNE (experiments): 16 = the count kernel prefetches the rows into L2
   bool phase_events = false;   // record the event between the count and the merge kernels (it serialises them)
   uint64_t* d_nchanges = nullptr;
   uint64_t* d_chunk_total = nullptr;  // [MAX_CHUNKS] host calls: the change count as it stood when chunk i was done
@@ -170,15 +168,16 @@ struct ZeroLayout {
 };
 
 // How a batch is brought into "a path's updates adjacent, in arrival order":
-//   direct (default)    no sort: per-path counts, then the batch is merged where it lies (bb_direct.cuh)
+//   grouping (default)  O(batch) passes, singles stay in arrival order (bb_group.cuh)
 //   counting sort       BB_CFG_ORDERED_CHANGES / BB_CFG_FULL_SORT, when the scan over the rows is cheap
 //                       next to the batch: the item list is ascending in path id
 //   radix sort          otherwise, or with BB_CFG_RADIX_SORT
 bool ordered_cfg(const bb_ctx* c) { return (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0; }
 
-bool use_direct(const bb_ctx* c) {
+bool use_grouping(const bb_ctx* c) {
   return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT));
 }
+
 
 bool use_counting_sort(const bb_ctx* c, uint64_t n) {
   if (c->cfg.flags & BB_CFG_RADIX_SORT) return false;
@@ -205,13 +204,18 @@ ZeroLayout zero_layout(const bb_ctx* c, uint64_t n) {
 // size every scratch buffer of the device pipeline for batches of up to n updates
 int reserve_dev(bb_ctx* c, uint64_t n) {
   BB_CUDA(c, c->st_idx.ensure(n));
-  if (use_direct(c)) {
-    if (!c->dm_off) BB_CUDA(c, cudaMalloc((void**)&c->dm_off, c->cfg.capacity * sizeof(uint32_t)));
-    BB_CUDA(c, c->dm_slab.ensure((n / 3 + 1) * bb::DM_SHORT));
-    BB_CUDA(c, c->dm_slab_pid.ensure(n / 3 + 1));
-    BB_CUDA(c, c->dm_long_pid.ensure(n / 9 + 1));
-    BB_CUDA(c, c->dm_litems.ensure(n));
-    BB_CUDA(c, c->dm_lscratch.ensure(n));
+  if (use_grouping(c)) {
+    if (!c->cs_cnt) {  // per-path update counts (zero between calls) and run descriptors
+      BB_CUDA(c, cudaMalloc((void**)&c->cs_cnt, c->cfg.capacity * sizeof(uint32_t)));
+      BB_CUDA(c, cudaMalloc((void**)&c->cg_off, c->cfg.capacity * sizeof(uint2)));
+      BB_CUDA(c, cudaMemsetAsync(c->cs_cnt, 0, c->cfg.capacity * sizeof(uint32_t), c->stream));
+      BB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    BB_CUDA(c, c->items_a.ensure(n));
+    BB_CUDA(c, c->items_b.ensure(n));
+    BB_CUDA(c, c->st_ent.ensure(5 * n));
+    BB_CUDA(c, c->cs_long.ensure(n / 8 + 1));
+    BB_CUDA(c, c->hot_list.ensure(n / bb::HOT_MIN + 16));
     return BB_OK;
   }
   if (!c->cs_cnt) {
@@ -259,62 +263,6 @@ void fill_params(const bb_ctx* c, bb::Params& p, bb::IndexArgs& ix) {
   }
 }
 
-// The default pipeline (bb_direct.cuh): count -> merge where the batch lies -> multi-update paths.
-int merge_direct(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, uint32_t idx_base, bool append,
-                 const uint32_t* call_rej) {
-  using namespace bb;
-  const uint64_t n = in->n;
-  DmArgs a;
-  a.path_id = in->path_id;
-  a.n = n;
-  a.capacity = c->cfg.capacity;
-  a.table = c->table;
-  a.head = reinterpret_cast<const uint4*>(in->head);
-  a.clk = reinterpret_cast<const uint4*>(in->clk);
-  a.val = reinterpret_cast<const uint4*>(in->val);
-  a.off = c->dm_off;
-  a.rank = c->st_idx.p;
-  a.slab = c->dm_slab.p;
-  a.slab_pid = c->dm_slab_pid.p;
-  a.long_pid = c->dm_long_pid.p;
-  a.litems = c->dm_litems.p;
-  a.lscratch = c->dm_lscratch.p;
-  a.ctr = c->dm_ctr + (size_t)c->dm_parity * DC_WORDS;
-  a.ctr_next = c->dm_ctr + (size_t)(c->dm_parity ^ 1u) * DC_WORDS;
-  c->dm_parity ^= 1u;
-  a.verdict = out->verdict;
-  a.n_changes = reinterpret_cast<unsigned long long*>(out->n_changes);
-  a.out_idx = out->idx;
-  a.out_head = reinterpret_cast<uint4*>(out->head);
-  a.out_clk = reinterpret_cast<uint4*>(out->clk);
-  a.out_val = reinterpret_cast<uint4*>(out->val);
-  a.cap = out->cap;
-  a.seq_base = c->seq;
-  a.idx_base = idx_base;
-  a.zero_changes = append ? 0u : 1u;
-  a.ordinal = c->batches_since_sync;
-  a.err = c->d_err;
-  a.rej = call_rej ? call_rej : a.ctr + DC_REJ;
-  fill_params(c, a.p, a.ix);
-  a.tl = c->d_tl;
-  a.tune = c->dm_tune;
-  if (c->d_tl) {
-    static const unsigned long long tl_init[6] = {~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
-    BB_CUDA(c, cudaMemcpyAsync(c->d_tl, tl_init, sizeof(tl_init), cudaMemcpyHostToDevice, s));
-  }
-  BB_LAUNCH_PDL(c, k_dm_count, std::min<uint32_t>(div_up(n, DM1_T), (uint32_t)c->n_sm * c->k1_ctas), DM1_T, 0, s, a);
-  if (!append && c->phase_events) mark(c, EV_SORT, s);  // an event here ends the overlap of K1's tail with K2's prologue
-  const uint32_t g3 = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(n, 3 * DM3_T), (uint32_t)c->n_sm * 2u));
-  if (c->index_mask) {
-    BB_LAUNCH_PDL(c, k_dm_merge<true>, div_up(n, DM_T), DM_T, sizeof(DmSmem), s, a);
-    BB_LAUNCH_PDL(c, k_dm_multi<true>, g3, DM3_T, 0, s, a);
-  } else {
-    BB_LAUNCH_PDL(c, k_dm_merge<false>, div_up(n, DM_T), DM_T, sizeof(DmSmem), s, a);
-    BB_LAUNCH_PDL(c, k_dm_multi<false>, g3, DM3_T, 0, s, a);
-  }
-  return BB_OK;
-}
-
 // One batch (or one chunk of a host call: `idx_base` = arrival index of its first update,
 // `append` = keep adding to *out->n_changes instead of starting a new change set; `call_rej` = the word
 // that says the whole host call is rejected).
@@ -323,10 +271,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   using namespace bb;
   const uint64_t n = in->n;
   if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
-  const bool direct = use_direct(c);
+  const bool grouped = use_grouping(c);
   if (!append) {
     mark(c, EV_START, s);
-    if (!direct || n == 0) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+    if (!grouped || n == 0) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
   }
   if (n == 0) {
     if (!append) {
@@ -340,21 +288,32 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     if (rc) return rc;
   }
   ++c->batches_since_sync;
-  if (direct) {
-    int rc = merge_direct(c, in, out, s, idx_base, append, call_rej);
-    if (rc) return rc;
-    if (!append) mark(c, EV_MERGE, s);
-    c->seq += n;
-    return BB_OK;
-  }
   const ZeroLayout z = zero_layout(c, n);
   uint32_t* zp = c->zero.p;
-  BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
-  uint32_t* rej = zp + z.cs_ctr + 5;  // this batch's reject word
+  if (!grouped) BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
+  uint32_t* rej = grouped ? nullptr : zp + z.cs_ctr + 5;  // this batch's reject word
   const uint32_t ordinal = c->batches_since_sync;
+  uint32_t* gctr = nullptr;
 
   uint64_t* src = c->items_a.p;
-  if (use_counting_sort(c, n)) {
+  if (grouped) {
+    // default: count, then group (singles in arrival order, multi-update paths in claimed runs behind them); the
+    // five launches and the merge behind them are chained with programmatic dependent launch
+    const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
+    gctr = c->cg_ctr + (size_t)c->cg_parity * CG_CTR_WORDS;
+    uint32_t* gnext = c->cg_ctr + (size_t)(c->cg_parity ^ 1u) * CG_CTR_WORDS;
+    c->cg_parity ^= 1u;
+    rej = gctr + CG_CTR_REJ;
+    BB_LAUNCH_PDL(c, k_cg_count, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, gctr, gnext,
+                  c->d_err, ordinal, append ? (uint64_t*)nullptr : out->n_changes,
+                  (const uint4*)((c->tune & 16u) ? c->table : nullptr));
+    BB_LAUNCH_PDL(c, k_cg_classify, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->cg_off, src,
+                  gctr, c->cs_long.p);
+    BB_LAUNCH_PDL(c, k_cg_place, g4, CS_THREADS, 0, s, in->path_id, n, c->st_idx.p, c->cg_off, c->cs_cnt, src, gctr);
+    BB_LAUNCH_PDL(c, k_cg_fix, div_up(n, CS_THREADS), CS_THREADS, 0, s, src, c->cg_off, gctr);
+    BB_LAUNCH_PDL(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, 0, s, src, c->items_b.p, c->cs_long.p, gctr + CG_CTR_LONG,
+                  gctr + CG_CTR_NEXT, gctr + CG_CTR_SINGLE);
+  } else if (use_counting_sort(c, n)) {
     // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
     const uint32_t g = div_up(n, CS_THREADS);
     const uint64_t cap = c->cfg.capacity;
@@ -382,7 +341,7 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
       dst = t;
     }
   }
-  if (!append) mark(c, EV_SORT, s);
+  if (!append && (!grouped || c->phase_events)) mark(c, EV_SORT, s);  // (an event here ends the overlap of the launches)
   if (c->cfg.flags & BB_CFG_ORDERED_CHANGES)
     BB_CUDA(c, cudaMemcpyAsync(c->d_chg_base, out->n_changes, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
 
@@ -403,9 +362,12 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.cap = out->cap;
   ma.st_idx = c->st_idx.p;
   ma.st_ent = c->st_ent.p;
-  ma.tile_state = zp + z.merge_state;
-  ma.ticket = zp + z.tickets + MAX_PASSES;
+  ma.tile_state = grouped ? nullptr : zp + z.merge_state;
+  ma.ticket = grouped ? nullptr : zp + z.tickets + MAX_PASSES;
   ma.num_tiles = z.merge_tiles;
+  ma.hot_list = c->hot_list.p;
+  ma.n_hot = grouped ? gctr + CG_CTR_NHOT : nullptr;
+  ma.hot_cap = grouped ? (uint32_t)std::min<uint64_t>(c->hot_list.cap, 0x7FFFFFFFull) : 0u;
   ma.seq_base = c->seq;
   ma.idx_base = idx_base;
   ma.chg_base = c->d_chg_base;
@@ -413,7 +375,15 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.rej = call_rej ? call_rej : rej;
   fill_params(c, ma.p, ma.ix);
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
-  if (c->index_mask) {
+  if (grouped) {  // hot keys are handed to k_merge_hot, a CTA per segment (exits at once when there are none)
+    if (c->index_mask) {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, k_merge_hot<true>, HOT_CTAS, HOT_T, 0, s, ma);
+    } else {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
+    }
+  } else if (c->index_mask) {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
   } else {
@@ -608,15 +578,13 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
     delete c;
     return BB_ERR_CUDA;
   }
-  // k_merge_stage: 7 x 27.7 KB, k_dm_merge: 6 x 36 KB of dynamic shared memory per SM: ask for the full carve-out
+  // k_merge_stage: 7 x 27.7 KB of static shared memory per SM: ask for the full carve-out
   cudaFuncSetAttribute(bb::k_merge_stage<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_dm_merge<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_dm_merge<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_dm_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bb::DmSmem));
-  cudaFuncSetAttribute(bb::k_dm_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(bb::DmSmem));
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
@@ -629,8 +597,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMemcpyAsync(c->d_err, err_clear, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_callrej, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
-            cudaMalloc((void**)&c->dm_ctr, 2 * bb::DC_WORDS * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemsetAsync(c->dm_ctr, 0, 2 * bb::DC_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
+            cudaMalloc((void**)&c->cg_ctr, 2 * bb::CG_CTR_WORDS * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->cg_ctr, 0, 2 * bb::CG_CTR_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chunk_total, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
@@ -655,9 +623,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return BB_ERR_CUDA;
   }
-  if (const char* e = getenv("BB_DM_TUNE")) c->dm_tune = (uint32_t)strtoul(e, nullptr, 10);
-  if (const char* e = getenv("BB_K1_CTAS")) c->k1_ctas = (uint32_t)std::max(1l, std::min(8l, strtol(e, nullptr, 10)));
-  if (getenv("BB_TIMELINE")) cudaMalloc((void**)&c->d_tl, 6 * sizeof(unsigned long long));
+  if (const char* e = getenv("BB_TUNE")) c->tune = (uint32_t)strtoul(e, nullptr, 10);
   if (prev_dev >= 0 && prev_dev != cfg->device) cudaSetDevice(prev_dev);  // every entry point selects the ctx's device itself
   *out = c;
   return BB_OK;
@@ -685,13 +651,13 @@ int bb_destroy(bb_ctx* c) {
   if (c->d_err) cudaFree(c->d_err);
   if (c->cs_cnt) cudaFree(c->cs_cnt);
   if (c->cs_off) cudaFree(c->cs_off);
-  if (c->dm_off) cudaFree(c->dm_off);
-  if (c->d_tl) cudaFree(c->d_tl);
-  if (c->dm_ctr) cudaFree(c->dm_ctr);
+  if (c->cg_off) cudaFree(c->cg_off);
+  if (c->cg_ctr) cudaFree(c->cg_ctr);
+  c->hot_list.release();
   if (c->d_callrej) cudaFree(c->d_callrej);
   if (c->d_chunk_total) cudaFree(c->d_chunk_total);
   c->cs_long.release(); c->cs_tile.release();
-  c->dm_slab.release(); c->dm_slab_pid.release(); c->dm_long_pid.release(); c->dm_litems.release(); c->dm_lscratch.release();
+
   if (c->d_nchanges) cudaFree(c->d_nchanges);
   if (c->d_chg_base) cudaFree(c->d_chg_base);
   for (int i = 0; i < MAX_CHUNKS; ++i) {
@@ -1029,16 +995,6 @@ int bb_index_stats(bb_ctx* c, uint32_t field, uint64_t* n_dense, uint64_t* n_ext
 }
 
 uint64_t bb_launch_count(const bb_ctx* c) { return c ? c->launches : 0; }
-
-/* diagnostics, not part of the ABI header: out[6] = {K1 first start, last end, K2 ..., K3 ...} in ns of the last
- * direct-pipeline merge, relative to K1's start (needs BB_TIMELINE=1 in the environment at bb_create) */
-int bb_debug_timeline(bb_ctx* c, double out[6]) {
-  if (!c || !c->d_tl) return BB_ERR_STATE;
-  unsigned long long h[6];
-  if (cudaMemcpy(h, c->d_tl, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return BB_ERR_CUDA;
-  for (int i = 0; i < 6; ++i) out[i] = (double)(long long)(h[i] - h[0]);
-  return BB_OK;
-}
 
 int bb_phase_events(bb_ctx* c, int on) {
   if (!c) return BB_ERR_ARG;

@@ -194,6 +194,7 @@ def test_device_pointer_entry_matches_host_entry():
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     stream = side.cuda_stream
+    eng.phase_events(True)  # the event between the front end and the merge (off by default: it serialises them)
     eng.merge_dev(bs, cs, stream)
     eng.sync(stream)
     k = int(o_n.item())
