@@ -1,32 +1,36 @@
 #!/usr/bin/env python
-"""bench.py - the BASELINE.json metric on BASELINE.json's config.
+"""bench.py - the BASELINE.json metric on BASELINE.json's configs.
 
-A "step" = one pass of the hot path over one synthetic batch: 1 M conflicting
-updates (F=4 fields each => 4 M field-merges) merged into a resident table of
-2.5 M records (10 M fields) per GPU  (BASELINE.json configs[1]; SURVEY.md 8d
-"Config 2", uniform-key variant - the one the 8d roofline figure is worked on).
+A "step" = one pass of the hot path over one synthetic batch of conflicting updates (F=4 fields each).
 
-  value   field-merges/s, whole job, inputs already resident in HBM
-          (bb_merge_batch_dev; CUDA events on the launching stream, max over ranks)
-  e2e     same metric through the reference-facing C-ABI call bb_merge_batch with
-          pinned HOST buffers: H2D of the batch and D2H of decisions + change set
-          inside the timed region
-  roofline      the dominant kernel (k_merge_stage): algorithmic bytes / its mean launch
-                duration inside the timed region / measured HBM peak
-  cpu_baseline  the typed C oracle (oracle/bullet_oracle.c, a restatement of the
-                reference's JS: kind "port"), 1 thread, bounded sample
-  --impl reference   the same oracle on every host thread (the reference itself is
-                JavaScript and there is no JS engine on the box: see DESIGN.md)
+  N = 1   config 2 (BASELINE.json configs[1]): 1 M updates merged into a resident table of 2.5 M
+          records (10 M fields), uniform keys - the variant the 8d roofline figure is worked on.
+  N > 1   config 3 (configs[2]): the table is sharded by a hash of the path id over the N GPUs, 31.25 M records
+          (125 M fields, 4 GB of rows) and a 2 M-update batch per GPU and step - 250 M records / 1 B fields / 16 M
+          updates per step at N = 8, exactly the stated config; every batch is routed to its owning shards by the
+          library's fused pack + all-to-all over NVLink peer memory (routing of batch i+1 overlaps the merge of
+          batch i).  Weak scaling: the per-GPU shard is fixed.
 
-N > 1 (torchrun, one rank per GPU): the table is sharded by path id (global table =
-N x the per-GPU table), every rank submits its own 1 M batch, updates are routed to
-their owner by the library's fused pack + all-to-all over NVLink peer memory and
-merged there, routing of batch i+1 overlapping the merge of batch i; weak scaling
-(per-GPU work fixed).
+  value   field-merges/s, whole job, inputs already resident in HBM (bb_merge_batch_dev / bb_router_*; CUDA events
+          on the launching stream, max over ranks)
+  e2e     same metric through the reference-facing C-ABI call with pinned HOST buffers: H2D of the batch and D2H
+          of decisions + change set inside the timed region
+  parity  step 0 of the very workload that is timed, compared bit for bit (decisions, change set, every touched
+          row) with the typed C oracle on the host; per shard at N > 1; query hit multisets against numpy.  A
+          mismatch fails the run.
+  roofline      the dominant kernel (k_merge_stage): algorithmic bytes / its mean launch duration / measured HBM peak,
+                plus the same for the whole step (pipeline_frac)
+  cpu_baseline  the typed C oracle (oracle/bullet_oracle.c, a restatement of the reference's JS: kind "port"),
+                1 thread, bounded sample
+  zipf    the "conflicting" Zipf(0.8) variant of config 2, default configuration, without and with an index
+  query   config 4: index build + range(20,30) + equals(role,'admin') over --query-records nodes per GPU
+  --impl reference   the same C oracle on every host thread.  The reference itself is JavaScript and no JS engine
+                exists on the box: every ratio against this arm is against the C PORT, not Node.js.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -39,10 +43,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE line
 
-N_RECORDS = 2_500_000   # per GPU: 10 M fields
-BATCH = 1_000_000       # updates per step per GPU
-N_BATCHES = 4           # distinct pre-generated batches, cycled
 F = 4
+N_BATCHES = 4            # distinct pre-generated batches, cycled
+CFG2 = dict(records=2_500_000, batch=1_000_000)
+CFG3 = dict(records=31_250_000, batch=2_000_000, image=1 << 22)  # per GPU; the table image is tiled over the shard
+REFERENCE_KIND = "C port of the reference's JavaScript (oracle/bullet_oracle.c); Node.js itself was not run: no JS engine on the box"
 
 
 def parse():
@@ -51,24 +56,29 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--records", type=int, default=N_RECORDS)
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--records", type=int, default=0, help="records per GPU (default: config 2 at N=1, config 3 at N>1)")
+    ap.add_argument("--batch", type=int, default=0, help="updates per GPU and step")
     ap.add_argument("--keys", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--query-records", type=int, default=100_000_000,
                     help="nodes per GPU for the index build + range/equals scans (BASELINE config 4)")
     ap.add_argument("--no-query", action="store_true")
-    ap.add_argument("--merge-kernel", default="stage", choices=["stage", "pipe"],
-                    help="k_merge_stage (one CTA per 128-update tile; default) or k_merge_pipe (BB_CFG_CTA_PIPE)")
+    ap.add_argument("--no-zipf", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the step-0 comparison with the oracle (debugging only)")
     ap.add_argument("--front-end", default="group", choices=["group", "full", "radix"],
                     help="how a batch is grouped by path: the library default, BB_CFG_FULL_SORT or BB_CFG_RADIX_SORT")
-    return ap.parse_args()
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base = CFG2 if world == 1 else CFG3
+    a.records = a.records or base["records"]
+    a.batch = a.batch or base["batch"]
+    return a
 
 
 def ncu_traffic(kernel, expect_default):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
-    (profiles/traffic.json, written by scripts/make_profiles.py); null when the run is not the captured workload."""
+    (profiles/traffic.json); null when the run is not the captured workload."""
     if not expect_default:
         return None
     try:
@@ -146,71 +156,201 @@ class ClockSampler:
         }
 
 
-def make_workload(args, rank, world=1):
-    """Table image of one shard (every shard is loaded with the same image) and this rank's batches.
-    Sharded runs keep the per-GPU workload of the single-GPU run (weak scaling): the global table has
-    world x records rows, a batch row drawn for image row r goes to a uniformly drawn owner q as global
-    path id r * world + q (owner = id % world, local row = id // world = r), so every shard still sees
-    ~batch updates spread over all of its `records` rows, with clocks built against the row they hit."""
+# ---------------------------------------------------------------------------------------------- workloads
+def key_bits_for(world, records):
+    """Hashed sharding needs ids < 2^key_bits with 2^key_bits >= world * records (bullet_js_b200/shard.py)."""
+    return int(np.ceil(np.log2(world * records)))
+
+
+def shard_mix_inverse(x, key_bits):
+    """Inverse of shard.shard_mix (each step of the finaliser is a bijection of [0, 2^key_bits))."""
+    x = np.asarray(x, np.uint64)
+    mask = np.uint64((1 << key_bits) - 1)
+    s = np.uint64((key_bits + 1) // 2)
+    with np.errstate(over="ignore"):
+        for mul in (0x94D049BB133111EB, 0xBF58476D1CE4E5B9, 0x9E3779B97F4A7C15):
+            x = x ^ (x >> s)  # 2 s >= key_bits: the xor-shift is its own inverse
+            x = (x * np.uint64(pow(mul, -1, 1 << key_bits))) & mask
+    return x
+
+
+def make_workload(args, rank, world):
+    """-> (image, batches, meta).  N = 1: the table IS the image (row i == path id i).  N > 1 (config 3): every shard
+    holds `cap` rows, local row r = image row r % len(image) (the image tiled); a batch row drawn against image row p
+    goes to a uniformly drawn owner q and tile t: local row r = t * len(image) + p, scrambled id x = r * world + q,
+    global path id = shard_mix^-1(x).  So every shard sees ~batch updates spread uniformly over ALL of its rows,
+    with clocks built against the row they hit, and the path ids look like the hashed ids they are."""
     from bullet_js_b200 import synth
 
-    rng = synth.rng_for(2, salt=rank)
-    table = synth.make_table(args.records, rng if world == 1 else synth.rng_for(2, salt=1000))
-    batches = [synth.make_batch(table, args.batch, rng, keys=args.keys) for _ in range(N_BATCHES)]
-    if world > 1:
-        for b in batches:
-            b.path_id[:] = b.path_id * np.uint64(world) + rng.integers(0, world, b.n).astype(np.uint64)
-    return table, batches
+    rng = synth.rng_for(2 if world == 1 else 3, salt=rank)
+    if world == 1:
+        image = synth.make_table(args.records, rng)
+        batches = [synth.make_batch(image, args.batch, rng, keys=args.keys) for _ in range(N_BATCHES)]
+        return image, batches, dict(capacity=args.records, key_bits=0, tiles=1)
+    kb = key_bits_for(world, args.records)
+    cap = (1 << kb) // world
+    n_img = min(CFG3["image"], cap)
+    assert cap % n_img == 0
+    image = synth.make_table(n_img, synth.rng_for(3, salt=1000))  # the same image on every rank
+    batches = [sharded_batch(image, args.batch, synth.rng_for(3, salt=rank * 16 + j), args.keys, world, kb, cap)
+               for j in range(N_BATCHES)]
+    return image, batches, dict(capacity=cap, key_bits=kb, tiles=cap // n_img)
 
 
+def sharded_batch(image, n, rng, keys, world, kb, cap):
+    from bullet_js_b200 import synth
+
+    b = synth.make_batch(image, n, rng, keys=keys)
+    tiles = cap // image.n
+    r = rng.integers(0, tiles, n).astype(np.uint64) * np.uint64(image.n) + b.path_id
+    q = rng.integers(0, world, n).astype(np.uint64)
+    b.path_id[:] = shard_mix_inverse(r * np.uint64(world) + q, kb)
+    return b
+
+
+def workload_config(args, world, meta=None):
+    if world == 1:
+        wl = (f"config2: {args.records * F // 1_000_000}M-field table ({args.records} records x {F} fields, 128 B rows), "
+              f"{args.batch}-update conflicting batch per step, {args.keys} keys, clock mix 40/20/25/5/5/5")
+    else:
+        wl = (f"config3: {world * args.records * F / 1e9:.2f}B-field table sharded by key hash over {world} GPUs "
+              f"({args.records} records = {args.records * 128 / 2**30:.1f} GiB of rows per GPU), {world * args.batch}-update "
+              f"batch per step ({args.batch} submitted per GPU, routed all-to-all), {args.keys} keys, clock mix 40/20/25/5/5/5")
+    return {
+        "workload": wl, "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
+        "keys": args.keys, "front_end": args.front_end,
+        "sharding": "none" if world == 1 else f"splitmix64-style bijective hash of the path id (key_bits {meta['key_bits'] if meta else '?'}) % {world}",
+        "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2; "
+              "every step merges into a pristine copy of the table",
+    }
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """The reference's algorithm on the host cores: typed C restatement, all threads."""
+    """The reference's algorithm on the host cores: typed C restatement, all threads (see REFERENCE_KIND)."""
     if rank != 0:
         return
     from bullet_js_b200 import capi, synth
     from oracle.typed import TypedOracle
 
-    table, batches = make_workload(args, 0)  # one rank's share: the single-GPU workload
+    ref_args = argparse.Namespace(**vars(args))
+    if world > 1:  # one rank's share of config 3 is not a sensible CPU sample: the single-GPU workload instead
+        ref_args.records, ref_args.batch = CFG2["records"], CFG2["batch"]
+    image, batches, _ = make_workload(ref_args, 0, 1)
     cores = os.cpu_count() or 1
-    cfg = capi.make_config(args.records, **synth.synth_ranks(args.records))
+    cfg = capi.make_config(ref_args.records, **synth.synth_ranks(ref_args.records))
     orc = TypedOracle(cfg)
-    out = capi.ChangeBuffers(args.batch)
+    out = capi.ChangeBuffers(ref_args.batch)
     dt = 0.0
     for i in range(args.warmup + args.steps):
-        orc.table[:] = table.rows  # every step merges into the pristine table (not timed)
+        orc.table[:] = image.rows  # every step merges into the pristine table (not timed)
         t0 = time.perf_counter()
         orc.merge(batches[i % N_BATCHES], threads=cores, out=out)
         if i >= args.warmup:
             dt += time.perf_counter() - t0
-    v = args.steps * args.batch * F / dt
+    v = args.steps * ref_args.batch * F / dt
     line = {
         "impl": "reference", "metric": "crdt_field_merges_per_sec", "value": v, "unit": "field-merges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
-        "data": "synthetic", "config": workload_config(args, world),
+        "data": "synthetic", "config": workload_config(ref_args, 1),
         "cpu_baseline": {"value": v, "unit": "field-merges/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x {args.batch} updates on the same table, path-sharded over {cores} threads"},
+                         "sample": f"{args.steps} x {ref_args.batch} updates on the same table, path-sharded over {cores} threads"},
         "e2e": {"value": v, "unit": "field-merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is JavaScript; no JS engine on the box, so this is the C restatement (oracle/bullet_oracle.c)",
+        "reference_kind": REFERENCE_KIND,
     }
     print(json.dumps(line))
 
 
-def run_queries(args, rank, world, local_rank, dev, table, dist):
-    """BASELINE config 4: index('users','age') build + range(20,30) + equals(role,'admin') over
-    --query-records nodes per GPU (the 2.5 M-record image tiled), every rank scanning its shard;
-    results all-gathered (counts, then padded payload) when world > 1."""
+# ---------------------------------------------------------------------------------------------- helpers (GPU)
+class DevOut:
+    """Device-resident change-set buffers of one merge call."""
+
+    def __init__(self, torch, dev, cap):
+        from bullet_js_b200 import capi
+
+        self.cap = cap
+        self.ver = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.n = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.idx = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.head = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
+        self.clk = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+        self.val = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
+        self.cs = capi.BBChanges(cap=cap, verdict=self.ver.data_ptr(), n_changes=self.n.data_ptr(), idx=self.idx.data_ptr(),
+                                 head=self.head.data_ptr(), clk=self.clk.data_ptr(), val=self.val.data_ptr())
+
+    def changes(self, m):
+        """The first m verdicts + the change set, copied to the host, in arrival order."""
+        from bullet_js_b200 import codec
+
+        k = int(self.n.item())
+        return codec.Changes.from_verdicts(
+            self.ver[:m].cpu().numpy().view(np.uint32), self.idx[:k].cpu().numpy().view(np.uint32),
+            self.head[: k * 16].cpu().numpy().view(codec.HEAD_DTYPE),
+            self.clk[: k * 32].cpu().numpy().view(np.uint32).reshape(k, 8),
+            self.val[: k * 32].cpu().numpy().view(np.uint64).reshape(k, 4))
+
+
+def to_dev(torch, dev, a):
+    return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+
+def dev_batch(torch, dev, b):
+    from bullet_js_b200 import capi
+
+    t = (to_dev(torch, dev, b.path_id), to_dev(torch, dev, b.head), to_dev(torch, dev, b.clk), to_dev(torch, dev, b.val))
+    return t, capi.BBBatch(n=b.n, path_id=t[0].data_ptr(), head=t[1].data_ptr(), clk=t[2].data_ptr(), val=t[3].data_ptr())
+
+
+def oracle_check(cfg, rows, batch, got, read_rows, indexed_field=None):
+    """Replay `batch` over `rows` (row i of `rows` is path id i of the batch) with the typed oracle and compare
+    decisions, change set and every touched row with what the device produced.  -> (ok, detail)."""
+    from oracle.typed import TypedOracle
+
+    orc = TypedOracle(cfg)
+    orc.table[: len(rows)] = rows
+    if indexed_field is not None:
+        orc.index_create(indexed_field)
+    want = orc.merge(batch, threads=1 if indexed_field is not None else (os.cpu_count() or 1))
+    if not got.same_as(want):
+        same_shape = got.decision.shape == want.decision.shape
+        bad = int(np.argmax(got.decision != want.decision)) if same_shape and (got.decision != want.decision).any() else -1
+        return False, f"decisions / change set differ (first differing decision at update {bad})"
+    touched = np.unique(batch.path_id)
+    have, expect = read_rows(touched), orc.table[touched.astype(np.int64)]
+    have["xcnt"] = 0  # device-private index bookkeeping (include/bullet_b200.h), not part of the reference's state
+    expect["xcnt"] = 0
+    if not np.array_equal(have, expect):
+        return False, "table rows differ after the batch"
+    return True, f"{batch.n} updates, {len(want.idx)} accepted, {touched.size} rows compared bit for bit"
+
+
+def compact_for_oracle(image_rows, tile_rows, batch_local):
+    """Oracle-sized view of a huge shard: the distinct local rows a batch touches become ids 0..d-1."""
+    from bullet_js_b200 import codec
+
+    uniq, inv = np.unique(batch_local.path_id, return_inverse=True)
+    rows = image_rows[(uniq % np.uint64(tile_rows)).astype(np.int64)]
+    b = codec.Batch(inv.astype(np.uint64), batch_local.head, batch_local.clk, batch_local.val)
+    return uniq, rows, b
+
+
+# ---------------------------------------------------------------------------------------------- config 4
+def run_queries(args, rank, world, local_rank, dev, image, dist):
+    """BASELINE config 4: index('users','age') + index('users','role') build, range(age,20,30), equals(role,'admin')
+    over --query-records nodes per GPU (the image tiled), every rank scanning its shard; at world > 1 the hit ids are
+    all-gathered.  Parity: the hit MULTISETS of this rank's scans against a numpy evaluation of the table image."""
     import torch
 
     from bullet_js_b200 import capi, codec, synth
     from bullet_js_b200.engine import Engine
 
     nq = args.query_records
-    eng = Engine(nq, device=local_rank, post_getdata=True, **synth.synth_ranks(args.records))
-    base = np.arange(table.n, dtype=np.uint64)
-    for off in range(0, nq, table.n):
-        m = min(table.n, nq - off)
-        eng.table_load(base[:m] + np.uint64(off), table.rows[:m])
+    eng = Engine(nq, device=local_rank, post_getdata=True, **synth.synth_ranks(image.n))
+    base = np.arange(image.n, dtype=np.uint64)
+    for off in range(0, nq, image.n):
+        m = min(image.n, nq - off)
+        eng.table_load(base[:m] + np.uint64(off), image.rows[:m])
     t0 = time.perf_counter()
     eng.index_create(0, extra_capacity=1 << 16)
     build_ms_age = eng.phase_ms("scan")
@@ -223,8 +363,6 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
     hits = torch.zeros(cap, dtype=torch.int32, device=dev)
     cnt = torch.zeros(2, dtype=torch.int64, device=dev)
     hs = capi.BBHits(cap=cap, node=hits.data_ptr(), n_dense=cnt.data_ptr(), n_extra=cnt[1:].data_ptr())
-    import ctypes as C
-
     lo = capi.BBBound(num=20.0, rank=0, flags=0, reserved=0)
     hi = capi.BBBound(num=30.0, rank=0, flags=0, reserved=0)
     admin = codec.KEY_STR | 0
@@ -235,12 +373,29 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
     def equals_dev():
         eng._check(eng.lib.bb_query_equals_dev(eng._h, 2, admin, C.byref(hs), C.c_void_p(stream)))
 
-    out = {}
+    # what the reference would return, as a set of node ids: numpy over the image, tiled like the table
+    age = image.rows["val"][:, 0].view(np.float64)
+    role = image.rows["val"][:, 2]
+    want = {"range": np.nonzero((age >= 20.0) & (age <= 30.0))[0], "equals": np.nonzero(role == 0)[0]}
+
+    def expected_count(sel):
+        full, rest = divmod(nq, image.n)
+        return full * sel.size + int(np.searchsorted(sel, rest))
+
+    out, parity = {}, {}
     reps = 10
     for name, fn in (("range", range_dev), ("equals", equals_dev)):
         for _ in range(3):
             fn()
         eng.sync(stream)
+        nh = int(cnt.sum().item())
+        if not args.no_parity:  # every hit id maps back to an image row that satisfies the predicate, each node once
+            got = np.sort(hits[:nh].cpu().numpy().view(np.uint32).astype(np.int64))
+            ok = nh == expected_count(want[name])
+            if ok:
+                ok = bool(np.isin(got % image.n, want[name]).all()) and bool((np.diff(got) > 0).all())
+            parity[name] = "ok" if ok else "MISMATCH"
+            del got
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -252,8 +407,9 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         kernel_ms = float(np.mean([eng.phase_ms("scan", j) for j in range(reps)]))
-        nh = int(cnt.sum().item())
         out[name] = {"ms": ms, "scan_ms": kernel_ms, "hits": nh}
+    range_dev()
+    eng.sync(stream)
     # e2e through the host entry points (pinned output, D2H of the hits inside the timed region)
     hn = out["range"]["hits"] + 16
     h_node = torch.zeros(hn, dtype=torch.int32).pin_memory()
@@ -264,8 +420,9 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
     for _ in range(5):
         eng.query_range_raw(0, lo, hi, hhs)
     e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
-    assert int(h_cnt.sum()) == out["range"]["hits"]
-    if dist is not None:  # all-gather(v) of the result ids: counts first, then the padded payload
+    if int(h_cnt.sum()) != out["range"]["hits"]:
+        parity["range"] = "MISMATCH"
+    if dist is not None:  # all-gather(v) of the result ids: counts first, then the padded payload (u32 local ids)
         t = torch.tensor([out["range"]["ms"], out["equals"]["ms"], e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out["range"]["ms"], out["equals"]["ms"], e2e_ms = (float(x) for x in t)
@@ -273,17 +430,19 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
         counts = torch.zeros(world, device=dev, dtype=torch.int64)
         dist.all_gather_into_tensor(counts, n_local)
         mx = int(counts.max().item())
-        range_dev()
-        gids = hits[:mx].to(torch.int64) * world + rank  # local row -> global path id
-        allh = torch.zeros(world * mx, device=dev, dtype=torch.int64)
+        allh = torch.zeros(world * mx, device=dev, dtype=torch.int32)
+        torch.cuda.synchronize()
+        dist.all_gather_into_tensor(allh, hits[:mx])
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.all_gather_into_tensor(allh, gids)
+        dist.all_gather_into_tensor(allh, hits[:mx])  # the reader derives global id = local * world + rank
         g1.record()
         torch.cuda.synchronize()
         out["allgather_ms"] = g0.elapsed_time(g1)
-        out["allgather_bytes"] = int(world * mx * 8)
+        out["allgather_bytes"] = int(world * mx * 4)
+        out["allgather_api"] = ("torch.distributed all_gather_into_tensor (NCCL) of the u32 local hit ids, padded to the largest "
+                                "shard's count; the library has no gather entry point yet")
     peak, _ = peaks()
     res = {
         "workload": f"config4: index(age)+index(role) build, range(age,20,30), equals(role,'admin') over {nq} nodes/GPU",
@@ -294,8 +453,11 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
         "range_ms": out["range"]["ms"], "equals_ms": out["equals"]["ms"],
         "index_build_ms": {"age": build_ms_age, "role": build_ms_role, "wall_both": build_wall * 1e3},
         "index_build_rows_per_sec": nq * world / (build_ms_age * 1e-3),
+        "index_build_roofline": {"algorithmic_bytes_per_row": 20.0, "achieved": 20.0 * nq / (build_ms_age * 1e-3) / 1e9,
+                                 "frac": 20.0 * nq / (build_ms_age * 1e-3) / 1e9 / peak},
         "e2e_range": {"rows_per_sec": nq * world / (e2e_ms * 1e-3), "ms": e2e_ms, "d2h_bytes": out["range"]["hits"] * 4 + 16,
                       "api": "bb_query_range (host hit buffer, synchronous)"},
+        "parity": parity,
         "roofline": {"bound": "hbm", "kernel": "k_index_scan", "unit": "GB/s", "peak": peak,
                      "achieved": (8.0 * nq + 4.0 * out["range"]["hits"]) / (out["range"]["scan_ms"] * 1e-3) / 1e9,
                      "bytes_per_row": 8.0 + 4.0 * out["range"]["hits"] / nq, "kernel_ms": out["range"]["scan_ms"],
@@ -305,23 +467,54 @@ def run_queries(args, rank, world, local_rank, dev, table, dist):
     # the measured peak is a COPY (half reads, half writes); this kernel is a pure read stream and can exceed it:
     # also report it against the data-sheet HBM3e figure the profiling recipe quotes
     res["roofline"]["frac_of_nominal_7700"] = res["roofline"]["achieved"] / 7700.0
-    for k in ("allgather_ms", "allgather_bytes"):
+    for k in ("allgather_ms", "allgather_bytes", "allgather_api"):
         if k in out:
             res[k] = out[k]
     eng.close()
     return res
 
 
-def workload_config(args, world):
-    return {
-        "workload": f"config2: {args.records * F // 1_000_000}M-field table/GPU ({args.records} records x {F} fields, 128 B rows), "
-                    f"{args.batch}-update conflicting batch/GPU/step, {args.keys} keys, clock mix 40/20/25/5/5/5",
-        "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
-        "keys": args.keys, "front_end": args.front_end, "merge_kernel": args.merge_kernel, "hot_keys": args.keys == "zipf", "sharding": f"path_id % {world}" if world > 1 else "none",
-        "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2",
-    }
+# ---------------------------------------------------------------------------------------------- zipf section
+def run_zipf(args, local_rank, dev, image, stream, torch):
+    """The "conflicting" variant SURVEY 8d names: Zipf(0.8) keys (the hottest path takes ~1 % of the batch), default
+    configuration, without and with an index on `age`; each checked against the oracle."""
+    from bullet_js_b200 import synth
+    from bullet_js_b200.engine import Engine
+
+    n = args.batch
+    rng = synth.rng_for(2, salt=77)
+    zb = [synth.make_batch(image, n, rng, keys="zipf") for _ in range(2)]
+    ids = np.arange(args.records, dtype=np.uint64)
+    res = {"workload": f"{n}-update Zipf(0.8) batch over {args.records} records",
+           "hottest_path_updates": int(np.bincount(zb[0].path_id.astype(np.int64)).max())}
+    for label, indexed in (("default", False), ("indexed_age", True)):
+        engines = []
+        for _ in range(4):
+            e = Engine(args.records, device=local_rank, post_getdata=indexed, **synth.synth_ranks(args.records))
+            e.table_load(ids, image.rows)
+            if indexed:
+                e.index_create(0, extra_capacity=2 * n)
+            e.reserve(n, host_entry=False)
+            engines.append(e)
+        out = DevOut(torch, dev, n)
+        d_in = [dev_batch(torch, dev, b) for b in zb]
+        engines[0].merge_dev(d_in[0][1], out.cs, stream)
+        engines[0].sync(stream)
+        ok, detail = (True, "skipped") if args.no_parity else oracle_check(
+            engines[0].cfg, image.rows, zb[0], out.changes(n), lambda t: engines[0].table_read(t), indexed_field=0 if indexed else None)
+        ms = []
+        for j, e in enumerate(engines[1:]):
+            e.merge_dev(d_in[(j + 1) % 2][1], out.cs, stream)
+            e.sync(stream)
+            ms.append(e.phase_ms("device"))
+        res[label] = {"ms_per_batch": float(np.mean(ms)), "field_merges_per_sec": n * F / (float(np.mean(ms)) * 1e-3),
+                      "parity": "ok" if ok else "MISMATCH: " + detail}
+        for e in engines:
+            e.close()
+    return res
 
 
+# ---------------------------------------------------------------------------------------------- main
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -333,7 +526,7 @@ def main():
 
     import torch
 
-    from bullet_js_b200 import capi, codec, synth
+    from bullet_js_b200 import capi, codec, shard, synth
     from bullet_js_b200.engine import Engine
 
     if not torch.cuda.is_available():
@@ -346,22 +539,31 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    table, batches = make_workload(args, rank, world)
+    image, batches, meta = make_workload(args, rank, world)
     n, K, W = args.batch, args.steps, args.warmup
-    # Every step merges into a PRISTINE copy of the table (one bb_ctx per step, all
-    # loaded with the same image): the batches' clocks are built relative to that image,
-    # so re-merging into an already-merged table would turn the workload into "all
-    # historical".  It also means no step ever finds its table in L2.
-    ids = np.arange(args.records, dtype=np.uint64)
-    per_engine = args.records * (128 + 12) + args.batch * 120  # table + counters + per-batch scratch, bytes
-    if (W + K) * per_engine > 0.8 * torch.cuda.get_device_properties(dev).total_memory:
-        raise SystemExit(f"--steps {K}: {W + K} pristine tables of {per_engine >> 20} MiB do not fit this GPU; use fewer steps")
+    capacity, kb = meta["capacity"], meta["key_bits"]
+    ranks_kw = synth.synth_ranks(image.n)
+    # Every step merges into a PRISTINE copy of the table (one bb_ctx per step, all loaded with the same image): the
+    # batches' clocks are built relative to that image, so re-merging into an already-merged table would turn the
+    # workload into "all historical".  It also means no step ever finds its table in L2.
+    per_engine = capacity * (128 + 12) + n * 2 * 60 + (160 << 20)  # table + per-path scratch + per-batch scratch + load staging
+    total_mem = torch.cuda.get_device_properties(dev).total_memory
+    if (W + K) * per_engine > 0.75 * total_mem:
+        K = max(3, int(0.75 * total_mem // per_engine) - W)
+        print(f"[bench] {W + args.steps} pristine tables of {per_engine >> 20} MiB do not fit: timing {K} steps", file=sys.stderr)
+    ids = np.arange(capacity, dtype=np.uint64)
+
+    def load_pristine(e):
+        step = 1 << 20  # (bounded staging buffers inside the library)
+        for t in range(meta["tiles"]):  # the image, tiled over the shard
+            for o in range(0, image.n, step):
+                e.table_load(ids[t * image.n + o: t * image.n + min(o + step, image.n)], image.rows[o:o + step])
+
     engines = []
     for _ in range(W + K):
-        e = Engine(args.records, device=local_rank, full_sort=args.front_end == "full",
-                   radix_sort=args.front_end == "radix", cta_pipe=args.merge_kernel == "pipe", hot_keys=args.keys == "zipf", **synth.synth_ranks(args.records))
-        e.table_load(ids, table.rows)
-        e.reserve(args.batch * world, host_entry=(world == 1))
+        e = Engine(capacity, device=local_rank, full_sort=args.front_end == "full", radix_sort=args.front_end == "radix", **ranks_kw)
+        load_pristine(e)
+        e.reserve(n * (2 if world > 1 else 1), host_entry=(world == 1))
         engines.append(e)
     eng = engines[0]
 
@@ -375,47 +577,55 @@ def main():
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
 
-    # ---- device-resident inputs and outputs
-    def to_dev(a):
-        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
-
-    d_in = [(to_dev(b.path_id), to_dev(b.head), to_dev(b.clk), to_dev(b.val)) for b in batches]
-    cap = n * (world if world > 1 else 1)  # a rank may receive more than it sent
-    o_ver = torch.zeros(cap, dtype=torch.int32, device=dev)
-    o_n = torch.zeros(1, dtype=torch.int64, device=dev)
-    o_idx = torch.zeros(cap, dtype=torch.int32, device=dev)
-    o_head = torch.zeros(cap * 16, dtype=torch.uint8, device=dev)
-    o_clk = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
-    o_val = torch.zeros(cap * 32, dtype=torch.uint8, device=dev)
-    cs = capi.BBChanges(cap=cap, verdict=o_ver.data_ptr(), n_changes=o_n.data_ptr(), idx=o_idx.data_ptr(),
-                        head=o_head.data_ptr(), clk=o_clk.data_ptr(), val=o_val.data_ptr())
+    d_in = [dev_batch(torch, dev, b) for b in batches]
+    cap = n * (2 if world > 1 else 1)  # a shard receives ~n updates of a uniform batch; twice that is the slot size
+    out = DevOut(torch, dev, cap)
 
     router = None
     if world > 1:
-        from bullet_js_b200.shard import Router
-
-        router = Router(world, rank, n, local_rank)
-        r_in = [capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
-                for p, h, c, v in d_in]
+        router = shard.Router(world, rank, n, local_rank, recv_capacity=cap, key_bits=kb)
 
     def step_dev(i, last):
-        """One step.  Sharded: merge batch i (already routed into slot i % 2), then route batch
-        i + 1 while that merge runs - the routing never depends on the table."""
-        p, h, c, v = d_in[i % N_BATCHES]
+        """One step.  Sharded: merge batch i (already routed into slot i % 2), then route batch i + 1 while that
+        merge runs - the routing never depends on the table."""
         if router is None:
-            bs = capi.BBBatch(n=n, path_id=p.data_ptr(), head=h.data_ptr(), clk=c.data_ptr(), val=v.data_ptr())
-            engines[i].merge_dev(bs, cs, stream)
+            engines[i].merge_dev(d_in[i % N_BATCHES][1], out.cs, stream)
             return n
-        m = router.merge(engines[i], i % 2, cs, stream)
+        m = router.merge(engines[i], i % 2, out.cs, stream)
         if not last:
-            router.route(r_in[(i + 1) % N_BATCHES], (i + 1) % 2)
+            router.route(d_in[(i + 1) % N_BATCHES][1], (i + 1) % 2)
         return m
 
+    # ---- warm-up; step 0 doubles as the parity check of the timed workload
+    parity = {}
     sampler = ClockSampler(local_rank)
     if router is not None:
-        router.route(r_in[0], 0)
+        router.route(d_in[0][1], 0)
     for i in range(W):
-        step_dev(i, False)
+        m0 = step_dev(i, False)
+        if i == 0 and not args.no_parity:
+            eng.sync(stream)
+            got = out.changes(m0)
+            if world == 1:
+                ok, detail = oracle_check(eng.cfg, image.rows, batches[0], got, lambda t: eng.table_read(t))
+                parity["merge"] = "ok" if ok else "MISMATCH: " + detail
+                parity["n"] = detail
+            else:
+                # what this shard received, in (source rank, arrival) order: every rank's first batch, regenerated
+                recv = []
+                for src in range(world):
+                    b = batches[0] if src == rank else sharded_batch(image, n, synth.rng_for(3, salt=src * 16), args.keys, world, kb, capacity)
+                    mine = np.nonzero(shard.owner_of(b.path_id, world, kb) == rank)[0]
+                    recv.append(codec.Batch(shard.local_row(b.path_id[mine], world, kb), b.head[mine], b.clk[mine], b.val[mine]))
+                rb = codec.Batch(*(np.concatenate([getattr(x, f) for x in recv]) for f in ("path_id", "head", "clk", "val")))
+                uniq, rows, cb = compact_for_oracle(image.rows, image.n, rb)
+                ok = rb.n == m0
+                detail = f"received {m0}, expected {rb.n}"
+                if ok:
+                    ocfg = capi.make_config(max(len(uniq), 1), **ranks_kw)
+                    ok, detail = oracle_check(ocfg, rows, cb, got, lambda t: eng.table_read(uniq[t.astype(np.int64)]))
+                parity["shard"] = "ok" if ok else "MISMATCH: " + detail
+                parity["n"] = "rank 0: " + detail
     eng.sync(stream)
     barrier()
     sampler.start()
@@ -428,17 +638,17 @@ def main():
         merged += step_dev(W + i, i == K - 1)
     e1.record()
     barrier()
-    launches = sum(e.launch_count() for e in engines) - launches0 + (router.launches if router else 0)
+    launches = sum(e.launch_count() for e in engines) - launches0 + ((router.launches if router else 0))
     for e in engines:
         e.sync(stream)
     dev_ms = e0.elapsed_time(e1)
     sent = (router.sent_bytes - sent0) if router else 0
-    # phase timings of the timed steps (events recorded inside the library on the same stream)
+    acc_frac = float(out.n.item()) / max(1, (merged // K))
     ph = {"device": float(np.mean([engines[W + j].phase_ms("device") for j in range(K)]))}
     if world == 1:  # per-kernel split: a few extra steps with the event between the front end and the merge recorded
         Kp = min(K, 5)
         for e in engines[:Kp]:
-            e.table_load(ids, table.rows)
+            load_pristine(e)
             e.phase_events(True)
         for i in range(Kp):
             step_dev(i, False)
@@ -446,17 +656,12 @@ def main():
         torch.cuda.synchronize()
         for name in ("sort", "merge"):
             ph[name] = float(np.mean([engines[j].phase_ms(name) for j in range(Kp)]))
-        ph["device_with_phase_events"] = float(np.mean([engines[j].phase_ms("device") for j in range(Kp)]))
         for e in engines[:Kp]:
             e.phase_events(False)
-    else:
-        ph["sort"] = ph["merge"] = float("nan")
-    acc_frac = float(o_n.item()) / max(1, (merged // K))
 
-    # ---- e2e through bb_merge_batch with pinned host buffers
+    # ---- e2e through the reference-facing call with pinned host buffers
     def pinned(a):
-        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
-        return t
+        return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
 
     e2e = None
     if world == 1:
@@ -469,9 +674,16 @@ def main():
                for a, b_, c_, d_ in h_in]
         Ke = min(K, 20)
         for e in engines[: W + Ke]:
-            e.table_load(ids, table.rows)  # pristine again
+            load_pristine(e)
         for i in range(W):
             engines[i].merge_raw(hbs[i % N_BATCHES], hcs)
+        if not args.no_parity:  # the host entry's output (chunked, three streams) of step W-1 against the oracle too
+            k = int(h_n.view(torch.int64)[0])
+            hg = codec.Changes.from_verdicts(h_ver.numpy().view(np.uint32), h_idx.numpy().view(np.uint32)[:k],
+                                             h_head.numpy().view(codec.HEAD_DTYPE)[:k], h_clk.numpy().view(np.uint32).reshape(-1, 8)[:k],
+                                             h_val.numpy().view(np.uint64).reshape(-1, 4)[:k])
+            okh, detail = oracle_check(eng.cfg, image.rows, batches[(W - 1) % N_BATCHES], hg, lambda t: engines[W - 1].table_read(t))
+            parity["host_entry"] = "ok" if okh else "MISMATCH: " + detail
         torch.cuda.synchronize()
         d2h = 0
         t0 = time.perf_counter()
@@ -484,30 +696,33 @@ def main():
         e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
                "d2h_bytes_per_step": d2h // Ke, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
                "api": "bb_merge_batch (pinned host buffers, synchronous)"}
-    elif world > 1:
-        # sharded e2e: every rank's batch starts in pinned HOST memory; H2D, route (all-to-all over NVLink),
-        # merge on the owning shards, then D2H of the decisions and the change set - all inside the timed region
+    else:
+        # sharded e2e: every rank's batch starts in pinned HOST memory; H2D, route (all-to-all over NVLink), merge on the
+        # owning shards, then D2H of the decisions and the change set - all inside the timed region
         h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
         hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
         h_ver, h_idx, h_head, h_clk, h_val = hp(4 * cap), hp(4 * cap), hp(16 * cap), hp(32 * cap), hp(32 * cap)
-        stage = tuple(torch.empty_like(x) for x in d_in[0])  # device landing buffers of the H2D copies
+        h_n = torch.zeros(1, dtype=torch.int64).pin_memory()
+        stage = tuple(torch.empty_like(x) for x in d_in[0][0])  # device landing buffers of the H2D copies
         r_stage = capi.BBBatch(n=n, path_id=stage[0].data_ptr(), head=stage[1].data_ptr(), clk=stage[2].data_ptr(),
                                val=stage[3].data_ptr())
         Ke = min(K, 10)
         for e in engines[: W + Ke]:
-            e.table_load(ids, table.rows)  # pristine again
+            load_pristine(e)
 
         def step_e2e(i):
             for dst, src in zip(stage, h_in[i % N_BATCHES]):
                 dst.copy_(src, non_blocking=True)
             router.route(r_stage, i % 2, stream)
-            m = router.merge(engines[i], i % 2, cs, stream)
-            k = int(o_n.item())  # D2H of the count (synchronises the stream)
-            h_ver[: 4 * m].copy_(o_ver.view(torch.uint8)[: 4 * m], non_blocking=True)
-            h_idx[: 4 * k].copy_(o_idx.view(torch.uint8)[: 4 * k], non_blocking=True)
-            h_head[: 16 * k].copy_(o_head[: 16 * k], non_blocking=True)
-            h_clk[: 32 * k].copy_(o_clk[: 32 * k], non_blocking=True)
-            h_val[: 32 * k].copy_(o_val[: 32 * k], non_blocking=True)
+            m = router.merge(engines[i], i % 2, out.cs, stream)
+            h_n.copy_(out.n, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            k = int(h_n[0])
+            h_ver[: 4 * m].copy_(out.ver.view(torch.uint8)[: 4 * m], non_blocking=True)
+            h_idx[: 4 * k].copy_(out.idx.view(torch.uint8)[: 4 * k], non_blocking=True)
+            h_head[: 16 * k].copy_(out.head[: 16 * k], non_blocking=True)
+            h_clk[: 32 * k].copy_(out.clk[: 32 * k], non_blocking=True)
+            h_val[: 32 * k].copy_(out.val[: 32 * k], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return m, 4 * m + 8 + 84 * k
 
@@ -530,6 +745,31 @@ def main():
                "d2h_bytes_per_step": int(float(t[2]) / world / Ke), "ms_per_step": float(tmax[0]) / Ke * 1e3, "steps": Ke,
                "api": "pinned host batch -> H2D -> bb_router_route_dev -> bb_merge_batch_dev -> D2H of verdicts + change set, "
                       "per rank, max over ranks"}
+    # ---- the same shard WITHOUT routing: every rank merges batches it owns entirely (what one GPU does alone on this
+    # shard shape); value / (N x this) is the efficiency of the routed job on config 3 itself
+    unrouted = None
+    if world > 1:
+        Ku = min(K, 6)
+        for e in engines[:Ku + 1]:
+            load_pristine(e)
+        lb = []
+        for j in range(2):
+            b = synth.make_batch(image, n, synth.rng_for(3, salt=5000 + rank * 16 + j), keys=args.keys)
+            b.path_id[:] = synth.rng_for(3, salt=6000 + rank * 16 + j).integers(0, meta["tiles"], n).astype(np.uint64) * np.uint64(image.n) + b.path_id
+            lb.append(dev_batch(torch, dev, b))
+        engines[0].merge_dev(lb[0][1], out.cs, stream)
+        engines[0].sync(stream)
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for i in range(Ku):
+            engines[1 + i].merge_dev(lb[i % 2][1], out.cs, stream)
+        u1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([u0.elapsed_time(u1) / Ku], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        unrouted = {"ms_per_step": float(t[0]), "per_gpu_field_merges_per_sec": n * F / (float(t[0]) * 1e-3), "steps": Ku,
+                    "note": "local row ids, bb_merge_batch_dev only: the per-GPU rate on this shard shape with no exchange"}
     clocks = sampler.stop()
 
     # ---- max over ranks
@@ -540,71 +780,102 @@ def main():
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dev_ms, merged_total = float(tmax[0]), float(tsum[1])
+        if not args.no_parity:
+            bad = torch.tensor([0 if parity.get("shard") == "ok" else 1], device=dev)
+            dist.all_reduce(bad)
+            if int(bad.item()) and parity.get("shard") == "ok":
+                parity["shard"] = "MISMATCH on another rank"
+            parity["shards_checked"] = world
     else:
         merged_total = float(merged)
 
-    # ---- roofline of the dominant kernel (k_merge_stage), SURVEY 8d figure
+    # ---- roofline of the dominant kernel (k_merge_stage) and of the whole step, SURVEY 8d figure
     peak, peak_src = peaks()
-    distinct = float(np.mean([np.unique(b.path_id).size for b in batches])) / n
+    if world == 1:
+        distinct = float(np.mean([np.unique(b.path_id).size for b in batches])) / n
+    else:  # what a shard sees per update: ~n updates uniform over its `capacity` rows
+        distinct = float(capacity) * (1.0 - np.exp(-float(n) / capacity)) / n
     bytes_per_update = 84 + 68 * acc_frac + 256 * distinct
     per_launch_updates = merged / K
-    achieved = bytes_per_update * per_launch_updates / (ph["merge"] * 1e-3) / 1e9
     pipeline = bytes_per_update * per_launch_updates / (ph["device"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_merge_stage", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_per_update * per_launch_updates, "bytes_per_update": bytes_per_update,
+            "accepted_frac": acc_frac, "distinct_paths_per_update": distinct,
+            "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak, "phase_ms": ph,
+            "traffic": ncu_traffic("k_merge_stage", world == 1 and args.records == CFG2["records"] and n == CFG2["batch"]
+                                   and args.keys == "uniform" and args.front_end == "group")}
+    if "merge" in ph:
+        roof["achieved"] = bytes_per_update * per_launch_updates / (ph["merge"] * 1e-3) / 1e9
+        roof["kernel_ms"] = ph["merge"]
+    else:  # sharded runs do not split the step: the whole device step stands in for the kernel
+        roof["achieved"] = pipeline
+        roof["kernel_ms"] = ph["device"]
+    roof["frac"] = roof["achieved"] / peak
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.typed import TypedOracle
 
         orc = TypedOracle(eng.cfg)
-        out = capi.ChangeBuffers(n)
+        cout = capi.ChangeBuffers(n)
         done, dtc = 0, 0.0
         while dtc < args.cpu_seconds and done < 64:
-            orc.table[:] = table.rows  # pristine table, not timed
+            orc.table[:] = image.rows  # pristine table, not timed
             t0 = time.perf_counter()
-            orc.merge(batches[done % N_BATCHES], out=out)
+            orc.merge(batches[done % N_BATCHES], out=cout)
             dtc += time.perf_counter() - t0
             done += 1
         cpu = {"value": done * n * F / dtc, "unit": "field-merges/s", "cores": 1, "kind": "port",
                "sample": f"{done} x {n}-update batches of the same workload on the same table, "
-                         f"oracle/bullet_oracle.c single thread, {dtc:.1f} s"}
+                         f"oracle/bullet_oracle.c single thread, {dtc:.1f} s", "reference_kind": REFERENCE_KIND}
 
     for e in engines:
         e.close()
     engines = []
+    if router is not None:
+        router.close()
+    zipf = None
+    if world == 1 and not args.no_zipf and args.keys == "uniform":
+        zipf = run_zipf(args, local_rank, dev, image, stream, torch)
     query = None
     if not args.no_query:
-        query = run_queries(args, rank, world, local_rank, dev, table, dist)
+        query = run_queries(args, rank, world, local_rank, dev, image, dist)
+        if not args.no_parity:
+            parity["query"] = "ok" if all(v == "ok" for v in query["parity"].values()) else "MISMATCH"
+            if dist is not None:
+                bad = torch.tensor([0 if parity["query"] == "ok" else 1], device=dev)
+                dist.all_reduce(bad)
+                if int(bad.item()):
+                    parity["query"] = "MISMATCH"
 
+    failed = [k for k, v in parity.items() if isinstance(v, str) and v.startswith("MISMATCH")]
+    if zipf:
+        failed += [f"zipf.{k}" for k in ("default", "indexed_age") if zipf[k]["parity"] != "ok"]
     if rank == 0:
         line = {
             "metric": "crdt_field_merges_per_sec", "value": merged_total * F / (dev_ms * 1e-3),
             "unit": "field-merges/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32+f64",
-            "data": "synthetic", "config": workload_config(args, world),
+            "data": "synthetic", "config": workload_config(args, world, meta),
             "updates_per_sec": merged_total / (dev_ms * 1e-3),
-            "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_merge_stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": ncu_traffic("k_merge_stage", world == 1 and args.records == N_RECORDS and args.batch == BATCH
-                                                and args.keys == "uniform" and args.front_end == "group"
-                                                and args.merge_kernel == "stage"),
-                         "algorithmic_bytes_per_launch": bytes_per_update * per_launch_updates, "peak_source": peak_src,
-                         "bytes_per_update": bytes_per_update, "accepted_frac": acc_frac,
-                         "distinct_paths_per_update": distinct, "kernel_ms": ph["merge"],
-                         "pipeline_achieved": pipeline, "pipeline_frac": pipeline / peak,
-                         "phase_ms": ph},
-            "cpu_baseline": cpu, "clocks": clocks, "query": query,
+            "e2e": e2e, "gpu_launches": launches, "parity": parity,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "zipf": zipf, "query": query,
+            "reference_kind": REFERENCE_KIND,
         }
         if world > 1:  # the all-to-all of rank 0, against the measured NVLink peer-copy rate (B200_PROFILING.md)
+            line["unrouted_shard"] = unrouted
+            line["routing_efficiency_on_config3"] = line["value"] / (world * unrouted["per_gpu_field_merges_per_sec"])
             gbs = sent / (dev_ms * 1e-3) / 1e9
             line["alltoall"] = {"sent_bytes_per_step": sent // K, "gb_per_s_per_gpu": gbs, "nvlink_peak": 770.0,
-                                "frac": gbs / 770.0, "overlapped_with_merge": True, "last_route_ms": router.last_ms(),
-                                "api": "bb_router_route_dev (counts all-gather over NCCL, then one pack kernel storing rows straight into the owners' receive slots over NVLink)"}
+                                "frac": gbs / 770.0, "overlapped_with_merge": True,
+                                "api": "bb_router_route_dev (counts through peer-mapped flags, then one pack kernel storing rows "
+                                       "straight into the owners' receive slots over NVLink)"}
         print(json.dumps(line))
-    for e in engines:
-        e.close()
     if dist is not None:
         dist.destroy_process_group()
+    if failed:
+        print(f"[bench] PARITY FAILURE: {failed}: {parity} {zipf}", file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

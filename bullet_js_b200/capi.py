@@ -72,7 +72,7 @@ EXPORTS = [
     "bb_index_create", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
-    "bb_router_last_error", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
+    "bb_router_last_error", "bb_router_set_sharding", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
     "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms", "bb_phase_events",
 ]
@@ -134,6 +134,8 @@ def load():
     lib.bb_router_unique_id.restype = i32
     lib.bb_router_create.argtypes = [C.c_int32, u32, u32, C.c_char_p, u64, u64, C.POINTER(vp)]
     lib.bb_router_create.restype = i32
+    lib.bb_router_set_sharding.argtypes = [vp, u32]
+    lib.bb_router_set_sharding.restype = i32
     lib.bb_router_destroy.argtypes = [vp]
     lib.bb_router_destroy.restype = i32
     lib.bb_router_last_error.argtypes = [vp]

@@ -11,17 +11,37 @@ namespace bb {
 // inside every destination - so that the owner, which concatenates what it receives in source-rank
 // order, replays each path in (source rank, arrival index) order.  Three small launches: per-tile
 // destination counts, one CTA scanning them (tile-major inside destination-major), the scatter.
+// Owner and local row of a path id.  key_bits == 0: owner = id % world, row = id / world (ids that are dense and
+// evenly spread).  Otherwise the id (< 2^key_bits) first goes through a splitmix64-style finaliser restricted to
+// key_bits bits - odd multiplications and xor-shifts, each a bijection of [0, 2^key_bits) - so that strided or
+// clustered ids still spread evenly, and the scrambled id is split the same way; a shard then holds
+// ceil(2^key_bits / world) rows.  bullet_js_b200/shard.py mirrors it for the host.
+__host__ __device__ __forceinline__ uint64_t shard_mix(uint64_t id, uint32_t key_bits) {
+  if (key_bits == 0) return id;
+  const uint64_t mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
+  const uint32_t s = (key_bits + 1) / 2;
+  uint64_t x = id & mask;
+  x = (x * 0x9E3779B97F4A7C15ull) & mask;
+  x ^= x >> s;
+  x = (x * 0xBF58476D1CE4E5B9ull) & mask;
+  x ^= x >> s;
+  x = (x * 0x94D049BB133111EBull) & mask;
+  x ^= x >> s;
+  return x;
+}
+
 constexpr int RT_THREADS = 1024;   // updates per tile of the count / scatter kernels
 constexpr int RS_THREADS = 256;    // threads of the single scan CTA
 constexpr int RT_MAX_WORLD = 16;
 
 __global__ void __launch_bounds__(RT_THREADS) k_route_count(const uint64_t* __restrict__ path_id, uint64_t n,
-                                                            uint32_t world, uint32_t* __restrict__ tile_cnt) {
+                                                            uint32_t world, uint32_t key_bits,
+                                                            uint32_t* __restrict__ tile_cnt) {
   __shared__ uint32_t s_cnt[RT_MAX_WORLD];
   if (threadIdx.x < RT_MAX_WORLD) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
-  const uint32_t d = i < n ? (uint32_t)(path_id[i] % world) : world;
+  const uint32_t d = i < n ? (uint32_t)(shard_mix(path_id[i], key_bits) % world) : world;
   for (uint32_t r = 0; r < world; ++r) {
     const uint32_t m = __ballot_sync(0xffffffffu, d == r);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[r], __popc(m));
@@ -58,6 +78,7 @@ struct RouteArgs {
   uint64_t* o_path; uint4* o_head; uint4* o_clk; uint4* o_val;                      // [n] packed out
   uint64_t n;
   uint32_t world;
+  uint32_t key_bits;
   const uint32_t* tile_off;  // [tiles][world] from k_route_scan
 };
 
@@ -72,6 +93,7 @@ struct RouteP2PArgs {
   uint32_t me;
   uint64_t n;
   uint32_t world;
+  uint32_t key_bits;
   uint32_t bulk;  // 1: runs leave with cp.async.bulk (default); 0: with per-thread 16-byte stores
   const uint32_t* tile_off;
 };
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
   const uint32_t tiles = (uint32_t)((a.n + RT_THREADS - 1) / RT_THREADS);
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
   const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
-  const uint64_t p = i < a.n ? a.path_id[i] : 0;
+  const uint64_t p = i < a.n ? shard_mix(a.path_id[i], a.key_bits) : 0;
   const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
   uint4 h, c0, c1, v0, v1;
   if (i < a.n) {
@@ -278,7 +300,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter(const RouteArgs a)
   __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint64_t i = (uint64_t)blockIdx.x * RT_THREADS + threadIdx.x;
-  const uint64_t p = i < a.n ? a.path_id[i] : 0;
+  const uint64_t p = i < a.n ? shard_mix(a.path_id[i], a.key_bits) : 0;
   const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
   uint32_t below = 0;
   for (uint32_t r = 0; r < a.world; ++r) {

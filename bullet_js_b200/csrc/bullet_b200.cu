@@ -856,12 +856,12 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
 }
 
 // the three pack launches; `tiles_buf` holds [tiles][world] words
-static cudaError_t launch_pack(uint32_t world, const bb_batch* in, bb_batch* out, uint64_t* counts, uint32_t* tiles_buf,
-                        cudaStream_t s) {
+static cudaError_t launch_pack(uint32_t world, uint32_t key_bits, const bb_batch* in, bb_batch* out, uint64_t* counts,
+                               uint32_t* tiles_buf, cudaStream_t s) {
   using namespace bb;
   const uint64_t n = in->n;
   const uint32_t tiles = div_up(n, RT_THREADS);
-  bb_launch(k_route_count, tiles, RT_THREADS, 0, s, false, in->path_id, n, world, tiles_buf);
+  bb_launch(k_route_count, tiles, RT_THREADS, 0, s, false, in->path_id, n, world, key_bits, tiles_buf);
   bb_launch(k_route_scan, 1, RS_THREADS, 0, s, false, tiles_buf, tiles, world, counts);
   RouteArgs a;
   a.path_id = in->path_id;
@@ -874,6 +874,7 @@ static cudaError_t launch_pack(uint32_t world, const bb_batch* in, bb_batch* out
   a.o_val = reinterpret_cast<uint4*>(const_cast<uint64_t*>(out->val));
   a.n = n;
   a.world = world;
+  a.key_bits = key_bits;
   a.tile_off = tiles_buf;
   bb_launch(k_route_scatter, tiles, RT_THREADS, 0, s, false, a);
   return cudaGetLastError();
@@ -895,7 +896,7 @@ int bb_route_pack_dev(bb_ctx* c, uint32_t world, const bb_batch* in, bb_batch* o
     return fail(c, BB_ERR_ARG, "null buffer");
   BB_CUDA(c, c->route_tiles.ensure((size_t)div_up(n, RT_THREADS) * world));
   c->launches += 3;
-  BB_CUDA(c, launch_pack(world, in, out, counts, c->route_tiles.p, s));
+  BB_CUDA(c, launch_pack(world, 0, in, out, counts, c->route_tiles.p, s));
   return BB_OK;
 }
 
@@ -1080,6 +1081,7 @@ constexpr size_t ROUTE_W[4] = {8, 16, 32, 32};  // bytes per update of path / he
 struct bb_router {
   int device = 0;
   uint32_t world = 0, rank = 0;
+  uint32_t key_bits = 0;  // sharding function, bb_router_set_sharding
   uint64_t max_batch = 0, cap = 0;
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;
@@ -1344,20 +1346,26 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
     BB_RCUDA(r, cudaStreamWaitEvent(sp, r->ev_in, 0));
     if (flags) BB_RCUDA(r, cudaStreamWaitEvent(s, r->ev_in, 0));
   }
-  if (flags) BB_RCUDA(r, cudaStreamWaitEvent(sp, r->ready[slot], 0));
+  if (flags) {
+    BB_RCUDA(r, cudaStreamWaitEvent(sp, r->ready[slot], 0));
+    // Publishing this route's counts is what lets every peer's scatter kernel start storing into OUR copy of the
+    // slot: not before our merge of what the slot held has finished reading it (a peer only needs its own
+    // merged[slot] and everybody's counts flag, so without this a fast peer would overwrite a slow shard's input).
+    BB_RCUDA(r, cudaStreamWaitEvent(sp, r->merged[slot], 0));
+  }
   BB_RCUDA(r, cudaStreamWaitEvent(s, r->merged[slot], 0));  // the merge that last read this slot is done
   const auto h0 = std::chrono::steady_clock::now();
   cudaEventRecord(r->tev[0], sp);
   const uint32_t tiles = div_up(n, bb::RT_THREADS);
   if (n && r->p2p) {  // the scatter waits until every rank's counts are known
-    bb_launch(bb::k_route_count, tiles, bb::RT_THREADS, 0, sp, false, in->path_id, n, W, tile_buf);
+    bb_launch(bb::k_route_count, tiles, bb::RT_THREADS, 0, sp, false, in->path_id, n, W, r->key_bits, tile_buf);
     bb_launch(bb::k_route_scan, 1, bb::RS_THREADS, 0, sp, false, tile_buf, tiles, W, cnt_buf);
     r->launches += 2;
     BB_RCUDA(r, cudaGetLastError());
   } else if (n) {
     bb_batch packed{n, reinterpret_cast<uint64_t*>(r->send[0]), reinterpret_cast<bb_head*>(r->send[1]),
                     reinterpret_cast<uint32_t*>(r->send[2]), reinterpret_cast<uint64_t*>(r->send[3])};
-    BB_RCUDA(r, launch_pack(W, in, &packed, r->d_counts, r->tiles, s));
+    BB_RCUDA(r, launch_pack(W, r->key_bits, in, &packed, r->d_counts, r->tiles, s));
     r->launches += 3;
   } else {
     BB_RCUDA(r, cudaMemsetAsync(cnt_buf, 0, W * sizeof(uint64_t), sp));
@@ -1404,6 +1412,7 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
       a.me = me;
       a.n = n;
       a.world = W;
+      a.key_bits = r->key_bits;
       a.bulk = r->bulk ? 1u : 0u;
       a.tile_off = tile_buf;
       bb_launch(bb::k_route_scatter_p2p, std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s, false, a);
@@ -1459,6 +1468,12 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
   r->sent_bytes += (so[W] - (so[me + 1] - so[me])) * 88;
   r->n_recv[slot] = ro[W];
   *n_recv = ro[W];
+  return BB_OK;
+}
+
+int bb_router_set_sharding(bb_router* r, uint32_t key_bits) {
+  if (!r || key_bits > 40) return rfail(r, BB_ERR_ARG, "key_bits must be 0 (id % world) or 1..40");
+  r->key_bits = key_bits;
   return BB_OK;
 }
 

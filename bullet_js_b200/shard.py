@@ -1,6 +1,8 @@
 """Key-sharded table across the GPUs of one box.
 
-One process per GPU.  Path id `p` lives on rank `p % world` as local row `p // world`.  A step of the product
+One process per GPU.  Path id `p` lives on rank `owner_of(p)` as local row `local_row(p)`: `p % world` / `p // world`
+by default, or - `key_bits` given - the same split of the id hashed by a bijective splitmix64-style finaliser
+(`shard_mix`), which spreads strided or clustered ids evenly (SURVEY 8e specifies a splitmix64 hash).  A step of the product
 path (`Router` -> the library's native router, bb_router_* in include/bullet_b200.h):
 
   1. every rank counts its batch by owner (k_route_count / k_route_scan) and publishes the counts straight into
@@ -34,12 +36,33 @@ from . import capi
 ROW_BYTES = {"path": 8, "head": 16, "clk": 32, "val": 32}
 
 
-def owner_of(path_id, world: int):
-    return path_id % world
+def shard_mix(path_id, key_bits: int = 0):
+    """The library's sharding function (csrc/bb_route.cuh shard_mix): identity for key_bits == 0, otherwise a
+    splitmix64-style finaliser restricted to key_bits bits - a bijection of [0, 2**key_bits)."""
+    x = np.asarray(path_id, dtype=np.uint64)
+    if key_bits == 0:
+        return x
+    mask = np.uint64((1 << key_bits) - 1)
+    s = np.uint64((key_bits + 1) // 2)
+    x = x & mask
+    with np.errstate(over="ignore"):
+        for mul in (0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB):
+            x = (x * np.uint64(mul)) & mask
+            x = x ^ (x >> s)
+    return x
 
 
-def local_row(path_id, world: int):
-    return path_id // world
+def owner_of(path_id, world: int, key_bits: int = 0):
+    return shard_mix(path_id, key_bits) % np.uint64(world)
+
+
+def local_row(path_id, world: int, key_bits: int = 0):
+    return shard_mix(path_id, key_bits) // np.uint64(world)
+
+
+def shard_capacity(world: int, key_bits: int, n_ids: int = 0) -> int:
+    """Rows a shard's table needs: ceil(2**key_bits / world) with hashed sharding, ceil(n_ids / world) without."""
+    return -(-(1 << key_bits) // world) if key_bits else -(-n_ids // world)
 
 
 class Exchange:
@@ -84,7 +107,8 @@ class Router:
     used to hand rank 0's NCCL id to the other ranks.  `route` and `merge` are separate so that
     routing batch i+1 overlaps merging batch i."""
 
-    def __init__(self, world: int, rank: int, batch: int, device_index: int, dist=None, recv_capacity: int = 0):
+    def __init__(self, world: int, rank: int, batch: int, device_index: int, dist=None, recv_capacity: int = 0,
+                 key_bits: int = 0):
         import ctypes as C
 
         if dist is None:
@@ -103,6 +127,9 @@ class Router:
         if rc:
             raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(None) or b"").decode())
         self._h = h
+        self.key_bits = key_bits
+        if key_bits:
+            self._check(self.lib.bb_router_set_sharding(self._h, key_bits))
 
     def _check(self, rc):
         if rc:
@@ -148,7 +175,7 @@ class Router:
             self._h = None
 
 
-def route_on_host(world: int, rank: int, batch, dist, merge_fn):
+def route_on_host(world: int, rank: int, batch, dist, merge_fn, key_bits: int = 0):
     """The same routing with numpy packing (stable partition by owner) and torch.distributed on
     CPU tensors - used by the gloo tests to check the exchange logic and the replay order; the
     product path is `Router` (CUDA pack + NCCL)."""
@@ -156,10 +183,10 @@ def route_on_host(world: int, rank: int, batch, dist, merge_fn):
 
     from . import codec
 
-    owner = owner_of(batch.path_id, np.uint64(world)).astype(np.int64)
+    owner = owner_of(batch.path_id, world, key_bits).astype(np.int64)
     order = np.argsort(owner, kind="stable")
     send_counts = np.bincount(owner, minlength=world).astype(np.int64)
-    packed = codec.Batch(local_row(batch.path_id[order], np.uint64(world)), batch.head[order], batch.clk[order],
+    packed = codec.Batch(local_row(batch.path_id[order], world, key_bits), batch.head[order], batch.clk[order],
                          batch.val[order])
     ex = Exchange(dist, world, rank)
     rc = ex.counts(torch.from_numpy(send_counts)).tolist()

@@ -302,8 +302,11 @@ int bb_query_range_dev(bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb
 /* Entries currently held by the index (dense + overflow); synchronises. */
 int bb_index_stats(bb_ctx* ctx, uint32_t field, uint64_t* n_dense, uint64_t* n_extra);
 
-/* ---- sharding: the table is split over `world` ranks, path id p lives on
- *      rank p % world as local row p / world.  bb_route_pack_dev is the send side of the update
+/* ---- sharding: the table is split over `world` ranks.  With the default sharding function path id p
+ *      lives on rank p % world as local row p / world; bb_router_set_sharding(r, key_bits) switches a router to
+ *      hashed sharding: s = mix(p) is a splitmix64-style finaliser restricted to key_bits bits (a bijection of
+ *      [0, 2^key_bits), so a dense local row index still exists), owner = s % world, local row = s / world, and a
+ *      shard holds ceil(2^key_bits / world) rows.  Strided or clustered ids then spread evenly.  bb_route_pack_dev is the send side of the update
  *      routing: a stable partition of a device-resident batch by owner rank (arrival order kept
  *      inside every destination), path ids rewritten to local rows, counts[r] = updates for rank
  *      r (device, [world]).  The caller exchanges counts and the four packed arrays with an
@@ -337,6 +340,8 @@ int bb_router_unique_id(char id[BB_NCCL_ID_BYTES]); /* rank 0; hand the bytes to
 int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char id[BB_NCCL_ID_BYTES],
                      uint64_t max_batch, uint64_t recv_capacity, bb_router** out);
 int bb_router_destroy(bb_router* r);
+/* every rank must call it with the same key_bits (0 = id % world) before the first route; ids must be < 2^key_bits */
+int bb_router_set_sharding(bb_router* r, uint32_t key_bits);
 const char* bb_router_last_error(const bb_router* r);
 /* `in`: device batch; `in_stream`: stream the batch was produced on (0 = already complete). */
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);

@@ -100,13 +100,15 @@ class BulletB200 {
 
   /** the decision object of src/bullet-crt.js:164-279 for a device decision code */
   _decision(code, value, vectorClock) {
-    const accepted = code === 0 || code === 2 || code === 4 || code === 6;
+    // flag for flag what src/bullet-crt.js returns: :174-184 (no current state), :208-219 (identical), :222-232 (tie,
+    // by the sign of the value comparison), :237-248 (incoming dominates), :252-263 (historical), :268-278
+    // (concurrent: neither `incoming` nor `current`); `converge` is true in every branch
     return {
       defer: false,
       historical: code === 5,
-      converge: code === 6,
-      incoming: accepted,
-      current: code === 1 || code === 3 || code === 5,
+      converge: true,
+      incoming: code === 0 || code === 2 || code === 4,
+      current: code === 3 || code === 5,
       concurrent: code === 6,
       vectorClock,
       reason: REASONS[code],
@@ -142,7 +144,9 @@ class BulletB200 {
       broadcastData = { ...broadcastData, __vectorClock: vectorClock }; // src/bullet-crt.js:371-376
     }
     const decision = this._decision(code, value, vectorClock);
-    return { value, vectorClock, broadcastData, decision, doUpdate: decision.incoming };
+    // src/bullet-crt.js:383: decision.incoming || !currentVectorClock || decision.concurrent
+    const doUpdate = code === 0 || code === 2 || code === 4 || code === 6;
+    return { value, vectorClock, broadcastData, decision, doUpdate };
   }
 
   _installCrt() {

@@ -49,7 +49,8 @@ crt.handleUpdate = function (path, data, fromNetwork) {
   const r = origHandle.call(crt, path, data, fromNetwork);
   trace.decisions.push({ path: path, reason: r.decision.reason, incoming: !!r.decision.incoming,
                          current: !!r.decision.current, concurrent: !!r.decision.concurrent,
-                         historical: !!r.decision.historical, doUpdate: !!r.doUpdate });
+                         historical: !!r.decision.historical, converge: !!r.decision.converge,
+                         defer: !!r.decision.defer, doUpdate: !!r.doUpdate });
   return r;
 };
 const origApply = bullet._applyUpdate;
@@ -123,6 +124,12 @@ class JSRefBullet:
                 code = 2 if d["incoming"] else 3
             out.append(dict(path=d["path"], code=code, reason=d["reason"], doUpdate=d["doUpdate"]))
         return out
+
+    @property
+    def decision_flags(self):
+        """Every decision's flags exactly as the reference returned them (src/bullet-crt.js:174-184, 208-278)."""
+        keys = ("reason", "incoming", "current", "concurrent", "historical", "converge", "defer", "doUpdate")
+        return [{k: d[k] for k in keys} for d in to_py(self._trace.get("decisions"))]
 
     @property
     def changes(self):

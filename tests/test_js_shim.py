@@ -222,3 +222,41 @@ def test_quick_start_flow_with_the_shim():
     assert r["admins"] == ["users/alice"] and r["value"] == {"name": "Alice", "email": "alice@example.com", "role": "admin"}
     assert r["count"] == 1.0 and r["all"] == ["alice", "bob"] and r["seen"][-1] == "admin" and r["calls"] == 2.0
     assert list(r["clock"].values()) == [3.0] and r["clock"] == r["crt"]  # a first local write: {me: 3}, aliased
+
+
+FLAG_HARNESS = r"""
+const seen = [];
+const h = bullet.crt.handleUpdate;
+bullet.crt.handleUpdate = function (path, data, fromNetwork) {
+  const r = h.call(bullet.crt, path, data, fromNetwork);
+  const d = r.decision;
+  seen.push({ reason: d.reason, incoming: !!d.incoming, current: !!d.current, concurrent: !!d.concurrent,
+              historical: !!d.historical, converge: !!d.converge, defer: !!d.defer, doUpdate: !!r.doUpdate });
+  return r;
+};
+return seen;
+"""
+
+
+@pytest.mark.parametrize("k", [0, 3, 7])
+def test_shim_decision_flags_equal_the_reference(k):
+    """`handleUpdate(...).decision` is public surface: every flag of every update - incoming, current,
+    concurrent, historical, converge, defer - and doUpdate must be what the unmodified reference returns."""
+    case = STREAMS[k]
+    ops = golden_io.ops_of(case)
+    ref = ref_runner.JSRefBullet("p0", enable_indexing=False)
+    rt, bridge, r = boot(False, oracle_engine)
+    bullet = r.get("bullet")
+    seen = rt.eval(FLAG_HARNESS, bullet=bullet)
+    for path, value, clock in ops:
+        if clock is not None and isinstance(value, dict):  # the sync ingress, entry by entry (sync:560-566)
+            ref.handle_put(path, {**value, "__vectorClock": dict(clock)})
+            rt.method(bullet, "setData", path, from_py({**value, "__fromNetwork": True, "__vectorClock": dict(clock)}), False)
+        else:
+            ref.put(path, value)
+            rt.method(rt.method(bullet, "get", path), "put", from_py(value))
+    want, got = ref.decision_flags, to_py(seen)
+    assert len(want) == len(got) == len(ops)
+    assert got == want
+    assert {d["reason"] for d in want} >= {"no current state", "current vector clock dominates (incoming is historical)"}
+    assert any(d["concurrent"] for d in want) and all(d["converge"] for d in want)

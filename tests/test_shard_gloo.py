@@ -25,28 +25,39 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _shard_ids(rank, world, key_bits):
+    """Path ids owned by `rank`, and their local rows."""
+    all_ids = np.arange(N_REC, dtype=np.uint64)
+    ids = all_ids[shard.owner_of(all_ids, world, key_bits) == rank]
+    return ids.astype(np.int64), shard.local_row(ids, world, key_bits)
+
+
+def _worker(rank, world, port, q, key_bits):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         table = synth.make_table(N_REC, synth.rng_for(3))
         batch = synth.make_batch(table, N_UPD, synth.rng_for(3, salt=10 + rank), keys="zipf")
-        ids = np.arange(rank, N_REC, world)
-        cfg = capi.make_config(len(ids) + 1, **synth.synth_ranks(N_REC))
+        ids, rows = _shard_ids(rank, world, key_bits)
+        cfg = capi.make_config(shard.shard_capacity(world, key_bits, N_REC) + 1, **synth.synth_ranks(N_REC))
         orc = TypedOracle(cfg)
-        orc.load(ids // world, table.rows[ids])
-        ch, got = shard.route_on_host(world, rank, batch, dist, orc.merge)
-        q.put((rank, orc.table[: len(ids)].copy(), ch.decision.copy(), got.path_id.copy(), got.head["user"].copy()))
+        orc.load(rows, table.rows[ids])
+        ch, got = shard.route_on_host(world, rank, batch, dist, orc.merge, key_bits=key_bits)
+        q.put((rank, orc.table[rows.astype(np.int64)].copy(), ch.decision.copy(), got.path_id.copy(), got.head["user"].copy()))
     finally:
         dist.destroy_process_group()
 
 
+KEY_BITS = int(np.ceil(np.log2(N_REC)))
+
+
+@pytest.mark.parametrize("key_bits", [0, KEY_BITS])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_replay_equals_single_peer(world):
+def test_sharded_replay_equals_single_peer(world, key_bits):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, key_bits)) for r in range(world)]
     for p in procs:
         p.start()
     results = {}
@@ -65,14 +76,14 @@ def test_sharded_replay_equals_single_peer(world):
     dec = [ref.merge(b).decision for b in batches]
     for r in range(world):
         rows, decision, lpath, user = results[r]
-        ids = np.arange(r, N_REC, world)
+        ids, _ = _shard_ids(r, world, key_bits)
         assert np.array_equal(rows, ref.table[ids]), f"shard {r} differs from the single-peer table"
         # what the shard received, in order: source-rank-major, arrival order inside a source
         want_dec, want_path, want_user = [], [], []
         for src in range(world):
-            mine = np.nonzero(batches[src].path_id % world == r)[0]
+            mine = np.nonzero(shard.owner_of(batches[src].path_id, world, key_bits) == r)[0]
             want_dec.append(dec[src][mine])
-            want_path.append(batches[src].path_id[mine] // world)
+            want_path.append(shard.local_row(batches[src].path_id[mine], world, key_bits))
             want_user.append(batches[src].head["user"][mine])
         assert np.array_equal(lpath, np.concatenate(want_path))
         assert np.array_equal(user, np.concatenate(want_user))
