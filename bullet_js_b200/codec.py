@@ -30,7 +30,6 @@ CFG_POST_GETDATA = 1
 CFG_ORDERED_CHANGES = 2
 CFG_RADIX_SORT = 4
 CFG_FULL_SORT = 8
-CFG_CTA_PIPE = 32
 CFG_HOT_KEYS = 64
 
 DEC_NO_CURRENT, DEC_IDENTICAL, DEC_TIE_INCOMING, DEC_TIE_CURRENT = 0, 1, 2, 3

@@ -10,11 +10,11 @@ pytestmark = pytest.mark.gpu
 
 
 def engine_and_oracle(schema=None, capacity=256, post_getdata=False, ordered=False, radix=False, **kw):
-    """radix: False (defaults: grouping front end + k_merge_pipe) | True (radix sort) | "full" (counting sort by
-    path id) | "pipe" (grouping + k_merge_pipe instead of k_merge_stage) | "hot" (BB_CFG_HOT_KEYS: k_merge_hot takes over hot segments)."""
+    """radix: False (default: grouping front end, hot keys handed to k_merge_hot) | True (radix sort) | "full" (counting
+    sort by path id) | "hot" (the round-1 opt-in flag BB_CFG_HOT_KEYS: accepted and ignored)."""
     from bullet_js_b200.engine import Engine
 
-    sort = dict(radix_sort=radix is True, full_sort=radix == "full", cta_pipe=radix == "pipe", hot_keys=radix == "hot")
+    sort = dict(radix_sort=radix is True, full_sort=radix == "full", hot_keys=radix == "hot")
     if schema is not None:
         eng = Engine.for_schema(schema, capacity, post_getdata=post_getdata, ordered_changes=ordered, **sort)
     else:
@@ -31,7 +31,7 @@ def assert_same_table(eng, orc, n):
 
 @pytest.mark.parametrize("seed", range(4))
 @pytest.mark.parametrize("indexed", [False, True])
-@pytest.mark.parametrize("radix", [False, True, "full", "pipe", "hot"])
+@pytest.mark.parametrize("radix", [False, True, "full", "hot"])
 def test_random_js_streams(seed, indexed, radix):
     ops, _ref = streamgen.generate(100 + seed, 4000, 37, index_fields=("age",) if indexed else ())
     schema = streamgen.make_schema()
@@ -61,7 +61,7 @@ def test_kat_l_on_gpu():
     eng.close()
 
 
-@pytest.mark.parametrize("mode", ["default", "ordered", "radix", "full", "pipe", "hot"])
+@pytest.mark.parametrize("mode", ["default", "ordered", "radix", "full", "hot"])
 @pytest.mark.parametrize("keys", ["uniform", "zipf"])
 def test_synthetic_schema_stream(keys, mode):
     """SURVEY 8d schema at a size the oracle replays in a second: 50k records, 3 x 200k updates."""
@@ -69,7 +69,7 @@ def test_synthetic_schema_stream(keys, mode):
     rng = synth.rng_for(2, salt=1)
     table = synth.make_table(n_rec, rng)
     ordered = mode == "ordered"
-    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, radix={"radix": True, "full": "full", "pipe": "pipe", "hot": "hot"}.get(mode, False), **synth.synth_ranks(n_rec))
+    eng, orc = engine_and_oracle(None, n_rec, ordered=ordered, radix={"radix": True, "full": "full", "hot": "hot"}.get(mode, False), **synth.synth_ranks(n_rec))
     ids = np.arange(n_rec, dtype=np.uint64)
     eng.table_load(ids, table.rows)
     orc.load(ids, table.rows)
