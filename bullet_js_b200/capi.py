@@ -58,6 +58,11 @@ class BBHits(C.Structure):
     _fields_ = [("cap", C.c_uint64), ("node", C.c_void_p), ("n_dense", C.c_void_p), ("n_extra", C.c_void_p)]
 
 
+class BBGatheredHits(C.Structure):
+    """bb_gathered_hits: the all-gathered result of a sharded query (device pointer + per-rank offsets)."""
+    _fields_ = [("node", C.c_void_p), ("offset", C.c_uint64 * 17), ("total", C.c_uint64)]
+
+
 class BulletB200Error(RuntimeError):
     def __init__(self, code, msg=""):
         self.code = code
@@ -69,10 +74,11 @@ EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
     "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
-    "bb_index_create", "bb_query_equals", "bb_query_count", "bb_query_range",
+    "bb_index_create", "bb_index_create_fields", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
     "bb_router_last_error", "bb_router_set_sharding", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
+    "bb_router_query_reserve", "bb_router_query_range", "bb_router_query_equals", "bb_router_query_fetch",
     "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms", "bb_phase_events",
 ]
@@ -114,6 +120,8 @@ def load():
     lib.bb_sync.argtypes = [vp, vp]
     lib.bb_sync.restype = i32
     u32 = C.c_uint32
+    lib.bb_index_create_fields.argtypes = [vp, u32, u64]
+    lib.bb_index_create_fields.restype = i32
     lib.bb_index_create.argtypes = [vp, u32, u64]
     lib.bb_index_create.restype = i32
     lib.bb_query_equals.argtypes = [vp, u32, u64, C.POINTER(BBHits)]
@@ -146,6 +154,14 @@ def load():
     lib.bb_router_acquire.restype = i32
     lib.bb_router_release.argtypes = [vp, u32, vp]
     lib.bb_router_release.restype = i32
+    lib.bb_router_query_reserve.argtypes = [vp, u64]
+    lib.bb_router_query_reserve.restype = i32
+    lib.bb_router_query_range.argtypes = [vp, vp, u32, C.POINTER(BBBound), C.POINTER(BBBound), C.POINTER(BBGatheredHits), vp]
+    lib.bb_router_query_range.restype = i32
+    lib.bb_router_query_equals.argtypes = [vp, vp, u32, u64, C.POINTER(BBGatheredHits), vp]
+    lib.bb_router_query_equals.restype = i32
+    lib.bb_router_query_fetch.argtypes = [vp, u64, u64, vp]
+    lib.bb_router_query_fetch.restype = i32
     lib.bb_router_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
     lib.bb_router_last_ms.restype = i32
     lib.bb_router_sent_bytes.argtypes = [vp]

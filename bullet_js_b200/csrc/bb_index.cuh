@@ -132,19 +132,55 @@ __device__ __forceinline__ void index_hook(const IndexArgs& ix, uint32_t node, c
 }
 
 // ---------------------------------------------------------------- K4: index build
-// One thread per row: `field in value` and value[field] not null -> its key (query:58-66, 82-85).
-// Reads the value slot and the header word of each 128-byte row (two 32-byte sectors).
-__global__ void __launch_bounds__(256) k_index_build(const uint4* __restrict__ table, uint64_t capacity, int f,
-                                                     uint64_t* __restrict__ pcol) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= capacity) return;
-  const uint32_t meta = reinterpret_cast<const uint32_t*>(table + i * 8 + 6)[2];
-  uint64_t k = BB_KEY_NONE;
-  if (kind_of(meta) == BB_KIND_OBJ) {
-    const uint32_t t = tag_of(meta, f);
-    if (t != BB_TAG_ABSENT && t != BB_TAG_NULL) k = canon_key(t, reinterpret_cast<const uint64_t*>(table + i * 8)[f]);
+// One thread per row, every requested field in the same pass: `field in value` and value[field] not null -> its key
+// (query:58-66, 82-85).  Reads the first 48 bytes of each row (values + header word: one 64-byte DRAM access, see
+// row_chunk in bb_kernels.cuh) and writes 8 bytes per row and field; the padding element of an odd-sized column
+// gets BB_KEY_NONE here, so the column needs no clearing pass.
+struct BuildArgs {
+  const uint4* table;
+  uint64_t capacity, padded;  // rows; elements per column (capacity rounded up to even)
+  uint32_t mask;              // fields to build
+  uint64_t* pcol[F];
+};
+
+// A warp covers 32 rows: four lanes fetch the first 64 bytes of a row (one full DRAM access, 8 rows per load
+// instruction instead of 32 scattered 16-byte pieces), the lane that holds a value slot computes its key, and
+// the keys are transposed with shuffles so that every column is written as one coalesced 256-byte run.
+__global__ void __launch_bounds__(256) k_index_build(const BuildArgs a) {
+  const int lane = threadIdx.x & 31, c = lane & 3;
+  const uint64_t row0 = ((uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (row0 >= a.padded) return;
+  uint4 v[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint64_t r = row0 + it * 8 + (lane >> 2);
+    v[it] = r < a.capacity ? a.table[r * 8 + c] : make_uint4(0, 0, 0, 0);  // device chunks 0, 1: values; 2: orders + header
   }
-  pcol[i] = k;
+  uint64_t key[4][2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const uint32_t meta = __shfl_sync(0xffffffffu, v[it].z, (lane & ~3) | 2);
+    const bool obj = kind_of(meta) == BB_KIND_OBJ;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f = 2 * c + h;  // the field whose value this lane holds (lanes with c >= 2 hold none)
+      const uint32_t t = f < F ? (meta >> (BB_HDR_TAG_SHIFT + 3 * f)) & 7u : BB_TAG_ABSENT;
+      const uint64_t val = h ? ((uint64_t)v[it].z | ((uint64_t)v[it].w << 32)) : ((uint64_t)v[it].x | ((uint64_t)v[it].y << 32));
+      key[it][h] = (obj && t != BB_TAG_ABSENT && t != BB_TAG_NULL) ? canon_key(t, val) : BB_KEY_NONE;
+    }
+  }
+  const uint64_t row = row0 + lane;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    if (!((a.mask >> f) & 1u)) continue;  // (warp-uniform)
+    uint64_t out = BB_KEY_NONE;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {  // row `lane` of this warp was fetched in round lane / 8 by lanes 4 * (lane % 8) ..
+      const uint64_t k = __shfl_sync(0xffffffffu, key[it][f & 1], (lane & 7) * 4 + (f >> 1));
+      if ((lane >> 3) == it) out = k;
+    }
+    if (row < a.padded) a.pcol[f][row] = out;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_fill_u64(uint64_t* __restrict__ p, uint64_t n, uint64_t v) {

@@ -496,8 +496,16 @@ struct MergeArgs {
 
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
+// In HBM a row's eight 16-byte chunks are stored in the order 0, 1, 6, 7, 2, 3, 4, 5 of the public bb_row: the values,
+// the header word (kind, tags, key order), the flags and the creation sequence - everything an index build or a
+// scan of the stored values needs - sit in the FIRST 64 bytes, the two clocks' counts in the second.  A random
+// row access is two 64-byte DRAM accesses either way; a pass that only needs the first half moves half the bytes.
+// bb_table_load / bb_table_read convert; everything else goes through unpack_row / pack_row.
+__host__ __device__ constexpr int row_chunk(int c) { return c < 2 ? c : (c >= 6 ? c - 4 : c + 2); }
+
 __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
-  const uint4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+  const uint4 q0 = q[row_chunk(0)], q1 = q[row_chunk(1)], q2 = q[row_chunk(2)], q3 = q[row_chunk(3)], q4 = q[row_chunk(4)],
+              q5 = q[row_chunk(5)], q6 = q[row_chunk(6)], q7 = q[row_chunk(7)];
   r.s.val[0] = u64_of(q0.x, q0.y); r.s.val[1] = u64_of(q0.z, q0.w);
   r.s.val[2] = u64_of(q1.x, q1.y); r.s.val[3] = u64_of(q1.z, q1.w);
   r.m.cnt[0] = q2.x; r.m.cnt[1] = q2.y; r.m.cnt[2] = q2.z; r.m.cnt[3] = q2.w;
@@ -516,16 +524,16 @@ __device__ __forceinline__ void unpack_row(const uint4* q, RowState& r) {
 }
 
 __device__ __forceinline__ void pack_row(uint4* q, const RowState& r) {
-  q[0] = make_uint4((uint32_t)r.s.val[0], (uint32_t)(r.s.val[0] >> 32), (uint32_t)r.s.val[1], (uint32_t)(r.s.val[1] >> 32));
-  q[1] = make_uint4((uint32_t)r.s.val[2], (uint32_t)(r.s.val[2] >> 32), (uint32_t)r.s.val[3], (uint32_t)(r.s.val[3] >> 32));
-  q[2] = make_uint4(r.m.cnt[0], r.m.cnt[1], r.m.cnt[2], r.m.cnt[3]);
-  q[3] = make_uint4(r.m.cnt[4], r.m.cnt[5], r.m.cnt[6], r.m.cnt[7]);
-  q[4] = make_uint4(r.v.cnt[0], r.v.cnt[1], r.v.cnt[2], r.v.cnt[3]);
-  q[5] = make_uint4(r.v.cnt[4], r.v.cnt[5], r.v.cnt[6], r.v.cnt[7]);
-  q[6] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
+  q[row_chunk(0)] = make_uint4((uint32_t)r.s.val[0], (uint32_t)(r.s.val[0] >> 32), (uint32_t)r.s.val[1], (uint32_t)(r.s.val[1] >> 32));
+  q[row_chunk(1)] = make_uint4((uint32_t)r.s.val[2], (uint32_t)(r.s.val[2] >> 32), (uint32_t)r.s.val[3], (uint32_t)(r.s.val[3] >> 32));
+  q[row_chunk(2)] = make_uint4(r.m.cnt[0], r.m.cnt[1], r.m.cnt[2], r.m.cnt[3]);
+  q[row_chunk(3)] = make_uint4(r.m.cnt[4], r.m.cnt[5], r.m.cnt[6], r.m.cnt[7]);
+  q[row_chunk(4)] = make_uint4(r.v.cnt[0], r.v.cnt[1], r.v.cnt[2], r.v.cnt[3]);
+  q[row_chunk(5)] = make_uint4(r.v.cnt[4], r.v.cnt[5], r.v.cnt[6], r.v.cnt[7]);
+  q[row_chunk(6)] = make_uint4(r.m.order, r.v.order, r.s.meta, r.s.ord);
   const uint32_t flags = (r.m.present ? BB_ROW_M_PRESENT : 0u) | (r.v.present ? BB_ROW_V_PRESENT : 0u) |
                          (r.alias ? BB_ROW_ALIAS : 0u);
-  q[7] = make_uint4(flags, r.xcnt, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
+  q[row_chunk(7)] = make_uint4(flags, r.xcnt, (uint32_t)r.cseq, (uint32_t)(r.cseq >> 32));
 }
 
 // update payload / change entry as 5 x uint4: [head][clk lo][clk hi][val lo][val hi]
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(256) k_table_scatter(uint4* __restrict__ table
     atomicOr(err, 1u);
     return;
   }
-  table[p * 8 + (t & 7)] = rows[t];
+  table[p * 8 + row_chunk((int)(t & 7))] = rows[t];  // public bb_row chunk order -> the order rows have in HBM
 }
 
 __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table, const uint64_t* __restrict__ ids,
@@ -1005,7 +1013,7 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
     }
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[q];
+  for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[row_chunk(q)];
 }
 
 }  // namespace bb

@@ -111,6 +111,10 @@ struct RouteCtl {
   uint64_t cflag[2][RT_MAX_WORLD];                  // [slot][source]: that source's counts row is in
   uint64_t bflag[2][RT_MAX_WORLD];                  // [slot][source]: that source's rows have landed
   uint64_t err;
+  // sharded queries: every rank's hit count, then "my hit ids have landed everywhere"
+  uint64_t qcount[RT_MAX_WORLD];
+  uint64_t qcflag[RT_MAX_WORLD];
+  uint64_t qbflag[RT_MAX_WORLD];
 };
 
 struct RouteCtlPeers {
@@ -158,6 +162,83 @@ __global__ void __launch_bounds__(32) k_route_barrier(RouteCtlPeers peers, uint3
     __threadfence_system();  // cumulative: the previous kernel's stores (visible to this thread) go first
     st_sys(&peers.ctl[t]->bflag[slot][me], epoch);
     spin_until(&peers.ctl[me]->bflag[slot][t], epoch, &peers.ctl[me]->err);
+  }
+  __threadfence_system();
+}
+
+// ---------------------------------------------------------------- sharded queries: all-gather(v) of the hit ids
+// through peer memory.  Every rank has scanned its shard (k_index_scan) into a local buffer; the counts go to
+// everybody's control block, then ONE kernel per rank stores its hit ids straight into every rank's result buffer
+// (peer-mapped, NVLink) at the offset the counts give it - rank-major, each rank's hits as one run - and an
+// epoch-flag barrier tells the readers that all runs are in.
+struct QueryPushArgs {
+  const uint32_t* hits;              // this rank's local hit ids
+  const unsigned long long* n_hits;  // [2] dense + overflow matches of the local scan (device)
+  uint64_t hits_cap;                 // elements of `hits`: a scan that matched more publishes a poisoned count
+  uint32_t* dst[RT_MAX_WORLD];       // every rank's result buffer
+  uint64_t dst_cap;                  // elements
+  RouteCtlPeers peers;
+  uint64_t* counts_out;              // [world + 1] local copy of everybody's count + overflow marker, for the host
+  uint32_t me, world;
+  uint64_t epoch;
+};
+
+__global__ void __launch_bounds__(32) k_query_publish(QueryPushArgs a) {
+  const uint32_t t = threadIdx.x;
+  uint64_t mine = a.n_hits[0] + a.n_hits[1];
+  if (mine > a.hits_cap) mine = 1ull << 62;  // more matches than the local buffer holds: every rank reports BB_ERR_CAPACITY
+  if (t < a.world) {
+    st_sys(&a.peers.ctl[t]->qcount[a.me], mine);
+    __threadfence_system();
+    st_sys(&a.peers.ctl[t]->qcflag[a.me], a.epoch);
+    spin_until(&a.peers.ctl[a.me]->qcflag[t], a.epoch, &a.peers.ctl[a.me]->err);
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k_query_push(QueryPushArgs a) {
+  __shared__ uint64_t s_off, s_n, s_total;
+  if (threadIdx.x == 0) {
+    uint64_t off = 0, total = 0;
+    for (uint32_t q = 0; q < a.world; ++q) {
+      const uint64_t c = ld_sys(&a.peers.ctl[a.me]->qcount[q]);
+      if (q < a.me) off += c;
+      total += c;
+      if (blockIdx.x == 0) a.counts_out[q] = c;  // (private copy: a fast peer may publish its next query's count)
+    }
+    if (blockIdx.x == 0) a.counts_out[a.world] = total > a.dst_cap ? 1ull : 0ull;
+    s_off = off;
+    s_n = a.n_hits[0] + a.n_hits[1];  // (== qcount[me] whenever total fits)
+    s_total = total;
+  }
+  __syncthreads();
+  if (s_total > a.dst_cap) return;  // every rank sees the same counts and skips: reported to the host
+  const uint64_t n = s_n, off = s_off;
+  // 16-byte stores over NVLink: the run starts at the same offset in every destination, so one scalar head brings all
+  // of them to a 16-byte boundary; the source side is read with scalar (coalesced) loads
+  const uint64_t h4 = (4 - (off & 3)) & 3, head = h4 < n ? h4 : n, quads = (n - head) >> 2, tail0 = head + (quads << 2);
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = t; g < quads; g += nt) {
+    const uint32_t* src = a.hits + head + (g << 2);
+    const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+    for (uint32_t q = 0; q < a.world; ++q) {
+      const uint32_t d = (a.me + q) % a.world;  // every rank starts with itself: the peers' ingress is spread
+      *reinterpret_cast<uint4*>(a.dst[d] + off + head + (g << 2)) = v;
+    }
+  }
+  if (t < head + (n - tail0)) {
+    const uint64_t i = t < head ? t : tail0 + (t - head);
+    const uint32_t v = a.hits[i];
+    for (uint32_t q = 0; q < a.world; ++q) a.dst[q][off + i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_query_barrier(RouteCtlPeers peers, uint32_t me, uint32_t world, uint64_t epoch) {
+  const uint32_t t = threadIdx.x;
+  if (t < world) {
+    __threadfence_system();  // cumulative: the push kernel's stores go first
+    st_sys(&peers.ctl[t]->qbflag[me], epoch);
+    spin_until(&peers.ctl[me]->qbflag[t], epoch, &peers.ctl[me]->err);
   }
   __threadfence_system();
 }

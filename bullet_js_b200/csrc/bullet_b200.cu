@@ -414,15 +414,22 @@ int collect_device_error(bb_ctx* c, cudaStream_t s) {
   return BB_OK;
 }
 
-// (re)initialise the index on field f from the current table
-int index_fill(bb_ctx* c, int f, cudaStream_t s) {
-  bb_ctx::IndexDev& ix = c->index[f];
-  const uint64_t cap2 = (c->cfg.capacity + 1) & ~1ull;
-  BB_CUDA(c, cudaMemsetAsync(ix.pcol, 0xFF, cap2 * sizeof(uint64_t), s));
-  BB_CUDA(c, cudaMemsetAsync(ix.xkey, 0xFF, ix.xslots * sizeof(uint64_t), s));
-  BB_CUDA(c, cudaMemsetAsync(ix.xnode, 0xFF, ix.xslots * sizeof(uint32_t), s));
-  BB_CUDA(c, cudaMemsetAsync(c->d_xused + f, 0, sizeof(uint32_t), s));
-  BB_LAUNCH(c, bb::k_index_build, div_up(c->cfg.capacity, 256), 256, s, c->table, c->cfg.capacity, f, ix.pcol);
+// (re)initialise the indices on the fields of `mask` from the current table: ONE pass over the rows for all of them
+int index_fill(bb_ctx* c, uint32_t mask, cudaStream_t s) {
+  bb::BuildArgs a;
+  a.table = c->table;
+  a.capacity = c->cfg.capacity;
+  a.padded = (c->cfg.capacity + 1) & ~1ull;
+  a.mask = mask;
+  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+    bb_ctx::IndexDev& ix = c->index[f];
+    a.pcol[f] = ix.pcol;
+    if (!((mask >> f) & 1u)) continue;
+    BB_CUDA(c, cudaMemsetAsync(ix.xkey, 0xFF, ix.xslots * sizeof(uint64_t), s));
+    BB_CUDA(c, cudaMemsetAsync(ix.xnode, 0xFF, ix.xslots * sizeof(uint32_t), s));
+    BB_CUDA(c, cudaMemsetAsync(c->d_xused + f, 0, sizeof(uint32_t), s));
+  }
+  BB_LAUNCH(c, bb::k_index_build, div_up(a.padded, 256), 256, s, a);  // 8 warps x 32 rows per CTA
   return BB_OK;
 }
 
@@ -681,11 +688,10 @@ int bb_table_clear(bb_ctx* c) {
   if (!c) return BB_ERR_ARG;
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   BB_CUDA(c, cudaMemsetAsync(c->table, 0, c->cfg.capacity * sizeof(bb_row), c->stream));
-  for (int f = 0; f < BB_MAX_FIELDS; ++f)
-    if (c->index[f].live) {
-      int rc = index_fill(c, f, c->stream);
-      if (rc) return rc;
-    }
+  if (c->index_mask) {
+    int rc = index_fill(c, c->index_mask, c->stream);
+    if (rc) return rc;
+  }
   BB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->seq = 0;
   return BB_OK;
@@ -900,37 +906,52 @@ int bb_route_pack_dev(bb_ctx* c, uint32_t world, const bb_batch* in, bb_batch* o
   return BB_OK;
 }
 
-int bb_index_create(bb_ctx* c, uint32_t field, uint64_t extra_capacity) {
+int bb_index_create_fields(bb_ctx* c, uint32_t field_mask, uint64_t extra_capacity) {
   if (!c) return BB_ERR_ARG;
-  if (field >= c->cfg.n_fields) return fail(c, BB_ERR_ARG, "field slot out of range");
-  if (c->index[field].live) return BB_OK;  // query:33-35
+  if (field_mask == 0 || (field_mask >> c->cfg.n_fields)) return fail(c, BB_ERR_ARG, "field slot out of range");
+  const uint32_t todo = field_mask & ~c->index_mask;  // creating an index that exists is a no-op (query:33-35)
+  if (!todo) return BB_OK;
   if (!(c->cfg.flags & BB_CFG_POST_GETDATA))
     return fail(c, BB_ERR_STATE, "indices need a ctx created with BB_CFG_POST_GETDATA");
   if (extra_capacity >= (1ull << 31)) return fail(c, BB_ERR_ARG, "extra_capacity too large");
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
-  bb_ctx::IndexDev& ix = c->index[field];
   uint64_t slots = 1024;
   while (slots - (slots >> 3) <= extra_capacity + 1) slots <<= 1;
   const uint64_t cap2 = (c->cfg.capacity + 1) & ~1ull;
-  if (cudaMalloc((void**)&ix.pcol, cap2 * sizeof(uint64_t)) != cudaSuccess ||
-      cudaMalloc((void**)&ix.xkey, slots * sizeof(uint64_t)) != cudaSuccess ||
-      cudaMalloc((void**)&ix.xnode, slots * sizeof(uint32_t)) != cudaSuccess) {
-    if (ix.pcol) cudaFree(ix.pcol);
-    if (ix.xkey) cudaFree(ix.xkey);
-    if (ix.xnode) cudaFree(ix.xnode);
-    ix = bb_ctx::IndexDev();
-    return fail(c, BB_ERR_CUDA, "index allocation failed", cudaGetLastError());
+  for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+    if (!((todo >> f) & 1u)) continue;
+    bb_ctx::IndexDev& ix = c->index[f];
+    if (cudaMalloc((void**)&ix.pcol, cap2 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc((void**)&ix.xkey, slots * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc((void**)&ix.xnode, slots * sizeof(uint32_t)) != cudaSuccess) {
+      for (int g = 0; g <= f; ++g) {
+        if (!((todo >> g) & 1u)) continue;
+        bb_ctx::IndexDev& iy = c->index[g];
+        if (iy.pcol) cudaFree(iy.pcol);
+        if (iy.xkey) cudaFree(iy.xkey);
+        if (iy.xnode) cudaFree(iy.xnode);
+        iy = bb_ctx::IndexDev();
+      }
+      return fail(c, BB_ERR_CUDA, "index allocation failed", cudaGetLastError());
+    }
+    ix.xslots = slots;
   }
-  ix.xslots = slots;
   begin_call(c);
   mark(c, EV_Q0, c->stream);
-  int rc = index_fill(c, (int)field, c->stream);
+  int rc = index_fill(c, todo, c->stream);
   if (rc) return rc;
   mark(c, EV_Q1, c->stream);
   BB_CUDA(c, cudaStreamSynchronize(c->stream));
-  ix.live = true;
-  c->index_mask |= 1u << field;
+  for (int f = 0; f < BB_MAX_FIELDS; ++f)
+    if ((todo >> f) & 1u) c->index[f].live = true;
+  c->index_mask |= todo;
   return BB_OK;
+}
+
+int bb_index_create(bb_ctx* c, uint32_t field, uint64_t extra_capacity) {
+  if (!c) return BB_ERR_ARG;
+  if (field >= c->cfg.n_fields) return fail(c, BB_ERR_ARG, "field slot out of range");
+  return bb_index_create_fields(c, 1u << field, extra_capacity);
 }
 
 int bb_query_equals(bb_ctx* c, uint32_t field, uint64_t key, bb_hits* out) {
@@ -1106,6 +1127,15 @@ struct bb_router {
   bb::RouteCtl* ctl = nullptr; // this rank's control block (peer-mapped by everybody)
   bb::RouteCtlPeers ctl_peers{};
   uint64_t epoch = 0;
+  // sharded queries: local hits, peer-mapped result buffers, counts for the host
+  uint32_t* q_local = nullptr;
+  uint64_t q_local_cap = 0;
+  uint32_t* q_result = nullptr;            // this rank's copy of the gathered result
+  uint32_t* q_peer[bb::RT_MAX_WORLD]{};    // everybody's; our own entry = q_result
+  uint64_t q_cap = 0;
+  uint64_t* d_qcounts = nullptr;           // [world + 1]
+  uint64_t* h_qcounts = nullptr;           // pinned
+  uint64_t q_epoch = 0;
   // two-stream route (flag_sync): `prep` counts + publishes the next batch while `stream` still exchanges
   cudaStream_t prep = nullptr;
   uint32_t* tiles2[2]{};          // per-slot tile offsets (the scatter of one batch and the count of the next overlap)
@@ -1237,6 +1267,12 @@ int bb_router_destroy(bb_router* r) {
   for (uint32_t q = 0; q < r->world; ++q)
     for (int j = 0; j < 8; ++j)
       if (q != r->rank && r->peer[q][j / 4][j % 4]) cudaIpcCloseMemHandle(r->peer[q][j / 4][j % 4]);
+  for (uint32_t q = 0; q < r->world; ++q)
+    if (q != r->rank && r->q_peer[q]) cudaIpcCloseMemHandle(r->q_peer[q]);
+  if (r->q_result) cudaFree(r->q_result);
+  if (r->q_local) cudaFree(r->q_local);
+  if (r->d_qcounts) cudaFree(r->d_qcounts);
+  if (r->h_qcounts) cudaFreeHost(r->h_qcounts);
   if (r->d_bar) cudaFree(r->d_bar);
   if (r->d_counts) cudaFree(r->d_counts);
   if (r->d_matrix) cudaFree(r->d_matrix);
@@ -1511,6 +1547,98 @@ int bb_router_release(bb_router* r, uint32_t slot, void* stream) {
   if (!r || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
   BB_RCUDA(r, cudaSetDevice(r->device));
   BB_RCUDA(r, cudaEventRecord(r->merged[slot], (cudaStream_t)stream));
+  return BB_OK;
+}
+
+/* ---- sharded queries ------------------------------------------------------------------------------------ */
+int bb_router_query_reserve(bb_router* r, uint64_t max_total_hits) {
+  if (!r || max_total_hits == 0) return rfail(r, BB_ERR_ARG, "bad argument");
+  if (!r->p2p) return rfail(r, BB_ERR_STATE, "sharded queries need the peers' memory mapped (cudaIpc); BB_ROUTER_NO_P2P is set or mapping failed");
+  if (r->q_result) return rfail(r, BB_ERR_STATE, "query buffers already reserved");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  const uint32_t W = r->world, me = r->rank;
+  BB_RCUDA(r, cudaMalloc((void**)&r->q_local, max_total_hits * sizeof(uint32_t)));  // one rank's hits <= everybody's
+  r->q_local_cap = max_total_hits;
+  BB_RCUDA(r, cudaMalloc((void**)&r->q_result, max_total_hits * sizeof(uint32_t)));
+  r->q_cap = max_total_hits;
+  BB_RCUDA(r, cudaMalloc((void**)&r->d_qcounts, (W + 1) * sizeof(uint64_t)));
+  BB_RCUDA(r, cudaMallocHost((void**)&r->h_qcounts, (W + 1) * sizeof(uint64_t)));
+  r->q_peer[me] = r->q_result;
+  if (W == 1) return BB_OK;
+  constexpr size_t HB = sizeof(cudaIpcMemHandle_t);
+  std::string host(HB * W, '\0');
+  char* d_all = nullptr;
+  bool ok = cudaMalloc((void**)&d_all, HB * W) == cudaSuccess;
+  cudaIpcMemHandle_t h;
+  ok = ok && cudaIpcGetMemHandle(&h, r->q_result) == cudaSuccess;
+  memcpy(&host[HB * me], &h, HB);
+  ok = ok && cudaMemcpyAsync(d_all + HB * me, &host[HB * me], HB, cudaMemcpyHostToDevice, r->stream) == cudaSuccess;
+  const bool sent = g_nccl.AllGather(d_all ? d_all + HB * me : nullptr, d_all, HB, ncclUint8, r->comm, r->stream) == ncclSuccess;
+  ok = ok && sent && cudaMemcpyAsync(&host[0], d_all, HB * W, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+       cudaStreamSynchronize(r->stream) == cudaSuccess;
+  for (uint32_t q = 0; ok && q < W; ++q) {
+    if (q == me) continue;
+    memcpy(&h, &host[HB * q], HB);
+    void* p = nullptr;
+    ok = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    r->q_peer[q] = (uint32_t*)p;
+  }
+  if (d_all) cudaFree(d_all);
+  if (!ok) return rfail(r, BB_ERR_CUDA, "mapping the peers' query result buffers failed");
+  return BB_OK;
+}
+
+static int router_query(bb_router* r, bb_ctx* c, uint32_t field, const bb::Pred& pred, bb_gathered_hits* out, void* stream) {
+  if (!r || !c || !out || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
+  if (!r->q_result) return rfail(r, BB_ERR_STATE, "bb_router_query_reserve first");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  begin_call(c);
+  int rc = scan_dev(c, field, pred, r->q_local, r->q_local_cap, s);
+  if (rc) return rfail(r, rc, bb_last_error(c));
+  bb::QueryPushArgs a;
+  a.hits = r->q_local;
+  a.n_hits = c->d_counters;
+  a.hits_cap = r->q_local_cap;
+  for (uint32_t q = 0; q < r->world; ++q) a.dst[q] = r->q_peer[q];
+  a.dst_cap = r->q_cap;
+  a.peers = r->ctl_peers;
+  a.counts_out = r->d_qcounts;
+  a.me = r->rank;
+  a.world = r->world;
+  a.epoch = ++r->q_epoch;
+  bb_launch(bb::k_query_publish, 1, 32, 0, s, false, a);
+  bb_launch(bb::k_query_push, (uint32_t)(c->n_sm * 4), 256, 0, s, false, a);
+  bb_launch(bb::k_query_barrier, 1, 32, 0, s, false, r->ctl_peers, r->rank, r->world, a.epoch);
+  r->launches += 3;
+  BB_RCUDA(r, cudaGetLastError());
+  BB_RCUDA(r, cudaMemcpyAsync(r->h_qcounts, r->d_qcounts, (r->world + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  BB_RCUDA(r, cudaStreamSynchronize(s));
+  if (r->h_qcounts[r->world]) return rfail(r, BB_ERR_CAPACITY, "gathered result larger than bb_router_query_reserve's max_total_hits");
+  out->node = r->q_result;
+  out->offset[0] = 0;
+  for (uint32_t q = 0; q < r->world; ++q) out->offset[q + 1] = out->offset[q] + r->h_qcounts[q];
+  out->total = out->offset[r->world];
+  return BB_OK;
+}
+
+int bb_router_query_range(bb_router* r, bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb_bound* hi,
+                          bb_gathered_hits* out, void* stream) {
+  if (!lo || !hi) return rfail(r, BB_ERR_ARG, "null argument");
+  return router_query(r, ctx, field, range_pred(lo, hi), out, stream);
+}
+
+int bb_router_query_equals(bb_router* r, bb_ctx* ctx, uint32_t field, uint64_t key, bb_gathered_hits* out, void* stream) {
+  bb::Pred p{};
+  p.mode = 0;
+  p.eq = key;
+  return router_query(r, ctx, field, p, out, stream);
+}
+
+int bb_router_query_fetch(bb_router* r, uint64_t first, uint64_t n, uint32_t* host_out) {
+  if (!r || !r->q_result || (n && !host_out) || first + n > r->q_cap) return rfail(r, BB_ERR_ARG, "bad argument");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  if (n) BB_RCUDA(r, cudaMemcpy(host_out, r->q_result + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return BB_OK;
 }
 

@@ -102,6 +102,15 @@ class Engine:
             extra_capacity = max(4 * self.capacity, 1 << 16)
         self._check(self.lib.bb_index_create(self._h, field, int(extra_capacity)))
 
+    def index_create_fields(self, fields, extra_capacity: int | None = None):
+        """Several indices in one pass over the table."""
+        if extra_capacity is None:
+            extra_capacity = max(4 * self.capacity, 1 << 16)
+        mask = 0
+        for f in fields:
+            mask |= 1 << int(f)
+        self._check(self.lib.bb_index_create_fields(self._h, mask, int(extra_capacity)))
+
     def _hits(self, out, field):
         return out or capi.HitBuffers(sum(self.index_stats(field)))  # every entry could match
 

@@ -111,7 +111,7 @@ class Router:
                  key_bits: int = 0):
         import ctypes as C
 
-        if dist is None:
+        if dist is None and world > 1:
             import torch.distributed as dist
         self.lib = capi.load()
         self.world, self.rank = world, rank
@@ -121,7 +121,8 @@ class Router:
             if rc:
                 raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(None) or b"").decode())
         box = [idbuf.raw]
-        dist.broadcast_object_list(box, src=0)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
         h = C.c_void_p()
         rc = self.lib.bb_router_create(device_index, world, rank, box[0], batch, recv_capacity, C.byref(h))
         if rc:
@@ -153,6 +154,34 @@ class Router:
         engine.merge_dev(rb, cs, stream)
         self._check(self.lib.bb_router_release(self._h, slot, C.c_void_p(stream)))
         return int(rb.n)
+
+    # ---- sharded queries (src/bullet-query.js:186-210, 221-261 over a table that spans the ranks)
+    def query_reserve(self, max_total_hits: int):
+        """Collective, once: buffers for this rank's scan and for the gathered result on every rank."""
+        self._check(self.lib.bb_router_query_reserve(self._h, int(max_total_hits)))
+
+    def query_range(self, engine, field: int, lo: capi.BBBound, hi: capi.BBBound, stream: int) -> capi.BBGatheredHits:
+        """Collective: every rank scans its shard and stores its local hit ids into every rank's result buffer over
+        NVLink.  The result (device memory) is rank 0's hits, then rank 1's, ...: offset[q] .. offset[q + 1]."""
+        import ctypes as C
+
+        out = capi.BBGatheredHits()
+        self._check(self.lib.bb_router_query_range(self._h, engine._h, field, C.byref(lo), C.byref(hi), C.byref(out),
+                                                   C.c_void_p(stream)))
+        return out
+
+    def query_equals(self, engine, field: int, key: int, stream: int) -> capi.BBGatheredHits:
+        import ctypes as C
+
+        out = capi.BBGatheredHits()
+        self._check(self.lib.bb_router_query_equals(self._h, engine._h, field, int(key), C.byref(out), C.c_void_p(stream)))
+        return out
+
+    def query_fetch(self, first: int, n: int) -> np.ndarray:
+        """n gathered local hit ids starting at `first`, copied to the host."""
+        host = np.empty(max(int(n), 1), np.uint32)
+        self._check(self.lib.bb_router_query_fetch(self._h, int(first), int(n), host.ctypes.data))
+        return host[: int(n)]
 
     def last_ms(self) -> dict:
         import ctypes as C

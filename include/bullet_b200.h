@@ -91,7 +91,9 @@ typedef struct bb_head {
   uint32_t user;      /* opaque to the library; copied from update to change entry */
 } bb_head;
 
-/* Device-resident table row, one per interned path id; 128 bytes, 128-aligned.
+/* Table row, one per interned path id; 128 bytes.  This struct is the IMPORT / EXPORT format of bb_table_load and
+ * bb_table_read; in HBM the library keeps the same eight 16-byte chunks in the order 0, 1, 6, 7, 2, 3, 4, 5 (values,
+ * header, flags and cseq in the first 64 bytes, the clock counts in the second: an index build reads half a row).
  * State per path is (S, M, V, a) of SURVEY.md 8a:
  *   S = val/hdr, M = meta[path].vectorClock, V = crt.vectorClocks.get(path),
  *   a = M and V are the same JS object (src/bullet.js:198-203 stores the
@@ -263,6 +265,8 @@ int bb_sync(bb_ctx* ctx, void* stream);
  * the reference.  BB_ERR_CAPACITY is reported (by the merge call or bb_sync) when
  * the overflow set is full. */
 int bb_index_create(bb_ctx* ctx, uint32_t field, uint64_t extra_capacity);
+/* Several indices at once (bit f of field_mask = field slot f): ONE pass over the table builds all of them. */
+int bb_index_create_fields(bb_ctx* ctx, uint32_t field_mask, uint64_t extra_capacity);
 
 /* One side of range(): ToNumber(bound) for numeric keys (NaN never matches), and,
  * when the bound is a JS string, its place in the dictionary order for string
@@ -347,6 +351,27 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
+/* Sharded queries (src/bullet-query.js:186-210, 221-261 over a table that spans the router's ranks).  Collective:
+ * every rank calls with the same field and predicate and its own shard's ctx.  Each rank scans its shard
+ * (k_index_scan), the counts travel through the peer-mapped control blocks, and one kernel per rank stores its u32
+ * LOCAL hit ids straight into every rank's result buffer over NVLink at the offset the counts give it: on return
+ * out->node (device memory owned by the router, valid until the next query) holds rank 0's hits, then rank 1's, ...;
+ * out->offset[q] .. offset[q+1] is rank q's run.  A hit h of rank q is the node with scrambled id h * world + q
+ * (path id = that, or its shard_mix inverse with hashed sharding).  The call synchronises `stream`.
+ * bb_router_query_reserve (collective, once): max_total_hits = capacity of the gathered result on every rank (a
+ * query that matches more returns BB_ERR_CAPACITY on every rank).  Needs the peers' memory mapped (same box); W = 1
+ * works too. */
+typedef struct bb_gathered_hits {
+  const uint32_t* node; /* device */
+  uint64_t offset[17];
+  uint64_t total;
+} bb_gathered_hits;
+int bb_router_query_reserve(bb_router* r, uint64_t max_total_hits);
+int bb_router_query_range(bb_router* r, bb_ctx* ctx, uint32_t field, const bb_bound* lo, const bb_bound* hi,
+                          bb_gathered_hits* out, void* stream);
+int bb_router_query_equals(bb_router* r, bb_ctx* ctx, uint32_t field, uint64_t key, bb_gathered_hits* out, void* stream);
+/* convenience: copy n gathered ids starting at `first` to host memory (synchronous) */
+int bb_router_query_fetch(bb_router* r, uint64_t first, uint64_t n, uint32_t* host_out);
 /* Telemetry of the most recent route, ms: device time of [count by owner, counts exchange (+ wait for the
  * exchange stream's turn), pack + exchange, completion barrier], then host time of the call (twice). */
 int bb_router_last_ms(bb_router* r, double out[6]);

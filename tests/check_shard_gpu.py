@@ -29,6 +29,44 @@ from oracle.typed import TypedOracle  # noqa: E402
 N_REC, N_UPD, ROUNDS = 200_000, 300_000, 4
 
 
+def check_queries(rank, world, local, kb, table, ids, rows_local, router, stream):
+    """Sharded equals / range through the library (bb_router_query_*): every rank scans its shard and pushes its hit
+    ids into every rank's result buffer over NVLink.  Each rank checks the WHOLE gathered result - every rank's run -
+    against a numpy evaluation of the table image (multisets per run; src/bullet-query.js:186-210, 221-261)."""
+    all_ids = np.arange(N_REC, dtype=np.uint64)
+    own = shard.owner_of(all_ids, world, kb)
+    loc = shard.local_row(all_ids, world, kb)
+    cap = shard.shard_capacity(world, kb, N_REC) + 1
+    qe = Engine(cap, device=local, post_getdata=True, **synth.synth_ranks(N_REC))
+    qe.table_load(rows_local, table.rows[ids])
+    qe.index_create_fields((0, 2), extra_capacity=1 << 12)
+    router.query_reserve(N_REC + 64)
+    age = table.rows["val"][:, 0].view(np.float64)
+    role = table.rows["val"][:, 2]
+    ok = True
+    cases = [("range(age,20,30)", (age >= 20.0) & (age <= 30.0), lambda: router.query_range(
+                  qe, 0, capi.BBBound(num=20.0, rank=0, flags=0, reserved=0), capi.BBBound(num=30.0, rank=0, flags=0, reserved=0), stream)),
+             ("range(age,200,300)", np.zeros(N_REC, bool), lambda: router.query_range(
+                  qe, 0, capi.BBBound(num=200.0, rank=0, flags=0, reserved=0), capi.BBBound(num=300.0, rank=0, flags=0, reserved=0), stream)),
+             ("equals(role,admin)", role == 0, lambda: router.query_equals(qe, 2, codec.KEY_STR | 0, stream)),
+             ("range(age,1,99)", (age >= 1.0) & (age <= 99.0), lambda: router.query_range(
+                  qe, 0, capi.BBBound(num=1.0, rank=0, flags=0, reserved=0), capi.BBBound(num=99.0, rank=0, flags=0, reserved=0), stream))]
+    for name, sel, fn in cases:
+        for rep in range(2):  # twice: the second call reuses the buffers and the epoch flags
+            g = fn()
+            got = router.query_fetch(0, g.total)
+            good = True
+            for q in range(world):
+                run = np.sort(got[g.offset[q]: g.offset[q + 1]].astype(np.int64))
+                want = np.sort(loc[sel & (own == q)].astype(np.int64))
+                good = good and np.array_equal(run, want)
+            good = good and g.total == int(sel.sum())
+        print(f"[rank {rank}] sharded {name}: {g.total} hits gathered from {world} ranks: {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+    qe.close()
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -108,6 +146,7 @@ def main():
     good = np.array_equal(rows, ref.table[ids])
     print(f"[rank {rank}] shard table after {ROUNDS} pipelined rounds: {'OK' if good else 'MISMATCH'}", flush=True)
     ok = ok and good
+    ok = check_queries(rank, world, local, kb, table, ids, rows_local, router, stream) and ok
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     router.close()

@@ -158,3 +158,44 @@ def test_ordered_hits():
     want = np.nonzero((ages >= 20) & (ages <= 30))[0]
     assert int(hb.n_extra[0]) == 0 and np.array_equal(got, want.astype(np.uint32))
     eng.close()
+
+
+def test_router_queries_single_rank_and_multi_field_build():
+    """bb_router_query_* on a one-rank router (the same kernels as the multi-GPU path: scan, counts through the
+    control block, push into the result buffer, epoch barrier) and bb_index_create_fields (one pass, several
+    indices) against the oracle, overflow entries included."""
+    import torch
+
+    from bullet_js_b200 import shard
+
+    ops, _ref = streamgen.generate(911, 6000, 53, index_fields=("age", "role"))
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    eng, orc = pair(schema, 64)
+    eng.index_create_fields((0, 2))
+    orc.index_create(0)
+    orc.index_create(2)
+    assert eng.merge(batch).same_as(orc.merge(batch))
+    router = shard.Router(1, 0, 1024, 0)
+    stream = torch.cuda.Stream().cuda_stream
+    router.query_reserve(4096)
+    for lo, hi in itertools.product(BOUNDS[:6], BOUNDS[:6]):
+        bl, bh = schema.bound(lo, False), schema.bound(hi, True)
+        g = router.query_range(eng, 0, capi.bound_struct(bl), capi.bound_struct(bh), stream)
+        want = orc.query_range(0, bl, bh)
+        assert g.total == len(want) and g.offset[1] == g.total
+        assert np.array_equal(np.sort(router.query_fetch(0, g.total)), np.sort(want)), (lo, hi)
+    for v in EQ_VALUES:
+        key = schema.index_key(v)
+        if key is None:
+            continue
+        g = router.query_equals(eng, 2, key, stream)
+        assert np.array_equal(np.sort(router.query_fetch(0, g.total)), np.sort(orc.query_equals(2, key))), v
+    # a result larger than the reserved capacity is reported, not truncated
+    small = shard.Router(1, 0, 1024, 0)
+    small.query_reserve(1)
+    with pytest.raises(capi.BulletB200Error):
+        small.query_range(eng, 0, capi.bound_struct(schema.bound(-1e9, False)), capi.bound_struct(schema.bound(1e9, True)), stream)
+    small.close()
+    router.close()
+    eng.close()
