@@ -499,6 +499,36 @@ def run_queries(args, rank, world, local_rank, dev, image, dist):
     return res
 
 
+def pcie_probe(torch, dev, nbytes, dist):
+    """What the box's PCIe path gives this process while every rank does the same: H2D alone, D2H alone and both at once
+    (pinned buffers, two streams, `nbytes` each way) - the ceiling the e2e numbers live under."""
+    h_a, h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_a, d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    out = {}
+    for name, up, down in (("h2d", True, False), ("d2h", False, True), ("both", True, True)):
+        for timed in (False, True):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                if up:
+                    with torch.cuda.stream(s1):
+                        d_a.copy_(h_a, non_blocking=True)
+                if down:
+                    with torch.cuda.stream(s2):
+                        h_b.copy_(d_b, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 4
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name + "_gb_per_s_per_gpu_per_direction"] = nbytes / float(t[0]) / 1e9
+    out["note"] = "measured in this run with every rank copying at once; max time over ranks"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- zipf section
 def run_zipf(args, local_rank, dev, image, stream, torch):
     """The "conflicting" variant SURVEY 8d names: Zipf(0.8) keys (the hottest path takes ~1 % of the batch), default
@@ -684,92 +714,6 @@ def main():
         for e in engines[:Kp]:
             e.phase_events(False)
 
-    # ---- e2e through the reference-facing call with pinned host buffers
-    def pinned(a):
-        return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
-
-    e2e = None
-    if world == 1:
-        h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
-        hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
-        h_ver, h_n, h_idx, h_head, h_clk, h_val = hp(4 * n), hp(8), hp(4 * n), hp(16 * n), hp(32 * n), hp(32 * n)
-        hcs = capi.BBChanges(cap=n, verdict=h_ver.data_ptr(), n_changes=h_n.data_ptr(), idx=h_idx.data_ptr(),
-                             head=h_head.data_ptr(), clk=h_clk.data_ptr(), val=h_val.data_ptr())
-        hbs = [capi.BBBatch(n=n, path_id=a.data_ptr(), head=b_.data_ptr(), clk=c_.data_ptr(), val=d_.data_ptr())
-               for a, b_, c_, d_ in h_in]
-        Ke = min(K, 20)
-        for e in engines[: W + Ke]:
-            load_pristine(e)
-        for i in range(W):
-            engines[i].merge_raw(hbs[i % N_BATCHES], hcs)
-        if not args.no_parity:  # the host entry's output (chunked, three streams) of step W-1 against the oracle too
-            k = int(h_n.view(torch.int64)[0])
-            hg = codec.Changes.from_verdicts(h_ver.numpy().view(np.uint32), h_idx.numpy().view(np.uint32)[:k],
-                                             h_head.numpy().view(codec.HEAD_DTYPE)[:k], h_clk.numpy().view(np.uint32).reshape(-1, 8)[:k],
-                                             h_val.numpy().view(np.uint64).reshape(-1, 4)[:k])
-            okh, detail = oracle_check(eng.cfg, image.rows, batches[(W - 1) % N_BATCHES], hg, lambda t: engines[W - 1].table_read(t))
-            parity["host_entry"] = "ok" if okh else "MISMATCH: " + detail
-        torch.cuda.synchronize()
-        d2h = 0
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            engines[W + i].merge_raw(hbs[(W + i) % N_BATCHES], hcs)
-            k = int(h_n.view(torch.int64)[0])
-            d2h += 4 * n + 8 + k * 84
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
-               "d2h_bytes_per_step": d2h // Ke, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
-               "api": "bb_merge_batch (pinned host buffers, synchronous)"}
-    else:
-        # sharded e2e: every rank's batch starts in pinned HOST memory; H2D, route (all-to-all over NVLink), merge on the
-        # owning shards, then D2H of the decisions and the change set - all inside the timed region
-        h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
-        hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
-        h_ver, h_idx, h_head, h_clk, h_val = hp(4 * cap), hp(4 * cap), hp(16 * cap), hp(32 * cap), hp(32 * cap)
-        h_n = torch.zeros(1, dtype=torch.int64).pin_memory()
-        stage = tuple(torch.empty_like(x) for x in d_in[0][0])  # device landing buffers of the H2D copies
-        r_stage = capi.BBBatch(n=n, path_id=stage[0].data_ptr(), head=stage[1].data_ptr(), clk=stage[2].data_ptr(),
-                               val=stage[3].data_ptr())
-        Ke = min(K, 10)
-        for e in engines[: W + Ke]:
-            load_pristine(e)
-
-        def step_e2e(i):
-            for dst, src in zip(stage, h_in[i % N_BATCHES]):
-                dst.copy_(src, non_blocking=True)
-            router.route(r_stage, i % 2, stream)
-            m = router.merge(engines[i], i % 2, out.cs, stream)
-            h_n.copy_(out.n, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            k = int(h_n[0])
-            h_ver[: 4 * m].copy_(out.ver.view(torch.uint8)[: 4 * m], non_blocking=True)
-            h_idx[: 4 * k].copy_(out.idx.view(torch.uint8)[: 4 * k], non_blocking=True)
-            h_head[: 16 * k].copy_(out.head[: 16 * k], non_blocking=True)
-            h_clk[: 32 * k].copy_(out.clk[: 32 * k], non_blocking=True)
-            h_val[: 32 * k].copy_(out.val[: 32 * k], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return m, 4 * m + 8 + 84 * k
-
-        for i in range(W):
-            step_e2e(i)
-        barrier()
-        t0 = time.perf_counter()
-        d2h = me = 0
-        for i in range(Ke):
-            m, b_ = step_e2e(W + i)
-            me += m
-            d2h += b_
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt, float(me), float(d2h)], device=dev, dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(t[1]) * F / float(tmax[0]), "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
-               "d2h_bytes_per_step": int(float(t[2]) / world / Ke), "ms_per_step": float(tmax[0]) / Ke * 1e3, "steps": Ke,
-               "api": "pinned host batch -> H2D -> bb_router_route_dev -> bb_merge_batch_dev -> D2H of verdicts + change set, "
-                      "per rank, max over ranks"}
     # ---- the same shard WITHOUT routing: every rank merges batches it owns entirely (what one GPU does alone on this
     # shard shape); value / (N x this) is the efficiency of the routed job on config 3 itself
     unrouted = None
@@ -795,6 +739,108 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         unrouted = {"ms_per_step": float(t[0]), "per_gpu_field_merges_per_sec": n * F / (float(t[0]) * 1e-3), "steps": Ku,
                     "note": "local row ids, bb_merge_batch_dev only: the per-GPU rate on this shard shape with no exchange"}
+    # ---- e2e through the reference-facing host entry points, pinned host buffers, copies inside the timed region.
+    # The contexts of this section are created with BB_CFG_COMPACT_CHANGES (an accepted update that is stored exactly as
+    # it came in gets no entry - the caller has it already): same decisions, table and (rebuilt) change set, about half
+    # the bytes on the return link.
+    def pinned(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).pin_memory()
+
+    for e in engines:
+        e.close()
+    Ke = min(K, 20 if world == 1 else 10)
+    e_eng = []
+    for _ in range(W + Ke):
+        e = Engine(capacity, device=local_rank, compact_changes=True, **ranks_kw)
+        load_pristine(e)
+        e.reserve(cap, host_entry=True)
+        e_eng.append(e)
+    h_in = [tuple(pinned(x) for x in (b.path_id, b.head, b.clk, b.val)) for b in batches]
+    hp = lambda nbytes: torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    h_ver, h_n, h_idx, h_head, h_clk, h_val = hp(4 * cap), hp(8), hp(4 * cap), hp(16 * cap), hp(32 * cap), hp(32 * cap)
+    hcs = capi.BBChanges(cap=cap, verdict=h_ver.data_ptr(), n_changes=h_n.data_ptr(), idx=h_idx.data_ptr(),
+                         head=h_head.data_ptr(), clk=h_clk.data_ptr(), val=h_val.data_ptr())
+    hbs = [capi.BBBatch(n=n, path_id=a.data_ptr(), head=b_.data_ptr(), clk=c_.data_ptr(), val=d_.data_ptr())
+           for a, b_, c_, d_ in h_in]
+
+    def host_changes(m, rb):
+        k = int(h_n.view(torch.int64)[0])
+        return codec.Changes.from_verdicts(h_ver.numpy().view(np.uint32)[:m], h_idx.numpy().view(np.uint32)[:k],
+                                           h_head.numpy().view(codec.HEAD_DTYPE)[:k], h_clk.numpy().view(np.uint32).reshape(-1, 8)[:k],
+                                           h_val.numpy().view(np.uint64).reshape(-1, 4)[:k], rb)
+
+    pcie = pcie_probe(torch, dev, n * 88, dist)
+    if world == 1:
+        for i in range(W):
+            e_eng[i].merge_raw(hbs[i % N_BATCHES], hcs)
+        if not args.no_parity:  # the host entry's output (chunked, three streams, compact) of step W-1 against the oracle too
+            hg = host_changes(n, batches[(W - 1) % N_BATCHES])
+            okh, detail = oracle_check(eng.cfg, image.rows, batches[(W - 1) % N_BATCHES], hg, lambda t: e_eng[W - 1].table_read(t))
+            parity["host_entry"] = "ok" if okh else "MISMATCH: " + detail
+        torch.cuda.synchronize()
+        d2h = 0
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            e_eng[W + i].merge_raw(hbs[(W + i) % N_BATCHES], hcs)
+            k = int(h_n.view(torch.int64)[0])
+            d2h += 4 * n + 8 + k * 84
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": Ke * n * F / dt, "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
+               "d2h_bytes_per_step": d2h // Ke, "ms_per_step": dt / Ke * 1e3, "steps": Ke,
+               "api": "bb_merge_batch (pinned host buffers, synchronous; ctx with BB_CFG_COMPACT_CHANGES)", "pcie": pcie}
+    else:
+        # sharded: every rank's batch starts in pinned HOST memory; bb_router_merge_batch copies it in piece by piece,
+        # routes every piece all-to-all over NVLink, merges on the owning shards and returns each shard's verdicts +
+        # change entries to its rank's host buffers - all inside the timed region
+        hrouter = shard.Router(world, rank, n, local_rank, recv_capacity=cap, key_bits=kb)
+        PIECES = 4
+
+        def step_e2e(i):
+            m, counts = hrouter.merge_batch(e_eng[i], hbs[i % N_BATCHES], hcs, PIECES)
+            return m, counts, 4 * m + 8 + 84 * int(h_n.view(torch.int64)[0])
+
+        for i in range(W):
+            m, counts, _ = step_e2e(i)
+            if i == 0 and not args.no_parity:
+                # what this shard received: piece by piece, inside a piece by source rank (include/bullet_b200.h)
+                chunk = -(-n // PIECES)
+                recv = []
+                for j in range(PIECES):
+                    for src in range(world):
+                        b = batches[0] if src == rank else sharded_batch(image, n, synth.rng_for(3, salt=src * 16), args.keys, world, kb, capacity)
+                        b = b.slice(j * chunk, min((j + 1) * chunk, n))
+                        mine = np.nonzero(shard.owner_of(b.path_id, world, kb) == rank)[0]
+                        recv.append(codec.Batch(shard.local_row(b.path_id[mine], world, kb), b.head[mine], b.clk[mine], b.val[mine]))
+                rb = codec.Batch(*(np.concatenate([getattr(x, f) for x in recv]) for f in ("path_id", "head", "clk", "val")))
+                okh = rb.n == m and counts.ravel().tolist() == [x.n for x in recv]
+                detail = f"received {m}, expected {rb.n}"
+                if okh:
+                    uniq, rows, cb = compact_for_oracle(image.rows, image.n, rb)
+                    ocfg = capi.make_config(max(len(uniq), 1), **ranks_kw)
+                    okh, detail = oracle_check(ocfg, rows, cb, host_changes(m, rb), lambda t: e_eng[0].table_read(uniq[t.astype(np.int64)]))
+                parity["host_entry"] = "ok" if okh else "MISMATCH: " + detail
+        barrier()
+        t0 = time.perf_counter()
+        d2h = me = 0
+        for i in range(Ke):
+            m, _, b_ = step_e2e(W + i)
+            me += m
+            d2h += b_
+        barrier()
+        dt = time.perf_counter() - t0
+        hrouter.close()
+        t = torch.tensor([dt, float(me), float(d2h)], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(t[1]) * F / float(tmax[0]), "unit": "field-merges/s", "h2d_bytes_per_step": n * 88,
+               "d2h_bytes_per_step": int(float(t[2]) / world / Ke), "ms_per_step": float(tmax[0]) / Ke * 1e3, "steps": Ke,
+               "api": f"bb_router_merge_batch (pinned host buffers in and out, {PIECES} pipelined pieces: H2D -> pack + NVLink all-to-all -> "
+                      "merge on the owning shard -> D2H of that shard's verdicts + compact change set), per rank, max over ranks",
+               "pcie": pcie}
+    for e in e_eng:
+        e.close()
     clocks = sampler.stop()
 
     # ---- max over ranks

@@ -78,7 +78,7 @@ EXPORTS = [
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
     "bb_router_last_error", "bb_router_set_sharding", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
-    "bb_router_query_reserve", "bb_router_query_range", "bb_router_query_equals", "bb_router_query_fetch",
+    "bb_router_merge_batch", "bb_router_query_reserve", "bb_router_query_range", "bb_router_query_equals", "bb_router_query_fetch",
     "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms", "bb_phase_events",
 ]
@@ -154,6 +154,8 @@ def load():
     lib.bb_router_acquire.restype = i32
     lib.bb_router_release.argtypes = [vp, u32, vp]
     lib.bb_router_release.restype = i32
+    lib.bb_router_merge_batch.argtypes = [vp, vp, C.POINTER(BBBatch), C.POINTER(BBChanges), u32, C.POINTER(u64), vp]
+    lib.bb_router_merge_batch.restype = i32
     lib.bb_router_query_reserve.argtypes = [vp, u64]
     lib.bb_router_query_reserve.restype = i32
     lib.bb_router_query_range.argtypes = [vp, vp, u32, C.POINTER(BBBound), C.POINTER(BBBound), C.POINTER(BBGatheredHits), vp]
@@ -240,7 +242,7 @@ class ChangeBuffers:
                          idx=_ptr(self.idx), head=_ptr(self.head), clk=_ptr(self.clk),
                          val=_ptr(self.val))
 
-    def result(self, n: int) -> codec.Changes:
+    def result(self, n: int, batch: "codec.Batch | None" = None) -> codec.Changes:
         k = int(self.n_changes[0])
         return codec.Changes.from_verdicts(self.verdict[:n], self.idx[:k], self.head[:k], self.clk[:k],
-                                           self.val[:k])
+                                           self.val[:k], batch)

@@ -31,6 +31,7 @@ CFG_ORDERED_CHANGES = 2
 CFG_RADIX_SORT = 4
 CFG_FULL_SORT = 8
 CFG_HOT_KEYS = 64
+CFG_COMPACT_CHANGES = 128
 
 DEC_NO_CURRENT, DEC_IDENTICAL, DEC_TIE_INCOMING, DEC_TIE_CURRENT = 0, 1, 2, 3
 DEC_INCOMING, DEC_HISTORICAL, DEC_CONCURRENT = 4, 5, 6
@@ -385,6 +386,7 @@ class Batch:
 
 
 NO_SLOT = 0x1FFFFFFF
+SLOT_ECHO = 0x1FFFFFFE  # BB_CFG_COMPACT_CHANGES: accepted, the entry is the update itself
 
 
 @dataclass
@@ -398,21 +400,42 @@ class Changes:
     val: np.ndarray       # u64[k, 4]
 
     @staticmethod
-    def from_verdicts(verdict, idx, head, clk, val) -> "Changes":
+    def from_verdicts(verdict, idx, head, clk, val, batch: "Batch | None" = None) -> "Changes":
         """bb_changes -> arrival order: walk verdict[] and follow the slots (the
-        library stores entries path-major; include/bullet_b200.h)."""
+        library stores entries path-major; include/bullet_b200.h).  With BB_CFG_COMPACT_CHANGES an
+        accepted update whose entry would repeat it bit for bit carries SLOT_ECHO instead of a slot:
+        its entry is rebuilt from `batch` (the caller's own input), as the header defines it."""
         verdict = np.asarray(verdict, np.uint32)
         decision = (verdict >> 29).astype(np.uint8)
         slot = verdict & NO_SLOT
-        acc = np.nonzero(slot != NO_SLOT)[0]
+        echo = slot == SLOT_ECHO
+        emitted = (slot != NO_SLOT) & ~echo
+        acc = np.nonzero(emitted)[0]
         order = slot[acc].astype(np.int64)
         k = len(idx)
         if acc.size != k or (k and (np.sort(order) != np.arange(k)).any()):
             raise ValueError("verdict slots are not a permutation of the change set")
         if k and not np.array_equal(np.asarray(idx)[order], acc.astype(np.uint32)):
             raise ValueError("verdict slot does not point at the update's own entry")
-        return Changes(decision, np.asarray(idx)[order].copy(), np.asarray(head)[order].copy(),
-                       np.asarray(clk)[order].copy(), np.asarray(val)[order].copy())
+        if not echo.any():
+            return Changes(decision, np.asarray(idx)[order].copy(), np.asarray(head)[order].copy(),
+                           np.asarray(clk)[order].copy(), np.asarray(val)[order].copy())
+        if batch is None:
+            raise ValueError("compact change set: the input batch is needed to rebuild the echoed entries")
+        every = np.nonzero(emitted | echo)[0]
+        o_head = np.zeros(every.size, HEAD_DTYPE)
+        o_clk = np.zeros((every.size, MAX_PEERS), np.uint32)
+        o_val = np.zeros((every.size, MAX_FIELDS), np.uint64)
+        is_echo = echo[every]
+        src = every[is_echo]
+        o_head[is_echo] = batch.head[src]
+        o_head["hdr"][is_echo] &= ~np.uint64(HDR_FLAVOUR_NET)
+        o_clk[is_echo] = batch.clk[src]
+        o_val[is_echo] = batch.val[src]
+        o_head[~is_echo] = np.asarray(head)[order]
+        o_clk[~is_echo] = np.asarray(clk)[order]
+        o_val[~is_echo] = np.asarray(val)[order]
+        return Changes(decision, every.astype(np.uint32), o_head, o_clk, o_val)
 
     def same_as(self, other: "Changes") -> bool:
         return (

@@ -557,7 +557,20 @@ __device__ __forceinline__ void pack_change(uint4* q, uint32_t user, const Value
   q[4] = make_uint4((uint32_t)v.val[2], (uint32_t)(v.val[2] >> 32), (uint32_t)v.val[3], (uint32_t)(v.val[3] >> 32));
 }
 
+// BB_CFG_COMPACT_CHANGES: is the change entry of an accepted update the update itself (payload u[0..4]), bit for bit?
+__device__ __forceinline__ bool echoes_update(const uint4* u, const Value& v, const Clock& c) {
+  const uint4 h = u[0], c0 = u[1], c1 = u[2], v0 = u[3], v1 = u[4];
+  uint32_t d = ((h.x & ~(uint32_t)BB_HDR_FLAVOUR_NET) ^ v.meta) | (h.y ^ v.ord) | (h.z ^ c.order);
+  d |= (c0.x ^ c.cnt[0]) | (c0.y ^ c.cnt[1]) | (c0.z ^ c.cnt[2]) | (c0.w ^ c.cnt[3]);
+  d |= (c1.x ^ c.cnt[4]) | (c1.y ^ c.cnt[5]) | (c1.z ^ c.cnt[6]) | (c1.w ^ c.cnt[7]);
+  const uint64_t e = (u64_of(v0.x, v0.y) ^ v.val[0]) | (u64_of(v0.z, v0.w) ^ v.val[1]) | (u64_of(v1.x, v1.y) ^ v.val[2]) |
+                     (u64_of(v1.z, v1.w) ^ v.val[3]);
+  return d == 0 && e == 0;
+}
+
 constexpr uint32_t NO_SLOT = BB_NO_SLOT;
+constexpr uint32_t SLOT_ECHO = BB_SLOT_ECHO;
+constexpr uint32_t RES_ECHO = 0x10u;  // s_res flag: accepted, no entry
 constexpr int MT = 128;    // sorted positions per CTA tile == threads per CTA
 constexpr int MT_WARPS = MT / 32;
 constexpr int HOT_MIN = 24;    // a segment with this many updates inside one tile goes to k_merge_hot whole
@@ -584,7 +597,7 @@ __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED, bool HOT = false>
+template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false>
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * ROW_Q];
@@ -688,8 +701,12 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       const bool net = unpack_update(h, u[1], u[2], u[3], u[4], c, x);
       const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + s_idx[p], ov, oc);
       if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
-      if (BB_DEC_ACCEPTED(code)) pack_change(u, h.w, ov, oc);
-      s_res[p] = code;
+      uint32_t res = code;
+      if (BB_DEC_ACCEPTED(code)) {
+        if (COMPACT && echoes_update(u, ov, oc)) res |= RES_ECHO;
+        else pack_change(u, h.w, ov, oc);
+      }
+      s_res[p] = res;
     }
     if (last && nvalid == MT && s_nextk == key) {  // the tile's last segment runs on into the next tiles
       uint32_t over = 0;
@@ -711,7 +728,14 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
                                        a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
         const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
         if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
-        if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
+        bool echo = false;
+        if (COMPACT && BB_DEC_ACCEPTED(code)) {
+          uint4 u5[UPD_Q] = {h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1], a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1]};
+          echo = echoes_update(u5, ov, oc);
+        }
+        if (echo) {
+          a.verdict[ui] = (code << 29) | SLOT_ECHO;
+        } else if (BB_DEC_ACCEPTED(code)) {  // compacted into the staging slots this segment owns
           const uint64_t sp = base + MT + over;
           pack_change(a.st_ent + sp * UPD_Q, h.w, ov, oc);
           a.st_idx[sp] = ui | (code << 29);
@@ -743,8 +767,10 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   for (int ww = MT_WARPS - 1; ww >= 0; --ww)
     if (s_hmask[ww]) first = ww * 32 + __ffs(s_hmask[ww]) - 1;
   const bool owned = valid && tid >= first && s_res[tid] != RES_HANDED;
-  const uint32_t code = owned ? s_res[tid] : 0xFFu;
-  const bool acc = owned && BB_DEC_ACCEPTED(code);
+  const uint32_t res = owned ? s_res[tid] : 0xFFu;
+  const uint32_t code = res & ~RES_ECHO;
+  const bool echo = COMPACT && owned && (res & RES_ECHO);
+  const bool acc = owned && !echo && BB_DEC_ACCEPTED(code);  // emits an entry
   const uint32_t amask = __ballot_sync(0xffffffffu, acc);
   if (lane == 0) s_wsum[w] = __popc(amask);
   __syncthreads();
@@ -782,7 +808,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   // ---- verdicts (arrival order), change set (path-major order), rows
   bool overflow = false;
   const uint64_t dest = obase + rank;
-  if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : NO_SLOT);
+  if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : echo ? SLOT_ECHO : NO_SLOT);
   if (acc) {
     if (dest < a.cap) {
       a.out_idx[dest] = a.idx_base + idx;
@@ -834,7 +860,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
 // accepted one, or the first local put, whose clock IS V) is final, that update's own result is exact, and its
 // thread publishes the row for the next round.  The post-write index hook (query:139-176) runs for every retired
 // update, in order, on the publishing thread.  Runs after k_merge_stage; exits at once when nothing is hot.
-template <bool INDEXED>
+template <bool INDEXED, bool COMPACT = false>
 __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_row[ROW_Q];
   __shared__ __align__(16) uint4 s_win[HOT_T * UPD_Q];  // payload window
@@ -946,7 +972,9 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
           }
           pack_row(s_row, r);
         }
-        if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
+        if (COMPACT && BB_DEC_ACCEPTED(code) && echoes_update(slot, ov, oc)) {
+          a.verdict[ui] = (code << 29) | SLOT_ECHO;
+        } else if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
           const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
           a.verdict[ui] = (code << 29) | (uint32_t)dest;
           if (dest < a.cap) {

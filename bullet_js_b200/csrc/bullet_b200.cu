@@ -376,7 +376,14 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   fill_params(c, ma.p, ma.ix);
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
   if (grouped) {  // hot keys are handed to k_merge_hot, a CTA per segment (exits at once when there are none)
-    if (c->index_mask) {
+    const bool compact = (c->cfg.flags & BB_CFG_COMPACT_CHANGES) != 0;
+    if (compact && c->index_mask) {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_hot<true, true>), HOT_CTAS, HOT_T, 0, s, ma);
+    } else if (compact) {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_hot<false, true>), HOT_CTAS, HOT_T, 0, s, ma);
+    } else if (c->index_mask) {
       BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<true>, HOT_CTAS, HOT_T, 0, s, ma);
     } else {
@@ -556,6 +563,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
     g_create_error = "bad bb_config (abi_version / n_fields / local_peer / capacity)";
     return BB_ERR_ARG;
   }
+  if ((cfg->flags & BB_CFG_COMPACT_CHANGES) && (cfg->flags & (BB_CFG_ORDERED_CHANGES | BB_CFG_RADIX_SORT | BB_CFG_FULL_SORT))) {
+    g_create_error = "BB_CFG_COMPACT_CHANGES goes with the default pipeline only (not ORDERED_CHANGES / RADIX_SORT / FULL_SORT)";
+    return BB_ERR_ARG;
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
@@ -592,6 +603,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && n_sm > 0) c->n_sm = n_sm;
@@ -1298,7 +1311,7 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
   *out = nullptr;
   if (world < 1 || world > bb::RT_MAX_WORLD || rank >= world || max_batch == 0 || max_batch >= 0xFFFFFFFFull)
     return rfail(nullptr, BB_ERR_ARG, "bad world / rank / max_batch");
-  if (!nccl_load()) return rfail(nullptr, BB_ERR_CUDA, "libnccl.so.2 not found");
+  if (world > 1 && !nccl_load()) return rfail(nullptr, BB_ERR_CUDA, "libnccl.so.2 not found");  // one rank: no communicator
   if (cudaSetDevice(device) != cudaSuccess) return rfail(nullptr, BB_ERR_CUDA, "cudaSetDevice failed");
   bb_router* r = new (std::nothrow) bb_router();
   if (!r) return rfail(nullptr, BB_ERR_ARG, "out of host memory");
@@ -1349,7 +1362,7 @@ int bb_router_create(int32_t device, uint32_t world, uint32_t rank, const char i
   }
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
-  ncclResult_t e = g_nccl.CommInitRank(&r->comm, (int)world, u, (int)rank);
+  ncclResult_t e = world > 1 ? g_nccl.CommInitRank(&r->comm, (int)world, u, (int)rank) : ncclSuccess;
   if (e != ncclSuccess) {
     g_router_error = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(e);
     r->comm = nullptr;
@@ -1416,7 +1429,8 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
     BB_RCUDA(r, cudaGetLastError());
     d_matrix = r->ctl->matrix[slot];
   } else {
-    BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
+    if (W > 1) BB_RNCCL(r, g_nccl.AllGather(r->d_counts, r->d_matrix, W, ncclUint64, r->comm, s));
+    else BB_RCUDA(r, cudaMemcpyAsync(r->d_matrix, r->d_counts, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
   }
   uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
   BB_RCUDA(r, cudaMemcpyAsync(hm, d_matrix, (size_t)W * W * sizeof(uint64_t), cudaMemcpyDeviceToHost, sp));
@@ -1547,6 +1561,124 @@ int bb_router_release(bb_router* r, uint32_t slot, void* stream) {
   if (!r || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
   BB_RCUDA(r, cudaSetDevice(r->device));
   BB_RCUDA(r, cudaEventRecord(r->merged[slot], (cudaStream_t)stream));
+  return BB_OK;
+}
+
+/* ---- host entry of the sharded path ------------------------------------------------------------------------- */
+// Collective.  Every rank's batch (HOST buffers, arrival order) is cut into `chunks` pieces; piece j of every rank is
+// routed (H2D on the copy-in stream -> pack + NVLink all-to-all into receive slot j % 2), merged into the owning
+// shards, and the verdicts + change entries of what THIS shard received go back to the host - H2D of piece j+1, the
+// exchange of piece j+1, the merge of piece j and the D2H of piece j-1 all overlap.
+int bb_router_merge_batch(bb_router* r, bb_ctx* c, const bb_batch* in, bb_changes* out, uint32_t chunks,
+                          uint64_t* n_received, uint64_t* recv_counts) {
+  if (!r || !c || !in || !out || !out->n_changes || !out->verdict || !n_received)
+    return rfail(r, BB_ERR_ARG, "null argument");
+  if (chunks == 0) chunks = 4;
+  if (chunks > (uint32_t)MAX_CHUNKS) return rfail(r, BB_ERR_ARG, "at most 8 chunks");
+  const uint64_t n = in->n;
+  if (n && (!in->path_id || !in->head || !in->clk || !in->val)) return rfail(r, BB_ERR_ARG, "null buffer");
+  if (c->cfg.flags & BB_CFG_ORDERED_CHANGES) return rfail(r, BB_ERR_STATE, "the sharded host entry needs the default change-set layout");
+  const uint64_t chunk = (n + chunks - 1) / chunks;
+  if (chunk > r->max_batch) return rfail(r, BB_ERR_CAPACITY, "a chunk is larger than the router's max_batch");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  const uint32_t W = r->world, me = r->rank;
+  cudaStream_t s = c->stream;
+  begin_call(c);
+  mark(c, EV_H2D0, s);
+  {
+    int rc = reserve_io(c, std::max<uint64_t>(std::max<uint64_t>(n, out->cap), 1));
+    if (rc == BB_OK) rc = reserve_dev(c, r->cap);
+    if (rc) return rfail(r, rc, bb_last_error(c));
+  }
+  BB_RCUDA(r, cudaEventRecord(c->ev_in[0], s));  // the side streams start after what is queued on ours
+  BB_RCUDA(r, cudaStreamWaitEvent(c->s_h2d, c->ev_in[0], 0));
+  BB_RCUDA(r, cudaStreamWaitEvent(c->s_d2h, c->ev_in[0], 0));
+  mark(c, EV_START, s);
+  BB_RCUDA(r, cudaMemsetAsync(c->d_nchanges, 0, sizeof(uint64_t), s));
+  bb_changes dout{out->cap, c->io_verdict.p, c->d_nchanges, c->io_out_idx.p, reinterpret_cast<bb_head*>(c->io_out_head.p),
+                  reinterpret_cast<uint32_t*>(c->io_out_clk.p), reinterpret_cast<uint64_t*>(c->io_out_val.p)};
+  auto copy_in_and_route = [&](uint32_t j) -> int {
+    const uint64_t o = std::min<uint64_t>((uint64_t)j * chunk, n), m = std::min<uint64_t>(chunk, n - o);
+    if (m) {
+      BB_RCUDA(r, cudaMemcpyAsync(c->io_path.p + o, in->path_id + o, m * 8, cudaMemcpyHostToDevice, c->s_h2d));
+      BB_RCUDA(r, cudaMemcpyAsync(c->io_head.p + o, in->head + o, m * 16, cudaMemcpyHostToDevice, c->s_h2d));
+      BB_RCUDA(r, cudaMemcpyAsync(c->io_clk.p + 2 * o, in->clk + 8 * o, m * 32, cudaMemcpyHostToDevice, c->s_h2d));
+      BB_RCUDA(r, cudaMemcpyAsync(c->io_val.p + 2 * o, in->val + 4 * o, m * 32, cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    bb_batch din{m, c->io_path.p + o, reinterpret_cast<const bb_head*>(c->io_head.p + o),
+                 reinterpret_cast<const uint32_t*>(c->io_clk.p + 2 * o), reinterpret_cast<const uint64_t*>(c->io_val.p + 2 * o)};
+    uint64_t dummy = 0;
+    return bb_router_route_dev(r, &din, j & 1u, &dummy, c->s_h2d);
+  };
+  int rc = copy_in_and_route(0);
+  if (rc) return rc;
+  uint64_t voff = 0, done = 0;
+  for (uint32_t j = 0; j < chunks; ++j) {
+    if (j + 1 < chunks) {
+      rc = copy_in_and_route(j + 1);
+      if (rc) return rc;
+    }
+    bb_batch rb;
+    rc = bb_router_acquire(r, j & 1u, s, &rb);
+    if (rc) return rc;
+    const uint64_t m = rb.n;
+    if (recv_counts) {
+      const uint64_t* hm = r->h_matrix + (size_t)(j & 1u) * W * W;
+      for (uint32_t q = 0; q < W; ++q) recv_counts[(size_t)j * W + q] = hm[(size_t)q * W + me];
+    }
+    if (voff + m > out->cap) return rfail(r, BB_ERR_CAPACITY, "change-set buffers too small for what this shard received");
+    bb_changes dchunk = dout;
+    dchunk.verdict = c->io_verdict.p + voff;
+    rc = merge_dev(c, &rb, &dchunk, s, (uint32_t)voff, true, nullptr);
+    if (rc) return rfail(r, rc, bb_last_error(c));
+    rc = bb_router_release(r, j & 1u, s);
+    if (rc) return rc;
+    BB_RCUDA(r, cudaMemcpyAsync(c->d_chunk_total + j, c->d_nchanges, sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    BB_RCUDA(r, cudaEventRecord(c->ev_done[j], s));
+    // ship piece j's verdicts and entries while the next piece is exchanged and merged
+    BB_RCUDA(r, cudaStreamWaitEvent(c->s_d2h, c->ev_done[j], 0));
+    BB_RCUDA(r, cudaMemcpyAsync(c->h_nchanges + j, c->d_chunk_total + j, 8, cudaMemcpyDeviceToHost, c->s_d2h));
+    BB_RCUDA(r, cudaEventRecord(c->ev_cnt[j], c->s_d2h));
+    if (m) BB_RCUDA(r, cudaMemcpyAsync(out->verdict + voff, c->io_verdict.p + voff, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    voff += m;
+    if (j > 0) {  // entries of piece j-1: its count is on the host by now (no stall: piece j is already queued)
+      BB_RCUDA(r, cudaEventSynchronize(c->ev_cnt[j - 1]));
+      const uint64_t k = c->h_nchanges[j - 1];
+      if (k > out->cap) return rfail(r, BB_ERR_CAPACITY, "change-set buffer too small");
+      if (k > done) {
+        if (!out->idx || !out->head || !out->clk || !out->val) return rfail(r, BB_ERR_ARG, "null buffer");
+        const uint64_t cnt = k - done;
+        BB_RCUDA(r, cudaMemcpyAsync(out->idx + done, c->io_out_idx.p + done, cnt * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        BB_RCUDA(r, cudaMemcpyAsync(out->head + done, c->io_out_head.p + done, cnt * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+        BB_RCUDA(r, cudaMemcpyAsync(out->clk + 8 * done, c->io_out_clk.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+        BB_RCUDA(r, cudaMemcpyAsync(out->val + 4 * done, c->io_out_val.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+        done = k;
+      }
+    }
+  }
+  mark(c, EV_SORT, s);
+  mark(c, EV_MERGE, s);
+  {
+    BB_RCUDA(r, cudaEventSynchronize(c->ev_cnt[chunks - 1]));
+    const uint64_t k = c->h_nchanges[chunks - 1];
+    if (k > out->cap) return rfail(r, BB_ERR_CAPACITY, "change-set buffer too small");
+    if (k > done) {
+      if (!out->idx || !out->head || !out->clk || !out->val) return rfail(r, BB_ERR_ARG, "null buffer");
+      const uint64_t cnt = k - done;
+      BB_RCUDA(r, cudaMemcpyAsync(out->idx + done, c->io_out_idx.p + done, cnt * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_RCUDA(r, cudaMemcpyAsync(out->head + done, c->io_out_head.p + done, cnt * 16, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_RCUDA(r, cudaMemcpyAsync(out->clk + 8 * done, c->io_out_clk.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+      BB_RCUDA(r, cudaMemcpyAsync(out->val + 4 * done, c->io_out_val.p + 2 * done, cnt * 32, cudaMemcpyDeviceToHost, c->s_d2h));
+      done = k;
+    }
+  }
+  BB_RCUDA(r, cudaEventRecord(c->ev_cnt[0], c->s_d2h));
+  BB_RCUDA(r, cudaStreamWaitEvent(s, c->ev_cnt[0], 0));
+  mark(c, EV_D2H, s);
+  rc = collect_device_error(c, s);  // synchronises everything
+  if (rc) return rfail(r, rc, bb_last_error(c));
+  *out->n_changes = done;
+  *n_received = voff;
   return BB_OK;
 }
 

@@ -15,7 +15,7 @@ from . import capi, codec
 class Engine:
     def __init__(self, capacity: int, *, local_peer: int = 0, n_fields: int = codec.MAX_FIELDS,
                  device: int = 0, post_getdata: bool = False, ordered_changes: bool = False, radix_sort: bool = False,
-                 full_sort: bool = False, hot_keys: bool = False, rank_object: int = 0, rank_true: int = 0,
+                 full_sort: bool = False, hot_keys: bool = False, compact_changes: bool = False, rank_object: int = 0, rank_true: int = 0,
                  rank_false: int = 0, rank_nan: int = 0):
         self.lib = capi.load()
         self.cfg = capi.make_config(
@@ -24,7 +24,8 @@ class Engine:
             | (codec.CFG_ORDERED_CHANGES if ordered_changes else 0)
             | (codec.CFG_RADIX_SORT if radix_sort else 0)
             | (codec.CFG_FULL_SORT if full_sort else 0)
-            | (codec.CFG_HOT_KEYS if hot_keys else 0), rank_object=rank_object,
+            | (codec.CFG_HOT_KEYS if hot_keys else 0)
+            | (codec.CFG_COMPACT_CHANGES if compact_changes else 0), rank_object=rank_object,
             rank_true=rank_true, rank_false=rank_false, rank_nan=rank_nan)
         h = C.c_void_p()
         rc = self.lib.bb_create(C.byref(self.cfg), C.byref(h))
@@ -78,7 +79,8 @@ class Engine:
         out = out or capi.ChangeBuffers(batch.n)
         bs, cs = capi.batch_struct(batch), out.struct()
         self._check(self.lib.bb_merge_batch(self._h, C.byref(bs), C.byref(cs)))
-        return out.result(batch.n)
+        self.last_emitted = int(out.n_changes[0])  # entries that crossed the link (fewer with compact_changes)
+        return out.result(batch.n, batch)
 
     def merge_raw(self, bs: capi.BBBatch, cs: capi.BBChanges):
         """bb_merge_batch on prebuilt structs (pinned buffers, no numpy copies)."""

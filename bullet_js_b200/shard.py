@@ -116,7 +116,7 @@ class Router:
         self.lib = capi.load()
         self.world, self.rank = world, rank
         idbuf = C.create_string_buffer(capi.NCCL_ID_BYTES)
-        if rank == 0:
+        if rank == 0 and world > 1:  # a one-rank router needs no communicator
             rc = self.lib.bb_router_unique_id(idbuf)
             if rc:
                 raise capi.BulletB200Error(rc, (self.lib.bb_router_last_error(None) or b"").decode())
@@ -154,6 +154,18 @@ class Router:
         engine.merge_dev(rb, cs, stream)
         self._check(self.lib.bb_router_release(self._h, slot, C.c_void_p(stream)))
         return int(rb.n)
+
+    def merge_batch(self, engine, bs: capi.BBBatch, cs: capi.BBChanges, chunks: int = 0):
+        """Collective host entry (bb_router_merge_batch): this rank's HOST batch in, verdicts + change entries of what
+        this shard received out (host buffers of `cs`).  Returns (n_received, recv_counts[chunks, world])."""
+        import ctypes as C
+
+        k = chunks or 4
+        counts = np.zeros((k, self.world), np.uint64)
+        n = C.c_uint64(0)
+        self._check(self.lib.bb_router_merge_batch(self._h, engine._h, C.byref(bs), C.byref(cs), k, C.byref(n),
+                                                   counts.ctypes.data))
+        return int(n.value), counts
 
     # ---- sharded queries (src/bullet-query.js:186-210, 221-261 over a table that spans the ranks)
     def query_reserve(self, max_total_hits: int):

@@ -162,6 +162,16 @@ typedef struct bb_config {
  * a whole CTA evaluates 256 of the path's updates per round against the row and retires everything up to the first
  * state-changing one, indexed collections included.  The round-1 opt-in flag is accepted and ignored. */
 #define BB_CFG_HOT_KEYS 64u
+/* Compact change set.  Most accepted updates win outright ("incoming dominates", "identical clocks: incoming"): what the
+ * reference stores (decision.value, decision.vectorClock) is then the incoming update itself, bit for bit, and shipping
+ * it back to the caller that just sent it wastes the return link.  With this flag such an update gets NO entry: its
+ * verdict carries slot BB_SLOT_ECHO and its entry is by definition
+ *   idx = i, head = { in.head[i].hdr & ~BB_HDR_FLAVOUR_NET, in.head[i].clk_order, in.head[i].user },
+ *   clk = in.clk[i], val = in.val[i].
+ * Entries are emitted only where the stored state differs from the update: first writes (the incoming clock is
+ * discarded, crt:172-185), local puts (the clock is V, crt:358), concurrent merges (crt:266-278).  Decisions, table
+ * and index are identical to the default; n_changes counts emitted entries only. */
+#define BB_CFG_COMPACT_CHANGES 128u
 
 typedef struct bb_ctx bb_ctx;
 
@@ -186,6 +196,7 @@ typedef struct bb_batch {
  * sort by walking verdict[] and following the slots.  A batch is limited to
  * 2^29-2 updates. */
 #define BB_NO_SLOT 0x1FFFFFFFu
+#define BB_SLOT_ECHO 0x1FFFFFFEu /* BB_CFG_COMPACT_CHANGES: accepted, the entry is the update itself */
 #define BB_VERDICT_CODE(v) ((uint32_t)(v) >> 29)
 #define BB_VERDICT_SLOT(v) ((uint32_t)(v) & BB_NO_SLOT)
 typedef struct bb_changes {
@@ -351,6 +362,19 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
+/* Host entry of the sharded path (the batched ingress of src/bullet-network-sync.js:551-569 for a table that spans the
+ * router's ranks).  Collective: every rank passes its own batch in HOST memory (pinned recommended) and the same
+ * `chunks` (1..8, 0 = 4).  Each rank's batch is cut into `chunks` pieces in arrival order; piece j of every rank is
+ * copied in, exchanged (fused pack + all-to-all over NVLink) and merged by the owning shards while piece j+1 is on its
+ * way in and piece j-1's results are on their way out.  A shard replays what it receives piece by piece, inside a
+ * piece in (source rank, arrival index) order - the same as one peer replaying rank 0's piece 0, rank 1's piece 0, ...,
+ * rank 0's piece 1, ...  Results stay sharded: `out` (host) receives verdict[] for the *n_received updates this shard
+ * received, in that replay order, and their change entries (idx = position in the replay order);
+ * recv_counts[j * world + q] (optional) = updates of rank q's piece j this shard received, which is what maps a
+ * verdict back to (source rank, arrival index).  ctx must not have BB_CFG_ORDERED_CHANGES; BB_CFG_COMPACT_CHANGES
+ * works as usual (BB_SLOT_ECHO refers to the received update).  Synchronous. */
+int bb_router_merge_batch(bb_router* r, bb_ctx* ctx, const bb_batch* in, bb_changes* out, uint32_t chunks,
+                          uint64_t* n_received, uint64_t* recv_counts);
 /* Sharded queries (src/bullet-query.js:186-210, 221-261 over a table that spans the router's ranks).  Collective:
  * every rank calls with the same field and predicate and its own shard's ctx.  Each rank scans its shard
  * (k_index_scan), the counts travel through the peer-mapped control blocks, and one kernel per rank stores its u32

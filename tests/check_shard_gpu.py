@@ -67,6 +67,55 @@ def check_queries(rank, world, local, kb, table, ids, rows_local, router, stream
     return ok
 
 
+def check_host_entry(rank, world, local, kb, table, ids, rows_local, router, batches):
+    """bb_router_merge_batch: host buffers in, this shard's verdicts + change entries out, pieces pipelined; a ctx with
+    BB_CFG_COMPACT_CHANGES so that the echoed entries are rebuilt from what the shard RECEIVED.  Expectation: one oracle
+    replaying rank 0's piece 0, rank 1's piece 0, ..., rank 0's piece 1, ... (include/bullet_b200.h)."""
+    CH = 3
+    eng = Engine(shard.shard_capacity(world, kb, N_REC) + 1, device=local, compact_changes=True, **synth.synth_ranks(N_REC))
+    eng.table_load(rows_local, table.rows[ids])
+    ref = TypedOracle(capi.make_config(N_REC, **synth.synth_ranks(N_REC)))
+    ref.load(np.arange(N_REC), table.rows)
+    cap = N_UPD * world
+    ok = True
+    for rnd in range(2):
+        mine = batches[rnd][rank]
+        out = capi.ChangeBuffers(cap)
+        m, counts = router.merge_batch(eng, capi.batch_struct(mine), out.struct(), CH)
+        chunk = -(-N_UPD // CH)
+        recv, want_dec, want_entries = [], [], []
+        for j in range(CH):
+            for src in range(world):
+                b = batches[rnd][src].slice(j * chunk, min((j + 1) * chunk, N_UPD))
+                ch = ref.merge(b)
+                sel = np.nonzero(shard.owner_of(b.path_id, world, kb) == rank)[0]
+                good_count = int(counts[j, src]) == sel.size
+                ok = ok and good_count
+                recv.append(codec.Batch(shard.local_row(b.path_id[sel], world, kb), b.head[sel], b.clk[sel], b.val[sel]))
+                want_dec.append(ch.decision[sel])
+                pos = {int(i): t for t, i in enumerate(ch.idx.tolist())}
+                for i in sel.tolist():
+                    t = pos.get(i)
+                    if t is not None:
+                        want_entries.append((ch.head[t].tobytes(), ch.clk[t].tobytes(), ch.val[t].tobytes()))
+        rb = codec.Batch(*(np.concatenate([getattr(x, f) for x in recv]) for f in ("path_id", "head", "clk", "val")))
+        want_dec = np.concatenate(want_dec)
+        good = m == rb.n == len(want_dec)
+        if good:
+            got = out.result(m, rb)  # echoed entries rebuilt from the received updates
+            good = np.array_equal(got.decision, want_dec) and len(got.idx) == len(want_entries)
+            good = good and [(got.head[t].tobytes(), got.clk[t].tobytes(), got.val[t].tobytes()) for t in range(len(got.idx))] == want_entries
+            good = good and int(out.n_changes[0]) < len(want_entries)  # something was echoed
+        print(f"[rank {rank}] host entry round {rnd}: received {m} in {CH} pieces, {int(out.n_changes[0])} entries shipped of "
+              f"{len(want_entries)} accepted: {'OK' if good else 'MISMATCH'}", flush=True)
+        ok = ok and good
+    rows = eng.table_read(rows_local)
+    good = np.array_equal(rows, ref.table[ids])
+    print(f"[rank {rank}] shard table after the host-entry rounds: {'OK' if good else 'MISMATCH'}", flush=True)
+    eng.close()
+    return ok and good
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -147,6 +196,7 @@ def main():
     print(f"[rank {rank}] shard table after {ROUNDS} pipelined rounds: {'OK' if good else 'MISMATCH'}", flush=True)
     ok = ok and good
     ok = check_queries(rank, world, local, kb, table, ids, rows_local, router, stream) and ok
+    ok = check_host_entry(rank, world, local, kb, table, ids, rows_local, router, batches) and ok
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     router.close()

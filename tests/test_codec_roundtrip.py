@@ -74,3 +74,31 @@ def test_string_dictionary_is_utf16_ordered():
     by_id = [d.string(i) for i in range(len(d))]
     assert by_id == sorted(streamgen.STRINGS, key=lambda s: s.encode("utf-16-be", "surrogatepass"))
     assert math.isnan(codec.js_string_to_number("abc")) and codec.js_string_to_number(" 12 ") == 12.0
+
+
+def test_from_verdicts_rebuilds_echoed_entries():
+    """BB_CFG_COMPACT_CHANGES (include/bullet_b200.h): slot BB_SLOT_ECHO = "the entry is the update itself" - idx = i,
+    head = the update's header without the flavour bit, clk / val = the update's."""
+    import numpy as np
+
+    from bullet_js_b200 import codec
+
+    b = codec.Batch.empty(4)
+    b.head["hdr"] = np.array([0x10 | codec.HDR_FLAVOUR_NET, 0x21, 0x30 | codec.HDR_FLAVOUR_NET, 0x40], np.uint64)
+    b.head["clk_order"] = [7, 8, 9, 10]
+    b.head["user"] = [100, 101, 102, 103]
+    b.clk[:] = np.arange(32, dtype=np.uint32).reshape(4, 8)
+    b.val[:] = np.arange(16, dtype=np.uint64).reshape(4, 4)
+    verdict = np.array([4 << 29 | codec.SLOT_ECHO, 5 << 29 | codec.NO_SLOT, 6 << 29 | 0, 2 << 29 | codec.SLOT_ECHO], np.uint32)
+    e_head = np.zeros(1, codec.HEAD_DTYPE)
+    e_head["hdr"], e_head["clk_order"], e_head["user"] = 0x99, 5, 102
+    e_clk, e_val = np.full((1, 8), 3, np.uint32), np.full((1, 4), 4, np.uint64)
+    ch = codec.Changes.from_verdicts(verdict, np.array([2], np.uint32), e_head, e_clk, e_val, b)
+    assert ch.decision.tolist() == [4, 5, 6, 2] and ch.idx.tolist() == [0, 2, 3]
+    assert ch.head["hdr"].tolist() == [0x10, 0x99, 0x40] and ch.head["user"].tolist() == [100, 102, 103]
+    assert ch.head["clk_order"].tolist() == [7, 5, 10]
+    assert np.array_equal(ch.clk[0], b.clk[0]) and np.array_equal(ch.clk[1], e_clk[0]) and np.array_equal(ch.val[2], b.val[3])
+    import pytest
+
+    with pytest.raises(ValueError):
+        codec.Changes.from_verdicts(verdict, np.array([2], np.uint32), e_head, e_clk, e_val)

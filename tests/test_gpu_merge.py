@@ -345,3 +345,97 @@ def test_native_router_single_rank(p2p, monkeypatch):
     assert lib.bb_router_sent_bytes(h) == 0
     lib.bb_router_destroy(h)
     eng.close()
+
+
+@pytest.mark.parametrize("indexed", [False, True])
+def test_compact_change_set(indexed):
+    """BB_CFG_COMPACT_CHANGES: an accepted update whose stored (value, clock) is the update itself gets slot
+    BB_SLOT_ECHO and no entry; rebuilt from the caller's own input (codec.Changes.from_verdicts) the change set is the
+    oracle's, entry for entry - JS streams with every decision code, then big uniform + Zipf batches (hot-key kernel,
+    segments past their tile, chunked host call)."""
+    from bullet_js_b200.engine import Engine
+
+    ops, _ref = streamgen.generate(140, 4000, 37, index_fields=("age",) if indexed else ())
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    eng = Engine.for_schema(schema, 64, post_getdata=indexed, compact_changes=True)
+    orc = TypedOracle(eng.cfg)
+    if indexed:
+        eng.index_create(0)
+        orc.index_create(0)
+    got, want = eng.merge(batch), orc.merge(batch)
+    assert got.same_as(want)
+    assert 0 < eng.last_emitted < len(want.idx)  # something was echoed, something was not
+    assert_same_table_x(eng, orc, 64)
+    eng.close()
+
+    n_rec = 3000
+    rng = synth.rng_for(2, salt=33)
+    table = synth.make_table(n_rec, rng)
+    eng = Engine(n_rec, post_getdata=indexed, compact_changes=True, **synth.synth_ranks(n_rec))
+    orc = TypedOracle(eng.cfg)
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    if indexed:
+        eng.index_create(0, extra_capacity=1 << 20)
+        orc.index_create(0)
+    for keys in ("uniform", "zipf"):
+        b = synth.make_batch(table, 150_000, rng, keys=keys)
+        got, want = eng.merge(b), orc.merge(b)
+        assert got.same_as(want), keys
+        assert eng.last_emitted < len(want.idx)
+    assert_same_table_x(eng, orc, n_rec)
+    eng.close()
+
+
+def assert_same_table_x(eng, orc, n):
+    ids = np.arange(n, dtype=np.uint64)
+    got, want = eng.table_read(ids), orc.read(ids)
+    got["xcnt"] = 0  # device-private index bookkeeping
+    want["xcnt"] = 0
+    assert np.array_equal(got, want)
+
+
+def test_compact_needs_the_default_pipeline():
+    from bullet_js_b200.engine import Engine
+
+    with pytest.raises(capi.BulletB200Error):
+        Engine(16, compact_changes=True, ordered_changes=True)
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_router_host_entry_single_rank(compact):
+    """bb_router_merge_batch on a one-rank router: host buffers in, pieces pipelined through both receive slots,
+    verdicts + entries out in replay order (piece by piece) - the oracle merging the pieces one after the other."""
+    from bullet_js_b200 import shard
+    from bullet_js_b200.engine import Engine
+
+    n_rec, n, pieces = 3000, 200_000, 3
+    rng = synth.rng_for(2, salt=35)
+    table = synth.make_table(n_rec, rng)
+    eng = Engine(n_rec, compact_changes=compact, **synth.synth_ranks(n_rec))
+    orc = TypedOracle(eng.cfg)
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    router = shard.Router(1, 0, n, 0)
+    chunk = -(-n // pieces)
+    for keys in ("uniform", "zipf"):
+        b = synth.make_batch(table, n, rng, keys=keys)
+        out = capi.ChangeBuffers(n)
+        m, counts = router.merge_batch(eng, capi.batch_struct(b), out.struct(), pieces)
+        assert m == n and counts.ravel().tolist() == [chunk, chunk, n - 2 * chunk]
+        got = out.result(m, b)
+        want = [orc.merge(b.slice(j * chunk, min((j + 1) * chunk, n))) for j in range(pieces)]
+        assert np.array_equal(got.decision, np.concatenate([w.decision for w in want]))
+        assert np.array_equal(got.idx, np.concatenate([w.idx + j * chunk for j, w in enumerate(want)]))
+        for f in ("head", "clk", "val"):
+            assert np.array_equal(getattr(got, f), np.concatenate([getattr(w, f) for w in want])), f
+    assert_same_table(eng, orc, n_rec)
+    # too small a change buffer is reported
+    small = capi.ChangeBuffers(1000)
+    with pytest.raises(capi.BulletB200Error):
+        router.merge_batch(eng, capi.batch_struct(b), small.struct(), pieces)
+    router.close()
+    eng.close()
