@@ -66,6 +66,10 @@ def parse():
     ap.add_argument("--no-query", action="store_true")
     ap.add_argument("--no-zipf", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the step-0 comparison with the oracle (debugging only)")
+    ap.add_argument("--config", default="merge", choices=["merge", "mesh"],
+                    help="merge: configs 2 / 3 / 4 (the default line); mesh: BASELINE config 5, mesh-topology sync replay (bench_mesh.py)")
+    ap.add_argument("--mesh-ops", type=int, default=10_000_000, help="--config mesh: log entries per peer")
+    ap.add_argument("--mesh-batch", type=int, default=1_000_000, help="--config mesh: updates per replayed batch")
     ap.add_argument("--front-end", default="group", choices=["group", "full", "radix"],
                     help="how a batch is grouped by path: the library default, BB_CFG_FULL_SORT or BB_CFG_RADIX_SORT")
     a = ap.parse_args()
@@ -577,6 +581,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+
+    if args.config == "mesh":
+        import bench_mesh
+
+        args.records = CFG2["records"] if args.records in (CFG2["records"], CFG3["records"]) else args.records
+        bench_mesh.run(args, rank, world, local_rank, sys.modules[__name__])
         return
 
     import torch

@@ -583,6 +583,12 @@ constexpr int HOT_CTAS = 148;
 // number: conflict-free both for the 8-lanes-per-row copies and for the one-thread-per-row unpack
 // (LDS.128 / STS.128 by 32 rows at once), and 2 KB smaller than a padded stride.
 __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ (r & 7)); }
+// Rows staged by the copy engine (cp.async.bulk, one 128-byte copy per row) land as they are in HBM - no swizzle
+// possible - so they sit at a 144-byte stride instead: eight consecutive rows' chunk c fall into eight different
+// 16-byte bank groups, conflict-free for the one-thread-per-row unpack as well.
+constexpr int ROW_QT = ROW_Q + 1;
+template <bool TMA>
+__device__ __forceinline__ int row_at(int r, int c) { return TMA ? r * ROW_QT + c : row_slot(r, c); }
 
 // One CTA == one tile of MT sorted positions, in three phases with all global traffic
 // asynchronous and coalesced and all resolver work out of shared memory:
@@ -597,10 +603,11 @@ __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false>
+template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false, bool TMA = false>
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
-  __shared__ __align__(16) uint4 s_row[MT * ROW_Q];
+  __shared__ __align__(16) uint4 s_row[MT * (TMA ? ROW_QT : ROW_Q)];
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_idx[MT], s_res[MT];
   __shared__ uint32_t s_hmask[MT_WARPS], s_wsum[MT_WARPS];
   __shared__ uint32_t s_tile, s_over, s_ex, s_nextk;
@@ -643,13 +650,29 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       cp_async16(&s_upd[(wbase + e) * UPD_Q + 3 + half], a.val + 2 * (uint64_t)eidx + half);
     }
   }
+  if (TMA) {  // rows: one 128-byte bulk copy each, issued by the segment's own thread, all completing on one mbarrier
+    if (tid == 0) {
+      mbar_init(&s_bar, MT);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (is_head) {
+      mbar_arrive_expect_tx(&s_bar, ROW_Q * 16);
+      bulk_g2s(&s_row[row_at<true>(tid, 0)], a.table + (uint64_t)key * ROW_Q, ROW_Q * 16, &s_bar);
+    } else {
+      mbar_arrive(&s_bar);
+    }
+    cp_async_wait_all();
+    mbar_wait(&s_bar, 0);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
-    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
-    if ((hmask >> e) & 1u) cp_async16(&s_row[row_slot(wbase + e, chunk)], a.table + (uint64_t)ekey * ROW_Q + chunk);
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+      const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+      if ((hmask >> e) & 1u) cp_async16(&s_row[row_slot(wbase + e, chunk)], a.table + (uint64_t)ekey * ROW_Q + chunk);
+    }
+    cp_async_wait_all();
   }
-  cp_async_wait_all();
   __syncthreads();
 
   // ---- resolve: thread == segment head
@@ -690,7 +713,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
     {
       uint4 q[ROW_Q];
 #pragma unroll
-      for (int c = 0; c < ROW_Q; ++c) q[c] = s_row[row_slot(tid, c)];
+      for (int c = 0; c < ROW_Q; ++c) q[c] = s_row[row_at<TMA>(tid, c)];
       unpack_row(q, r);
     }
     for (int p = tid; p < end; ++p) {
@@ -750,7 +773,12 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       uint4 q[ROW_Q];
       pack_row(q, r);
 #pragma unroll
-      for (int c = 0; c < ROW_Q; ++c) s_row[row_slot(tid, c)] = q[c];
+      for (int c = 0; c < ROW_Q; ++c) s_row[row_at<TMA>(tid, c)] = q[c];
+    }
+    if (TMA) {  // the row goes home with one bulk store, issued by the thread that wrote it (a handed-over row is untouched)
+      fence_proxy_async_smem();
+      bulk_s2g(a.table + (uint64_t)key * ROW_Q, &s_row[row_at<true>(tid, 0)], ROW_Q * 16);
+      bulk_commit();
     }
     if (INDEXED) {
 #pragma unroll
@@ -783,11 +811,13 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   }
   const uint32_t over_cnt = s_over;
   // rows first: nothing below them depends on where the tile's entries land
+  if (!TMA) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int e = j * 4 + (lane >> 3), chunk = lane & 7;
-    const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
-    if ((hmask >> e) & 1u) a.table[(uint64_t)ekey * ROW_Q + chunk] = s_row[row_slot(wbase + e, chunk)];
+    for (int j = 0; j < 8; ++j) {
+      const int e = j * 4 + (lane >> 3), chunk = lane & 7;
+      const uint32_t ekey = __shfl_sync(0xffffffffu, key, e);
+      if ((hmask >> e) & 1u) a.table[(uint64_t)ekey * ROW_Q + chunk] = s_row[row_slot(wbase + e, chunk)];
+    }
   }
   if (ORDERED) {  // change set in path-major order: chain the tile totals (decoupled look-back)
     if (w == 0) {
@@ -849,23 +879,125 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
     }
   }
   if (overflow) atomicOr(a.err, 2u);
+  if (TMA) bulk_wait_read_all();  // the bulk stores have read their rows: shared memory may go
 }
 
 // ---------------------------------------------------------------- K2h: hot keys
 // A path that takes thousands of a batch's updates (Zipf) is a serial chain for the thread that owns it: ~1 us per
 // update.  But a network-flavour update is decided by (its clock, M, S) alone - V and the alias flag, the only things
 // a REJECTED update changes, do not enter - and M, S change only when an update is accepted.  So one CTA per hot
-// segment (handed over by k_merge_stage after HOT_SERIAL updates past its tile) evaluates the next 256 updates in
-// parallel against the row in shared memory; everything in front of the first state-changing update (the first
-// accepted one, or the first local put, whose clock IS V) is final, that update's own result is exact, and its
-// thread publishes the row for the next round.  The post-write index hook (query:139-176) runs for every retired
-// update, in order, on the publishing thread.  Runs after k_merge_stage; exits at once when nothing is hot.
+// segment (handed over by k_merge_stage) stages a WINDOW of the segment's next 256 updates in shared memory and
+// evaluates all of them in parallel against the row; everything in front of the first state-changing update (the
+// first accepted one, or the first local put, whose clock IS V) is final, that update's own result is exact, its
+// thread publishes the row - and the REST OF THE WINDOW is evaluated again against the new row, straight from shared
+// memory: a window costs one trip to global memory plus one short pass per state change in it, not one trip per
+// state change.
+// The post-write index hook (query:139-176) of a retired run is the op sequence R(k0) A(a_j) R(k0) A(a_j+1) ... on the
+// node's entry set (k0 = key of the unchanged stored value, a_j = key of update j's value), whose net effect is: k0
+// removed, every a_j != k0 present, and k0 present again only if the run's last rejected update carried it.  The
+// retiring thread applies exactly that, and a per-segment cache of keys KNOWN PRESENT (shared memory, probed by all
+// threads in parallel) lets it skip every update whose key is already in the index - on a hot node nearly all of them.
+constexpr int HOT_CACHE = 256;            // slots per field of the known-present cache
+constexpr uint64_t HC_TOMB = 0xFFFFFFFFFFFFFFFEull;
+
+__device__ __forceinline__ uint32_t hc_hash(uint64_t k) { return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ull) >> 56); }
+
+__device__ __forceinline__ bool hc_has(const uint64_t* c, uint64_t k) {
+  uint32_t i = hc_hash(k);
+  for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
+    const uint64_t v = c[i];
+    if (v == k) return true;
+    if (v == BB_KEY_NONE) return false;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void hc_put(uint64_t* c, uint32_t& used, uint64_t k) {
+  if (used >= (uint32_t)(HOT_CACHE * 3 / 4)) return;  // full: the key simply is not cached
+  uint32_t i = hc_hash(k);
+  for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
+    const uint64_t v = c[i];
+    if (v == k) return;
+    if (v == BB_KEY_NONE || v == HC_TOMB) {
+      if (v == BB_KEY_NONE) ++used;
+      c[i] = k;
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ void hc_erase(uint64_t* c, uint64_t k) {
+  uint32_t i = hc_hash(k);
+  for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
+    const uint64_t v = c[i];
+    if (v == k) {
+      c[i] = HC_TOMB;
+      return;
+    }
+    if (v == BB_KEY_NONE) return;
+  }
+}
+
+// the key the hook removes / adds for field f of value v (query:153-167): BB_KEY_NONE when there is nothing to do
+__device__ __forceinline__ uint64_t hook_key(const Value& v, int f) {
+  if (kind_of(v.meta) != BB_KIND_OBJ) return BB_KEY_NONE;
+  const uint32_t t = tag_of(v.meta, f);
+  if (t == BB_TAG_ABSENT || prim_falsy(t, v.val[f])) return BB_KEY_NONE;
+  return canon_key(t, v.val[f]);
+}
+
+// one node's entry set of field f, as the retiring thread of k_merge_hot sees it
+struct HotIndex {
+  const IndexArgs& ix;
+  uint32_t node;
+  uint64_t* prim;     // [F] shared: the node's entries in the dense columns
+  uint64_t* cache;    // [F][HOT_CACHE] shared: keys known present
+  uint32_t* used;     // [F] shared
+  uint64_t* absent;   // [F] shared: one key known absent (the last one removed)
+  uint32_t& xcnt;
+  uint32_t* err;
+
+  __device__ __forceinline__ void remove(int f, uint64_t k) {
+    if (k == BB_KEY_NONE || absent[f] == k) return;
+    if (prim[f] == k) {
+      prim[f] = BB_KEY_NONE;
+    } else if (xcnt_get(xcnt, f)) {
+      const int64_t slot = x_find(ix, f, node, k);
+      if (slot >= 0) {
+        x_remove_at(ix, f, slot);
+        if (xcnt_get(xcnt, f) != 0xFFu) xcnt -= 1u << (8 * f);
+      }
+    }
+    hc_erase(cache + f * HOT_CACHE, k);
+    absent[f] = k;
+  }
+  __device__ __forceinline__ void add(int f, uint64_t k) {
+    if (k == BB_KEY_NONE) return;
+    uint64_t* c = cache + f * HOT_CACHE;
+    if (hc_has(c, k)) return;
+    if (absent[f] == k) absent[f] = BB_KEY_NONE;
+    if (prim[f] != k && !(xcnt_get(xcnt, f) && x_find(ix, f, node, k) >= 0)) {
+      if (prim[f] == BB_KEY_NONE) {
+        prim[f] = k;
+      } else if (x_insert(ix, f, node, k)) {
+        if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
+      } else {
+        atomicOr(err, ERR_XFULL);
+        return;
+      }
+    }
+    hc_put(c, used[f], k);
+  }
+};
+
 template <bool INDEXED, bool COMPACT = false>
 __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_row[ROW_Q];
   __shared__ __align__(16) uint4 s_win[HOT_T * UPD_Q];  // payload window
-  __shared__ uint64_t s_prim[F];
-  __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_loc[HOT_WARPS];
+  __shared__ uint64_t s_prim[F], s_k0[F], s_absent[F];
+  __shared__ uint64_t s_cache[INDEXED ? F * HOT_CACHE : 1];
+  __shared__ uint32_t s_used[F];
+  __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_loc[HOT_WARPS], s_need[HOT_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
@@ -878,19 +1010,22 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
     uint64_t gp0 = (uint64_t)he.y | ((uint64_t)he.z << 32);
     __syncthreads();
     if (tid < ROW_Q) s_row[tid] = a.table[(uint64_t)hkey * ROW_Q + tid];
-    if (INDEXED && tid < F) s_prim[tid] = ((a.ix.mask >> tid) & 1u) ? a.ix.pcol[tid][hkey] : BB_KEY_NONE;
-    __syncthreads();
-    // the window is a ring: position p lives in slot p % HOT_T, so a round only fetches the payloads that ENTER the
-    // window (as many as the previous round retired); the positions behind it are pulled into L2 a window ahead
-    uint64_t staged_end = gp0;
-    while (true) {
+    if (INDEXED) {
+      if (tid < F) {
+        s_prim[tid] = ((a.ix.mask >> tid) & 1u) ? a.ix.pcol[tid][hkey] : BB_KEY_NONE;
+        s_absent[tid] = BB_KEY_NONE;
+        s_used[tid] = 0;
+      }
+      for (int i = tid; i < F * HOT_CACHE; i += HOT_T) s_cache[i] = BB_KEY_NONE;
+    }
+    while (true) {  // one window of the segment per turn
       const uint64_t gp = gp0 + tid;
       const uint64_t it = gp < a.n ? a.sorted[gp] : ~0ull;
       const bool mine = gp < a.n && (uint32_t)(it >> 32) == hkey;  // the segment's positions are a prefix of the window
       const uint32_t ui = (uint32_t)it;
-      uint4* slot = &s_win[(gp & (HOT_T - 1)) * UPD_Q];
-      if (gp >= staged_end) {
-        const uint64_t gq = gp + HOT_T;
+      uint4* slot = &s_win[tid * UPD_Q];
+      {
+        const uint64_t gq = gp + HOT_T;  // the next window's payloads: into L2 while this one is replayed
         if (gq < a.n) {
           const uint64_t iq = a.sorted[gq];
           if ((uint32_t)(iq >> 32) == hkey) {
@@ -901,7 +1036,8 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
           }
         }
       }
-      if (mine && gp >= staged_end) {
+      __syncthreads();  // the previous window's slots (and, first turn, the row) are no longer / now in use
+      if (mine) {
         cp_async16(slot, a.head + ui);
         cp_async16(slot + 1, a.clk + 2 * (uint64_t)ui);
         cp_async16(slot + 2, a.clk + 2 * (uint64_t)ui + 1);
@@ -909,93 +1045,143 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         cp_async16(slot + 4, a.val + 2 * (uint64_t)ui + 1);
       }
       cp_async_wait_all();
-      uint32_t code = 0;
-      bool net = true;
+      const uint32_t bm = __ballot_sync(0xffffffffu, mine);
+      if (lane == 0) s_cnt[w] = __popc(bm);
+      __syncthreads();
+      int nseg = 0;
+#pragma unroll
+      for (int ww = 0; ww < HOT_WARPS; ++ww) nseg += (int)s_cnt[ww];
+      if (nseg == 0) break;
       uint4 h = make_uint4(0, 0, 0, 0);
-      RowState r;
-      Clock oc;
-      Value ov;
+      Clock c;
+      Value x;
+      bool net = true;
       if (mine) {
         h = slot[0];
-        Clock c;
-        Value x;
         net = unpack_update(h, slot[1], slot[2], slot[3], slot[4], c, x);
-        unpack_row(s_row, r);
-        code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
       }
-      const bool stop = mine && (BB_DEC_ACCEPTED(code) || !net);
-      const uint32_t bm = __ballot_sync(0xffffffffu, mine), bs = __ballot_sync(0xffffffffu, stop),
-                     bl = __ballot_sync(0xffffffffu, mine && !net);
-      if (lane == 0) {
-        s_cnt[w] = __popc(bm);
-        s_stop[w] = bs;
-        s_loc[w] = bl;
-      }
-      __syncthreads();  // also: every thread has unpacked the row and its window slot is in shared memory
-      int nseg = 0, first = HOT_T;
-      bool f_local = false;
+      uint64_t akey[F];  // what the hook adds for this update
+      if (INDEXED) {
 #pragma unroll
-      for (int ww = HOT_WARPS - 1; ww >= 0; --ww) {
-        nseg += (int)s_cnt[ww];
-        if (s_stop[ww]) {
-          const int b = __ffs(s_stop[ww]) - 1;
-          first = ww * 32 + b;
-          f_local = (s_loc[ww] >> b) & 1u;
+        for (int f = 0; f < F; ++f) akey[f] = (mine && ((a.ix.mask >> f) & 1u)) ? hook_key(x, f) : BB_KEY_NONE;
+      }
+      int base = 0;  // window positions [0, base) are retired
+      while (base < nseg) {
+        const bool live = mine && tid >= base;
+        uint32_t code = 0;
+        RowState r;
+        Clock oc;
+        Value ov;
+        if (live) {
+          unpack_row(s_row, r);
+          code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
         }
-      }
-      if (nseg == 0) break;
-      // retired this round: up to and including the first stop - unless that is a local put further in, whose
-      // clock depends on the V the updates in front of it leave: it waits for the next round's position 0
-      const int retired = first >= nseg ? nseg : ((f_local && first > 0) ? first : first + 1);
-      if (tid < retired) {
-        if (tid == retired - 1) {  // its copy is the exact state after the retired updates
-          if (INDEXED) {
-            // the retired updates in front of this one were rejected network updates, after which the node reads
-            // as the round's initial S
-            RowState r0;
-            unpack_row(s_row, r0);
-            if (kind_of(r0.s.meta) == BB_KIND_NONE || falsy_primitive(r0.s)) materialise_empty_object(r0.s);
-            uint64_t prim[F];
+        if (INDEXED && tid < F) {  // k0: what a rejected update's hook removes - the node as it reads now
+          RowState r0;
+          unpack_row(s_row, r0);
+          if (kind_of(r0.s.meta) == BB_KIND_NONE || falsy_primitive(r0.s)) materialise_empty_object(r0.s);
+          s_k0[tid] = ((a.ix.mask >> tid) & 1u) ? hook_key(r0.s, tid) : BB_KEY_NONE;
+        }
+        const bool stop = live && (BB_DEC_ACCEPTED(code) || !net);
+        const uint32_t bs = __ballot_sync(0xffffffffu, stop), bl = __ballot_sync(0xffffffffu, live && !net);
+        if (lane == 0) {
+          s_stop[w] = bs;
+          s_loc[w] = bl;
+        }
+        __syncthreads();  // every live thread has unpacked the row
+        int first = HOT_T;
+        bool f_local = false;
 #pragma unroll
-            for (int f = 0; f < F; ++f) prim[f] = s_prim[f];
-            uint32_t xcnt = r0.xcnt;
-            for (int j = 0; j < retired; ++j) {
-              const uint4* sj = &s_win[((gp0 + j) & (HOT_T - 1)) * UPD_Q];
-              Clock cj;
-              Value xj;
-              unpack_update(sj[0], sj[1], sj[2], sj[3], sj[4], cj, xj);
-              index_hook(a.ix, hkey, j == retired - 1 ? r.s : r0.s, xj, prim, xcnt, a.err);
+        for (int ww = HOT_WARPS - 1; ww >= 0; --ww) {
+          if (s_stop[ww]) {
+            const int b = __ffs(s_stop[ww]) - 1;
+            first = ww * 32 + b;
+            f_local = (s_loc[ww] >> b) & 1u;
+          }
+        }
+        // retired this pass: up to and including the first stop - unless that is a local put further in, whose
+        // clock depends on the V the updates in front of it leave: it waits for the next pass, where it is first
+        const int end = first >= nseg ? nseg : ((f_local && first > base) ? first : first + 1);
+        const bool retiring = live && tid < end;
+        if (INDEXED) {  // which retired updates does the hook have anything to do for?
+          bool need = false;
+          if (retiring && tid < end - 1) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              const uint64_t k = akey[f];
+              if (k == BB_KEY_NONE) continue;
+              if (k == s_k0[f]) need = need || tid == end - 2;  // added, then removed again by the next update's hook
+              else need = need || !hc_has(s_cache + f * HOT_CACHE, k);
             }
-            r.xcnt = xcnt;
+          }
+          const uint32_t nb = __ballot_sync(0xffffffffu, need);
+          if (lane == 0) s_need[w] = nb;
+          __syncthreads();
+        }
+        if (retiring) {
+          if (tid == end - 1) {  // its copy is the exact state after the retired updates
+            if (INDEXED) {
+              uint32_t xcnt = r.xcnt;
+              HotIndex hx{a.ix, hkey, s_prim, s_cache, s_used, s_absent, xcnt, a.err};
+              if (end - 1 > base) {
 #pragma unroll
-            for (int f = 0; f < F; ++f) s_prim[f] = prim[f];
+                for (int f = 0; f < F; ++f)
+                  if ((a.ix.mask >> f) & 1u) hx.remove(f, s_k0[f]);
+                for (int ww = base >> 5; ww <= (end - 2) >> 5; ++ww) {
+                  uint32_t m = s_need[ww];
+                  while (m) {
+                    const int j = ww * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint4* sj = &s_win[j * UPD_Q];
+                    Clock cj;
+                    Value xj;
+                    unpack_update(sj[0], sj[1], sj[2], sj[3], sj[4], cj, xj);
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                      if (!((a.ix.mask >> f) & 1u)) continue;
+                      const uint64_t k = hook_key(xj, f);
+                      if (k == s_k0[f] && j != end - 2) continue;
+                      hx.add(f, k);
+                    }
+                  }
+                }
+              }
+#pragma unroll
+              for (int f = 0; f < F; ++f) {  // this update's own hook, against the node as it reads after it
+                if (!((a.ix.mask >> f) & 1u)) continue;
+                hx.remove(f, hook_key(r.s, f));
+                hx.add(f, akey[f]);
+              }
+              r.xcnt = xcnt;
+            }
+            pack_row(s_row, r);
           }
-          pack_row(s_row, r);
-        }
-        if (COMPACT && BB_DEC_ACCEPTED(code) && echoes_update(slot, ov, oc)) {
-          a.verdict[ui] = (code << 29) | SLOT_ECHO;
-        } else if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
-          const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
-          a.verdict[ui] = (code << 29) | (uint32_t)dest;
-          if (dest < a.cap) {
-            uint4 q[UPD_Q];
-            pack_change(q, h.w, ov, oc);
-            a.out_idx[dest] = a.idx_base + ui;
-            a.out_head[dest] = q[0];
-            a.out_clk[2 * dest] = q[1];
-            a.out_clk[2 * dest + 1] = q[2];
-            a.out_val[2 * dest] = q[3];
-            a.out_val[2 * dest + 1] = q[4];
+          if (COMPACT && BB_DEC_ACCEPTED(code) && echoes_update(slot, ov, oc)) {
+            a.verdict[ui] = (code << 29) | SLOT_ECHO;
+          } else if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
+            const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
+            a.verdict[ui] = (code << 29) | (uint32_t)dest;
+            if (dest < a.cap) {
+              uint4 q[UPD_Q];
+              pack_change(q, h.w, ov, oc);
+              a.out_idx[dest] = a.idx_base + ui;
+              a.out_head[dest] = q[0];
+              a.out_clk[2 * dest] = q[1];
+              a.out_clk[2 * dest + 1] = q[2];
+              a.out_val[2 * dest] = q[3];
+              a.out_val[2 * dest + 1] = q[4];
+            } else {
+              overflow = true;
+            }
           } else {
-            overflow = true;
+            a.verdict[ui] = (code << 29) | NO_SLOT;
           }
-        } else {
-          a.verdict[ui] = (code << 29) | NO_SLOT;
         }
+        base = end;
+        __syncthreads();  // the published row (and the index cache) are visible; s_stop / s_loc / s_need may be rewritten
       }
-      staged_end = gp0 + HOT_T;
-      gp0 += (uint64_t)retired;
-      __syncthreads();  // the published row is visible; retired slots and s_cnt / s_stop / s_loc may be rewritten
+      gp0 += (uint64_t)nseg;
+      if (nseg < HOT_T) break;  // the segment ended inside this window
     }
     __syncthreads();
     if (tid < ROW_Q) a.table[(uint64_t)hkey * ROW_Q + tid] = s_row[tid];

@@ -106,6 +106,7 @@ struct bb_ctx {
   } index[BB_MAX_FIELDS];
   uint32_t index_mask = 0;
   uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
+  bool rows_tma = false;  // A/B: rows of k_merge_stage staged and written back with cp.async.bulk
   unsigned long long* d_counters = nullptr;  // [2] dense / overflow matches of the running query
   unsigned long long* h_counters = nullptr;  // pinned [2]
   DevBuf<uint32_t> route_tiles;            // [tiles][world] of bb_route_pack_dev
@@ -386,6 +387,9 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     } else if (c->index_mask) {
       BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<true>, HOT_CTAS, HOT_T, 0, s, ma);
+    } else if (c->rows_tma) {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, false, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
     } else {
       BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
@@ -604,6 +608,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] != '0';
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
