@@ -77,18 +77,22 @@ class BulletNode:
 
 
 class _Collection:
-    def __init__(self, name: str, schema: codec.Schema, capacity: int, device: int):
+    def __init__(self, name: str, schema: codec.Schema, capacity: int, device: int, track_modified: bool = False):
         self.name, self.schema = name, schema
-        self.engine = Engine.for_schema(schema, capacity, device=device, post_getdata=True)
+        self.engine = Engine.for_schema(schema, capacity, device=device, post_getdata=True, track_modified=track_modified)
         self.indexed: set[int] = set()
+        self.epoch_ms: list[float] = [0.0]  # Date.now() of merge call k (meta.lastModified at call granularity); [0] unused
 
     def slot(self, field: str) -> int:
         return self.schema.fields.index(field)
 
 
 class Bullet:
-    def __init__(self, collections: dict[str, codec.Schema], capacity: int = 1 << 16, device: int = 0):
-        self._c = {name: _Collection(name, schema, capacity, device) for name, schema in collections.items()}
+    def __init__(self, collections: dict[str, codec.Schema], capacity: int = 1 << 16, device: int = 0,
+                 track_modified: bool = False, clock: Callable[[], float] | None = None):
+        self._c = {name: _Collection(name, schema, capacity, device, track_modified) for name, schema in collections.items()}
+        self.track_modified = track_modified
+        self._now = clock or (lambda: time.time() * 1000.0)  # Date.now()
         self.log: list[dict] = []          # src/bullet.js:206-215
         self.listeners: dict[str, list] = {}
         self.decisions: list[int] = []     # decision code of every setData, arrival order
@@ -133,6 +137,8 @@ class Bullet:
             run = updates[i:j]
             batch = codec.encode_updates(col.schema, run)
             ch = col.engine.merge(batch)
+            while len(col.epoch_ms) <= col.engine.epoch:  # lastModified of everything this call accepted (src/bullet.js:201)
+                col.epoch_ms.append(self._now())
             self.decisions.extend(ch.decision.tolist())
             for entry in codec.decode_changes(col.schema, batch, ch):   # arrival order
                 self._apply_effects(entry["path"], entry["value"], entry["vectorClock"])
@@ -178,12 +184,32 @@ class Bullet:
             meta.update(m)
         return store, meta
 
-    def collect_sync_entries(self, since: float = 0):
+    def collect_sync_entries(self, since: float = 0, filter_records: bool = False):
         """What a reference peer would be sent for a full sync request (src/bullet-network-sync.js:592-664),
-        in chunks of 50 (`:713-723`)."""
+        in chunks of 50 (`:713-723`).  With `track_modified` the rows are selected ON THE DEVICE (bb_sync_collect):
+        `since` (a Date.now() value) becomes the ordinal of the first merge call at or after it, only the selected
+        rows cross PCIe, and every entry carries the lastModified of the call that last wrote its path.
+        `filter_records`: also filter whole records by their own lastModified (the reference never does: it looks
+        meta up at the leaf path, src/bullet-network-sync.js:627-636)."""
         from . import persist
 
-        store, meta = self.export_reference_state()
+        if not self.track_modified:
+            store, meta = self.export_reference_state()
+            return persist.chunk_sync_data(persist.collect_full_sync_data(store, meta, since))
+        store, meta = {}, {}
+        for name, col in self._c.items():
+            since_epoch = 0
+            if since > 0:  # first call whose time is >= since; none: one past the last call
+                since_epoch = next((k for k in range(1, len(col.epoch_ms)) if col.epoch_ms[k] >= since), len(col.epoch_ms))
+            ids, rows, ep = col.engine.sync_collect(since_epoch, filter_records)
+            records, m = persist.export_collection(col.schema, name, ids, rows)
+            for pid, e in zip(ids.tolist(), ep.tolist()):
+                path = col.schema.paths.name(int(pid))
+                if path in m and e:
+                    m[path]["lastModified"] = col.epoch_ms[e]
+            if records:
+                store[name] = records
+            meta.update(m)
         return persist.chunk_sync_data(persist.collect_full_sync_data(store, meta, since))
 
     # ---- reads (src/bullet.js:115-129; materialising like the reference's _getData)

@@ -73,7 +73,7 @@ class BulletB200Error(RuntimeError):
 EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
-    "bb_merge_batch", "bb_merge_batch_dev", "bb_sync",
+    "bb_merge_batch", "bb_merge_batch_dev", "bb_sync", "bb_epoch", "bb_sync_collect",
     "bb_index_create", "bb_index_create_fields", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
@@ -120,6 +120,10 @@ def load():
     lib.bb_sync.argtypes = [vp, vp]
     lib.bb_sync.restype = i32
     u32 = C.c_uint32
+    lib.bb_epoch.argtypes = [vp]
+    lib.bb_epoch.restype = u64
+    lib.bb_sync_collect.argtypes = [vp, u64, u32, u64, vp, vp, vp, C.POINTER(u64)]
+    lib.bb_sync_collect.restype = i32
     lib.bb_index_create_fields.argtypes = [vp, u32, u64]
     lib.bb_index_create_fields.restype = i32
     lib.bb_index_create.argtypes = [vp, u32, u64]

@@ -32,6 +32,8 @@ CFG_RADIX_SORT = 4
 CFG_FULL_SORT = 8
 CFG_HOT_KEYS = 64
 CFG_COMPACT_CHANGES = 128
+CFG_TRACK_MODIFIED = 256
+COLLECT_FILTER_RECORDS = 1
 
 DEC_NO_CURRENT, DEC_IDENTICAL, DEC_TIE_INCOMING, DEC_TIE_CURRENT = 0, 1, 2, 3
 DEC_INCOMING, DEC_HISTORICAL, DEC_CONCURRENT = 4, 5, 6

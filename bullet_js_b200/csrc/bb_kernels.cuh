@@ -488,6 +488,8 @@ struct MergeArgs {
   uint64_t seq_base;
   uint32_t idx_base;       // added to the arrival indices this launch reports (chunked host calls)
   const uint64_t* chg_base;  // ORDERED: entries already in the change set when the launch began
+  uint32_t* epoch_col;     // BB_CFG_TRACK_MODIFIED: [capacity] ordinal of the merge call that last wrote the row, or null
+  uint32_t epoch;          // this call's ordinal
   uint32_t* err;           // sticky until bb_sync: bit1 change buffer too small, bit2 overflow set full
   const uint32_t* rej;     // bit0: THIS batch was rejected by the front end (path id out of range): touch nothing
   Params p;
@@ -587,7 +589,7 @@ __device__ __forceinline__ int row_slot(int r, int c) { return r * ROW_Q + (c ^ 
 // possible - so they sit at a 144-byte stride instead: eight consecutive rows' chunk c fall into eight different
 // 16-byte bank groups, conflict-free for the one-thread-per-row unpack as well.
 constexpr int ROW_QT = ROW_Q + 1;
-template <bool TMA>
+template <int TMA>
 __device__ __forceinline__ int row_at(int r, int c) { return TMA ? r * ROW_QT + c : row_slot(r, c); }
 
 // One CTA == one tile of MT sorted positions, in three phases with all global traffic
@@ -603,7 +605,7 @@ __device__ __forceinline__ int row_at(int r, int c) { return TMA ? r * ROW_QT + 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false, bool TMA = false>
+template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false, int TMA = 0>  // TMA: 1 = rows, 2 = rows + payloads by bulk copy
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * (TMA ? ROW_QT : ROW_Q)];
@@ -640,14 +642,16 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   if (tid == MT - 1) s_nextk = base + MT < a.n ? (uint32_t)(a.sorted[base + MT] >> 32) : ~0u;
 
   // ---- stage: lane pairs fetch whole 32-byte clocks / values, 8 lanes fetch one 128-byte row
-  if (valid) cp_async16(&s_upd[tid * UPD_Q], a.head + idx);
+  if (TMA < 2) {
+    if (valid) cp_async16(&s_upd[tid * UPD_Q], a.head + idx);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int e = j * 16 + (lane >> 1), half = lane & 1;
-    const uint32_t eidx = __shfl_sync(0xffffffffu, idx, e);
-    if (wbase + e < nvalid) {
-      cp_async16(&s_upd[(wbase + e) * UPD_Q + 1 + half], a.clk + 2 * (uint64_t)eidx + half);
-      cp_async16(&s_upd[(wbase + e) * UPD_Q + 3 + half], a.val + 2 * (uint64_t)eidx + half);
+    for (int j = 0; j < 2; ++j) {
+      const int e = j * 16 + (lane >> 1), half = lane & 1;
+      const uint32_t eidx = __shfl_sync(0xffffffffu, idx, e);
+      if (wbase + e < nvalid) {
+        cp_async16(&s_upd[(wbase + e) * UPD_Q + 1 + half], a.clk + 2 * (uint64_t)eidx + half);
+        cp_async16(&s_upd[(wbase + e) * UPD_Q + 3 + half], a.val + 2 * (uint64_t)eidx + half);
+      }
     }
   }
   if (TMA) {  // rows: one 128-byte bulk copy each, issued by the segment's own thread, all completing on one mbarrier
@@ -656,13 +660,16 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       mbar_fence_init();
     }
     __syncthreads();
-    if (is_head) {
-      mbar_arrive_expect_tx(&s_bar, ROW_Q * 16);
-      bulk_g2s(&s_row[row_at<true>(tid, 0)], a.table + (uint64_t)key * ROW_Q, ROW_Q * 16, &s_bar);
-    } else {
-      mbar_arrive(&s_bar);
+    const uint32_t tx = (is_head ? ROW_Q * 16u : 0u) + (TMA == 2 && valid ? UPD_Q * 16u : 0u);
+    if (tx) mbar_arrive_expect_tx(&s_bar, tx);
+    else mbar_arrive(&s_bar);
+    if (is_head) bulk_g2s(&s_row[row_at<1>(tid, 0)], a.table + (uint64_t)key * ROW_Q, ROW_Q * 16, &s_bar);
+    if (TMA == 2 && valid) {  // the update's three pieces: header 16 B, clock 32 B, values 32 B
+      bulk_g2s(&s_upd[tid * UPD_Q], a.head + idx, 16, &s_bar);
+      bulk_g2s(&s_upd[tid * UPD_Q + 1], a.clk + 2 * (uint64_t)idx, 32, &s_bar);
+      bulk_g2s(&s_upd[tid * UPD_Q + 3], a.val + 2 * (uint64_t)idx, 32, &s_bar);
     }
-    cp_async_wait_all();
+    if (TMA < 2) cp_async_wait_all();
     mbar_wait(&s_bar, 0);
   } else {
 #pragma unroll
@@ -751,6 +758,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
                                        a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
         const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
         if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
+        if (BB_DEC_ACCEPTED(code) && a.epoch_col) a.epoch_col[key] = a.epoch;  // meta[path].lastModified (src/bullet.js:201)
         bool echo = false;
         if (COMPACT && BB_DEC_ACCEPTED(code)) {
           uint4 u5[UPD_Q] = {h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1], a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1]};
@@ -777,7 +785,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
     }
     if (TMA) {  // the row goes home with one bulk store, issued by the thread that wrote it (a handed-over row is untouched)
       fence_proxy_async_smem();
-      bulk_s2g(a.table + (uint64_t)key * ROW_Q, &s_row[row_at<true>(tid, 0)], ROW_Q * 16);
+      bulk_s2g(a.table + (uint64_t)key * ROW_Q, &s_row[row_at<1>(tid, 0)], ROW_Q * 16);
       bulk_commit();
     }
     if (INDEXED) {
@@ -839,6 +847,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   bool overflow = false;
   const uint64_t dest = obase + rank;
   if (owned) a.verdict[idx] = (code << 29) | (acc ? (uint32_t)dest : echo ? SLOT_ECHO : NO_SLOT);
+  if ((acc || echo) && a.epoch_col) a.epoch_col[key] = a.epoch;  // meta[path].lastModified (src/bullet.js:201), per merge call
   if (acc) {
     if (dest < a.cap) {
       a.out_idx[dest] = a.idx_base + idx;
@@ -997,7 +1006,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ uint64_t s_prim[F], s_k0[F], s_absent[F];
   __shared__ uint64_t s_cache[INDEXED ? F * HOT_CACHE : 1];
   __shared__ uint32_t s_used[F];
-  __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_loc[HOT_WARPS], s_need[HOT_WARPS];
+  __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_need[HOT_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
@@ -1074,6 +1083,17 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         Value ov;
         if (live) {
           unpack_row(s_row, r);
+          if (!net && tid > base) {
+            // A local put's clock is V, and V is what the update in front of it left (crt:187-197 stores the merged
+            // clock on every call).  If this put turns out to be the pass's first stop, everything in front of it was
+            // a rejected network update, and a rejected update leaves nothing behind but V := its merged clock: the
+            // state this put meets is the row with the ONE update in front of it applied.
+            const uint4* sp = &s_win[(tid - 1) * UPD_Q];
+            Clock cp;
+            Value xp;
+            const bool netp = unpack_update(sp[0], sp[1], sp[2], sp[3], sp[4], cp, xp);
+            resolve_step(a.p, r, netp, cp, xp, a.seq_base + ui, ov, oc);
+          }
           code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
         }
         if (INDEXED && tid < F) {  // k0: what a rejected update's hook removes - the node as it reads now
@@ -1083,25 +1103,15 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
           s_k0[tid] = ((a.ix.mask >> tid) & 1u) ? hook_key(r0.s, tid) : BB_KEY_NONE;
         }
         const bool stop = live && (BB_DEC_ACCEPTED(code) || !net);
-        const uint32_t bs = __ballot_sync(0xffffffffu, stop), bl = __ballot_sync(0xffffffffu, live && !net);
-        if (lane == 0) {
-          s_stop[w] = bs;
-          s_loc[w] = bl;
-        }
+        const uint32_t bs = __ballot_sync(0xffffffffu, stop);
+        if (lane == 0) s_stop[w] = bs;
         __syncthreads();  // every live thread has unpacked the row
         int first = HOT_T;
-        bool f_local = false;
 #pragma unroll
-        for (int ww = HOT_WARPS - 1; ww >= 0; --ww) {
-          if (s_stop[ww]) {
-            const int b = __ffs(s_stop[ww]) - 1;
-            first = ww * 32 + b;
-            f_local = (s_loc[ww] >> b) & 1u;
-          }
-        }
-        // retired this pass: up to and including the first stop - unless that is a local put further in, whose
-        // clock depends on the V the updates in front of it leave: it waits for the next pass, where it is first
-        const int end = first >= nseg ? nseg : ((f_local && first > base) ? first : first + 1);
+        for (int ww = HOT_WARPS - 1; ww >= 0; --ww)
+          if (s_stop[ww]) first = ww * 32 + __ffs(s_stop[ww]) - 1;
+        // retired this pass: up to and including the first stop
+        const int end = first >= nseg ? nseg : first + 1;
         const bool retiring = live && tid < end;
         if (INDEXED) {  // which retired updates does the hook have anything to do for?
           bool need = false;
@@ -1156,6 +1166,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
             }
             pack_row(s_row, r);
           }
+          if (BB_DEC_ACCEPTED(code) && a.epoch_col) a.epoch_col[hkey] = a.epoch;
           if (COMPACT && BB_DEC_ACCEPTED(code) && echoes_update(slot, ov, oc)) {
             a.verdict[ui] = (code << 29) | SLOT_ECHO;
           } else if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
@@ -1178,7 +1189,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
           }
         }
         base = end;
-        __syncthreads();  // the published row (and the index cache) are visible; s_stop / s_loc / s_need may be rewritten
+        __syncthreads();  // the published row (and the index cache) are visible; s_stop / s_need may be rewritten
       }
       gp0 += (uint64_t)nseg;
       if (nseg < HOT_T) break;  // the segment ended inside this window
@@ -1228,6 +1239,55 @@ __global__ void __launch_bounds__(256) k_table_gather(uint4* __restrict__ table,
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) rows[i * 8 + q] = row[row_chunk(q)];
+}
+
+// ---------------------------------------------------------------- sync producer (src/bullet-network-sync.js:592-664)
+// _collectFullSyncData(since): every stored path whose meta.lastModified is not older than `since` (:602, :633: an entry
+// is skipped only if since > 0 AND it has a lastModified AND that is < since).  lastModified lives here as the ordinal
+// of the merge call that last wrote the row (0 = never written by a merge: loaded, i.e. "no lastModified").  A warp
+// looks at 32 rows (header chunk + epoch word), the selected ones are compacted with one atomic per warp, and each
+// selected row is copied out by 8 lanes as 128 contiguous bytes, in the public bb_row chunk order.
+__global__ void __launch_bounds__(256) k_sync_collect(const uint4* __restrict__ table, const uint32_t* __restrict__ epoch_col,
+                                                      uint64_t capacity, uint32_t since, uint32_t filter_records, uint64_t cap,
+                                                      uint64_t* __restrict__ out_id, uint4* __restrict__ out_rows,
+                                                      uint32_t* __restrict__ out_epoch, unsigned long long* __restrict__ n_out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+  bool take = false;
+  uint32_t ep = 0;
+  if (row < capacity) {
+    const uint32_t meta = reinterpret_cast<const uint32_t*>(table + row * ROW_Q + row_chunk(6))[2];
+    ep = epoch_col ? epoch_col[row] : 0u;
+    // the reference looks lastModified up at the LEAF path: a record written as a whole has leaves without meta, which
+    // `since` therefore never filters (:627-636) - unless the caller asks for the records' own lastModified to count
+    const uint32_t kind = kind_of(meta);
+    take = kind != BB_KIND_NONE && !((kind == BB_KIND_PRIM || filter_records) && since > 0 && ep != 0 && ep < since);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const uint64_t dest = base + __popc(m & ((1u << lane) - 1u));
+  if (take && dest < cap) {
+    out_id[dest] = row;
+    out_epoch[dest] = ep;
+  }
+  const uint64_t row0 = row - lane;
+  for (uint32_t rest = m; rest;) {  // four selected rows per pass, 8 lanes each
+    const int g = lane >> 3, c = lane & 7;
+    int l = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = rest ? __ffs(rest) - 1 : -1;
+      if (k == g) l = b;
+      if (rest) rest &= rest - 1;
+    }
+    if (l >= 0) {
+      const uint64_t d = base + __popc(m & ((1u << l) - 1u));
+      if (d < cap) out_rows[d * ROW_Q + c] = table[(row0 + l) * ROW_Q + row_chunk(c)];
+    }
+  }
 }
 
 }  // namespace bb

@@ -106,7 +106,9 @@ struct bb_ctx {
   } index[BB_MAX_FIELDS];
   uint32_t index_mask = 0;
   uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
-  bool rows_tma = false;  // A/B: rows of k_merge_stage staged and written back with cp.async.bulk
+  uint32_t* epoch_col = nullptr;  // BB_CFG_TRACK_MODIFIED: per row, the ordinal of the merge call that last wrote it
+  uint64_t epoch = 0;             // ordinal of the most recent merge call
+  int rows_tma = 1;       // rows of k_merge_stage staged and written back with cp.async.bulk (BB_MERGE_TMA=0: cp.async, for A/B)
   unsigned long long* d_counters = nullptr;  // [2] dense / overflow matches of the running query
   unsigned long long* h_counters = nullptr;  // pinned [2]
   DevBuf<uint32_t> route_tiles;            // [tiles][world] of bb_route_pack_dev
@@ -372,23 +374,30 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.seq_base = c->seq;
   ma.idx_base = idx_base;
   ma.chg_base = c->d_chg_base;
+  ma.epoch_col = c->epoch_col;
+  ma.epoch = (uint32_t)c->epoch;
   ma.err = c->d_err;
   ma.rej = call_rej ? call_rej : rej;
   fill_params(c, ma.p, ma.ix);
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
   if (grouped) {  // hot keys are handed to k_merge_hot, a CTA per segment (exits at once when there are none)
+    // rows staged and written back by the copy engine (cp.async.bulk + mbarrier); BB_MERGE_TMA=0 keeps the cp.async
+    // (LDGSTS) staging of the plain variant for A/B measurements
     const bool compact = (c->cfg.flags & BB_CFG_COMPACT_CHANGES) != 0;
     if (compact && c->index_mask) {
-      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true, true, 1>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, (k_merge_hot<true, true>), HOT_CTAS, HOT_T, 0, s, ma);
     } else if (compact) {
-      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, true, 1>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, (k_merge_hot<false, true>), HOT_CTAS, HOT_T, 0, s, ma);
     } else if (c->index_mask) {
-      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, true, true, false, 1>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<true>, HOT_CTAS, HOT_T, 0, s, ma);
+    } else if (c->rows_tma == 2) {
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, false, 2>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
     } else if (c->rows_tma) {
-      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, false, true>), z.merge_tiles, MT, 0, s, ma);
+      BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true, false, 1>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
     } else {
       BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, 0, s, ma);
@@ -606,10 +615,12 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_merge_stage<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] != '0';
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] - '0';  // 0: cp.async, 1: rows by bulk copy (default), 2: rows + payloads
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
@@ -642,6 +653,9 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
          cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming) == cudaSuccess;
   for (int r = 0; ok && r < EV_RING; ++r)
     for (int i = 0; ok && i < EV_COUNT; ++i) ok = cudaEventCreate(&c->ev[r][i]) == cudaSuccess;
+  if (ok && (cfg->flags & BB_CFG_TRACK_MODIFIED))
+    ok = cudaMalloc((void**)&c->epoch_col, cfg->capacity * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMemsetAsync(c->epoch_col, 0, cfg->capacity * sizeof(uint32_t), c->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
   if (!ok) {
     g_create_error = std::string("CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -672,6 +686,7 @@ int bb_destroy(bb_ctx* c) {
   }
   if (c->d_xused) cudaFree(c->d_xused);
   if (c->d_counters) cudaFree(c->d_counters);
+  if (c->epoch_col) cudaFree(c->epoch_col);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
   if (c->d_err) cudaFree(c->d_err);
@@ -707,6 +722,8 @@ int bb_table_clear(bb_ctx* c) {
   if (!c) return BB_ERR_ARG;
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   BB_CUDA(c, cudaMemsetAsync(c->table, 0, c->cfg.capacity * sizeof(bb_row), c->stream));
+  if (c->epoch_col) BB_CUDA(c, cudaMemsetAsync(c->epoch_col, 0, c->cfg.capacity * sizeof(uint32_t), c->stream));
+  c->epoch = 0;
   if (c->index_mask) {
     int rc = index_fill(c, c->index_mask, c->stream);
     if (rc) return rc;
@@ -747,6 +764,42 @@ int bb_table_read(bb_ctx* c, uint64_t n, const uint64_t* path_id, bb_row* rows_o
   return collect_device_error(c, s);
 }
 
+uint64_t bb_epoch(const bb_ctx* c) { return c ? c->epoch : 0; }
+
+// _collectFullSyncData(since) on the device: filter + compaction of the table rows (k_sync_collect), then only the
+// selected rows cross PCIe.
+int bb_sync_collect(bb_ctx* c, uint64_t since_epoch, uint32_t flags, uint64_t cap, uint64_t* path_id_out, bb_row* rows_out,
+                    uint32_t* epoch_out, uint64_t* n_out) {
+  if (!c || !n_out || (cap && (!path_id_out || !rows_out || !epoch_out))) return fail(c, BB_ERR_ARG, "null argument");
+  if (since_epoch && !c->epoch_col)
+    return fail(c, BB_ERR_STATE, "a `since` filter needs a ctx created with BB_CFG_TRACK_MODIFIED");
+  BB_CUDA(c, cudaSetDevice(c->cfg.device));
+  cudaStream_t s = c->stream;
+  const uint64_t m = cap ? cap : 1;
+  BB_CUDA(c, c->io_path.ensure(m));
+  BB_CUDA(c, c->io_rows.ensure(m * 8));
+  BB_CUDA(c, c->io_verdict.ensure(m));
+  begin_call(c);
+  mark(c, EV_Q0, s);
+  BB_CUDA(c, cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long), s));
+  BB_LAUNCH(c, bb::k_sync_collect, div_up(c->cfg.capacity, 256), 256, s, c->table, c->epoch_col, c->cfg.capacity,
+            (uint32_t)std::min<uint64_t>(since_epoch, 0xFFFFFFFFull), flags & BB_COLLECT_FILTER_RECORDS, cap, c->io_path.p, c->io_rows.p, c->io_verdict.p, c->d_counters);
+  mark(c, EV_Q1, s);
+  BB_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  int rc = collect_device_error(c, s);  // synchronises
+  if (rc) return rc;
+  const uint64_t k = c->h_counters[0];
+  *n_out = k;
+  if (k > cap) return fail(c, BB_ERR_CAPACITY, "more rows selected than the output buffers hold (n_out = how many)");
+  if (k) {
+    BB_CUDA(c, cudaMemcpyAsync(path_id_out, c->io_path.p, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaMemcpyAsync(rows_out, c->io_rows.p, k * sizeof(bb_row), cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaMemcpyAsync(epoch_out, c->io_verdict.p, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    BB_CUDA(c, cudaStreamSynchronize(s));
+  }
+  return BB_OK;
+}
+
 int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* stream) {
   if (!c || !in || !out) return fail(c, BB_ERR_ARG, "null argument");
   if (in->n && (!in->path_id || !in->head || !in->clk || !in->val || !out->verdict || !out->idx ||
@@ -755,6 +808,7 @@ int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* str
   if (!out->n_changes) return fail(c, BB_ERR_ARG, "null n_changes");
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   begin_call(c);
+  ++c->epoch;
   return merge_dev(c, in, out, stream ? (cudaStream_t)stream : c->stream);
 }
 
@@ -785,6 +839,7 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
   BB_CUDA(c, cudaSetDevice(c->cfg.device));
   cudaStream_t s = c->stream;
   begin_call(c);
+  ++c->epoch;
   mark(c, EV_H2D0, s);
   if (n == 0) {
     *out->n_changes = 0;
@@ -1590,6 +1645,7 @@ int bb_router_merge_batch(bb_router* r, bb_ctx* c, const bb_batch* in, bb_change
   const uint32_t W = r->world, me = r->rank;
   cudaStream_t s = c->stream;
   begin_call(c);
+  ++c->epoch;
   mark(c, EV_H2D0, s);
   {
     int rc = reserve_io(c, std::max<uint64_t>(std::max<uint64_t>(n, out->cap), 1));

@@ -15,7 +15,7 @@ from . import capi, codec
 class Engine:
     def __init__(self, capacity: int, *, local_peer: int = 0, n_fields: int = codec.MAX_FIELDS,
                  device: int = 0, post_getdata: bool = False, ordered_changes: bool = False, radix_sort: bool = False,
-                 full_sort: bool = False, hot_keys: bool = False, compact_changes: bool = False, rank_object: int = 0, rank_true: int = 0,
+                 full_sort: bool = False, hot_keys: bool = False, compact_changes: bool = False, track_modified: bool = False, rank_object: int = 0, rank_true: int = 0,
                  rank_false: int = 0, rank_nan: int = 0):
         self.lib = capi.load()
         self.cfg = capi.make_config(
@@ -25,7 +25,8 @@ class Engine:
             | (codec.CFG_RADIX_SORT if radix_sort else 0)
             | (codec.CFG_FULL_SORT if full_sort else 0)
             | (codec.CFG_HOT_KEYS if hot_keys else 0)
-            | (codec.CFG_COMPACT_CHANGES if compact_changes else 0), rank_object=rank_object,
+            | (codec.CFG_COMPACT_CHANGES if compact_changes else 0)
+            | (codec.CFG_TRACK_MODIFIED if track_modified else 0), rank_object=rank_object,
             rank_true=rank_true, rank_false=rank_false, rank_nan=rank_nan)
         h = C.c_void_p()
         rc = self.lib.bb_create(C.byref(self.cfg), C.byref(h))
@@ -94,6 +95,25 @@ class Engine:
         """Stable partition of a device batch by owner rank (bullet_js_b200/shard.py)."""
         self._check(self.lib.bb_route_pack_dev(self._h, world, C.byref(bs), C.byref(out), C.c_void_p(counts_ptr),
                                                C.c_void_p(stream)))
+
+    # ---- sync producer side (src/bullet-network-sync.js:592-664)
+    @property
+    def epoch(self) -> int:
+        """Ordinal of the most recent merge call (what an accepted update's row is stamped with)."""
+        return int(self.lib.bb_epoch(self._h))
+
+    def sync_collect(self, since_epoch: int = 0, filter_records: bool = False, cap: int | None = None):
+        """-> (path ids, rows, epochs) of the rows _collectFullSyncData(since) would visit, selected on the device."""
+        cap = self.capacity if cap is None else int(cap)
+        ids = np.zeros(max(cap, 1), np.uint64)
+        rows = np.zeros(max(cap, 1), codec.ROW_DTYPE)
+        ep = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_uint64(0)
+        self._check(self.lib.bb_sync_collect(self._h, int(since_epoch), codec.COLLECT_FILTER_RECORDS if filter_records else 0,
+                                             cap, ids.ctypes.data, rows.ctypes.data, ep.ctypes.data, C.byref(n)))
+        k = int(n.value)
+        order = np.argsort(ids[:k], kind="stable")  # warps finish in any order: ascending path id for the caller
+        return ids[:k][order], rows[:k][order], ep[:k][order]
 
     def sync(self, stream: int = 0):
         self._check(self.lib.bb_sync(self._h, C.c_void_p(stream)))

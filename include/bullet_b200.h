@@ -172,6 +172,10 @@ typedef struct bb_config {
  * discarded, crt:172-185), local puts (the clock is V, crt:358), concurrent merges (crt:266-278).  Decisions, table
  * and index are identical to the default; n_changes counts emitted entries only. */
 #define BB_CFG_COMPACT_CHANGES 128u
+/* Keep meta[path].lastModified (src/bullet.js:201) per row, at merge-call granularity: every accepted update stamps its
+ * row with the ordinal of the merge call it arrived in (bb_epoch).  The host maps ordinals to wall-clock time (one
+ * Date.now() per call); bb_sync_collect filters on it.  4 bytes per row. */
+#define BB_CFG_TRACK_MODIFIED 256u
 
 typedef struct bb_ctx bb_ctx;
 
@@ -362,6 +366,23 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
+/* Sync producer side: BulletNetworkSync._collectFullSyncData(since) (src/bullet-network-sync.js:592-664).
+ * bb_epoch: ordinal of the most recent merge call on this ctx (1, 2, ...; 0 before the first).
+ * bb_sync_collect: one pass over the table selects every stored path (kind != none) except those the reference skips -
+ * "since > 0 && meta.lastModified && meta.lastModified < since" (:602, :633), with lastModified = the ordinal of the
+ * call that last wrote the row; 0 = never written by a merge (loaded rows: no lastModified, never skipped) - and
+ * copies only the selected rows to the host: path ids (ascending within a warp's 32 rows, warps in any order), rows in
+ * the bb_row format, ordinals.  *n_out = rows selected; BB_ERR_CAPACITY if that exceeds cap (then nothing is copied).
+ * The entry list itself (leaf walk, wire shape :606-612) is the host's formatting of these rows
+ * (bullet_js_b200/persist.py).  since_epoch > 0 needs BB_CFG_TRACK_MODIFIED.
+ * The reference looks meta up at the LEAF path (:599, :628), so the leaves of a record that was written as a whole
+ * have no lastModified and `since` never filters them: by default a record row (kind object) is always selected and
+ * only primitive rows are filtered - exactly the reference's entry list.  BB_COLLECT_FILTER_RECORDS filters record rows
+ * by their own lastModified as well (what a delta sync between two B200 peers wants). */
+#define BB_COLLECT_FILTER_RECORDS 1u
+uint64_t bb_epoch(const bb_ctx* ctx);
+int bb_sync_collect(bb_ctx* ctx, uint64_t since_epoch, uint32_t flags, uint64_t cap, uint64_t* path_id_out,
+                    bb_row* rows_out, uint32_t* epoch_out, uint64_t* n_out);
 /* Host entry of the sharded path (the batched ingress of src/bullet-network-sync.js:551-569 for a table that spans the
  * router's ranks).  Collective: every rank passes its own batch in HOST memory (pinned recommended) and the same
  * `chunks` (1..8, 0 = 4).  Each rank's batch is cut into `chunks` pieces in arrival order; piece j of every rank is

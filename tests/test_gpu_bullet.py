@@ -142,3 +142,56 @@ def test_restart_export_sync_and_node_surface():
     want = persist.collect_full_sync_data(ref.store, ref.meta)
     assert [e for c in chunks for e in c] == want and all(len(c) <= 50 for c in chunks)
     db.close()
+
+
+def test_device_sync_producer_with_since():
+    """SURVEY 8f-2 on the device: bb_sync_collect (k_sync_collect) selects the rows _collectFullSyncData(since) visits -
+    every record, and the primitives whose lastModified (the merge call that last wrote them, BB_CFG_TRACK_MODIFIED) is
+    not older than `since` - and only those cross PCIe.  Expectation: persist.collect_full_sync_data (pinned to the
+    live reference, `since` included: tests/test_persist.py) over the literal oracle's store with the same stamps."""
+    import numpy as np
+
+    from bullet_js_b200 import persist
+    from bullet_js_b200.bullet import Bullet
+
+    now = [1000.0]
+
+    def clock():
+        now[0] += 10.0
+        return now[0]
+
+    sch = schemas()
+    sch["settings"] = codec.Schema(["v"], ["me", "peerA", "peerB"], codec.StringDict(["dark", "light", "en", "de"]), "me")
+    db, ref = Bullet(sch, capacity=64, track_modified=True, clock=clock), RefBullet("me")
+    stamps = {}
+
+    def put(path, value):
+        before = len(ref.changes)
+        db.get(path).put(value)
+        ref.put(path, value)
+        if len(ref.changes) > before:
+            stamps[path] = now[0]  # the mirror's Date.now() of this call
+
+    for k, v in USERS.items():
+        put(f"users/{k}", js(v))
+    put("settings/theme", "dark")
+    put("settings/lang", "en")
+    mid = now[0] + 1.0
+    put("users/user2", {"age": 36.0})
+    put("settings/theme", "light")
+    put("settings/theme", "dark")  # rejected ("dark" < "light"): lastModified stays
+    assert db.decisions == [d["code"] for d in ref.decisions]
+    meta = {p: dict(m, lastModified=stamps[p]) if p in stamps else dict(m) for p, m in ref.meta.items()}
+    for since in (0, 1.0, mid, now[0] + 1.0):
+        got = [e for c in db.collect_sync_entries(since) for e in c]
+        want = persist.collect_full_sync_data(ref.store, meta, since)
+        assert got == want, since
+    # records filtered by their own lastModified as well (not what the reference does): only what changed since `mid`
+    delta = [e["path"] for c in db.collect_sync_entries(mid, filter_records=True) for e in c]
+    assert delta == ["users/user2/age", "settings/theme"]
+    eng = db._c["users"].engine
+    ids, rows, ep = eng.sync_collect(0)
+    assert len(ids) == len(USERS) and ep.max() == eng.epoch and (np.diff(ids.astype(np.int64)) > 0).all()
+    with pytest.raises(Exception):
+        eng.sync_collect(0, cap=1)
+    db.close()

@@ -128,3 +128,18 @@ def test_sync_producer_equals_reference():
     assert any(e["vectorClock"] for e in got) and any(not e["vectorClock"] and "/" in e["path"][6:] for e in got)
     chunks = to_py(js.rt.method(js._sync, "_chunkSyncData", js.rt.method(js._sync, "_collectFullSyncData", 0.0)))
     assert [len(c) for c in persist.chunk_sync_data(got)] == [len(c) for c in chunks]
+    # the `since` filter (:602, :633): meta is looked up at the LEAF path, so it only ever drops paths that were written
+    # as leaves; the leaves of whole records have no lastModified and always travel (the interpreter's Date.now()
+    # advances 1 ms per call, so lastModified is a total order)
+    js.put("settings/lang", "en")
+    raw = to_py(js.bullet.get("meta"))
+    stamps = sorted(m["lastModified"] for m in raw.values() if m.get("lastModified"))
+    assert len(stamps) > 10
+    for since in (stamps[0], stamps[len(stamps) // 2], stamps[-1], stamps[-1] + 1.0):
+        want = to_py(js.rt.method(js._sync, "_collectFullSyncData", float(since)))
+        got = persist.collect_full_sync_data(js.store, raw, since)
+        assert [(e["path"], e["lastModified"]) for e in got] == [(e["path"], e["lastModified"]) for e in want]
+    dropped = {e["path"] for e in persist.collect_full_sync_data(js.store, raw)} - {e["path"] for e in got}
+    # only primitives written at their own path are ever filtered; every leaf of a whole record still travels
+    assert {"settings/theme", "settings/lang"} <= dropped and all(p in raw and p.count("/") == 1 for p in dropped)
+    assert any(e["path"].count("/") == 2 for e in got)
