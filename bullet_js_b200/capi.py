@@ -73,7 +73,7 @@ class BulletB200Error(RuntimeError):
 EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
-    "bb_merge_batch", "bb_merge_batch_dev", "bb_sync", "bb_epoch", "bb_sync_collect",
+    "bb_merge_batch", "bb_merge_batch_dev", "bb_merge_prepare_dev", "bb_sync", "bb_epoch", "bb_sync_collect",
     "bb_index_create", "bb_index_create_fields", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
@@ -115,6 +115,8 @@ def load():
     lib.bb_merge_batch.restype = i32
     lib.bb_merge_batch_dev.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges), vp]
     lib.bb_merge_batch_dev.restype = i32
+    lib.bb_merge_prepare_dev.argtypes = [vp, C.POINTER(BBBatch), vp]
+    lib.bb_merge_prepare_dev.restype = i32
     lib.bb_reserve.argtypes = [vp, u64, i32]
     lib.bb_reserve.restype = i32
     lib.bb_sync.argtypes = [vp, vp]

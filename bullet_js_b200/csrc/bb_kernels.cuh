@@ -907,6 +907,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
 // retiring thread applies exactly that, and a per-segment cache of keys KNOWN PRESENT (shared memory, probed by all
 // threads in parallel) lets it skip every update whose key is already in the index - on a hot node nearly all of them.
 constexpr int HOT_CACHE = 256;            // slots per field of the known-present cache
+constexpr int HOT_LOOK = 64;              // window positions evaluated per pass
 constexpr uint64_t HC_TOMB = 0xFFFFFFFFFFFFFFFEull;
 
 __device__ __forceinline__ uint32_t hc_hash(uint64_t k) { return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ull) >> 56); }
@@ -1076,7 +1077,10 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
       }
       int base = 0;  // window positions [0, base) are retired
       while (base < nseg) {
-        const bool live = mine && tid >= base;
+        // Only the next HOT_LOOK positions are evaluated in a pass: a pass costs the instructions of every warp that takes
+        // part (the resolver diverges by update type), and the next state change is rarely further away than that.
+        const int lim = min(nseg, base + HOT_LOOK);
+        const bool live = mine && tid >= base && tid < lim;
         uint32_t code = 0;
         RowState r;
         Clock oc;
@@ -1111,7 +1115,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         for (int ww = HOT_WARPS - 1; ww >= 0; --ww)
           if (s_stop[ww]) first = ww * 32 + __ffs(s_stop[ww]) - 1;
         // retired this pass: up to and including the first stop
-        const int end = first >= nseg ? nseg : first + 1;
+        const int end = first >= lim ? lim : first + 1;
         const bool retiring = live && tid < end;
         if (INDEXED) {  // which retired updates does the hook have anything to do for?
           bool need = false;
