@@ -224,7 +224,7 @@ def workload_config(args, world, meta=None):
         "workload": wl, "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
         "keys": args.keys, "front_end": args.front_end,
         "sharding": "none" if world == 1 else f"splitmix64-style bijective hash of the path id (key_bits {meta['key_bits'] if meta else '?'}) % {world}",
-        "pipelining": "sharded: route of batch i+1 beside the merge of batch i" if world > 1 else
+        "pipelining": "sharded: route of batch i+1 and the grouping front end of what it delivers beside the merge of batch i" if world > 1 else
                       "grouping front end of batch i+1 (bb_merge_prepare_dev, internal stream) beside the merge of batch i",
         "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2; "
               "every step merges into a pristine copy of the table",
@@ -666,6 +666,8 @@ def main():
         m = router.merge(engines[i], i % 2, out.cs, stream)
         if not last:
             router.route(d_in[(i + 1) % N_BATCHES][1], (i + 1) % 2)
+            if pipelined and i + 1 < len(engines):  # the owner groups what it is about to receive while it merges batch i
+                router.prepare(engines[i + 1], (i + 1) % 2)
         return m
 
     # ---- warm-up; step 0 doubles as the parity check of the timed workload

@@ -658,6 +658,17 @@ int bb_abi_version(void) { return BB_ABI_VERSION; }
 
 const char* bb_last_error(const bb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+// The prepared front end runs BESIDE a merge kernel that fills every SM (7 CTAs x 72 registers x 128 threads take the
+// whole register file): at the highest priority its CTAs get the slots the merge CTAs free as they retire, instead of
+// queueing behind the whole merge grid.  BB_FRONT_PRIO=0 keeps the default priority (A/B).
+static bool create_front_stream(cudaStream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (const char* e = getenv("BB_FRONT_PRIO"))
+    if (e[0] == '0') hi = 0;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi) == cudaSuccess;
+}
+
 int bb_create(const bb_config* cfg, bb_ctx** out) {
   if (!cfg || !out) {
     g_create_error = "null argument";
@@ -729,7 +740,7 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->cg_ctr, 3 * bb::CG_CTR_WORDS * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->cg_ctr, 0, 3 * bb::CG_CTR_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->s_front, cudaStreamNonBlocking) == cudaSuccess &&
+            create_front_stream(&c->s_front) &&
             cudaEventCreateWithFlags(&c->ev_prep_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_front[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_front[1], cudaEventDisableTiming) == cudaSuccess &&
@@ -1701,10 +1712,41 @@ int bb_router_set_sharding(bb_router* r, uint32_t key_bits) {
   return BB_OK;
 }
 
+static int router_counts(bb_router* r, uint32_t slot);
+
+static void router_received(bb_router* r, uint32_t slot, bb_batch* received) {
+  received->n = r->n_recv[slot];
+  received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);
+  received->head = reinterpret_cast<bb_head*>(r->recv[slot][1]);
+  received->clk = reinterpret_cast<uint32_t*>(r->recv[slot][2]);
+  received->val = reinterpret_cast<uint64_t*>(r->recv[slot][3]);
+}
+
+int bb_router_peek(bb_router* r, uint32_t slot, bb_batch* received, void** rows_stream) {
+  if (!r || !received || !rows_stream || slot > 1) return rfail(r, BB_ERR_ARG, "bad argument");
+  BB_RCUDA(r, cudaSetDevice(r->device));
+  int rc = router_counts(r, slot);
+  if (rc) return rc;
+  router_received(r, slot, received);
+  *rows_stream = r->stream;
+  return BB_OK;
+}
+
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received) {
   if (!r || !received || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
   BB_RCUDA(r, cudaSetDevice(r->device));
-  if (r->pending[slot]) {  // the counts of this slot's route: long on the host by now
+  {
+    int rc = router_counts(r, slot);
+    if (rc) return rc;
+  }
+  BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
+  router_received(r, slot, received);
+  return BB_OK;
+}
+
+// the counts of this slot's route (how many rows every rank sends to every rank): on the host soon after the route began
+static int router_counts(bb_router* r, uint32_t slot) {
+  if (r->pending[slot]) {
     BB_RCUDA(r, cudaEventSynchronize(r->counts_ev[slot]));
     const uint32_t W = r->world, me = r->rank;
     const uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
@@ -1722,12 +1764,6 @@ int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* recei
     r->n_recv[slot] = recv;
     r->sent_bytes += sent * 88;
   }
-  BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
-  received->n = r->n_recv[slot];
-  received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);
-  received->head = reinterpret_cast<bb_head*>(r->recv[slot][1]);
-  received->clk = reinterpret_cast<uint32_t*>(r->recv[slot][2]);
-  received->val = reinterpret_cast<uint64_t*>(r->recv[slot][3]);
   return BB_OK;
 }
 

@@ -374,6 +374,10 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
+/* The received batch of a routed slot as soon as its COUNTS are on the host - the rows may still be in flight on
+ * *rows_stream.  For bb_merge_prepare_dev(ctx, received, *rows_stream): the owner groups what it is about to receive while
+ * it still merges the previous batch.  bb_router_acquire later returns the same batch. */
+int bb_router_peek(bb_router* r, uint32_t slot, bb_batch* received, void** rows_stream);
 /* Sync producer side: BulletNetworkSync._collectFullSyncData(since) (src/bullet-network-sync.js:592-664).
  * bb_epoch: ordinal of the most recent merge call on this ctx (1, 2, ...; 0 before the first).
  * bb_sync_collect: one pass over the table selects every stored path (kind != none) except those the reference skips -
