@@ -224,8 +224,6 @@ def workload_config(args, world, meta=None):
         "workload": wl, "records_per_gpu": args.records, "batch_per_gpu": args.batch, "fields": F, "peers": 8,
         "keys": args.keys, "front_end": args.front_end,
         "sharding": "none" if world == 1 else f"splitmix64-style bijective hash of the path id (key_bits {meta['key_bits'] if meta else '?'}) % {world}",
-        "pipelining": "sharded: route of batch i+1 and the grouping front end of what it delivers beside the merge of batch i" if world > 1 else
-                      "grouping front end of batch i+1 (bb_merge_prepare_dev, internal stream) beside the merge of batch i",
         "l2": f"working set {args.records * 128 // 2**20} MiB table + {N_BATCHES} x {args.batch * 88 // 2**20} MiB batches > 126 MB L2; "
               "every step merges into a pristine copy of the table",
     }
@@ -653,21 +651,15 @@ def main():
     if world > 1:
         router = shard.Router(world, rank, n, local_rank, recv_capacity=cap, key_bits=kb)
 
-    def step_dev(i, last, pipelined=True):
-        """One step.  Single GPU: the grouping front end of batch i + 1 (table-independent, bb_merge_prepare_dev) is
-        enqueued on the library's internal stream, then batch i - prepared one step earlier - is merged.  Sharded: merge
-        batch i (already routed into slot i % 2), then route batch i + 1 while that merge runs - the routing never
-        depends on the table."""
+    def step_dev(i, last):
+        """One step.  Sharded: merge batch i (already routed into slot i % 2), then route batch i + 1 while that
+        merge runs - the routing never depends on the table."""
         if router is None:
-            if pipelined and not last and i + 1 < len(engines):
-                engines[i + 1].merge_prepare_dev(d_in[(i + 1) % N_BATCHES][1])
             engines[i].merge_dev(d_in[i % N_BATCHES][1], out.cs, stream)
             return n
         m = router.merge(engines[i], i % 2, out.cs, stream)
         if not last:
             router.route(d_in[(i + 1) % N_BATCHES][1], (i + 1) % 2)
-            if pipelined and i + 1 < len(engines):  # the owner groups what it is about to receive while it merges batch i
-                router.prepare(engines[i + 1], (i + 1) % 2)
         return m
 
     # ---- warm-up; step 0 doubles as the parity check of the timed workload
@@ -675,8 +667,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if router is not None:
         router.route(d_in[0][1], 0)
-    else:
-        engines[0].merge_prepare_dev(d_in[0][1])
     for i in range(W):
         m0 = step_dev(i, False)
         if i == 0 and not args.no_parity:
@@ -727,7 +717,7 @@ def main():
             load_pristine(e)
             e.phase_events(True)
         for i in range(Kp):
-            step_dev(i, False, pipelined=False)
+            step_dev(i, False)
         eng.sync(stream)
         torch.cuda.synchronize()
         for name in ("sort", "merge"):

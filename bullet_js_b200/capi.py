@@ -73,11 +73,11 @@ class BulletB200Error(RuntimeError):
 EXPORTS = [
     "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error",
     "bb_table_load", "bb_table_read", "bb_table_clear", "bb_reserve",
-    "bb_merge_batch", "bb_merge_batch_dev", "bb_merge_prepare_dev", "bb_sync", "bb_epoch", "bb_sync_collect",
+    "bb_merge_batch", "bb_merge_batch_dev", "bb_sync", "bb_epoch", "bb_sync_collect",
     "bb_index_create", "bb_index_create_fields", "bb_query_equals", "bb_query_count", "bb_query_range",
     "bb_query_equals_dev", "bb_query_range_dev", "bb_index_stats",
     "bb_route_pack_dev", "bb_router_unique_id", "bb_router_create", "bb_router_destroy",
-    "bb_router_last_error", "bb_router_set_sharding", "bb_router_route_dev", "bb_router_acquire", "bb_router_release", "bb_router_peek",
+    "bb_router_last_error", "bb_router_set_sharding", "bb_router_route_dev", "bb_router_acquire", "bb_router_release",
     "bb_router_merge_batch", "bb_router_query_reserve", "bb_router_query_range", "bb_router_query_equals", "bb_router_query_fetch",
     "bb_router_sent_bytes", "bb_router_launch_count", "bb_router_last_ms",
     "bb_launch_count", "bb_last_phase_ms", "bb_phase_ms", "bb_phase_events",
@@ -115,8 +115,6 @@ def load():
     lib.bb_merge_batch.restype = i32
     lib.bb_merge_batch_dev.argtypes = [vp, C.POINTER(BBBatch), C.POINTER(BBChanges), vp]
     lib.bb_merge_batch_dev.restype = i32
-    lib.bb_merge_prepare_dev.argtypes = [vp, C.POINTER(BBBatch), vp]
-    lib.bb_merge_prepare_dev.restype = i32
     lib.bb_reserve.argtypes = [vp, u64, i32]
     lib.bb_reserve.restype = i32
     lib.bb_sync.argtypes = [vp, vp]
@@ -158,8 +156,6 @@ def load():
     lib.bb_router_route_dev.restype = i32
     lib.bb_router_acquire.argtypes = [vp, u32, vp, C.POINTER(BBBatch)]
     lib.bb_router_acquire.restype = i32
-    lib.bb_router_peek.argtypes = [vp, u32, C.POINTER(BBBatch), C.POINTER(vp)]
-    lib.bb_router_peek.restype = i32
     lib.bb_router_release.argtypes = [vp, u32, vp]
     lib.bb_router_release.restype = i32
     lib.bb_router_merge_batch.argtypes = [vp, vp, C.POINTER(BBBatch), C.POINTER(BBChanges), u32, C.POINTER(u64), vp]

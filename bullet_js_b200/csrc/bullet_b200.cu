@@ -83,25 +83,8 @@ struct bb_ctx {
   uint32_t* cs_cnt = nullptr;
   uint32_t* cs_off = nullptr;
   uint2* cg_off = nullptr;     // grouping front end: (start, length) of a multi-update path's run, uint2[capacity]
-  uint32_t* cg_ctr = nullptr;  // [3][CG_CTR_WORDS] per-batch counters, sets used in turn (a batch's count kernel clears the next set)
-  uint32_t cg_next = 0;
-  // The grouping front end does not touch the table: bb_merge_prepare_dev runs it for the NEXT batch on `s_front` while
-  // the current batch is still being merged.  Item lists by batch parity; `rank_buf`, cg_off, cs_long, items_b are
-  // front-end only (front ends never overlap each other).
-  DevBuf<uint64_t> items_g[2];
-  DevBuf<uint32_t> rank_buf;
-  uint32_t grp_next = 0;
-  cudaStream_t s_front = nullptr;
-  cudaEvent_t ev_prep_in = nullptr, ev_front[2]{}, ev_merged[2]{};
-  bool merged_valid[2] = {false, false};
-  cudaEvent_t last_front_ev = nullptr;  // completes no earlier than the most recent front end (they share scratch)
-  struct Prepared {
-    bool pending = false;
-    const uint64_t* path_id = nullptr;
-    uint64_t n = 0;
-    uint32_t set = 0;
-    uint32_t* gctr = nullptr;
-  } prep;
+  uint32_t* cg_ctr = nullptr;  // [2][CG_CTR_WORDS] per-batch counters, sets used alternately
+  uint32_t cg_parity = 0;
   DevBuf<uint4> hot_list;      // segments k_merge_stage hands to k_merge_hot
   DevBuf<uint2> cs_long;       // sorted paths: segments longer than CS_SHORT, queued for k_cs_fix_long
   DevBuf<uint32_t> cs_tile;    // per-4096-row sums of cs_cnt
@@ -231,9 +214,7 @@ int reserve_dev(bb_ctx* c, uint64_t n) {
       BB_CUDA(c, cudaMemsetAsync(c->cs_cnt, 0, c->cfg.capacity * sizeof(uint32_t), c->stream));
       BB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    BB_CUDA(c, c->items_g[0].ensure(n));
-    BB_CUDA(c, c->items_g[1].ensure(n));
-    BB_CUDA(c, c->rank_buf.ensure(n));
+    BB_CUDA(c, c->items_a.ensure(n));
     BB_CUDA(c, c->items_b.ensure(n));
     BB_CUDA(c, c->st_ent.ensure(5 * n));
     BB_CUDA(c, c->cs_long.ensure(n / 8 + 1));
@@ -285,44 +266,6 @@ void fill_params(const bb_ctx* c, bb::Params& p, bb::IndexArgs& ix) {
   }
 }
 
-// The grouping front end of one batch on stream `s` (bb_group.cuh): five launches chained with programmatic dependent
-// launch.  Takes the next item-list set and the next counter set; `zero_n`: a change counter to clear, or null.
-struct FrontOut {
-  uint64_t* items = nullptr;
-  uint32_t* gctr = nullptr;
-  uint32_t set = 0;
-};
-
-int front_grouped(bb_ctx* c, const bb_batch* in, cudaStream_t s, uint64_t* zero_n, FrontOut* fo) {
-  using namespace bb;
-  const uint64_t n = in->n;
-  ++c->batches_since_sync;
-  const uint32_t ordinal = c->batches_since_sync;
-  const uint32_t set = c->grp_next;
-  c->grp_next ^= 1u;
-  // the merge that last read this item list (two batches ago) and this batch's next-next counter set must be done
-  if (c->merged_valid[set]) BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_merged[set], 0));
-  if (c->last_front_ev) BB_CUDA(c, cudaStreamWaitEvent(s, c->last_front_ev, 0));  // front ends share rank / run scratch
-  uint32_t* gctr = c->cg_ctr + (size_t)c->cg_next * CG_CTR_WORDS;
-  uint32_t* gnext = c->cg_ctr + (size_t)((c->cg_next + 1u) % 3u) * CG_CTR_WORDS;
-  c->cg_next = (c->cg_next + 1u) % 3u;
-  uint64_t* src = c->items_g[set].p;
-  uint32_t* rank = c->rank_buf.p;
-  const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
-  BB_LAUNCH_PDL(c, k_cg_count, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, rank, gctr, gnext,
-                c->d_err, ordinal, zero_n, (const uint4*)((c->tune & 16u) ? c->table : nullptr));
-  BB_LAUNCH_PDL(c, k_cg_classify, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, rank, c->cg_off, src,
-                gctr, c->cs_long.p);
-  BB_LAUNCH_PDL(c, k_cg_place, g4, CS_THREADS, 0, s, in->path_id, n, rank, c->cg_off, c->cs_cnt, src, gctr);
-  BB_LAUNCH_PDL(c, k_cg_fix, div_up(n, CS_THREADS), CS_THREADS, 0, s, src, c->cg_off, gctr);
-  BB_LAUNCH_PDL(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, 0, s, src, c->items_b.p, c->cs_long.p, gctr + CG_CTR_LONG,
-                gctr + CG_CTR_NEXT, gctr + CG_CTR_SINGLE);
-  fo->items = src;
-  fo->gctr = gctr;
-  fo->set = set;
-  return BB_OK;
-}
-
 // One batch (or one chunk of a host call: `idx_base` = arrival index of its first update,
 // `append` = keep adding to *out->n_changes instead of starting a new change set; `call_rej` = the word
 // that says the whole host call is rejected).
@@ -332,12 +275,9 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   const uint64_t n = in->n;
   if (n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
   const bool grouped = use_grouping(c);
-  const bool prepared = grouped && c->prep.pending;
-  if (prepared && (c->prep.path_id != in->path_id || c->prep.n != n))
-    return fail(c, BB_ERR_STATE, "a batch was prepared (bb_merge_prepare_dev): it must be the next one merged");
   if (!append) {
     mark(c, EV_START, s);
-    if (!grouped || n == 0 || prepared) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
+    if (!grouped || n == 0) BB_CUDA(c, cudaMemsetAsync(out->n_changes, 0, sizeof(uint64_t), s));
   }
   if (n == 0) {
     if (!append) {
@@ -350,34 +290,32 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     int rc = reserve_dev(c, n);  // no-op once the scratch is large enough
     if (rc) return rc;
   }
-  if (!grouped) ++c->batches_since_sync;
+  ++c->batches_since_sync;
   const ZeroLayout z = zero_layout(c, n);
   uint32_t* zp = c->zero.p;
   if (!grouped) BB_CUDA(c, cudaMemsetAsync(zp, 0, z.total * sizeof(uint32_t), s));
   uint32_t* rej = grouped ? nullptr : zp + z.cs_ctr + 5;  // this batch's reject word
   const uint32_t ordinal = c->batches_since_sync;
   uint32_t* gctr = nullptr;
-  uint32_t gset = 0;
 
   uint64_t* src = c->items_a.p;
-  if (prepared) {
-    // the front end of this batch ran (or is running) on the internal stream: wait for it instead of repeating it
-    c->prep.pending = false;
-    src = c->items_g[c->prep.set].p;
-    gctr = c->prep.gctr;
-    gset = c->prep.set;
-    rej = gctr + CG_CTR_REJ;
-    BB_CUDA(c, cudaStreamWaitEvent(s, c->ev_front[gset], 0));
-  } else if (grouped) {
+  if (grouped) {
     // default: count, then group (singles in arrival order, multi-update paths in claimed runs behind them); the
     // five launches and the merge behind them are chained with programmatic dependent launch
-    FrontOut fo;
-    int rc = front_grouped(c, in, s, append ? (uint64_t*)nullptr : out->n_changes, &fo);
-    if (rc) return rc;
-    src = fo.items;
-    gctr = fo.gctr;
-    gset = fo.set;
+    const uint32_t g4 = div_up(n, CS_THREADS * CS_ILP);
+    gctr = c->cg_ctr + (size_t)c->cg_parity * CG_CTR_WORDS;
+    uint32_t* gnext = c->cg_ctr + (size_t)(c->cg_parity ^ 1u) * CG_CTR_WORDS;
+    c->cg_parity ^= 1u;
     rej = gctr + CG_CTR_REJ;
+    BB_LAUNCH_PDL(c, k_cg_count, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, gctr, gnext,
+                  c->d_err, ordinal, append ? (uint64_t*)nullptr : out->n_changes,
+                  (const uint4*)((c->tune & 16u) ? c->table : nullptr));
+    BB_LAUNCH_PDL(c, k_cg_classify, g4, CS_THREADS, 0, s, in->path_id, n, c->cfg.capacity, c->cs_cnt, c->st_idx.p, c->cg_off, src,
+                  gctr, c->cs_long.p);
+    BB_LAUNCH_PDL(c, k_cg_place, g4, CS_THREADS, 0, s, in->path_id, n, c->st_idx.p, c->cg_off, c->cs_cnt, src, gctr);
+    BB_LAUNCH_PDL(c, k_cg_fix, div_up(n, CS_THREADS), CS_THREADS, 0, s, src, c->cg_off, gctr);
+    BB_LAUNCH_PDL(c, k_cs_fix_long, CS_LONG_CTAS, CS_THREADS, 0, s, src, c->items_b.p, c->cs_long.p, gctr + CG_CTR_LONG,
+                  gctr + CG_CTR_NEXT, gctr + CG_CTR_SINGLE);
   } else if (use_counting_sort(c, n)) {
     // K1': counting sort keyed by the row index (bb_kernels.cuh), arrival order restored per segment
     const uint32_t g = div_up(n, CS_THREADS);
@@ -472,39 +410,8 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, false>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, false>), z.merge_tiles, MT, s, ma);
   }
-  if (grouped) {  // this item list may be rebuilt once the merge that reads it is done
-    BB_CUDA(c, cudaEventRecord(c->ev_merged[gset], s));
-    c->merged_valid[gset] = true;
-    if (!prepared) c->last_front_ev = c->ev_merged[gset];  // (an event between the front end and the merge would end their overlap)
-  }
   if (!append) mark(c, EV_MERGE, s);
   c->seq += n;
-  return BB_OK;
-}
-
-// Table-independent half of the next merge, enqueued now on the internal stream.
-int merge_prepare(bb_ctx* c, const bb_batch* in, cudaStream_t in_stream) {
-  if (!use_grouping(c) || in->n == 0) return BB_OK;  // nothing to run ahead: bb_merge_batch_dev does all of it
-  if (c->prep.pending) return fail(c, BB_ERR_STATE, "one prepared batch at a time: merge it first");
-  if (in->n >= BB_NO_SLOT) return fail(c, BB_ERR_ARG, "batch larger than 2^29-2 updates");
-  {
-    int rc = reserve_dev(c, in->n);
-    if (rc) return rc;
-  }
-  if (in_stream) {
-    BB_CUDA(c, cudaEventRecord(c->ev_prep_in, in_stream));
-    BB_CUDA(c, cudaStreamWaitEvent(c->s_front, c->ev_prep_in, 0));
-  }
-  FrontOut fo;
-  int rc = front_grouped(c, in, c->s_front, nullptr, &fo);
-  if (rc) return rc;
-  BB_CUDA(c, cudaEventRecord(c->ev_front[fo.set], c->s_front));
-  c->last_front_ev = c->ev_front[fo.set];
-  c->prep.pending = true;
-  c->prep.path_id = in->path_id;
-  c->prep.n = in->n;
-  c->prep.set = fo.set;
-  c->prep.gctr = fo.gctr;
   return BB_OK;
 }
 
@@ -658,17 +565,6 @@ int bb_abi_version(void) { return BB_ABI_VERSION; }
 
 const char* bb_last_error(const bb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-// The prepared front end runs BESIDE a merge kernel that fills every SM (7 CTAs x 72 registers x 128 threads take the
-// whole register file): at the highest priority its CTAs get the slots the merge CTAs free as they retire, instead of
-// queueing behind the whole merge grid.  BB_FRONT_PRIO=0 keeps the default priority (A/B).
-static bool create_front_stream(cudaStream_t* s) {
-  int lo = 0, hi = 0;
-  cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  if (const char* e = getenv("BB_FRONT_PRIO"))
-    if (e[0] == '0') hi = 0;
-  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi) == cudaSuccess;
-}
-
 int bb_create(const bb_config* cfg, bb_ctx** out) {
   if (!cfg || !out) {
     g_create_error = "null argument";
@@ -738,14 +634,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMemcpyAsync(c->d_err, err_clear, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_callrej, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_callrej, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
-            cudaMalloc((void**)&c->cg_ctr, 3 * bb::CG_CTR_WORDS * sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemsetAsync(c->cg_ctr, 0, 3 * bb::CG_CTR_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
-            create_front_stream(&c->s_front) &&
-            cudaEventCreateWithFlags(&c->ev_prep_in, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&c->ev_front[0], cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&c->ev_front[1], cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&c->ev_merged[0], cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&c->ev_merged[1], cudaEventDisableTiming) == cudaSuccess &&
+            cudaMalloc((void**)&c->cg_ctr, 2 * bb::CG_CTR_WORDS * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->cg_ctr, 0, 2 * bb::CG_CTR_WORDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_nchanges, sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chunk_total, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess &&
             cudaMalloc((void**)&c->d_chg_base, sizeof(uint64_t)) == cudaSuccess &&
@@ -784,13 +674,6 @@ int bb_destroy(bb_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->items_a.release(); c->items_b.release(); c->zero.release(); c->st_idx.release();
-  c->items_g[0].release(); c->items_g[1].release(); c->rank_buf.release();
-  if (c->s_front) cudaStreamDestroy(c->s_front);
-  if (c->ev_prep_in) cudaEventDestroy(c->ev_prep_in);
-  for (int i = 0; i < 2; ++i) {
-    if (c->ev_front[i]) cudaEventDestroy(c->ev_front[i]);
-    if (c->ev_merged[i]) cudaEventDestroy(c->ev_merged[i]);
-  }
   c->st_ent.release();
   c->io_path.release(); c->io_head.release(); c->io_clk.release(); c->io_val.release();
   c->io_out_head.release(); c->io_out_clk.release(); c->io_out_val.release(); c->io_rows.release();
@@ -927,13 +810,6 @@ int bb_merge_batch_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, void* str
   begin_call(c);
   ++c->epoch;
   return merge_dev(c, in, out, stream ? (cudaStream_t)stream : c->stream);
-}
-
-int bb_merge_prepare_dev(bb_ctx* c, const bb_batch* in, void* in_stream) {
-  if (!c || !in) return fail(c, BB_ERR_ARG, "null argument");
-  if (in->n && !in->path_id) return fail(c, BB_ERR_ARG, "null buffer");
-  BB_CUDA(c, cudaSetDevice(c->cfg.device));
-  return merge_prepare(c, in, (cudaStream_t)in_stream);
 }
 
 int bb_reserve(bb_ctx* c, uint64_t max_batch, int host_entry) {
@@ -1712,41 +1588,10 @@ int bb_router_set_sharding(bb_router* r, uint32_t key_bits) {
   return BB_OK;
 }
 
-static int router_counts(bb_router* r, uint32_t slot);
-
-static void router_received(bb_router* r, uint32_t slot, bb_batch* received) {
-  received->n = r->n_recv[slot];
-  received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);
-  received->head = reinterpret_cast<bb_head*>(r->recv[slot][1]);
-  received->clk = reinterpret_cast<uint32_t*>(r->recv[slot][2]);
-  received->val = reinterpret_cast<uint64_t*>(r->recv[slot][3]);
-}
-
-int bb_router_peek(bb_router* r, uint32_t slot, bb_batch* received, void** rows_stream) {
-  if (!r || !received || !rows_stream || slot > 1) return rfail(r, BB_ERR_ARG, "bad argument");
-  BB_RCUDA(r, cudaSetDevice(r->device));
-  int rc = router_counts(r, slot);
-  if (rc) return rc;
-  router_received(r, slot, received);
-  *rows_stream = r->stream;
-  return BB_OK;
-}
-
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received) {
   if (!r || !received || slot > 1 || !stream) return rfail(r, BB_ERR_ARG, "bad argument (an explicit stream is required)");
   BB_RCUDA(r, cudaSetDevice(r->device));
-  {
-    int rc = router_counts(r, slot);
-    if (rc) return rc;
-  }
-  BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
-  router_received(r, slot, received);
-  return BB_OK;
-}
-
-// the counts of this slot's route (how many rows every rank sends to every rank): on the host soon after the route began
-static int router_counts(bb_router* r, uint32_t slot) {
-  if (r->pending[slot]) {
+  if (r->pending[slot]) {  // the counts of this slot's route: long on the host by now
     BB_RCUDA(r, cudaEventSynchronize(r->counts_ev[slot]));
     const uint32_t W = r->world, me = r->rank;
     const uint64_t* hm = r->h_matrix + (size_t)slot * W * W;
@@ -1764,6 +1609,12 @@ static int router_counts(bb_router* r, uint32_t slot) {
     r->n_recv[slot] = recv;
     r->sent_bytes += sent * 88;
   }
+  BB_RCUDA(r, cudaStreamWaitEvent((cudaStream_t)stream, r->ready[slot], 0));
+  received->n = r->n_recv[slot];
+  received->path_id = reinterpret_cast<uint64_t*>(r->recv[slot][0]);
+  received->head = reinterpret_cast<bb_head*>(r->recv[slot][1]);
+  received->clk = reinterpret_cast<uint32_t*>(r->recv[slot][2]);
+  received->val = reinterpret_cast<uint64_t*>(r->recv[slot][3]);
   return BB_OK;
 }
 

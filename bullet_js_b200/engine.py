@@ -91,10 +91,6 @@ class Engine:
     def merge_dev(self, bs: capi.BBBatch, cs: capi.BBChanges, stream: int = 0):
         self._check(self.lib.bb_merge_batch_dev(self._h, C.byref(bs), C.byref(cs), C.c_void_p(stream)))
 
-    def merge_prepare_dev(self, bs: capi.BBBatch, in_stream: int = 0):
-        """The table-independent half of the NEXT merge_dev (grouping front end), on the library's internal stream."""
-        self._check(self.lib.bb_merge_prepare_dev(self._h, C.byref(bs), C.c_void_p(in_stream)))
-
     def route_pack_dev(self, world: int, bs: capi.BBBatch, out: capi.BBBatch, counts_ptr: int, stream: int = 0):
         """Stable partition of a device batch by owner rank (bullet_js_b200/shard.py)."""
         self._check(self.lib.bb_route_pack_dev(self._h, world, C.byref(bs), C.byref(out), C.c_void_p(counts_ptr),

@@ -155,15 +155,6 @@ class Router:
         self._check(self.lib.bb_router_release(self._h, slot, C.c_void_p(stream)))
         return int(rb.n)
 
-    def prepare(self, engine, slot: int):
-        """Group what slot `slot` is receiving (bb_merge_prepare_dev on the received batch, as soon as its counts are
-        known) while the engine is still merging the previous batch; `merge` then finds the item list ready."""
-        import ctypes as C
-
-        rb, st = capi.BBBatch(), C.c_void_p()
-        self._check(self.lib.bb_router_peek(self._h, slot, C.byref(rb), C.byref(st)))
-        engine.merge_prepare_dev(rb, st.value or 0)
-
     def merge_batch(self, engine, bs: capi.BBBatch, cs: capi.BBChanges, chunks: int = 0):
         """Collective host entry (bb_router_merge_batch): this rank's HOST batch in, verdicts + change entries of what
         this shard received out (host buffers of `cs`).  Returns (n_received, recv_counts[chunks, world])."""

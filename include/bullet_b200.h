@@ -246,14 +246,6 @@ int bb_merge_batch_dev(bb_ctx* ctx, const bb_batch* in, bb_changes* out, void* s
  * path id >= capacity or a change buffer was too small.  A batch with a bad path id is rejected WHOLE (table
  * unchanged, its verdicts and change count undefined); batches enqueued after it are merged normally, and
  * bb_last_error names the first rejected batch by its ordinal since the previous bb_sync (1 = first). */
-/* Software pipelining across batches.  Bringing a batch into "a path's updates adjacent, in arrival order" (the grouping
- * front end) reads only the batch's path ids - not the table.  bb_merge_prepare_dev enqueues that half for `in` NOW, on
- * an internal stream, so that it runs beside whatever the merge stream is still doing (typically the merge of the
- * previous batch); the next bb_merge_batch_dev on this ctx must then be given the same batch (same path_id pointer and
- * n) and only waits for the prepared item list.  in_stream: the stream `in` is produced on (NULL = complete already).
- * One prepared batch at a time.  Results are those of an unprepared call.  No-op for ctxs that sort
- * (BB_CFG_ORDERED_CHANGES / RADIX_SORT / FULL_SORT). */
-int bb_merge_prepare_dev(bb_ctx* ctx, const bb_batch* in, void* in_stream);
 int bb_sync(bb_ctx* ctx, void* stream);
 
 /* ---- indices and queries: BulletQuery (src/bullet-query.js) --------------------
@@ -374,10 +366,6 @@ const char* bb_router_last_error(const bb_router* r);
 int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_t* n_recv, void* in_stream);
 int bb_router_acquire(bb_router* r, uint32_t slot, void* stream, bb_batch* received);
 int bb_router_release(bb_router* r, uint32_t slot, void* stream);
-/* The received batch of a routed slot as soon as its COUNTS are on the host - the rows may still be in flight on
- * *rows_stream.  For bb_merge_prepare_dev(ctx, received, *rows_stream): the owner groups what it is about to receive while
- * it still merges the previous batch.  bb_router_acquire later returns the same batch. */
-int bb_router_peek(bb_router* r, uint32_t slot, bb_batch* received, void** rows_stream);
 /* Sync producer side: BulletNetworkSync._collectFullSyncData(since) (src/bullet-network-sync.js:592-664).
  * bb_epoch: ordinal of the most recent merge call on this ctx (1, 2, ...; 0 before the first).
  * bb_sync_collect: one pass over the table selects every stored path (kind != none) except those the reference skips -

@@ -159,8 +159,6 @@ def main():
         received.append(router.merge(eng, rnd % 2, outs[rnd]["cs"], stream))
         if rnd + 1 < ROUNDS:
             router.route(d_in[rnd + 1][1], (rnd + 1) % 2)
-            if rnd % 2 == 0:  # every other round: group what is on its way in while the merge above still runs
-                router.prepare(eng, (rnd + 1) % 2)
     eng.sync(stream)
     torch.cuda.synchronize()
 

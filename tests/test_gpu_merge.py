@@ -439,68 +439,3 @@ def test_router_host_entry_single_rank(compact):
         router.merge_batch(eng, capi.batch_struct(b), small.struct(), pieces)
     router.close()
     eng.close()
-
-
-@pytest.mark.parametrize("indexed", [False, True])
-def test_prepared_batches_pipeline(indexed):
-    """bb_merge_prepare_dev: the grouping front end of batch i + 1 is enqueued on the library's internal stream before
-    batch i is merged (two item-list sets, three counter sets in turn); six batches through ONE ctx, uniform and Zipf,
-    a rejected batch in between - decisions, change sets and the table as the sequential oracle."""
-    import torch
-
-    from bullet_js_b200.engine import Engine
-
-    n_rec, n = 5000, 60_000
-    rng = synth.rng_for(2, salt=41)
-    table = synth.make_table(n_rec, rng)
-    eng = Engine(n_rec, post_getdata=indexed, **synth.synth_ranks(n_rec))
-    orc = TypedOracle(eng.cfg)
-    ids = np.arange(n_rec, dtype=np.uint64)
-    eng.table_load(ids, table.rows)
-    orc.load(ids, table.rows)
-    if indexed:
-        eng.index_create(0, extra_capacity=1 << 20)
-        orc.index_create(0)
-    dev = torch.device("cuda", 0)
-    side = torch.cuda.Stream(device=dev)
-    stream = side.cuda_stream
-    batches = [synth.make_batch(table, n, rng, keys="zipf" if j % 2 else "uniform") for j in range(6)]
-    batches[3].path_id[17] = n_rec + 5  # out of range: batch 3 is rejected whole, the pipeline goes on
-    d_in, outs = [], []
-    for b in batches:
-        t = [torch.from_numpy(x.view(np.uint8).reshape(-1).copy()).to(dev) for x in (b.path_id, b.head, b.clk, b.val)]
-        d_in.append((t, capi.BBBatch(n=b.n, path_id=t[0].data_ptr(), head=t[1].data_ptr(), clk=t[2].data_ptr(), val=t[3].data_ptr())))
-        o = {k: torch.zeros(n * w, dtype=torch.uint8, device=dev) for k, w in (("ver", 4), ("idx", 4), ("head", 16), ("clk", 32), ("val", 32))}
-        o["n"] = torch.zeros(1, dtype=torch.int64, device=dev)
-        o["cs"] = capi.BBChanges(cap=n, verdict=o["ver"].data_ptr(), n_changes=o["n"].data_ptr(), idx=o["idx"].data_ptr(),
-                                 head=o["head"].data_ptr(), clk=o["clk"].data_ptr(), val=o["val"].data_ptr())
-        outs.append(o)
-    torch.cuda.synchronize()
-    eng.merge_prepare_dev(d_in[0][1])
-    with pytest.raises(capi.BulletB200Error):  # one prepared batch at a time
-        eng.merge_prepare_dev(d_in[1][1])
-    with pytest.raises(capi.BulletB200Error):  # and it must be the next one merged
-        eng.merge_dev(d_in[1][1], outs[1]["cs"], stream)
-    for j in range(6):
-        eng.merge_dev(d_in[j][1], outs[j]["cs"], stream)  # asynchronous: batch j + 1 is prepared while this one runs
-        if j + 1 < 6 and j != 3:  # batch 4 is NOT prepared: prepared and plain calls mix
-            eng.merge_prepare_dev(d_in[j + 1][1])
-    try:
-        eng.sync(stream)
-        raised = False
-    except capi.BulletB200Error as e:
-        raised = e.code == capi.ERR_CAPACITY
-    assert raised  # batch 3
-    for j, b in enumerate(batches):
-        if j == 3:
-            continue
-        want = orc.merge(b)
-        o = outs[j]
-        k = int(o["n"].item())
-        got = codec.Changes.from_verdicts(
-            o["ver"].cpu().numpy().view(np.uint32)[:n], o["idx"].cpu().numpy().view(np.uint32)[:k],
-            o["head"].cpu().numpy().view(codec.HEAD_DTYPE)[:k], o["clk"].cpu().numpy().view(np.uint32).reshape(-1, 8)[:k],
-            o["val"].cpu().numpy().view(np.uint64).reshape(-1, 4)[:k])
-        assert got.same_as(want), j
-    assert_same_table_x(eng, orc, n_rec)
-    eng.close()
