@@ -2,7 +2,7 @@
 """Condenses what a gpurun profiling call left in gpurun_out/ into the tracked profiles/ directory:
 launch list (ncu --metrics gpu__time_duration.sum), the headline metrics of the `ncu --set full`
 captures (read with `ncu -i ... --page raw --csv`), and the bench lines of the same code.
-usage: scripts/make_profiles.py <tag> (files gpurun_out/*<tag>*), e.g. 36"""
+usage: scripts/make_profiles.py <tag> [round prefix] (files gpurun_out/*<tag>*), e.g. r2f r2"""
 import collections
 import csv
 import json
@@ -14,6 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
+RND = sys.argv[2] if len(sys.argv) > 2 else "r2"
 
 KEEP = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -46,12 +47,12 @@ def launches():
         a[0] += 1
         a[1] += us
     total = sum(a[1] for a in agg.values())
-    with open(os.path.join(PROF, "r1_launch_sequence.txt"), "w") as f:
+    with open(os.path.join(PROF, f"{RND}_launch_sequence.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400; "
-                "bench.py --steps 2 --warmup 3 --no-cpu-baseline --query-records 20000000\n"
+                "bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-zipf --query-records 20000000\n"
                 "# (cold-cache, serialised launches: compare shares, not absolutes)\n")
         f.write("\n".join(seq) + "\n")
-    with open(os.path.join(PROF, "r1_launches_summary.csv"), "w") as f:
+    with open(os.path.join(PROF, f"{RND}_launches_summary.csv"), "w") as f:
         f.write("kernel,launches,total_us,mean_us,share\n")
         for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"\"{name}\",{n},{us:.1f},{us / n:.2f},{us / total:.3f}\n")
@@ -63,7 +64,7 @@ def capture(name):
     r = list(csv.reader(raw.split("\n")))
     h, units, v = r[0], r[1], r[2]
     out = {"kernel": v[h.index("Kernel Name")]}
-    with open(os.path.join(PROF, f"r1_ncu_{name}.csv"), "w") as f:
+    with open(os.path.join(PROF, f"{RND}_ncu_{name}.csv"), "w") as f:
         f.write("metric,unit,value\n")
         f.write(f"kernel,,\"{out['kernel']}\"\n")
         for k in KEEP:
@@ -77,17 +78,20 @@ def capture(name):
 def main():
     launches()
     traffic = {}
-    for name, kern in (("merge", "k_merge_stage"), ("scan", "k_index_scan")):
+    for name, kern in (("merge", "k_merge_stage"), ("scan", "k_index_scan"), ("build", "k_index_build"), ("hot", "k_merge_hot")):
+        if not os.path.exists(os.path.join(OUT, f"prof{tag}_{name}.ncu-rep")):
+            continue
         m = capture(name)
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd = float(m["dram__bytes_read.sum"][0]) * scale[m["dram__bytes_read.sum"][1]]
         wr = float(m["dram__bytes_write.sum"][0]) * scale[m["dram__bytes_write.sum"][1]]
         traffic[kern] = {"bytes_per_launch": rd + wr, "read": rd, "write": wr,
                          "us_under_ncu": float(m["gpu__time_duration.sum"][0]),
-                         "source": f"profiles/r1_ncu_{name}.csv (ncu --set full --clock-control none, one launch)"}
+                         "source": f"profiles/{RND}_ncu_{name}.csv (ncu --set full --clock-control none, one launch)"}
     with open(os.path.join(PROF, "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
-    for src, dst in ((f"bench{tag}.json", "r1_bench_n1.json"), (f"bench{tag}_ref.json", "r1_bench_n1_reference.json")):
+    for src, dst in ((f"bench{tag}.json", f"{RND}_bench_n1.json"), (f"bench{tag}_ref.json", f"{RND}_bench_n1_reference.json"),
+                     (f"bench{tag}_mesh.json", f"{RND}_bench_mesh_n1.json")):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
     print(json.dumps(traffic, indent=1))
