@@ -620,7 +620,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] - '0';  // 0: cp.async, 1: rows by bulk copy (default), 2: rows + payloads
+  if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] - '0';
+ // 0: cp.async, 1: rows by bulk copy (default), 2: rows + payloads
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
     int n_sm = 0;
