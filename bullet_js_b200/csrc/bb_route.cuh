@@ -277,18 +277,26 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
   // PERSISTENT on a small grid (bb_router: 64 CTAs): the kernel is NVLink-bound and runs next to the
   // merge of the previous batch; one CTA per tile would take every SM's thread slots away from it
   const uint32_t tiles = (uint32_t)((a.n + RT_THREADS - 1) / RT_THREADS);
+  // a tile's rows travel global -> registers -> shared (partitioned) -> peer memory; the NEXT tile's rows are
+  // fetched into the registers while the copy engine still drains this tile's runs out of shared memory
+  uint64_t pid_raw = 0;
+  uint4 h, c0, c1, v0, v1;
+  auto fetch = [&](uint32_t tile) {
+    const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
+    if (tile < tiles && i < a.n) {
+      pid_raw = a.path_id[i];
+      h = a.head[i];
+      c0 = a.clk[2 * i];
+      c1 = a.clk[2 * i + 1];
+      v0 = a.val[2 * i];
+      v1 = a.val[2 * i + 1];
+    }
+  };
+  fetch(blockIdx.x);
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
   const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
-  const uint64_t p = i < a.n ? shard_mix(a.path_id[i], a.key_bits) : 0;
+  const uint64_t p = i < a.n ? shard_mix(pid_raw, a.key_bits) : 0;
   const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
-  uint4 h, c0, c1, v0, v1;
-  if (i < a.n) {
-    h = a.head[i];
-    c0 = a.clk[2 * i];
-    c1 = a.clk[2 * i + 1];
-    v0 = a.val[2 * i];
-    v1 = a.val[2 * i + 1];
-  }
   uint32_t below = 0;
   for (uint32_t r = 0; r < a.world; ++r) {
     const uint32_t m = __ballot_sync(0xffffffffu, d == r);
@@ -296,14 +304,21 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
     if (lane == 0) s_w[w][r] = __popc(m);
   }
   __syncthreads();
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (uint32_t r = 0; r < a.world; ++r) {
-      s_start[r] = run;
-      s_dst[r] = (int64_t)a.tile_off[(uint64_t)tile * a.world + r] + s_adj[r] - (int64_t)run;
-      for (int ww = 0; ww < RT_THREADS / 32; ++ww) run += s_w[ww][r];
+  if (w == 0) {  // lane r sums owner r's 32 warp counts, then an exclusive scan over the owners
+    uint32_t cnt = 0;
+    if (lane < (int)a.world)
+      for (int ww = 0; ww < RT_THREADS / 32; ++ww) cnt += s_w[ww][lane];
+    uint32_t run = cnt;
+#pragma unroll
+    for (int o = 1; o < RT_MAX_WORLD; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, run, o);
+      if (lane >= o) run += t;
     }
-    s_start[a.world] = run;
+    if (lane < (int)a.world) {
+      s_start[lane] = run - cnt;
+      s_dst[lane] = (int64_t)a.tile_off[(uint64_t)tile * a.world + lane] + s_adj[lane] - (int64_t)(run - cnt);
+      if (lane == (int)a.world - 1) s_start[a.world] = run;
+    }
   }
   __syncthreads();
   if (i < a.n) {
@@ -348,6 +363,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
       while ((uint32_t)tid >= s_start[r + 1]) ++r;
       a.d_path[r][(uint64_t)(s_dst[r] + (int64_t)tid)] = s_path[tid];
     }
+    fetch(tile + gridDim.x);  // the next tile's rows: in flight while the copy engine reads this tile's runs
     if (tid < (int)(3 * a.world)) bulk_wait_read_all();  // sources read: reusable
   } else {
   {  // rows of the tile in partitioned order: thread j moves row j
@@ -371,6 +387,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
       a.d_val[r][dst] = s_val[e];
     }
   }
+  fetch(tile + gridDim.x);
   }
   __syncthreads();  // shared memory is reused by the next tile
   }
