@@ -30,7 +30,9 @@ __host__ __device__ __forceinline__ uint64_t shard_mix(uint64_t id, uint32_t key
   return x;
 }
 
-constexpr int RT_THREADS = 1024;   // updates per tile of the count / scatter kernels
+constexpr int RT_THREADS = 512;    // updates per tile of the count / scatter kernels
+constexpr int RT_BLOCK = 256;      // threads of a k_route_scatter_p2p CTA: RT_RPT rows of the tile each.  The kernel runs BESIDE
+constexpr int RT_RPT = RT_THREADS / RT_BLOCK;  // the merge: a 1024-thread CTA with 88 KB of tile took 6 of an SM's 7 merge CTAs
 constexpr int RS_THREADS = 256;    // threads of the single scan CTA
 constexpr int RT_MAX_WORLD = 16;
 
@@ -245,13 +247,13 @@ __global__ void __launch_bounds__(32) k_query_barrier(RouteCtlPeers peers, uint3
 
 constexpr int RT_SMEM = RT_THREADS * 88;
 
-__global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2PArgs a) {
+__global__ void __launch_bounds__(RT_BLOCK) k_route_scatter_p2p(const RouteP2PArgs a) {
   BB_DYN_SMEM(s_raw);
-  uint4* s_head = reinterpret_cast<uint4*>(s_raw);                   // [1024]
-  uint4* s_clk = s_head + RT_THREADS;                                 // [2048]
-  uint4* s_val = s_clk + 2 * RT_THREADS;                              // [2048]
-  uint64_t* s_path = reinterpret_cast<uint64_t*>(s_val + 2 * RT_THREADS);  // [1024]
-  __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];
+  uint4* s_head = reinterpret_cast<uint4*>(s_raw);                   // [RT_THREADS]
+  uint4* s_clk = s_head + RT_THREADS;                                 // [2 * RT_THREADS]
+  uint4* s_val = s_clk + 2 * RT_THREADS;                              // [2 * RT_THREADS]
+  uint64_t* s_path = reinterpret_cast<uint64_t*>(s_val + 2 * RT_THREADS);  // [RT_THREADS]
+  __shared__ uint32_t s_w[RT_THREADS / 32][RT_MAX_WORLD];  // [warp-sized run of the tile][owner]
   __shared__ uint32_t s_start[RT_MAX_WORLD + 1];
   __shared__ int64_t s_dst[RT_MAX_WORLD];  // destination row of the owner's run minus its start in the tile
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -278,118 +280,126 @@ __global__ void __launch_bounds__(RT_THREADS) k_route_scatter_p2p(const RouteP2P
   // merge of the previous batch; one CTA per tile would take every SM's thread slots away from it
   const uint32_t tiles = (uint32_t)((a.n + RT_THREADS - 1) / RT_THREADS);
   // a tile's rows travel global -> registers -> shared (partitioned) -> peer memory; the NEXT tile's rows are
-  // fetched into the registers while the copy engine still drains this tile's runs out of shared memory
-  uint64_t pid_raw = 0;
-  uint4 h, c0, c1, v0, v1;
+  // fetched into the registers while the copy engine still drains this tile's runs out of shared memory.
+  // Thread t holds rows t, t + RT_BLOCK, ... of the tile: "virtual warp" k * (RT_BLOCK / 32) + w covers 32 consecutive rows.
+  uint64_t pid_raw[RT_RPT];
+  uint4 h[RT_RPT], c0[RT_RPT], c1[RT_RPT], v0[RT_RPT], v1[RT_RPT];
   auto fetch = [&](uint32_t tile) {
-    const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
-    if (tile < tiles && i < a.n) {
-      pid_raw = a.path_id[i];
-      h = a.head[i];
-      c0 = a.clk[2 * i];
-      c1 = a.clk[2 * i + 1];
-      v0 = a.val[2 * i];
-      v1 = a.val[2 * i + 1];
+    if (tile >= tiles) return;
+#pragma unroll
+    for (int k = 0; k < RT_RPT; ++k) {
+      const uint64_t i = (uint64_t)tile * RT_THREADS + k * RT_BLOCK + tid;
+      if (i < a.n) {
+        pid_raw[k] = a.path_id[i];
+        h[k] = a.head[i];
+        c0[k] = a.clk[2 * i];
+        c1[k] = a.clk[2 * i + 1];
+        v0[k] = a.val[2 * i];
+        v1[k] = a.val[2 * i + 1];
+      }
     }
   };
   fetch(blockIdx.x);
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-  const uint64_t i = (uint64_t)tile * RT_THREADS + tid;
-  const uint64_t p = i < a.n ? shard_mix(pid_raw, a.key_bits) : 0;
-  const uint32_t d = i < a.n ? (uint32_t)(p % a.world) : a.world;
-  uint32_t below = 0;
-  for (uint32_t r = 0; r < a.world; ++r) {
-    const uint32_t m = __ballot_sync(0xffffffffu, d == r);
-    if (d == r) below = __popc(m & lanemask_lt());
-    if (lane == 0) s_w[w][r] = __popc(m);
-  }
-  __syncthreads();
-  if (w == 0) {  // lane r sums owner r's 32 warp counts, then an exclusive scan over the owners
-    uint32_t cnt = 0;
-    if (lane < (int)a.world)
-      for (int ww = 0; ww < RT_THREADS / 32; ++ww) cnt += s_w[ww][lane];
-    uint32_t run = cnt;
+    uint64_t p[RT_RPT];
+    uint32_t d[RT_RPT], below[RT_RPT];
 #pragma unroll
-    for (int o = 1; o < RT_MAX_WORLD; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, run, o);
-      if (lane >= o) run += t;
-    }
-    if (lane < (int)a.world) {
-      s_start[lane] = run - cnt;
-      s_dst[lane] = (int64_t)a.tile_off[(uint64_t)tile * a.world + lane] + s_adj[lane] - (int64_t)(run - cnt);
-      if (lane == (int)a.world - 1) s_start[a.world] = run;
-    }
-  }
-  __syncthreads();
-  if (i < a.n) {
-    uint32_t lp = s_start[d] + below;
-    for (int ww = 0; ww < w; ++ww) lp += s_w[ww][d];
-    s_path[lp] = p / a.world;
-    s_head[lp] = h;
-    s_clk[2 * lp] = c0;
-    s_clk[2 * lp + 1] = c1;
-    s_val[2 * lp] = v0;
-    s_val[2 * lp + 1] = v1;
-  }
-  __syncthreads();
-  const uint32_t rows = s_start[a.world];
-  if (a.bulk) {
-    // Every (owner, array) run is contiguous in shared memory and in the owner's slot: ONE bulk copy each
-    // (cp.async.bulk shared -> global, to peer memory over NVLink).  The copy engine of the SM moves the
-    // bytes; no thread, register or LSU slot waits for the remote stores, so a handful of CTAs keeps
-    // NVLink busy and the merge kernel running next to them keeps its SMs to itself.
-    fence_proxy_async_smem();  // the partition above was written with st.shared
-    if (tid < (int)(3 * a.world)) {
-      const uint32_t r = tid / 3, arr = tid % 3;
-      const uint32_t first = s_start[r], cnt = s_start[r + 1] - first;
-      if (cnt) {
-        const uint64_t drow = (uint64_t)(s_dst[r] + (int64_t)first);
-        const void* src;
-        void* dst;
-        uint32_t bytes;
-        if (arr == 0) {
-          src = s_head + first, dst = a.d_head[r] + drow, bytes = cnt * 16u;
-        } else if (arr == 1) {
-          src = s_clk + 2 * first, dst = a.d_clk[r] + 2 * drow, bytes = cnt * 32u;
-        } else {
-          src = s_val + 2 * first, dst = a.d_val[r] + 2 * drow, bytes = cnt * 32u;
-        }
-        bulk_s2g(dst, src, bytes);
+    for (int k = 0; k < RT_RPT; ++k) {
+      const uint64_t i = (uint64_t)tile * RT_THREADS + k * RT_BLOCK + tid;
+      p[k] = i < a.n ? shard_mix(pid_raw[k], a.key_bits) : 0;
+      d[k] = i < a.n ? (uint32_t)(p[k] % a.world) : a.world;
+      below[k] = 0;
+      for (uint32_t r = 0; r < a.world; ++r) {
+        const uint32_t m = __ballot_sync(0xffffffffu, d[k] == r);
+        if (d[k] == r) below[k] = __popc(m & lanemask_lt());
+        if (lane == 0) s_w[k * (RT_BLOCK / 32) + w][r] = __popc(m);
       }
-      bulk_commit();
     }
-    if (tid < (int)rows) {  // the 8-byte local row ids: runs are not 16-byte aligned, plain stores
-      uint32_t r = 0;
-      while ((uint32_t)tid >= s_start[r + 1]) ++r;
-      a.d_path[r][(uint64_t)(s_dst[r] + (int64_t)tid)] = s_path[tid];
-    }
-    fetch(tile + gridDim.x);  // the next tile's rows: in flight while the copy engine reads this tile's runs
-    if (tid < (int)(3 * a.world)) bulk_wait_read_all();  // sources read: reusable
-  } else {
-  {  // rows of the tile in partitioned order: thread j moves row j
-    const uint32_t j = tid;
-    if (j < rows) {
-      uint32_t r = 0;
-      while (j >= s_start[r + 1]) ++r;
-      const uint64_t dst = (uint64_t)(s_dst[r] + (int64_t)j);
-      a.d_path[r][dst] = s_path[j];
-      a.d_head[r][dst] = s_head[j];
-    }
-  }
+    __syncthreads();
+    if (w == 0) {  // lane r sums owner r's run counts, then an exclusive scan over the owners
+      uint32_t cnt = 0;
+      if (lane < (int)a.world)
+        for (int ww = 0; ww < RT_THREADS / 32; ++ww) cnt += s_w[ww][lane];
+      uint32_t run = cnt;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {  // the 32-byte columns as 2048 16-byte pieces
-    const uint32_t e = tid + k * RT_THREADS, j = e >> 1;
-    if (j < rows) {
-      uint32_t r = 0;
-      while (j >= s_start[r + 1]) ++r;
-      const uint64_t dst = 2 * (uint64_t)(s_dst[r] + (int64_t)j) + (e & 1u);
-      a.d_clk[r][dst] = s_clk[e];
-      a.d_val[r][dst] = s_val[e];
+      for (int o = 1; o < RT_MAX_WORLD; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += t;
+      }
+      if (lane < (int)a.world) {
+        s_start[lane] = run - cnt;
+        s_dst[lane] = (int64_t)a.tile_off[(uint64_t)tile * a.world + lane] + s_adj[lane] - (int64_t)(run - cnt);
+        if (lane == (int)a.world - 1) s_start[a.world] = run;
+      }
     }
-  }
-  fetch(tile + gridDim.x);
-  }
-  __syncthreads();  // shared memory is reused by the next tile
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RT_RPT; ++k) {
+      const uint64_t i = (uint64_t)tile * RT_THREADS + k * RT_BLOCK + tid;
+      if (i < a.n) {
+        uint32_t lp = s_start[d[k]] + below[k];
+        for (int ww = 0; ww < k * (RT_BLOCK / 32) + w; ++ww) lp += s_w[ww][d[k]];
+        s_path[lp] = p[k] / a.world;
+        s_head[lp] = h[k];
+        s_clk[2 * lp] = c0[k];
+        s_clk[2 * lp + 1] = c1[k];
+        s_val[2 * lp] = v0[k];
+        s_val[2 * lp + 1] = v1[k];
+      }
+    }
+    __syncthreads();
+    const uint32_t rows = s_start[a.world];
+    if (a.bulk) {
+      // Every (owner, array) run is contiguous in shared memory and in the owner's slot: ONE bulk copy each
+      // (cp.async.bulk shared -> global, to peer memory over NVLink).  The copy engine of the SM moves the
+      // bytes; no thread, register or LSU slot waits for the remote stores, so a handful of CTAs keeps
+      // NVLink busy and the merge kernel running next to them keeps its SMs to itself.
+      fence_proxy_async_smem();  // the partition above was written with st.shared
+      if (tid < (int)(3 * a.world)) {
+        const uint32_t r = tid / 3, arr = tid % 3;
+        const uint32_t first = s_start[r], cnt = s_start[r + 1] - first;
+        if (cnt) {
+          const uint64_t drow = (uint64_t)(s_dst[r] + (int64_t)first);
+          const void* src;
+          void* dst;
+          uint32_t bytes;
+          if (arr == 0) {
+            src = s_head + first, dst = a.d_head[r] + drow, bytes = cnt * 16u;
+          } else if (arr == 1) {
+            src = s_clk + 2 * first, dst = a.d_clk[r] + 2 * drow, bytes = cnt * 32u;
+          } else {
+            src = s_val + 2 * first, dst = a.d_val[r] + 2 * drow, bytes = cnt * 32u;
+          }
+          bulk_s2g(dst, src, bytes);
+        }
+        bulk_commit();
+      }
+      for (uint32_t j = tid; j < rows; j += RT_BLOCK) {  // the 8-byte local row ids: runs are not 16-byte aligned, plain stores
+        uint32_t r = 0;
+        while (j >= s_start[r + 1]) ++r;
+        a.d_path[r][(uint64_t)(s_dst[r] + (int64_t)j)] = s_path[j];
+      }
+      fetch(tile + gridDim.x);  // the next tile's rows: in flight while the copy engine reads this tile's runs
+      if (tid < (int)(3 * a.world)) bulk_wait_read_all();  // sources read: reusable
+    } else {
+      for (uint32_t j = tid; j < rows; j += RT_BLOCK) {  // rows of the tile in partitioned order
+        uint32_t r = 0;
+        while (j >= s_start[r + 1]) ++r;
+        const uint64_t dst = (uint64_t)(s_dst[r] + (int64_t)j);
+        a.d_path[r][dst] = s_path[j];
+        a.d_head[r][dst] = s_head[j];
+      }
+      for (uint32_t e = tid; e < 2 * rows; e += RT_BLOCK) {  // the 32-byte columns as 16-byte pieces
+        const uint32_t j = e >> 1;
+        uint32_t r = 0;
+        while (j >= s_start[r + 1]) ++r;
+        const uint64_t dst = 2 * (uint64_t)(s_dst[r] + (int64_t)j) + (e & 1u);
+        a.d_clk[r][dst] = s_clk[e];
+        a.d_val[r][dst] = s_val[e];
+      }
+      fetch(tile + gridDim.x);
+    }
+    __syncthreads();  // shared memory is reused by the next tile
   }
   if (a.bulk && tid < (int)(3 * a.world)) bulk_wait_all();  // writes done
 }

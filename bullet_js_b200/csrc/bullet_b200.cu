@@ -1527,7 +1527,7 @@ int bb_router_route_dev(bb_router* r, const bb_batch* in, uint32_t slot, uint64_
       a.key_bits = r->key_bits;
       a.bulk = r->bulk ? 1u : 0u;
       a.tile_off = tile_buf;
-      bb_launch(bb::k_route_scatter_p2p, std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_THREADS, bb::RT_SMEM, s, false, a);
+      bb_launch(bb::k_route_scatter_p2p, std::min<uint32_t>(tiles, r->scatter_ctas), bb::RT_BLOCK, bb::RT_SMEM, s, false, a);
       r->launches += 1;
       BB_RCUDA(r, cudaGetLastError());
     }
