@@ -1196,7 +1196,7 @@ struct bb_router {
   uint64_t routed_n[2]{};
   uint32_t* tiles = nullptr;
   uint64_t sent_bytes = 0, launches = 0;
-  uint32_t scatter_ctas = 64;  // grid of the fused pack + exchange kernel (env BB_ROUTE_CTAS)
+  uint32_t scatter_ctas = 192;  // grid of the fused pack + exchange kernel (env BB_ROUTE_CTAS): 256-thread CTAs, 45 KB each
   bool bulk = true;            // runs leave with cp.async.bulk (env BB_ROUTE_BULK=0: per-thread stores)
   bool flag_sync = true;       // counts / completion through peer-mapped flags (env BB_ROUTE_NCCL_SYNC=1: NCCL all-gathers)
   bb::RouteCtl* ctl = nullptr; // this rank's control block (peer-mapped by everybody)
