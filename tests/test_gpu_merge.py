@@ -439,3 +439,31 @@ def test_router_host_entry_single_rank(compact):
         router.merge_batch(eng, capi.batch_struct(b), small.struct(), pieces)
     router.close()
     eng.close()
+
+
+@pytest.mark.parametrize("radix", [False, True, "full"])
+def test_far_out_of_range_id_in_a_smaller_second_batch(radix):
+    """A rejected batch must not make the merge kernels load through a stale / half-written item list (advisor,
+    round 1): a first batch leaves item lists and scratch behind, a SMALLER second batch carries path id 2**31 (far
+    outside the table, hundreds of GB away as a row address) - documented outcome: BB_ERR_CAPACITY, table unchanged,
+    context usable.  Every front end."""
+    n_rec = 2000
+    rng = synth.rng_for(0, salt=19)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = engine_and_oracle(None, n_rec, radix=radix, **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, table.rows)
+    orc.load(ids, table.rows)
+    b1 = synth.make_batch(table, 40_000, rng)
+    assert eng.merge(b1).same_as(orc.merge(b1))
+    b2 = synth.make_batch(table, 3_000, rng)
+    for bad in (2 ** 31, 2 ** 40 + 7, 2 ** 63):
+        b2.path_id[777] = bad
+        with pytest.raises(capi.BulletB200Error) as ei:
+            eng.merge(b2)
+        assert ei.value.code == capi.ERR_CAPACITY
+        assert np.array_equal(eng.table_read(ids), orc.read(ids))
+    b2.path_id[777] = 5
+    assert eng.merge(b2).same_as(orc.merge(b2))
+    assert_same_table(eng, orc, n_rec)
+    eng.close()
