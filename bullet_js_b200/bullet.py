@@ -77,9 +77,11 @@ class BulletNode:
 
 
 class _Collection:
-    def __init__(self, name: str, schema: codec.Schema, capacity: int, device: int, track_modified: bool = False):
+    def __init__(self, name: str, schema: codec.Schema, capacity: int, device: int, track_modified: bool = False,
+                 exact_order: bool = False):
         self.name, self.schema = name, schema
-        self.engine = Engine.for_schema(schema, capacity, device=device, post_getdata=True, track_modified=track_modified)
+        self.engine = Engine.for_schema(schema, capacity, device=device, post_getdata=True, track_modified=track_modified,
+                                        exact_order=exact_order)
         self.indexed: set[int] = set()
         self.epoch_ms: list[float] = [0.0]  # Date.now() of merge call k (meta.lastModified at call granularity); [0] unused
 
@@ -89,8 +91,11 @@ class _Collection:
 
 class Bullet:
     def __init__(self, collections: dict[str, codec.Schema], capacity: int = 1 << 16, device: int = 0,
-                 track_modified: bool = False, clock: Callable[[], float] | None = None):
-        self._c = {name: _Collection(name, schema, capacity, device, track_modified) for name, schema in collections.items()}
+                 track_modified: bool = False, clock: Callable[[], float] | None = None, exact_order: bool = False):
+        """exact_order: equals / range return the reference's exact lists - buckets in Map order, paths in Set order
+        (BB_CFG_EXACT_ORDER) - instead of the same nodes in device order."""
+        self._c = {name: _Collection(name, schema, capacity, device, track_modified, exact_order)
+                   for name, schema in collections.items()}
         self.track_modified = track_modified
         self._now = clock or (lambda: time.time() * 1000.0)  # Date.now()
         self.log: list[dict] = []          # src/bullet.js:206-215

@@ -33,6 +33,7 @@ CFG_FULL_SORT = 8
 CFG_HOT_KEYS = 64
 CFG_COMPACT_CHANGES = 128
 CFG_TRACK_MODIFIED = 256
+CFG_EXACT_ORDER = 512
 COLLECT_FILTER_RECORDS = 1
 
 DEC_NO_CURRENT, DEC_IDENTICAL, DEC_TIE_INCOMING, DEC_TIE_CURRENT = 0, 1, 2, 3

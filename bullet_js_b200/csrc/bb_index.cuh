@@ -32,7 +32,36 @@ struct IndexArgs {
   uint32_t* xnode[F];
   uint32_t xmask[F];   // slots - 1
   uint32_t* xused;     // [F] slots that have left the EMPTY state
+  // BB_CFG_EXACT_ORDER: every entry carries the tag of the add that inserted it, and the hook logs its
+  // EFFECTIVE adds / removes as events (key, field << 62 | tag) for the per-bucket replay that follows the batch
+  uint64_t* pseq[F];   // [capacity] tag of the node's dense entry
+  uint64_t* xseq[F];   // [slots]    tag of an overflow entry
+  uint64_t* ev_key;    // [ev_cap]
+  uint64_t* ev_tag;
+  uint32_t* ev_count;
+  uint32_t ev_cap;
 };
+
+// Event / entry tags: 4 * (sequence of the update) + 2 for its remove, + 3 for its add (the hook removes, then adds:
+// query:153-167); an entry put there by an index BUILD carries 4 * (creation sequence of its node): builds walk the
+// store in creation order (query:58-66) and everything a build inserts precedes everything a later update inserts.
+// (Bit 61 keeps an update's tags above every build tag whatever the two counters are: a table loaded with
+// bb_table_load brings its own creation sequences, and the update counter starts at zero.)
+constexpr uint64_t TAG_UPDATE = 1ull << 61;
+__device__ __forceinline__ uint64_t tag_remove(uint64_t seq) { return TAG_UPDATE | (4 * seq + 2); }
+__device__ __forceinline__ uint64_t tag_add(uint64_t seq) { return TAG_UPDATE | (4 * seq + 3); }
+__device__ __forceinline__ bool tag_is_add(uint64_t tag) { return (tag & 3u) != 2u; }
+constexpr uint64_t TAG_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ void log_event(const IndexArgs& ix, int f, uint64_t key, uint64_t tag, uint32_t* err) {
+  const uint32_t i = atomicAdd(ix.ev_count, 1u);
+  if (i < ix.ev_cap) {
+    ix.ev_key[i] = key;
+    ix.ev_tag[i] = ((uint64_t)f << 62) | tag;
+  } else {
+    atomicOr(err, ERR_XFULL);
+  }
+}
 
 // String(value) as a 64-bit key (query:126-131); value is a non-null primitive
 __device__ __forceinline__ uint64_t canon_key(uint32_t tag, uint64_t pay) {
@@ -69,8 +98,8 @@ __device__ __forceinline__ void x_remove_at(const IndexArgs& ix, int f, int64_t 
   ix.xnode[f][slot] = X_TOMB;
 }
 
-// (node, k) is known to be absent; false when the set is full
-__device__ __forceinline__ bool x_insert(const IndexArgs& ix, int f, uint32_t node, uint64_t k) {
+// (node, k) is known to be absent; the slot it went into, or -1 when the set is full
+__device__ __forceinline__ int64_t x_insert(const IndexArgs& ix, int f, uint32_t node, uint64_t k) {
   const uint32_t m = ix.xmask[f];
   uint32_t i = x_hash(node, k) & m;
   for (uint32_t probe = 0; probe <= m; ++probe, i = (i + 1) & m) {
@@ -78,23 +107,24 @@ __device__ __forceinline__ bool x_insert(const IndexArgs& ix, int f, uint32_t no
     if (n != X_EMPTY && n != X_TOMB) continue;
     if (n == X_EMPTY && atomicAdd(ix.xused + f, 1u) >= m - (m >> 3)) {  // keep 1/8 of the slots EMPTY
       atomicSub(ix.xused + f, 1u);
-      return false;
+      return -1;
     }
     if (atomicCAS(ix.xnode[f] + i, n, node) == n) {
       ix.xkey[f][i] = k;
-      return true;
+      return (int64_t)i;
     }
     if (n == X_EMPTY) atomicSub(ix.xused + f, 1u);  // another node took the slot
   }
-  return false;
+  return -1;
 }
 
 __device__ __forceinline__ uint32_t xcnt_get(uint32_t xcnt, int f) { return (xcnt >> (8 * f)) & 0xFFu; }
 
 // _updateIndices (query:139-176) for one setData on `node`: `after` is the node as _getData
 // sees it after the write, `x` the raw incoming value.  prim[f] caches pcol[f][node].
+template <bool EXACT = false>
 __device__ __forceinline__ void index_hook(const IndexArgs& ix, uint32_t node, const Value& after, const Value& x,
-                                           uint64_t (&prim)[F], uint32_t& xcnt, uint32_t* err) {
+                                           uint64_t (&prim)[F], uint32_t& xcnt, uint32_t* err, uint64_t seq = 0) {
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     if (!((ix.mask >> f) & 1u)) continue;
@@ -104,11 +134,13 @@ __device__ __forceinline__ void index_hook(const IndexArgs& ix, uint32_t node, c
         const uint64_t k = canon_key(t, after.val[f]);
         if (prim[f] == k) {
           prim[f] = BB_KEY_NONE;
+          if (EXACT) log_event(ix, f, k, tag_remove(seq), err);
         } else if (xcnt_get(xcnt, f)) {
           const int64_t slot = x_find(ix, f, node, k);
           if (slot >= 0) {
             x_remove_at(ix, f, slot);
             if (xcnt_get(xcnt, f) != 0xFFu) xcnt -= 1u << (8 * f);
+            if (EXACT) log_event(ix, f, k, tag_remove(seq), err);
           }
         }
       }
@@ -121,10 +153,21 @@ __device__ __forceinline__ void index_hook(const IndexArgs& ix, uint32_t node, c
         if (xcnt_get(xcnt, f) && x_find(ix, f, node, k) >= 0) continue;
         if (prim[f] == BB_KEY_NONE) {
           prim[f] = k;
-        } else if (x_insert(ix, f, node, k)) {
-          if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
+          if (EXACT) {
+            ix.pseq[f][node] = tag_add(seq);
+            log_event(ix, f, k, tag_add(seq), err);
+          }
         } else {
-          atomicOr(err, ERR_XFULL);
+          const int64_t slot = x_insert(ix, f, node, k);
+          if (slot >= 0) {
+            if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
+            if (EXACT) {
+              ix.xseq[f][slot] = tag_add(seq);
+              log_event(ix, f, k, tag_add(seq), err);
+            }
+          } else {
+            atomicOr(err, ERR_XFULL);
+          }
         }
       }
     }
@@ -245,6 +288,7 @@ struct ScanArgs {
   uint64_t cap;
   unsigned long long* counters;  // [2]: dense matches, overflow matches
   uint32_t which;          // 0: dense column (writes from 0), 1: overflow set (writes after counters[0])
+  uint32_t ref_or;         // OR-ed into the entry index when `nodes` is null (exact order: overflow hits leave as slot | 2^31)
   uint32_t* tile_state;    // [num_tiles] zeroed
   uint32_t* ticket;        // zeroed
   uint32_t num_tiles;
@@ -315,7 +359,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
       const int b = __ffs(flags) - 1;
       flags &= flags - 1;
       const uint64_t e = base + 2 * ((uint64_t)(b >> 1) * SC_THREADS + tid) + (b & 1);
-      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e] : (uint32_t)e;
+      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e] : ((uint32_t)e | a.ref_or);
       else overflow = true;
       ++d;
     }
@@ -367,16 +411,155 @@ __global__ void __launch_bounds__(SC_THREADS) k_index_scan(const ScanArgs a) {
     uint64_t d = obase + s_cnt[j * SC_WARPS + w] + lp;
     const uint64_t e = base + 2 * ((uint64_t)j * SC_THREADS + tid);
     if (hb & 1u) {
-      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e] : (uint32_t)e;
+      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e] : ((uint32_t)e | a.ref_or);
       else overflow = true;
       ++d;
     }
     if (hb & 2u) {
-      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e + 1] : (uint32_t)(e + 1);
+      if (d < a.cap) a.out[d] = a.nodes ? a.nodes[e + 1] : ((uint32_t)(e + 1) | a.ref_or);
       else overflow = true;
     }
   }
   if (overflow) atomicOr(a.err, ERR_HITS);
+}
+
+// ---------------------------------------------------------------- exact Map / Set order (BB_CFG_EXACT_ORDER)
+// The reference returns equals / range results in (bucket creation order, insertion order inside the bucket)
+// (query:89-93, 110-116, 204, 237-258).  Entries carry the tag of the add that inserted them (above); a bucket's
+// creation tag is that of the add that followed the last time its entry count was zero.  After every batch (and after
+// an index build) the logged events are sorted by (key, field, tag) and every bucket's run is replayed against a
+// per-field bucket table key -> (count, created); a query sorts its hits by (created, entry tag).
+struct BucketTable {
+  uint64_t* key;      // [slots] BB_KEY_NONE = empty
+  uint32_t* count;    // live entries
+  uint64_t* created;  // tag of the add that (re-)created the bucket
+  uint32_t mask;      // slots - 1
+};
+
+__device__ __forceinline__ uint32_t bucket_hash(uint64_t k) {
+  uint64_t h = (k ^ (k >> 33)) * 0xFF51AFD7ED558CCDull;
+  h ^= h >> 29;
+  return (uint32_t)(h * 0x9E3779B97F4A7C15ull >> 32);
+}
+
+// slot of `k`, inserting it if absent; -1 when the table is full
+__device__ __forceinline__ int64_t bucket_find_or_insert(const BucketTable& t, uint64_t k) {
+  uint32_t i = bucket_hash(k) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe, i = (i + 1) & t.mask) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(t.key + i);
+    if (cur == BB_KEY_NONE) cur = atomicCAS(reinterpret_cast<unsigned long long*>(t.key + i), (unsigned long long)BB_KEY_NONE, (unsigned long long)k);
+    if (cur == BB_KEY_NONE || cur == k) return (int64_t)i;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int64_t bucket_find(const BucketTable& t, uint64_t k) {
+  uint32_t i = bucket_hash(k) & t.mask;
+  for (uint32_t probe = 0; probe <= t.mask; ++probe, i = (i + 1) & t.mask) {
+    const uint64_t cur = t.key[i];
+    if (cur == k) return (int64_t)i;
+    if (cur == BB_KEY_NONE) return -1;
+  }
+  return -1;
+}
+
+// the entries an index BUILD inserted: tag = 4 * creation sequence of the node, one add event each
+__global__ void __launch_bounds__(256) k_exact_build_events(const uint4* __restrict__ table, uint64_t capacity, int f, IndexArgs ix,
+                                                            uint32_t* __restrict__ err) {
+  const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= capacity) return;
+  const uint64_t k = ix.pcol[f][row];
+  if (k == BB_KEY_NONE) return;
+  const uint4 q = table[row * 8 + 3];  // device chunk 3 = public chunk 7: flags, xcnt, cseq
+  const uint64_t cseq = (uint64_t)q.z | ((uint64_t)q.w << 32);
+  ix.pseq[f][row] = 4 * cseq;
+  log_event(ix, f, k, 4 * cseq, err);
+}
+
+// pads [n, padded) of a sort buffer with keys that sort last; n is read on the device (no host round trip)
+__global__ void __launch_bounds__(256) k_sort_pad(uint64_t* __restrict__ a, uint64_t* __restrict__ b, const uint32_t* __restrict__ n_dev,
+                                                  uint32_t n_host, uint32_t padded) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = n_dev ? min(*n_dev, padded) : n_host;
+  if (i >= n && i < padded) {
+    a[i] = ~0ull;
+    b[i] = ~0ull;
+  }
+}
+
+// one compare-exchange step of a bitonic sort of (a, b) pairs, lexicographic, with an optional payload
+__global__ void __launch_bounds__(256) k_bitonic_step(uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint32_t* __restrict__ v,
+                                                      uint32_t padded, uint32_t k, uint32_t j) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t l = i ^ j;
+  if (i >= padded || l <= i) return;
+  const uint64_t ai = a[i], bi = b[i], al = a[l], bl = b[l];
+  const bool greater = ai > al || (ai == al && bi > bl);
+  const bool up = (i & k) == 0;
+  if (greater == up) {
+    a[i] = al; b[i] = bl;
+    a[l] = ai; b[l] = bi;
+    if (v) {
+      const uint32_t t = v[i];
+      v[i] = v[l];
+      v[l] = t;
+    }
+  }
+}
+
+// sorted events: the thread on the first event of a (key, field) run replays the run against the bucket's state
+__global__ void __launch_bounds__(256) k_bucket_replay(const uint64_t* __restrict__ ev_key, const uint64_t* __restrict__ ev_tag,
+                                                       const uint32_t* __restrict__ n_dev, uint32_t cap, BucketTable t0, BucketTable t1,
+                                                       BucketTable t2, BucketTable t3, uint32_t* __restrict__ err) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = min(*n_dev, cap);
+  if (i >= n) return;
+  const uint64_t k = ev_key[i];
+  const uint32_t f = (uint32_t)(ev_tag[i] >> 62);
+  if (i > 0 && ev_key[i - 1] == k && (uint32_t)(ev_tag[i - 1] >> 62) == f) return;
+  const BucketTable& t = f == 0 ? t0 : f == 1 ? t1 : f == 2 ? t2 : t3;
+  const int64_t slot = bucket_find_or_insert(t, k);
+  if (slot < 0) {
+    atomicOr(err, ERR_XFULL);
+    return;
+  }
+  uint32_t count = t.count[slot];
+  uint64_t created = t.created[slot];
+  for (uint32_t e = i; e < n && ev_key[e] == k && (uint32_t)(ev_tag[e] >> 62) == f; ++e) {
+    const uint64_t tag = ev_tag[e] & TAG_MASK;
+    if (tag_is_add(tag)) {
+      if (count == 0) created = tag;  // the bucket is (re-)created at the end of the Map order (query:89-93)
+      ++count;
+    } else if (count) {
+      --count;                        // at zero the bucket is deleted (query:114-116)
+    }
+  }
+  t.count[slot] = count;
+  t.created[slot] = created;
+}
+
+// hit references of a scan (dense: node; overflow: slot | 2^31) -> sort keys (bucket created, entry tag) + node
+__global__ void __launch_bounds__(256) k_exact_hit_keys(const uint32_t* __restrict__ refs, uint32_t n, int f, IndexArgs ix, BucketTable t,
+                                                        uint64_t* __restrict__ a, uint64_t* __restrict__ b, uint32_t* __restrict__ node_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ref = refs[i];
+  uint64_t key, tag;
+  uint32_t node;
+  if (ref & 0x80000000u) {
+    const uint32_t slot = ref & 0x7FFFFFFFu;
+    node = ix.xnode[f][slot];
+    key = ix.xkey[f][slot];
+    tag = ix.xseq[f][slot];
+  } else {
+    node = ref;
+    key = ix.pcol[f][ref];
+    tag = ix.pseq[f][ref];
+  }
+  const int64_t slot = bucket_find(t, key);
+  a[i] = slot >= 0 ? t.created[slot] : ~0ull - 1;
+  b[i] = tag;
+  node_out[i] = node;
 }
 
 }  // namespace bb

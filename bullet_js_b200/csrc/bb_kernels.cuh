@@ -605,7 +605,8 @@ __device__ __forceinline__ int row_at(int r, int c) { return TMA ? r * ROW_QT + 
 // A segment that runs past its tile is finished by its owner straight from global memory.
 // 7 CTAs per SM at 72 registers.  (8 would fit the 27.7 KB of shared memory, but at 64 registers the resolver
 // spills and the kernel measured 6 % slower: 104 vs 99 us.)
-template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false, int TMA = 0>  // TMA: 1 = rows, 2 = rows + payloads by bulk copy
+// TMA: 1 = rows, 2 = rows + payloads by bulk copy; EXACT: entry tags + hook events for exact Map / Set query order
+template <bool ORDERED, bool INDEXED, bool HOT = false, bool COMPACT = false, int TMA = 0, bool EXACT = false>
 __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_upd[MT * UPD_Q];
   __shared__ __align__(16) uint4 s_row[MT * (TMA ? ROW_QT : ROW_Q)];
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
       Value x, ov;
       const bool net = unpack_update(h, u[1], u[2], u[3], u[4], c, x);
       const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + s_idx[p], ov, oc);
-      if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
+      if (INDEXED) index_hook<EXACT>(a.ix, key, r.s, x, prim, r.xcnt, a.err, a.seq_base + s_idx[p]);
       uint32_t res = code;
       if (BB_DEC_ACCEPTED(code)) {
         if (COMPACT && echoes_update(u, ov, oc)) res |= RES_ECHO;
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
         const bool net = unpack_update(h, a.clk[2 * (uint64_t)ui], a.clk[2 * (uint64_t)ui + 1],
                                        a.val[2 * (uint64_t)ui], a.val[2 * (uint64_t)ui + 1], c, x);
         const uint32_t code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
-        if (INDEXED) index_hook(a.ix, key, r.s, x, prim, r.xcnt, a.err);
+        if (INDEXED) index_hook<EXACT>(a.ix, key, r.s, x, prim, r.xcnt, a.err, a.seq_base + ui);
         if (BB_DEC_ACCEPTED(code) && a.epoch_col) a.epoch_col[key] = a.epoch;  // meta[path].lastModified (src/bullet.js:201)
         bool echo = false;
         if (COMPACT && BB_DEC_ACCEPTED(code)) {
@@ -989,7 +990,7 @@ struct HotIndex {
     if (prim[f] != k && !(xcnt_get(xcnt, f) && x_find(ix, f, node, k) >= 0)) {
       if (prim[f] == BB_KEY_NONE) {
         prim[f] = k;
-      } else if (x_insert(ix, f, node, k)) {
+      } else if (x_insert(ix, f, node, k) >= 0) {
         if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
       } else {
         atomicOr(err, ERR_XFULL);

@@ -103,7 +103,19 @@ struct bb_ctx {
     uint64_t* xkey = nullptr;
     uint32_t* xnode = nullptr;
     uint64_t xslots = 0;
+    // BB_CFG_EXACT_ORDER: entry tags and the bucket table key -> (count, created)
+    uint64_t* pseq = nullptr;
+    uint64_t* xseq = nullptr;
+    uint64_t* bkey = nullptr;
+    uint32_t* bcount = nullptr;
+    uint64_t* bcreated = nullptr;
+    uint64_t bslots = 0;
   } index[BB_MAX_FIELDS];
+  DevBuf<uint64_t> ev_key, ev_tag;   // hook events of the running batch, then sort buffers of a query
+  DevBuf<uint64_t> q_a, q_b;         // a query's sort keys (bucket created, entry tag)
+  DevBuf<uint32_t> ev_node;          // ... and its payload
+  uint32_t* d_evcount = nullptr;
+  uint32_t ev_padded = 0;            // events the buffers hold: a power of two (the sort pads in place)
   uint32_t index_mask = 0;
   uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
   uint32_t* epoch_col = nullptr;  // BB_CFG_TRACK_MODIFIED: per row, the ordinal of the merge call that last wrote it
@@ -178,7 +190,7 @@ struct ZeroLayout {
 bool ordered_cfg(const bb_ctx* c) { return (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0; }
 
 bool use_grouping(const bb_ctx* c) {
-  return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT));
+  return !(c->cfg.flags & (BB_CFG_RADIX_SORT | BB_CFG_ORDERED_CHANGES | BB_CFG_FULL_SORT | BB_CFG_EXACT_ORDER));
 }
 
 
@@ -263,7 +275,58 @@ void fill_params(const bb_ctx* c, bb::Params& p, bb::IndexArgs& ix) {
     ix.xkey[f] = c->index[f].xkey;
     ix.xnode[f] = c->index[f].xnode;
     ix.xmask[f] = c->index[f].live ? (uint32_t)(c->index[f].xslots - 1) : 0u;
+    ix.pseq[f] = c->index[f].pseq;
+    ix.xseq[f] = c->index[f].xseq;
   }
+  ix.ev_key = c->ev_key.p;
+  ix.ev_tag = c->ev_tag.p;
+  ix.ev_count = c->d_evcount;
+  ix.ev_cap = c->ev_padded;
+}
+
+bool exact_order(const bb_ctx* c) { return (c->cfg.flags & BB_CFG_EXACT_ORDER) != 0; }
+
+uint32_t pow2_at_least(uint64_t n) {
+  uint32_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+bb::BucketTable bucket_table(const bb_ctx* c, int f) {
+  const bb_ctx::IndexDev& ix = c->index[f];
+  return bb::BucketTable{ix.bkey, ix.bcount, ix.bcreated, ix.bslots ? (uint32_t)(ix.bslots - 1) : 0u};
+}
+
+// bitonic sort of the first `padded` (a power of two) pairs of (a, b), lexicographic, with an optional payload
+int bitonic_sort(bb_ctx* c, uint64_t* a, uint64_t* b, uint32_t* v, uint32_t padded, cudaStream_t s) {
+  for (uint32_t k = 2; k <= padded; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1)
+      BB_LAUNCH(c, bb::k_bitonic_step, div_up(padded, 256), 256, s, a, b, v, padded, k, j);
+  return BB_OK;
+}
+
+// BB_CFG_EXACT_ORDER: the events the hook (or an index build) logged -> sorted by (key, field, tag) -> replayed per bucket
+int process_events(bb_ctx* c, cudaStream_t s) {
+  const uint32_t padded = c->ev_padded;
+  if (padded == 0) return BB_OK;
+  BB_LAUNCH(c, bb::k_sort_pad, div_up(padded, 256), 256, s, c->ev_key.p, c->ev_tag.p, c->d_evcount, 0u, padded);
+  int rc = bitonic_sort(c, c->ev_key.p, c->ev_tag.p, nullptr, padded, s);
+  if (rc) return rc;
+  BB_LAUNCH(c, bb::k_bucket_replay, div_up(padded, 256), 256, s, c->ev_key.p, c->ev_tag.p, c->d_evcount, padded, bucket_table(c, 0),
+            bucket_table(c, 1), bucket_table(c, 2), bucket_table(c, 3), c->d_err);
+  BB_CUDA(c, cudaMemsetAsync(c->d_evcount, 0, sizeof(uint32_t), s));
+  return BB_OK;
+}
+
+// room for `n` events (a power of two, so that the sort can pad in place)
+int reserve_events(bb_ctx* c, uint64_t n) {
+  if (n > 0x40000000ull) return fail(c, BB_ERR_ARG, "batch too large for BB_CFG_EXACT_ORDER");
+  const uint32_t p = pow2_at_least(std::max<uint64_t>(n, 256));
+  if (p <= c->ev_padded) return BB_OK;
+  BB_CUDA(c, c->ev_key.ensure(p));
+  BB_CUDA(c, c->ev_tag.ensure(p));
+  c->ev_padded = p;
+  return BB_OK;
 }
 
 // One batch (or one chunk of a host call: `idx_base` = arrival index of its first update,
@@ -378,6 +441,11 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
   ma.epoch = (uint32_t)c->epoch;
   ma.err = c->d_err;
   ma.rej = call_rej ? call_rej : rej;
+  const bool exact = exact_order(c) && c->index_mask;
+  if (exact) {  // at most one effective remove + one effective add per update and index
+    int rc = reserve_events(c, 2 * n * (uint64_t)__builtin_popcount(c->index_mask));
+    if (rc) return rc;
+  }
   fill_params(c, ma.p, ma.ix);
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
   if (grouped) {  // hot keys are handed to k_merge_hot, a CTA per segment (exits at once when there are none)
@@ -403,6 +471,10 @@ int merge_dev(bb_ctx* c, const bb_batch* in, bb_changes* out, cudaStream_t s, ui
       BB_LAUNCH_PDL(c, (k_merge_stage<false, false, true>), z.merge_tiles, MT, 0, s, ma);
       BB_LAUNCH_PDL(c, k_merge_hot<false>, HOT_CTAS, HOT_T, 0, s, ma);
     }
+  } else if (exact) {  // entry tags + hook events, then the per-bucket replay (hot keys: serial, in order, by their owner thread)
+    BB_LAUNCH(c, (k_merge_stage<false, true, false, false, 0, true>), z.merge_tiles, MT, s, ma);
+    int rc = process_events(c, s);
+    if (rc) return rc;
   } else if (c->index_mask) {
     if (ordered) BB_LAUNCH(c, (k_merge_stage<true, true>), z.merge_tiles, MT, s, ma);
     else BB_LAUNCH(c, (k_merge_stage<false, true>), z.merge_tiles, MT, s, ma);
@@ -450,6 +522,23 @@ int index_fill(bb_ctx* c, uint32_t mask, cudaStream_t s) {
     BB_CUDA(c, cudaMemsetAsync(c->d_xused + f, 0, sizeof(uint32_t), s));
   }
   BB_LAUNCH(c, bb::k_index_build, div_up(a.padded, 256), 256, s, a);  // 8 warps x 32 rows per CTA
+  if (exact_order(c)) {  // the entries the build inserted enter the bucket tables in creation order (query:58-66)
+    for (int f = 0; f < BB_MAX_FIELDS; ++f) {
+      if (!((mask >> f) & 1u)) continue;
+      bb_ctx::IndexDev& ix = c->index[f];
+      BB_CUDA(c, cudaMemsetAsync(ix.bkey, 0xFF, ix.bslots * sizeof(uint64_t), s));
+      BB_CUDA(c, cudaMemsetAsync(ix.bcount, 0, ix.bslots * sizeof(uint32_t), s));
+      BB_CUDA(c, cudaMemsetAsync(ix.bcreated, 0, ix.bslots * sizeof(uint64_t), s));
+      int rc = reserve_events(c, c->cfg.capacity);
+      if (rc) return rc;
+      bb::Params p;
+      bb::IndexArgs ia;
+      fill_params(c, p, ia);
+      BB_LAUNCH(c, bb::k_exact_build_events, div_up(c->cfg.capacity, 256), 256, s, c->table, c->cfg.capacity, f, ia, c->d_err);
+      rc = process_events(c, s);
+      if (rc) return rc;
+    }
+  }
   return BB_OK;
 }
 
@@ -467,7 +556,7 @@ int launch_scan(bb_ctx* c, const bb::ScanArgs& a, uint32_t tiles, bool ordered, 
 }
 
 // both scans of one query; `hits` (device or null), counters land in c->d_counters
-int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, uint64_t cap, cudaStream_t s) {
+int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, uint64_t cap, cudaStream_t s, bool refs = false) {
   using namespace bb;
   if (field >= c->cfg.n_fields || !c->index[field].live)
     return fail(c, BB_ERR_STATE, "no index on this field (bb_index_create first)");
@@ -485,6 +574,7 @@ int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, ui
   a.counters = c->d_counters;
   a.err = c->d_err;
   a.p = pred;
+  a.ref_or = 0;
   a.keys = ix.pcol; a.nodes = nullptr; a.n = n0; a.which = 0;
   a.ticket = c->scan_zero.p; a.tile_state = c->scan_zero.p + 2; a.num_tiles = t0;
   const bool ordered = (c->cfg.flags & BB_CFG_ORDERED_CHANGES) != 0;
@@ -493,6 +583,10 @@ int scan_dev(bb_ctx* c, uint32_t field, const bb::Pred& pred, uint32_t* hits, ui
     if (rc) return rc;
   }
   a.keys = ix.xkey; a.nodes = ix.xnode; a.n = n1; a.which = 1;
+  if (refs) {  // exact order: hits leave as entry references (overflow: slot | 2^31), resolved by k_exact_hit_keys
+    a.nodes = nullptr;
+    a.ref_or = 0x80000000u;
+  }
   a.ticket = c->scan_zero.p + 1; a.tile_state = c->scan_zero.p + 2 + t0; a.num_tiles = t1;
   {
     int rc = launch_scan(c, a, t1, ordered, s);
@@ -532,13 +626,32 @@ int query_host(bb_ctx* c, uint32_t field, const bb::Pred& pred, bb_hits* out) {
   cudaStream_t s = c->stream;
   BB_CUDA(c, c->io_hits.ensure(out->cap ? out->cap : 1));
   begin_call(c);
-  int rc = scan_dev(c, field, pred, c->io_hits.p, out->cap, s);
+  const bool exact = exact_order(c);
+  int rc = scan_dev(c, field, pred, c->io_hits.p, out->cap, s, exact);
   if (rc) return rc;
   BB_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   rc = collect_device_error(c, s);  // synchronises
   if (rc) return rc;
   const uint64_t k = c->h_counters[0] + c->h_counters[1];
-  if (k) BB_CUDA(c, cudaMemcpyAsync(out->node, c->io_hits.p, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  const uint32_t* result = c->io_hits.p;
+  if (exact && k) {
+    // the reference's order (query:204, 237-258): buckets in creation order, inside a bucket in insertion order
+    if (k > out->cap) return fail(c, BB_ERR_CAPACITY, "hit buffer too small");
+    const uint32_t padded = pow2_at_least(k);
+    BB_CUDA(c, c->q_a.ensure(padded));
+    BB_CUDA(c, c->q_b.ensure(padded));
+    BB_CUDA(c, c->ev_node.ensure(padded));
+    bb::Params pp;
+    bb::IndexArgs ia;
+    fill_params(c, pp, ia);
+    BB_LAUNCH(c, bb::k_exact_hit_keys, div_up(k, 256), 256, s, c->io_hits.p, (uint32_t)k, (int)field, ia, bucket_table(c, (int)field),
+              c->q_a.p, c->q_b.p, c->ev_node.p);
+    BB_LAUNCH(c, bb::k_sort_pad, div_up(padded, 256), 256, s, c->q_a.p, c->q_b.p, (const uint32_t*)nullptr, (uint32_t)k, padded);
+    rc = bitonic_sort(c, c->q_a.p, c->q_b.p, c->ev_node.p, padded, s);
+    if (rc) return rc;
+    result = c->ev_node.p;
+  }
+  if (k) BB_CUDA(c, cudaMemcpyAsync(out->node, result, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   BB_CUDA(c, cudaStreamSynchronize(s));
   *out->n_dense = c->h_counters[0];
   *out->n_extra = c->h_counters[1];
@@ -578,6 +691,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   }
   if ((cfg->flags & BB_CFG_COMPACT_CHANGES) && (cfg->flags & (BB_CFG_ORDERED_CHANGES | BB_CFG_RADIX_SORT | BB_CFG_FULL_SORT))) {
     g_create_error = "BB_CFG_COMPACT_CHANGES goes with the default pipeline only (not ORDERED_CHANGES / RADIX_SORT / FULL_SORT)";
+    return BB_ERR_ARG;
+  }
+  if ((cfg->flags & BB_CFG_EXACT_ORDER) && (cfg->flags & (BB_CFG_ORDERED_CHANGES | BB_CFG_COMPACT_CHANGES))) {
+    g_create_error = "BB_CFG_EXACT_ORDER does not combine with ORDERED_CHANGES / COMPACT_CHANGES";
     return BB_ERR_ARG;
   }
   int ndev = 0;
@@ -645,6 +762,8 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
             cudaMalloc((void**)&c->d_xused, BB_MAX_FIELDS * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemsetAsync(c->d_xused, 0, BB_MAX_FIELDS * sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMalloc((void**)&c->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_evcount, sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemsetAsync(c->d_evcount, 0, sizeof(uint32_t), c->stream) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_err, 2 * sizeof(uint32_t)) == cudaSuccess &&
             cudaMallocHost((void**)&c->h_nchanges, MAX_CHUNKS * sizeof(uint64_t)) == cudaSuccess;
@@ -684,9 +803,17 @@ int bb_destroy(bb_ctx* c) {
     if (c->index[f].pcol) cudaFree(c->index[f].pcol);
     if (c->index[f].xkey) cudaFree(c->index[f].xkey);
     if (c->index[f].xnode) cudaFree(c->index[f].xnode);
+    if (c->index[f].pseq) cudaFree(c->index[f].pseq);
+    if (c->index[f].xseq) cudaFree(c->index[f].xseq);
+    if (c->index[f].bkey) cudaFree(c->index[f].bkey);
+    if (c->index[f].bcount) cudaFree(c->index[f].bcount);
+    if (c->index[f].bcreated) cudaFree(c->index[f].bcreated);
   }
+  c->q_a.release(); c->q_b.release();
   if (c->d_xused) cudaFree(c->d_xused);
   if (c->d_counters) cudaFree(c->d_counters);
+  if (c->d_evcount) cudaFree(c->d_evcount);
+  c->ev_key.release(); c->ev_tag.release(); c->ev_node.release();
   if (c->epoch_col) cudaFree(c->epoch_col);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->table) cudaFree(c->table);
@@ -1010,6 +1137,15 @@ int bb_index_create_fields(bb_ctx* c, uint32_t field_mask, uint64_t extra_capaci
       return fail(c, BB_ERR_CUDA, "index allocation failed", cudaGetLastError());
     }
     ix.xslots = slots;
+    if (exact_order(c)) {  // entry tags + bucket table (every entry could be a bucket of its own)
+      ix.bslots = pow2_at_least(2 * (c->cfg.capacity + extra_capacity) + 16);
+      if (cudaMalloc((void**)&ix.pseq, cap2 * sizeof(uint64_t)) != cudaSuccess ||
+          cudaMalloc((void**)&ix.xseq, slots * sizeof(uint64_t)) != cudaSuccess ||
+          cudaMalloc((void**)&ix.bkey, ix.bslots * sizeof(uint64_t)) != cudaSuccess ||
+          cudaMalloc((void**)&ix.bcount, ix.bslots * sizeof(uint32_t)) != cudaSuccess ||
+          cudaMalloc((void**)&ix.bcreated, ix.bslots * sizeof(uint64_t)) != cudaSuccess)
+        return fail(c, BB_ERR_CUDA, "index allocation failed (exact order)", cudaGetLastError());
+    }
   }
   begin_call(c);
   mark(c, EV_Q0, c->stream);

@@ -15,7 +15,7 @@ from . import capi, codec
 class Engine:
     def __init__(self, capacity: int, *, local_peer: int = 0, n_fields: int = codec.MAX_FIELDS,
                  device: int = 0, post_getdata: bool = False, ordered_changes: bool = False, radix_sort: bool = False,
-                 full_sort: bool = False, hot_keys: bool = False, compact_changes: bool = False, track_modified: bool = False, rank_object: int = 0, rank_true: int = 0,
+                 full_sort: bool = False, hot_keys: bool = False, compact_changes: bool = False, track_modified: bool = False, exact_order: bool = False, rank_object: int = 0, rank_true: int = 0,
                  rank_false: int = 0, rank_nan: int = 0):
         self.lib = capi.load()
         self.cfg = capi.make_config(
@@ -26,7 +26,8 @@ class Engine:
             | (codec.CFG_FULL_SORT if full_sort else 0)
             | (codec.CFG_HOT_KEYS if hot_keys else 0)
             | (codec.CFG_COMPACT_CHANGES if compact_changes else 0)
-            | (codec.CFG_TRACK_MODIFIED if track_modified else 0), rank_object=rank_object,
+            | (codec.CFG_TRACK_MODIFIED if track_modified else 0)
+            | (codec.CFG_EXACT_ORDER if exact_order else 0), rank_object=rank_object,
             rank_true=rank_true, rank_false=rank_false, rank_nan=rank_nan)
         h = C.c_void_p()
         rc = self.lib.bb_create(C.byref(self.cfg), C.byref(h))

@@ -176,6 +176,15 @@ typedef struct bb_config {
  * row with the ordinal of the merge call it arrived in (bb_epoch).  The host maps ordinals to wall-clock time (one
  * Date.now() per call); bb_sync_collect filters on it.  4 bytes per row. */
 #define BB_CFG_TRACK_MODIFIED 256u
+/* Exact query order.  The reference returns equals / range results in (Map order of the buckets, Set order
+ * inside a bucket) = (bucket creation, insertion) order (src/bullet-query.js:89-93, 110-116, 204, 237-258), a node twice
+ * when it has entries in two matching buckets.  With this flag every index entry carries the sequence tag of the add
+ * that inserted it, the merge logs the hook's effective adds / removes, a per-bucket replay after every batch (and after
+ * an index build) keeps key -> (count, creation tag), and bb_query_equals / bb_query_range sort their hits by
+ * (bucket creation, entry tag): the reference's exact list.  Costs a sort of the batch's events per merge call and
+ * 8 bytes per entry; implies the sorting front end (like BB_CFG_FULL_SORT).  The _dev and router query entry points
+ * keep returning multisets. */
+#define BB_CFG_EXACT_ORDER 512u
 
 typedef struct bb_ctx bb_ctx;
 

@@ -322,6 +322,35 @@ def test_gpu_equals_reference(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in STREAMS["cases"] if c.get("queries")], ids=[i for c, i in zip(STREAMS["cases"], STREAM_IDS) if c.get("queries")])
+def test_gpu_exact_query_order_equals_reference(case):
+    """with BB_CFG_EXACT_ORDER the device returns the reference's own result LISTS - recorded from the
+    reference's sources run unmodified (tests/golden/streams.json.gz): Map order of the buckets, Set order inside a
+    bucket, duplicates from stale entries in place.  Exact list equality, no sorting on either side."""
+    from bullet_js_b200.engine import Engine
+
+    schema, eng, codes, changes = typed_replay(
+        case, lambda schema, indexed: Engine.for_schema(schema, 64, post_getdata=indexed, exact_order=True))
+    n = len(schema.paths)
+    got = eng.table_read(np.arange(n, dtype=np.uint64))
+    assert_typed_matches(case, schema, codes, changes, {schema.paths.name(i): got[i] for i in range(n)})
+    checked = reordered = 0
+    for name, q in case["queries"].items():
+        f = FIELD_SLOT[name]
+        ids = lambda paths: [schema.paths.id(p) for p in paths]  # noqa: E731
+        for v, want in zip(EQ_VALUES, q["equals"]):
+            key = schema.index_key(v)
+            assert ([] if key is None else eng.query_equals(f, key).tolist()) == ids(want), (name, v)
+        for (lo, hi), want in zip(itertools.product(BOUNDS, BOUNDS), q["range"]):
+            got_ids = eng.query_range(f, schema.bound(lo, False), schema.bound(hi, True)).tolist()
+            assert got_ids == ids(want), (name, lo, hi)
+            checked += 1
+            reordered += got_ids != sorted(got_ids)
+    assert checked > 700 and reordered > 50
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_gpu_config1_equals_reference():
     from bullet_js_b200.engine import Engine
 

@@ -195,3 +195,42 @@ def test_device_sync_producer_with_since():
     with pytest.raises(Exception):
         eng.sync_collect(0, cap=1)
     db.close()
+
+
+def test_query_example_exact_order():
+    """KAT-Q1 and KAT-H of SURVEY 8c as EXACT lists through the mirror with exact_order=True (BB_CFG_EXACT_ORDER): the
+    example script's results in the reference's own order, the duplicate of a stale entry, and delete-then-add moving a
+    path to the end of its bucket - every list against the literal oracle's."""
+    from bullet_js_b200.bullet import Bullet
+
+    db, ref = Bullet(schemas(), capacity=64, exact_order=True), RefBullet("me")
+    for k, v in USERS.items():
+        db.get(f"users/{k}").put(js(v))
+        ref.put(f"users/{k}", js(v))
+    for k, v in PRODUCTS.items():
+        db.get(f"products/{k}").put(js(v))
+        ref.put(f"products/{k}", js(v))
+    db.index("users", "role").index("users", "age").index("users", "active")
+    db.index("products", "category").index("products", "price")
+    for x in ("role", "age", "active"):
+        ref.index("users", x)
+    for x in ("category", "price"):
+        ref.index("products", x)
+    order = lambda nodes: [n.path for n in nodes]
+    assert order(db.equals("users", "role", "admin")) == ["users/user1", "users/user6", "users/user10"]
+    assert order(db.range("users", "age", 30, 40)) == ["users/user2", "users/user5", "users/user8", "users/user10"]
+    assert order(db.range("products", "price", 100, 300)) == ["products/prod3", "products/prod6", "products/prod7", "products/prod9"]
+    # the hook path: stale entries (a node twice), buckets emptied and re-created at the end of the Map order
+    for path, value in (("users/user2", {"age": 31.0}), ("users/user5", {"age": 35.0}), ("users/user2", {"age": 35.0}),
+                        ("users/user8", {"role": "admin", "age": 39.0}), ("users/user1", {"role": "user"}),
+                        ("users/user1", {"role": "admin"}), ("users/user3", {"age": 42.0, "role": "admin"})):
+        db.get(path).put(js(value))
+        ref.put(path, js(value))
+    assert db.decisions == [d["code"] for d in ref.decisions]
+    for args in (("users", "role", "admin"), ("users", "role", "user"), ("users", "age", 35), ("users", "age", 31),
+                 ("users", "active", True)):
+        assert order(db.equals(*args)) == ref.equals(*[js(a) for a in args]), args
+    for args in (("users", "age", 0, 100), ("users", "age", 30, 40), ("users", "role", "a", "z"), ("users", "age", 31, 35)):
+        assert order(db.range(*args)) == ref.range(*[js(a) for a in args]), args
+    assert len(order(db.range("users", "age", 0, 100))) > len(USERS)  # stale entries: some node is listed twice
+    db.close()

@@ -199,3 +199,82 @@ def test_router_queries_single_rank_and_multi_field_build():
     small.close()
     router.close()
     eng.close()
+
+
+def exact_pair(schema, capacity, **kw):
+    from bullet_js_b200.engine import Engine
+
+    eng = (Engine.for_schema(schema, capacity, post_getdata=True, exact_order=True, **kw) if schema is not None
+           else Engine(capacity, post_getdata=True, exact_order=True, **kw))
+    return eng, TypedOracle(eng.cfg)
+
+
+def check_exact_queries(schema, eng, orc, fields, bounds, stride=1):
+    """equals / range as EXACT lists: the reference's (Map order of the buckets, Set order inside a bucket)."""
+    n, unsorted = 0, 0
+    for f in fields:
+        for v in EQ_VALUES:
+            key = schema.index_key(v)
+            if key is None:
+                continue
+            got, want = eng.query_equals(f, key), orc.query_equals(f, key)
+            assert got.tolist() == want.tolist(), (f, v)
+        for lo, hi in list(itertools.product(bounds, bounds))[::stride]:
+            bl, bh = schema.bound(lo, False), schema.bound(hi, True)
+            got, want = eng.query_range(f, bl, bh), orc.query_range(f, bl, bh)
+            assert got.tolist() == want.tolist(), (f, lo, hi)
+            n += 1
+            unsorted += len(want) > 1 and want.tolist() != sorted(want.tolist())
+    return n, unsorted
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_exact_map_and_set_order(seed):
+    """SURVEY 8f-1 on the device (BB_CFG_EXACT_ORDER): entry tags + the hook's effective add / remove events + the
+    per-bucket replay after every batch give bb_query_equals / bb_query_range the reference's exact result LISTS -
+    buckets in creation order (a bucket that emptied is re-created at the end), paths in insertion order, a node twice
+    when it sits in two matching buckets - on the JS-semantics streams: indices created before the first put, a late
+    index built from the store, batches of 1 to 1800 updates."""
+    ops, _ref = streamgen.generate(320 + seed, 3000, 37, index_fields=("age", "role"), late_index={"score": 1200})
+    schema = streamgen.make_schema()
+    batch = codec.encode_updates(schema, ops)
+    eng, orc = exact_pair(schema, 64)
+    for x in (eng, orc):
+        x.index_create(0)
+        x.index_create(2)
+    for lo, hi, late in ((0, 1, False), (1, 1200, False), (1200, 1201, True), (1201, 3000, False)):
+        if late:
+            eng.index_create(1)
+            orc.index_create(1)
+        assert eng.merge(batch.slice(lo, hi)).same_as(orc.merge(batch.slice(lo, hi))), (seed, lo, hi)
+    same_rows(eng, orc, 64)
+    n, unsorted = check_exact_queries(schema, eng, orc, (0, 1, 2), BOUNDS, stride=3)
+    assert n > 500 and unsorted > 50  # the reference's order is not node order: the test would notice a plain multiset
+    eng.close()
+
+
+def test_exact_order_synthetic_hot_keys_and_clear():
+    """The same on the synthetic schema: index build over 3 000 existing records (creation order), Zipf batches whose hot
+    nodes pile up stale entries, then bb_table_clear and a fresh start."""
+    n_rec = 3000
+    rng = synth.rng_for(4, salt=9)
+    table = synth.make_table(n_rec, rng)
+    eng, orc = exact_pair(None, n_rec, **synth.synth_ranks(n_rec))
+    ids = np.arange(n_rec, dtype=np.uint64)
+    perm = rng.permutation(n_rec)  # creation order != path id order
+    rows = table.rows.copy()
+    rows["cseq"][perm] = 1 + np.arange(n_rec, dtype=np.uint64)
+    eng.table_load(ids, rows)
+    orc.load(ids, rows)
+    schema = synth.synth_schema(n_rec)
+    for f in (0, 2):
+        eng.index_create(f, extra_capacity=1 << 18)
+        orc.index_create(f)
+    small = [20.0, 30.0, 0.0, 99.0, "admin", "user", "a", "zzz", None]
+    check_exact_queries(schema, eng, orc, (0, 2), small)
+    for keys in ("uniform", "zipf"):
+        b = synth.make_batch(table, 30_000, rng, keys=keys)
+        assert eng.merge(b).same_as(orc.merge(b))
+        n, unsorted = check_exact_queries(schema, eng, orc, (0, 2), small)
+        assert unsorted > 5
+    eng.close()
