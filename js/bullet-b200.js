@@ -35,6 +35,7 @@
 const { Schema, packEntries, unpackChanges, decodeClock } = require("./pack");
 
 const BB_CFG_POST_GETDATA = 1;
+const BB_CFG_EXACT_ORDER = 512;
 const ROW_M_PRESENT = 1, ROW_V_PRESENT = 2;
 
 const REASONS = [
@@ -61,7 +62,9 @@ class BulletB200 {
       capacity: options.capacity,
       nFields: options.fields.length,
       localPeer: this.schema.pslot.get(bullet.id),
-      flags: options.postGetData ? BB_CFG_POST_GETDATA : 0, // set it when an index hook is installed (query:151,169)
+      // postGetData: set it when an index hook is installed (query:151,169); exactOrder: device queries return the
+      // reference's exact (Map order, Set order) lists (BB_CFG_EXACT_ORDER) instead of the same nodes in device order
+      flags: (options.postGetData ? BB_CFG_POST_GETDATA : 0) | (options.exactOrder ? BB_CFG_EXACT_ORDER : 0),
       ...this.schema.ranks(),
     });
     this.calls = 0; // native merge calls (telemetry)
