@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
 // retiring thread applies exactly that, and a per-segment cache of keys KNOWN PRESENT (shared memory, probed by all
 // threads in parallel) lets it skip every update whose key is already in the index - on a hot node nearly all of them.
 constexpr int HOT_CACHE = 256;            // slots per field of the known-present cache
-constexpr int HOT_LOOK = 64;              // window positions evaluated per pass
+constexpr int HOT_LOOK = HOT_T;           // window positions classified per pass (the classification is cheap: all of them)
 constexpr uint64_t HC_TOMB = 0xFFFFFFFFFFFFFFFEull;
 
 __device__ __forceinline__ uint32_t hc_hash(uint64_t k) { return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ull) >> 56); }
@@ -1078,21 +1078,59 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
       }
       int base = 0;  // window positions [0, base) are retired
       while (base < nseg) {
-        // Only the next HOT_LOOK positions are evaluated in a pass: a pass costs the instructions of every warp that takes
-        // part (the resolver diverges by update type), and the next state change is rarely further away than that.
         const int lim = min(nseg, base + HOT_LOOK);
         const bool live = mine && tid >= base && tid < lim;
-        uint32_t code = 0;
+        // (1) Cheap and uniform: which of these positions are HISTORICAL for sure?  compareVectorClocks(I, M) < 0 with M
+        // present (crt:68-95, 251-263): the update is rejected, S and M stay, it leaves nothing behind but V := the merged
+        // clock and alias := 0 (crt:187-197) - nothing a later network update looks at.  Everything else (a local put, a
+        // dominating / concurrent / tied clock, a node that does not exist or reads as a falsy primitive and is about to
+        // be materialised) is a possible state change: the first such position ends the pass.
+        bool hist = false;
+        if (live && net) {
+          const uint4 m0 = s_row[row_chunk(2)], m1 = s_row[row_chunk(3)], hd = s_row[row_chunk(6)], fl = s_row[row_chunk(7)];
+          const uint32_t kind = kind_of(hd.z);
+          bool plain = kind == BB_KIND_OBJ;
+          if (kind == BB_KIND_PRIM) {
+            const uint4 v0 = s_row[row_chunk(0)];
+            plain = !prim_falsy(tag_of(hd.z, 0), u64_of(v0.x, v0.y));
+          }
+          const uint32_t mc[P] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          bool d1 = false, d2 = false;
+#pragma unroll
+          for (int sl = 0; sl < P; ++sl) {
+            d1 |= c.cnt[sl] > mc[sl];
+            d2 |= mc[sl] > c.cnt[sl];
+          }
+          hist = plain && (fl.x & BB_ROW_M_PRESENT) && d2 && !d1;
+        }
+        if (INDEXED && tid < F) {  // k0: what a rejected update's hook removes - the node as it reads now
+          RowState r0;
+          unpack_row(s_row, r0);
+          if (kind_of(r0.s.meta) == BB_KIND_NONE || falsy_primitive(r0.s)) materialise_empty_object(r0.s);
+          s_k0[tid] = ((a.ix.mask >> tid) & 1u) ? hook_key(r0.s, tid) : BB_KEY_NONE;
+        }
+        const bool stop = live && !hist;
+        const uint32_t bs = __ballot_sync(0xffffffffu, stop);
+        if (lane == 0) s_stop[w] = bs;
+        __syncthreads();  // every live thread has looked at the row
+        int first = HOT_T;
+#pragma unroll
+        for (int ww = HOT_WARPS - 1; ww >= 0; --ww)
+          if (s_stop[ww]) first = ww * 32 + __ffs(s_stop[ww]) - 1;
+        // retired this pass: up to and including the first stop
+        const int end = first >= lim ? lim : first + 1;
+        const bool retiring = live && tid < end;
+        // (2) ONE thread runs the resolver: the last retired position - the stop itself, or the last of a run of historical
+        // updates (whose V is what the row keeps).  Everything in front of it is historical by construction.
+        uint32_t code = BB_DEC_HISTORICAL;
         RowState r;
         Clock oc;
         Value ov;
-        if (live) {
+        if (retiring && tid == end - 1) {
           unpack_row(s_row, r);
           if (!net && tid > base) {
             // A local put's clock is V, and V is what the update in front of it left (crt:187-197 stores the merged
-            // clock on every call).  If this put turns out to be the pass's first stop, everything in front of it was
-            // a rejected network update, and a rejected update leaves nothing behind but V := its merged clock: the
-            // state this put meets is the row with the ONE update in front of it applied.
+            // clock on every call): the state this put meets is the row with the ONE update in front of it applied.
             const uint4* sp = &s_win[(tid - 1) * UPD_Q];
             Clock cp;
             Value xp;
@@ -1101,23 +1139,6 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
           }
           code = resolve_step(a.p, r, net, c, x, a.seq_base + ui, ov, oc);
         }
-        if (INDEXED && tid < F) {  // k0: what a rejected update's hook removes - the node as it reads now
-          RowState r0;
-          unpack_row(s_row, r0);
-          if (kind_of(r0.s.meta) == BB_KIND_NONE || falsy_primitive(r0.s)) materialise_empty_object(r0.s);
-          s_k0[tid] = ((a.ix.mask >> tid) & 1u) ? hook_key(r0.s, tid) : BB_KEY_NONE;
-        }
-        const bool stop = live && (BB_DEC_ACCEPTED(code) || !net);
-        const uint32_t bs = __ballot_sync(0xffffffffu, stop);
-        if (lane == 0) s_stop[w] = bs;
-        __syncthreads();  // every live thread has unpacked the row
-        int first = HOT_T;
-#pragma unroll
-        for (int ww = HOT_WARPS - 1; ww >= 0; --ww)
-          if (s_stop[ww]) first = ww * 32 + __ffs(s_stop[ww]) - 1;
-        // retired this pass: up to and including the first stop
-        const int end = first >= lim ? lim : first + 1;
-        const bool retiring = live && tid < end;
         if (INDEXED) {  // which retired updates does the hook have anything to do for?
           bool need = false;
           if (retiring && tid < end - 1) {
