@@ -1009,6 +1009,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ uint64_t s_cache[INDEXED ? F * HOT_CACHE : 1];
   __shared__ uint32_t s_used[F];
   __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_need[HOT_WARPS];
+  __shared__ unsigned long long s_claim;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
@@ -1076,6 +1077,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
 #pragma unroll
         for (int f = 0; f < F; ++f) akey[f] = (mine && ((a.ix.mask >> f) & 1u)) ? hook_key(x, f) : BB_KEY_NONE;
       }
+      uint32_t fin = BB_DEC_HISTORICAL;  // this position's final code (| RES_ECHO), known when it retires
       int base = 0;  // window positions [0, base) are retired
       while (base < nseg) {
         const int lim = min(nseg, base + HOT_LOOK);
@@ -1192,30 +1194,57 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
             }
             pack_row(s_row, r);
           }
-          if (BB_DEC_ACCEPTED(code) && a.epoch_col) a.epoch_col[hkey] = a.epoch;
-          if (COMPACT && BB_DEC_ACCEPTED(code) && echoes_update(slot, ov, oc)) {
-            a.verdict[ui] = (code << 29) | SLOT_ECHO;
-          } else if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
-            const uint64_t dest = atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), 1ull);
-            a.verdict[ui] = (code << 29) | (uint32_t)dest;
-            if (dest < a.cap) {
-              uint4 q[UPD_Q];
-              pack_change(q, h.w, ov, oc);
-              a.out_idx[dest] = a.idx_base + ui;
-              a.out_head[dest] = q[0];
-              a.out_clk[2 * dest] = q[1];
-              a.out_clk[2 * dest + 1] = q[2];
-              a.out_val[2 * dest] = q[3];
-              a.out_val[2 * dest + 1] = q[4];
-            } else {
-              overflow = true;
-            }
-          } else {
-            a.verdict[ui] = (code << 29) | NO_SLOT;
+          // nothing leaves for global memory inside the chain of passes (a slot claim is a round trip to L2): the verdict
+          // and, if accepted, the entry - written over the update's own payload slot - wait for the end of the window
+          fin = code;
+          if (BB_DEC_ACCEPTED(code)) {  // only the last retired one can be
+            if (COMPACT && echoes_update(slot, ov, oc)) fin = code | RES_ECHO;
+            else pack_change(slot, h.w, ov, oc);
           }
         }
         base = end;
         __syncthreads();  // the published row (and the index cache) are visible; s_stop / s_need may be rewritten
+      }
+      {  // ---- the window's results: ONE slot claim, then verdicts and entries
+        const bool emit = mine && BB_DEC_ACCEPTED(fin & ~RES_ECHO) && !(fin & RES_ECHO);
+        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        const uint32_t am = __ballot_sync(0xffffffffu, mine && BB_DEC_ACCEPTED(fin & ~RES_ECHO));
+        if (lane == 0) {
+          s_cnt[w] = __popc(em);
+          s_stop[w] = am;
+        }
+        __syncthreads();
+        uint32_t before = 0, total = 0, any_acc = 0;
+#pragma unroll
+        for (int ww = 0; ww < HOT_WARPS; ++ww) {
+          if (ww < w) before += s_cnt[ww];
+          total += s_cnt[ww];
+          any_acc |= s_stop[ww];
+        }
+        if (tid == 0) {
+          s_claim = total ? atomicAdd(reinterpret_cast<unsigned long long*>(a.n_changes), (unsigned long long)total) : 0ull;
+          if (any_acc && a.epoch_col) a.epoch_col[hkey] = a.epoch;  // meta[path].lastModified (src/bullet.js:201)
+        }
+        __syncthreads();
+        if (mine) {
+          const uint32_t fcode = fin & ~RES_ECHO;
+          if (emit) {
+            const uint64_t dest = s_claim + before + __popc(em & lanemask_lt());
+            a.verdict[ui] = (fcode << 29) | (uint32_t)dest;
+            if (dest < a.cap) {
+              a.out_idx[dest] = a.idx_base + ui;
+              a.out_head[dest] = slot[0];
+              a.out_clk[2 * dest] = slot[1];
+              a.out_clk[2 * dest + 1] = slot[2];
+              a.out_val[2 * dest] = slot[3];
+              a.out_val[2 * dest + 1] = slot[4];
+            } else {
+              overflow = true;
+            }
+          } else {
+            a.verdict[ui] = (fcode << 29) | ((fin & RES_ECHO) ? SLOT_ECHO : NO_SLOT);
+          }
+        }
       }
       gp0 += (uint64_t)nseg;
       if (nseg < HOT_T) break;  // the segment ended inside this window

@@ -25,7 +25,7 @@ const bullet = new Bullet({ disableNetwork: true, server: false, storage: true, 
                             enableIndexing: indexed });
 bullet.id = "p0";
 const shim = new BulletB200(bullet, native, { capacity: 64, postGetData: indexed, fields: fields, peers: peers, strings: strings,
-                                                deviceQueries: deviceQueries ? "users" : null });
+                                                deviceQueries: deviceQueries ? "users" : null, exactOrder: exactOrder });
 const changes = [];
 const origApply = bullet._applyUpdate;
 bullet._applyUpdate = function (path, value, vectorClock, fromNetwork) {
@@ -38,13 +38,13 @@ return { bullet: bullet, shim: shim, changes: changes, heard: heard };
 """
 
 
-def boot(indexed, make_engine, device_queries=False):
+def boot(indexed, make_engine, device_queries=False, exact_order=False):
     rt = Runtime(console=[])
     ref = ref_runner._reference_root()
     bridge = NativeBridge(rt, make_engine)
     r = rt.eval(HARNESS, Bullet=rt.require(os.path.join(ref, "src", "bullet.js")),
                 BulletB200=rt.require(os.path.join(ROOT, "js", "bullet-b200.js")), native=bridge.js_object(),
-                indexed=indexed, deviceQueries=device_queries, fields=from_py(streamgen.FIELDS), peers=from_py(streamgen.PEERS),
+                indexed=indexed, deviceQueries=device_queries, exactOrder=exact_order, fields=from_py(streamgen.FIELDS), peers=from_py(streamgen.PEERS),
                 strings=from_py(streamgen.STRINGS), snapshot=I.JSFunction("snapshot", lambda this, a: from_py(to_py(a[0]))))
     return rt, bridge, r
 
@@ -103,16 +103,40 @@ def test_reference_with_shim_equals_reference(k):
     assert len(to_py(r.get("heard"))) == len(changes) + 1  # the `users` listener: once at subscription, then per change
 
 
+def cuda_engine(cfg):
+    """The CUDA library itself behind the shim's addon surface (bb_create with the flags the SHIM asked for)."""
+    from bullet_js_b200 import codec
+    from bullet_js_b200.engine import Engine
+
+    assert cfg.flags & codec.CFG_EXACT_ORDER and cfg.flags & codec.CFG_POST_GETDATA  # js/bullet-b200.js set them
+    return Engine(int(cfg.capacity), local_peer=int(cfg.local_peer), n_fields=int(cfg.n_fields), post_getdata=True,
+                  exact_order=True, rank_object=int(cfg.rank_object), rank_true=int(cfg.rank_true),
+                  rank_false=int(cfg.rank_false), rank_nan=int(cfg.rank_nan))
+
+
+@pytest.mark.gpu
+def test_device_queries_through_the_shim_on_the_cuda_library():
+    """The same flow with libbulletb200.so behind the shim and `exactOrder: true` (BB_CFG_EXACT_ORDER): the unmodified
+    reference + js/bullet-b200.js + the CUDA kernels return the reference's own recorded result lists, in order.  Needs
+    the reference sources, so it runs where they are (this container, kernels emulated: BB_EMU_TESTS=1) and is skipped
+    on the GPU boxes, where /root/reference does not exist."""
+    run_device_queries(cuda_engine, exact_order=True)
+
+
 def test_device_queries_through_the_shim():
     """options.deviceQueries: bullet.index / equals / range / count answered by the library's index (built and kept
     by the merge kernel's hook) - with the typed oracle behind the addon the results come in the reference's exact
     (Map, Set) order, so they must equal the golden query results; keys and bounds are computed in JavaScript."""
+    run_device_queries(oracle_engine)
+
+
+def run_device_queries(make_engine, exact_order=False):
     import itertools
 
     from tests.test_oracle_query import BOUNDS, EQ_VALUES
 
     case = STREAMS[1]
-    rt, bridge, r = boot(True, oracle_engine, device_queries=True)
+    rt, bridge, r = boot(True, make_engine, device_queries=True, exact_order=exact_order)
     bullet, shim = r.get("bullet"), r.get("shim")
     for f in case["index_fields"]:
         rt.method(bullet, "index", "users", f)
