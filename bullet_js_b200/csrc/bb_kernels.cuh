@@ -999,6 +999,25 @@ struct HotIndex {
     }
     hc_put(c, used[f], k);
   }
+  // the same for a key whose thread has already looked it up in the index in parallel with the others of its run
+  // (`present`: found; otherwise verified absent) - no serial x_find on the retiring thread
+  __device__ __forceinline__ void add_looked_up(int f, uint64_t k, bool present) {
+    if (k == BB_KEY_NONE) return;
+    uint64_t* c = cache + f * HOT_CACHE;
+    if (hc_has(c, k)) return;  // an earlier update of this run brought it in
+    if (absent[f] == k) absent[f] = BB_KEY_NONE;
+    if (!present) {
+      if (prim[f] == BB_KEY_NONE) {
+        prim[f] = k;
+      } else if (x_insert(ix, f, node, k) >= 0) {
+        if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
+      } else {
+        atomicOr(err, ERR_XFULL);
+        return;
+      }
+    }
+    hc_put(c, used[f], k);
+  }
 };
 
 template <bool INDEXED, bool COMPACT = false>
@@ -1010,6 +1029,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ uint32_t s_used[F];
   __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_need[HOT_WARPS];
   __shared__ unsigned long long s_claim;
+  __shared__ uint8_t s_found[INDEXED ? HOT_T : 1];  // per window position: fields whose added key the thread found in the index
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
@@ -1144,13 +1164,22 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         if (INDEXED) {  // which retired updates does the hook have anything to do for?
           bool need = false;
           if (retiring && tid < end - 1) {
+            const uint32_t xc = s_row[row_chunk(7)].y;  // overflow entries of the node per field, as the pass begins
+            uint32_t found = 0;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
               const uint64_t k = akey[f];
               if (k == BB_KEY_NONE) continue;
-              if (k == s_k0[f]) need = need || tid == end - 2;  // added, then removed again by the next update's hook
-              else need = need || !hc_has(s_cache + f * HOT_CACHE, k);
+              if (k == s_k0[f]) {
+                need = need || tid == end - 2;  // added, then removed again by the next update's hook
+              } else if (!hc_has(s_cache + f * HOT_CACHE, k)) {
+                // not known present: look it up NOW, every thread of the run in parallel (the retiring thread would
+                // walk the overflow set once per key, one global round trip after the other)
+                need = true;
+                if (s_prim[f] == k || (xcnt_get(xc, f) && x_find(a.ix, f, hkey, k) >= 0)) found |= 1u << f;
+              }
             }
+            s_found[tid] = (uint8_t)found;
           }
           const uint32_t nb = __ballot_sync(0xffffffffu, need);
           if (lane == 0) s_need[w] = nb;
@@ -1178,8 +1207,11 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
                     for (int f = 0; f < F; ++f) {
                       if (!((a.ix.mask >> f) & 1u)) continue;
                       const uint64_t k = hook_key(xj, f);
-                      if (k == s_k0[f] && j != end - 2) continue;
-                      hx.add(f, k);
+                      if (k == s_k0[f]) {
+                        if (j == end - 2) hx.add(f, k);  // k0 was just removed above: the general path
+                        continue;
+                      }
+                      hx.add_looked_up(f, k, (s_found[j] >> f) & 1u);
                     }
                   }
                 }
