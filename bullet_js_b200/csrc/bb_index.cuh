@@ -128,7 +128,16 @@ __device__ __forceinline__ void index_hook(const IndexArgs& ix, uint32_t node, c
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     if (!((ix.mask >> f) & 1u)) continue;
-    if (kind_of(after.meta) == BB_KIND_OBJ) {  // if (oldData && oldData[field]) remove
+    // The common case - the update won outright, so the node now reads as the update itself - removes key k and adds
+    // key k again: k is in the set afterwards either way.  Without exact order (where delete + add moves the entry to
+    // the end of its bucket) that is "make sure k is there": one lookup instead of two plus a tombstone and an insert.
+    bool same = false;
+    if (!EXACT && kind_of(after.meta) == BB_KIND_OBJ && kind_of(x.meta) == BB_KIND_OBJ) {
+      const uint32_t ta = tag_of(after.meta, f), tx = tag_of(x.meta, f);
+      same = ta != BB_TAG_ABSENT && tx != BB_TAG_ABSENT && !prim_falsy(ta, after.val[f]) && !prim_falsy(tx, x.val[f]) &&
+             canon_key(ta, after.val[f]) == canon_key(tx, x.val[f]);
+    }
+    if (!same && kind_of(after.meta) == BB_KIND_OBJ) {  // if (oldData && oldData[field]) remove
       const uint32_t t = tag_of(after.meta, f);
       if (t != BB_TAG_ABSENT && !prim_falsy(t, after.val[f])) {
         const uint64_t k = canon_key(t, after.val[f]);

@@ -1219,7 +1219,8 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
 #pragma unroll
               for (int f = 0; f < F; ++f) {  // this update's own hook, against the node as it reads after it
                 if (!((a.ix.mask >> f) & 1u)) continue;
-                hx.remove(f, hook_key(r.s, f));
+                const uint64_t kr = hook_key(r.s, f);
+                if (kr != akey[f]) hx.remove(f, kr);  // (remove k, then add k: k is in the set afterwards either way)
                 hx.add(f, akey[f]);
               }
               r.xcnt = xcnt;
