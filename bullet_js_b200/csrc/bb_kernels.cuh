@@ -909,7 +909,6 @@ __global__ void __launch_bounds__(MT, 7) k_merge_stage(const MergeArgs a) {
 // threads in parallel) lets it skip every update whose key is already in the index - on a hot node nearly all of them.
 constexpr int HOT_CACHE = 256;            // slots per field of the known-present cache
 constexpr int HOT_LOOK = HOT_T;           // window positions classified per pass (the classification is cheap: all of them)
-constexpr uint64_t HC_TOMB = 0xFFFFFFFFFFFFFFFEull;
 
 __device__ __forceinline__ uint32_t hc_hash(uint64_t k) { return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ull) >> 56); }
 
@@ -929,24 +928,38 @@ __device__ __forceinline__ void hc_put(uint64_t* c, uint32_t& used, uint64_t k) 
   for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
     const uint64_t v = c[i];
     if (v == k) return;
-    if (v == BB_KEY_NONE || v == HC_TOMB) {
-      if (v == BB_KEY_NONE) ++used;
+    if (v == BB_KEY_NONE) {
+      ++used;
       c[i] = k;
       return;
     }
   }
 }
 
-__device__ __forceinline__ void hc_erase(uint64_t* c, uint64_t k) {
+// Deletion WITHOUT tombstones (backward shift): a hot node's stored value changes hundreds of times, each change removes
+// a key from the set, and tombstones would soon turn every miss into a walk over the whole table.
+__device__ __forceinline__ void hc_erase(uint64_t* c, uint32_t& used, uint64_t k) {
   uint32_t i = hc_hash(k);
   for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
     const uint64_t v = c[i];
-    if (v == k) {
-      c[i] = HC_TOMB;
-      return;
-    }
     if (v == BB_KEY_NONE) return;
+    if (v == k) break;
+    if (probe == HOT_CACHE - 1) return;
   }
+  uint32_t j = i;
+  for (int step = 0; step < HOT_CACHE; ++step) {
+    j = (j + 1) & (HOT_CACHE - 1);
+    const uint64_t v = c[j];
+    if (v == BB_KEY_NONE) break;
+    const uint32_t h = hc_hash(v);  // may v move back to the hole at i?  only if its home is not inside (i, j]
+    const bool inside = i <= j ? (h > i && h <= j) : (h > i || h <= j);
+    if (!inside) {
+      c[i] = v;
+      i = j;
+    }
+  }
+  c[i] = BB_KEY_NONE;
+  if (used) --used;
 }
 
 // the key the hook removes / adds for field f of value v (query:153-167): BB_KEY_NONE when there is nothing to do
@@ -979,7 +992,7 @@ struct HotIndex {
         if (xcnt_get(xcnt, f) != 0xFFu) xcnt -= 1u << (8 * f);
       }
     }
-    hc_erase(cache + f * HOT_CACHE, k);
+    hc_erase(cache + f * HOT_CACHE, used[f], k);
     absent[f] = k;
   }
   __device__ __forceinline__ void add(int f, uint64_t k) {
