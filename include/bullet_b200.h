@@ -402,7 +402,9 @@ int bb_sync_collect(bb_ctx* ctx, uint64_t since_epoch, uint32_t flags, uint64_t 
  * received, in that replay order, and their change entries (idx = position in the replay order);
  * recv_counts[j * world + q] (optional) = updates of rank q's piece j this shard received, which is what maps a
  * verdict back to (source rank, arrival index).  ctx must not have BB_CFG_ORDERED_CHANGES; BB_CFG_COMPACT_CHANGES
- * works as usual (BB_SLOT_ECHO refers to the received update).  Synchronous. */
+ * works as usual (BB_SLOT_ECHO refers to the received update).  Synchronous.  The call is a sequence of collectives:
+ * if it fails on one rank (too small a buffer, a CUDA error) the ranks are no longer in step - destroy the router and
+ * create a new one on every rank before routing again. */
 int bb_router_merge_batch(bb_router* r, bb_ctx* ctx, const bb_batch* in, bb_changes* out, uint32_t chunks,
                           uint64_t* n_received, uint64_t* recv_counts);
 /* Sharded queries (src/bullet-query.js:186-210, 221-261 over a table that spans the router's ranks).  Collective:
