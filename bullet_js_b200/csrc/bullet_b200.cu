@@ -26,7 +26,7 @@ thread_local std::string g_create_error;
 
 enum { EV_H2D0, EV_START, EV_SORT, EV_MERGE, EV_D2H, EV_Q0, EV_Q1, EV_COUNT };
 constexpr int EV_RING = 64;  // merge calls whose phase timings can still be queried
-constexpr int MAX_CHUNKS = 8;          // a host call is pipelined as up to this many chunks
+constexpr int MAX_CHUNKS = 16;         // a host call is pipelined as up to this many chunks (default: host_chunks)
 constexpr uint64_t MIN_CHUNK = 1 << 16;  // updates
 
 template <class T>
@@ -120,6 +120,7 @@ struct bb_ctx {
   uint32_t* d_xused = nullptr;             // [BB_MAX_FIELDS]
   uint32_t* epoch_col = nullptr;  // BB_CFG_TRACK_MODIFIED: per row, the ordinal of the merge call that last wrote it
   uint64_t epoch = 0;             // ordinal of the most recent merge call
+  uint32_t host_chunks = 8;  // pieces a bb_merge_batch call is pipelined in (env BB_HOST_CHUNKS, 1..16)
   int rows_tma = 1;       // rows of k_merge_stage staged and written back with cp.async.bulk (BB_MERGE_TMA=0: cp.async, for A/B)
   unsigned long long* d_counters = nullptr;  // [2] dense / overflow matches of the running query
   unsigned long long* h_counters = nullptr;  // pinned [2]
@@ -738,6 +739,10 @@ int bb_create(const bb_config* cfg, bb_ctx** out) {
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(bb::k_merge_stage<false, false, true, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (const char* e = getenv("BB_MERGE_TMA")) c->rows_tma = e[0] - '0';
+  if (const char* e = getenv("BB_HOST_CHUNKS")) {
+    const long v = strtol(e, nullptr, 10);
+    if (v >= 1 && v <= MAX_CHUNKS) c->host_chunks = (uint32_t)v;
+  }
  // 0: cp.async, 1: rows by bulk copy (default), 2: rows + payloads
   cudaFuncSetAttribute(bb::k_merge_stage<false, true, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   {
@@ -974,7 +979,7 @@ int bb_merge_batch(bb_ctx* c, const bb_batch* in, bb_changes* out) {
     mark(c, EV_START, s); mark(c, EV_SORT, s); mark(c, EV_MERGE, s); mark(c, EV_D2H, s);
     return BB_OK;
   }
-  uint64_t chunk = (n + MAX_CHUNKS - 1) / MAX_CHUNKS;
+  uint64_t chunk = (n + c->host_chunks - 1) / c->host_chunks;
   if (chunk < MIN_CHUNK) chunk = MIN_CHUNK;
   if (c->cfg.flags & BB_CFG_ORDERED_CHANGES) chunk = n;  // one path-major run, as promised
   const int nchunks = (int)((n + chunk - 1) / chunk);
@@ -1772,7 +1777,7 @@ int bb_router_merge_batch(bb_router* r, bb_ctx* c, const bb_batch* in, bb_change
   if (!r || !c || !in || !out || !out->n_changes || !out->verdict || !n_received)
     return rfail(r, BB_ERR_ARG, "null argument");
   if (chunks == 0) chunks = 4;
-  if (chunks > (uint32_t)MAX_CHUNKS) return rfail(r, BB_ERR_ARG, "at most 8 chunks");
+  if (chunks > (uint32_t)MAX_CHUNKS) return rfail(r, BB_ERR_ARG, "at most 16 chunks");
   const uint64_t n = in->n;
   if (n && (!in->path_id || !in->head || !in->clk || !in->val)) return rfail(r, BB_ERR_ARG, "null buffer");
   if (c->cfg.flags & BB_CFG_ORDERED_CHANGES) return rfail(r, BB_ERR_STATE, "the sharded host entry needs the default change-set layout");

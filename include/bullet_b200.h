@@ -394,7 +394,7 @@ int bb_sync_collect(bb_ctx* ctx, uint64_t since_epoch, uint32_t flags, uint64_t 
                     bb_row* rows_out, uint32_t* epoch_out, uint64_t* n_out);
 /* Host entry of the sharded path (the batched ingress of src/bullet-network-sync.js:551-569 for a table that spans the
  * router's ranks).  Collective: every rank passes its own batch in HOST memory (pinned recommended) and the same
- * `chunks` (1..8, 0 = 4).  Each rank's batch is cut into `chunks` pieces in arrival order; piece j of every rank is
+ * `chunks` (1..16, 0 = 4).  Each rank's batch is cut into `chunks` pieces in arrival order; piece j of every rank is
  * copied in, exchanged (fused pack + all-to-all over NVLink) and merged by the owning shards while piece j+1 is on its
  * way in and piece j-1's results are on their way out.  A shard replays what it receives piece by piece, inside a
  * piece in (source rank, arrival index) order - the same as one peer replaying rank 0's piece 0, rank 1's piece 0, ...,
