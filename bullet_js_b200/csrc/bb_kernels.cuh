@@ -912,54 +912,37 @@ constexpr int HOT_LOOK = HOT_T;           // window positions classified per pas
 
 __device__ __forceinline__ uint32_t hc_hash(uint64_t k) { return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ull) >> 56); }
 
-__device__ __forceinline__ bool hc_has(const uint64_t* c, uint64_t k) {
+// The hot node's entries of one field, as a WRITE-BACK set in shared memory: what is known about a key's presence in the
+// node's overflow entries.  Adds and removes of a retired run change this set only; the global overflow set is
+// brought up to date by all threads in parallel when the segment ends (or the set fills up).
+constexpr uint8_t HS_CLEAN = 1;   // in the global set
+constexpr uint8_t HS_NEW = 2;     // added here, not in the global set yet
+constexpr uint8_t HS_GONE = 3;    // in the global set, removed here
+constexpr uint8_t HS_ABSENT = 4;  // in neither
+
+__device__ __forceinline__ int hc_find(const uint64_t* c, uint64_t k) {
   uint32_t i = hc_hash(k);
   for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
     const uint64_t v = c[i];
-    if (v == k) return true;
-    if (v == BB_KEY_NONE) return false;
+    if (v == k) return (int)i;
+    if (v == BB_KEY_NONE) return -1;
   }
-  return false;
+  return -1;
 }
 
-__device__ __forceinline__ void hc_put(uint64_t* c, uint32_t& used, uint64_t k) {
-  if (used >= (uint32_t)(HOT_CACHE * 3 / 4)) return;  // full: the key simply is not cached
+// slot of k after inserting it with `state` if it was not there; -1: the set is full
+__device__ __forceinline__ int hc_put(uint64_t* c, uint8_t* st, uint32_t& used, uint64_t k, uint8_t state) {
+  if (used >= (uint32_t)(HOT_CACHE * 3 / 4)) return -1;
   uint32_t i = hc_hash(k);
   for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
-    const uint64_t v = c[i];
-    if (v == k) return;
-    if (v == BB_KEY_NONE) {
+    if (c[i] == BB_KEY_NONE) {
       ++used;
       c[i] = k;
-      return;
+      st[i] = state;
+      return (int)i;
     }
   }
-}
-
-// Deletion WITHOUT tombstones (backward shift): a hot node's stored value changes hundreds of times, each change removes
-// a key from the set, and tombstones would soon turn every miss into a walk over the whole table.
-__device__ __forceinline__ void hc_erase(uint64_t* c, uint32_t& used, uint64_t k) {
-  uint32_t i = hc_hash(k);
-  for (int probe = 0; probe < HOT_CACHE; ++probe, i = (i + 1) & (HOT_CACHE - 1)) {
-    const uint64_t v = c[i];
-    if (v == BB_KEY_NONE) return;
-    if (v == k) break;
-    if (probe == HOT_CACHE - 1) return;
-  }
-  uint32_t j = i;
-  for (int step = 0; step < HOT_CACHE; ++step) {
-    j = (j + 1) & (HOT_CACHE - 1);
-    const uint64_t v = c[j];
-    if (v == BB_KEY_NONE) break;
-    const uint32_t h = hc_hash(v);  // may v move back to the hole at i?  only if its home is not inside (i, j]
-    const bool inside = i <= j ? (h > i && h <= j) : (h > i || h <= j);
-    if (!inside) {
-      c[i] = v;
-      i = j;
-    }
-  }
-  c[i] = BB_KEY_NONE;
-  if (used) --used;
+  return -1;
 }
 
 // the key the hook removes / adds for field f of value v (query:153-167): BB_KEY_NONE when there is nothing to do
@@ -970,66 +953,116 @@ __device__ __forceinline__ uint64_t hook_key(const Value& v, int f) {
   return canon_key(t, v.val[f]);
 }
 
-// one node's entry set of field f, as the retiring thread of k_merge_hot sees it
+// Write the set back (called by every thread of the CTA at a uniform point): HS_NEW keys are inserted into the global
+// overflow set, HS_GONE keys removed from it, the node's per-field entry counts follow.  `clear`: forget everything.
+__device__ __forceinline__ void hot_flush(const IndexArgs& ix, uint32_t node, uint64_t* cache, uint8_t* state, uint32_t* used, int* dx,
+                                          uint32_t* xc, uint32_t* flush, bool clear, uint32_t* err) {
+  for (int i = threadIdx.x; i < F * HOT_CACHE; i += HOT_T) {
+    const int f = i / HOT_CACHE;
+    const uint64_t k = cache[i];
+    if (k != BB_KEY_NONE) {
+      if (state[i] == HS_NEW) {
+        if (x_insert(ix, f, node, k) >= 0) atomicAdd(&dx[f], 1);
+        else atomicOr(err, ERR_XFULL);
+        state[i] = HS_CLEAN;
+      } else if (state[i] == HS_GONE) {
+        const int64_t slot = x_find(ix, f, node, k);
+        if (slot >= 0) {
+          x_remove_at(ix, f, slot);
+          atomicAdd(&dx[f], -1);
+        }
+        state[i] = HS_ABSENT;
+      }
+      if (clear) cache[i] = BB_KEY_NONE;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t v = *xc;
+    for (int f = 0; f < F; ++f) {
+      const uint32_t o = xcnt_get(v, f);
+      if (o != 0xFFu) v = (v & ~(0xFFu << (8 * f))) | ((uint32_t)max(0, min(255, (int)o + dx[f])) << (8 * f));
+      dx[f] = 0;
+      if (clear) used[f] = 0;
+    }
+    *xc = v;
+    *flush = 0;
+  }
+  __syncthreads();
+}
+
+// one node's entry set, as the retiring thread of k_merge_hot sees it
 struct HotIndex {
   const IndexArgs& ix;
   uint32_t node;
   uint64_t* prim;     // [F] shared: the node's entries in the dense columns
-  uint64_t* cache;    // [F][HOT_CACHE] shared: keys known present
+  uint64_t* cache;    // [F][HOT_CACHE] shared: the write-back set's keys ...
+  uint8_t* state;     // ... and what is known about each
   uint32_t* used;     // [F] shared
-  uint64_t* absent;   // [F] shared: one key known absent (the last one removed)
-  uint32_t& xcnt;
+  uint32_t* xc;       // shared: the node's GLOBAL overflow entries per field (8 bits each, 0xFF = many), as of the last flush
+  uint32_t* flush;    // shared: set when the set is full (the next pass boundary writes it back and empties it)
   uint32_t* err;
 
+  __device__ __forceinline__ void xc_add(int f, int d) {
+    const uint32_t v = xcnt_get(*xc, f);
+    if (v == 0xFFu) return;
+    const uint32_t n = (uint32_t)max(0, min(255, (int)v + d));
+    *xc = (*xc & ~(0xFFu << (8 * f))) | (n << (8 * f));
+  }
+  __device__ __forceinline__ bool in_global(int f, uint64_t k) { return xcnt_get(*xc, f) && x_find(ix, f, node, k) >= 0; }
+
   __device__ __forceinline__ void remove(int f, uint64_t k) {
-    if (k == BB_KEY_NONE || absent[f] == k) return;
+    if (k == BB_KEY_NONE) return;
     if (prim[f] == k) {
       prim[f] = BB_KEY_NONE;
-    } else if (xcnt_get(xcnt, f)) {
-      const int64_t slot = x_find(ix, f, node, k);
+      return;
+    }
+    uint64_t* c = cache + f * HOT_CACHE;
+    uint8_t* st = state + f * HOT_CACHE;
+    const int i = hc_find(c, k);
+    if (i >= 0) {
+      if (st[i] == HS_CLEAN) st[i] = HS_GONE;
+      else if (st[i] == HS_NEW) st[i] = HS_ABSENT;
+      return;
+    }
+    const int64_t slot = xcnt_get(*xc, f) ? x_find(ix, f, node, k) : -1;
+    if (hc_put(c, st, used[f], k, slot >= 0 ? HS_GONE : HS_ABSENT) < 0) {  // full: straight to the global set
+      *flush = 1;
       if (slot >= 0) {
         x_remove_at(ix, f, slot);
-        if (xcnt_get(xcnt, f) != 0xFFu) xcnt -= 1u << (8 * f);
+        xc_add(f, -1);
       }
     }
-    hc_erase(cache + f * HOT_CACHE, used[f], k);
-    absent[f] = k;
   }
-  __device__ __forceinline__ void add(int f, uint64_t k) {
-    if (k == BB_KEY_NONE) return;
+  // `looked_up`: the key's own thread has looked it up in the global set (`present`) in parallel with the others of its run
+  __device__ __forceinline__ void add(int f, uint64_t k, bool looked_up = false, bool present = false) {
+    if (k == BB_KEY_NONE || prim[f] == k) return;
     uint64_t* c = cache + f * HOT_CACHE;
-    if (hc_has(c, k)) return;
-    if (absent[f] == k) absent[f] = BB_KEY_NONE;
-    if (prim[f] != k && !(xcnt_get(xcnt, f) && x_find(ix, f, node, k) >= 0)) {
-      if (prim[f] == BB_KEY_NONE) {
-        prim[f] = k;
-      } else if (x_insert(ix, f, node, k) >= 0) {
-        if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
-      } else {
-        atomicOr(err, ERR_XFULL);
-        return;
+    uint8_t* st = state + f * HOT_CACHE;
+    const int i = hc_find(c, k);
+    if (i >= 0) {
+      if (st[i] == HS_GONE) {
+        st[i] = HS_CLEAN;
+      } else if (st[i] == HS_ABSENT) {
+        if (prim[f] == BB_KEY_NONE) prim[f] = k;
+        else st[i] = HS_NEW;
       }
+      return;
     }
-    hc_put(c, used[f], k);
-  }
-  // the same for a key whose thread has already looked it up in the index in parallel with the others of its run
-  // (`present`: found; otherwise verified absent) - no serial x_find on the retiring thread
-  __device__ __forceinline__ void add_looked_up(int f, uint64_t k, bool present) {
-    if (k == BB_KEY_NONE) return;
-    uint64_t* c = cache + f * HOT_CACHE;
-    if (hc_has(c, k)) return;  // an earlier update of this run brought it in
-    if (absent[f] == k) absent[f] = BB_KEY_NONE;
-    if (!present) {
-      if (prim[f] == BB_KEY_NONE) {
-        prim[f] = k;
-      } else if (x_insert(ix, f, node, k) >= 0) {
-        if (xcnt_get(xcnt, f) != 0xFFu) xcnt += 1u << (8 * f);
-      } else {
-        atomicOr(err, ERR_XFULL);
-        return;
-      }
+    if (!looked_up) present = in_global(f, k);
+    if (present) {
+      if (hc_put(c, st, used[f], k, HS_CLEAN) < 0) *flush = 1;  // (not remembered: it will be looked up again)
+      return;
     }
-    hc_put(c, used[f], k);
+    if (prim[f] == BB_KEY_NONE) {
+      prim[f] = k;
+      return;
+    }
+    if (hc_put(c, st, used[f], k, HS_NEW) < 0) {  // full: straight to the global set
+      *flush = 1;
+      if (x_insert(ix, f, node, k) >= 0) xc_add(f, +1);
+      else atomicOr(err, ERR_XFULL);
+    }
   }
 };
 
@@ -1037,9 +1070,11 @@ template <bool INDEXED, bool COMPACT = false>
 __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
   __shared__ __align__(16) uint4 s_row[ROW_Q];
   __shared__ __align__(16) uint4 s_win[HOT_T * UPD_Q];  // payload window
-  __shared__ uint64_t s_prim[F], s_k0[F], s_absent[F];
+  __shared__ uint64_t s_prim[F], s_k0[F];
   __shared__ uint64_t s_cache[INDEXED ? F * HOT_CACHE : 1];
-  __shared__ uint32_t s_used[F];
+  __shared__ uint8_t s_cst[INDEXED ? F * HOT_CACHE : 1];
+  __shared__ uint32_t s_used[F], s_xc, s_flush;
+  __shared__ int s_dx[F];
   __shared__ uint32_t s_cnt[HOT_WARPS], s_stop[HOT_WARPS], s_need[HOT_WARPS];
   __shared__ unsigned long long s_claim;
   __shared__ uint8_t s_found[INDEXED ? HOT_T : 1];  // per window position: fields whose added key the thread found in the index
@@ -1058,11 +1093,14 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
     if (INDEXED) {
       if (tid < F) {
         s_prim[tid] = ((a.ix.mask >> tid) & 1u) ? a.ix.pcol[tid][hkey] : BB_KEY_NONE;
-        s_absent[tid] = BB_KEY_NONE;
         s_used[tid] = 0;
+        s_dx[tid] = 0;
       }
+      if (tid == 0) s_flush = 0;
       for (int i = tid; i < F * HOT_CACHE; i += HOT_T) s_cache[i] = BB_KEY_NONE;
     }
+    __syncthreads();
+    if (INDEXED && tid == 0) s_xc = s_row[row_chunk(7)].y;  // the node's global overflow entries per field
     while (true) {  // one window of the segment per turn
       const uint64_t gp = gp0 + tid;
       const uint64_t it = gp < a.n ? a.sorted[gp] : ~0ull;
@@ -1177,7 +1215,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         if (INDEXED) {  // which retired updates does the hook have anything to do for?
           bool need = false;
           if (retiring && tid < end - 1) {
-            const uint32_t xc = s_row[row_chunk(7)].y;  // overflow entries of the node per field, as the pass begins
+            const uint32_t xc = s_xc;  // the node's GLOBAL overflow entries per field
             uint32_t found = 0;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
@@ -1185,11 +1223,14 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
               if (k == BB_KEY_NONE) continue;
               if (k == s_k0[f]) {
                 need = need || tid == end - 2;  // added, then removed again by the next update's hook
-              } else if (!hc_has(s_cache + f * HOT_CACHE, k)) {
-                // not known present: look it up NOW, every thread of the run in parallel (the retiring thread would
-                // walk the overflow set once per key, one global round trip after the other)
+              } else if (s_prim[f] != k) {
+                const int i = hc_find(s_cache + f * HOT_CACHE, k);
+                const uint8_t st = i >= 0 ? s_cst[f * HOT_CACHE + i] : 0;
+                if (st == HS_CLEAN || st == HS_NEW) continue;  // known present: nothing to do
                 need = true;
-                if (s_prim[f] == k || (xcnt_get(xc, f) && x_find(a.ix, f, hkey, k) >= 0)) found |= 1u << f;
+                // nothing known about it: look it up in the global set NOW, every thread of the run in parallel (the
+                // retiring thread would walk the overflow set once per key, one global round trip after the other)
+                if (i < 0 && xcnt_get(xc, f) && x_find(a.ix, f, hkey, k) >= 0) found |= 1u << f;
               }
             }
             s_found[tid] = (uint8_t)found;
@@ -1201,8 +1242,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         if (retiring) {
           if (tid == end - 1) {  // its copy is the exact state after the retired updates
             if (INDEXED) {
-              uint32_t xcnt = r.xcnt;
-              HotIndex hx{a.ix, hkey, s_prim, s_cache, s_used, s_absent, xcnt, a.err};
+              HotIndex hx{a.ix, hkey, s_prim, s_cache, s_cst, s_used, &s_xc, &s_flush, a.err};
               if (end - 1 > base) {
 #pragma unroll
                 for (int f = 0; f < F; ++f)
@@ -1224,7 +1264,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
                         if (j == end - 2) hx.add(f, k);  // k0 was just removed above: the general path
                         continue;
                       }
-                      hx.add_looked_up(f, k, (s_found[j] >> f) & 1u);
+                      hx.add(f, k, true, (s_found[j] >> f) & 1u);
                     }
                   }
                 }
@@ -1236,7 +1276,6 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
                 if (kr != akey[f]) hx.remove(f, kr);  // (remove k, then add k: k is in the set afterwards either way)
                 hx.add(f, akey[f]);
               }
-              r.xcnt = xcnt;
             }
             pack_row(s_row, r);
           }
@@ -1250,6 +1289,7 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
         }
         base = end;
         __syncthreads();  // the published row (and the index cache) are visible; s_stop / s_need may be rewritten
+        if (INDEXED && s_flush) hot_flush(a.ix, hkey, s_cache, s_cst, s_used, s_dx, &s_xc, &s_flush, true, a.err);
       }
       {  // ---- the window's results: ONE slot claim, then verdicts and entries
         const bool emit = mine && BB_DEC_ACCEPTED(fin & ~RES_ECHO) && !(fin & RES_ECHO);
@@ -1296,6 +1336,11 @@ __global__ void __launch_bounds__(HOT_T) k_merge_hot(const MergeArgs a) {
       if (nseg < HOT_T) break;  // the segment ended inside this window
     }
     __syncthreads();
+    if (INDEXED) {  // the write-back set goes home: every thread takes its share of the inserts and removes
+      hot_flush(a.ix, hkey, s_cache, s_cst, s_used, s_dx, &s_xc, &s_flush, false, a.err);
+      if (tid == 0) reinterpret_cast<uint32_t*>(&s_row[row_chunk(7)])[1] = s_xc;  // the row's count of overflow entries
+      __syncthreads();
+    }
     if (tid < ROW_Q) a.table[(uint64_t)hkey * ROW_Q + tid] = s_row[tid];
     if (INDEXED && tid < F && ((a.ix.mask >> tid) & 1u)) a.ix.pcol[tid][hkey] = s_prim[tid];
   }
