@@ -242,3 +242,16 @@ def route_on_host(world: int, rank: int, batch, dist, merge_fn, key_bits: int = 
     for k, (_, dst) in arrays.items():
         dst.view(np.uint8).reshape(-1)[:] = recv[k].numpy()[: n_recv * ROW_BYTES[k]]
     return merge_fn(got), got
+
+
+def merge_batch_on_host(world: int, rank: int, batch, dist, merge_fn, pieces: int = 4, key_bits: int = 0):
+    """The replay order of bb_router_merge_batch (include/bullet_b200.h) restated over `route_on_host`: every rank's
+    batch is cut into `pieces` pieces in arrival order; piece j of every rank is routed and merged before piece j + 1 -
+    a shard replays piece by piece, inside a piece in (source rank, arrival index) order.  -> [(changes, received batch)]
+    per piece.  For the gloo tests; the product path is the native router."""
+    chunk = -(-batch.n // pieces) if batch.n else 0
+    out = []
+    for j in range(pieces):
+        lo, hi = min(j * chunk, batch.n), min((j + 1) * chunk, batch.n)
+        out.append(route_on_host(world, rank, batch.slice(lo, hi), dist, merge_fn, key_bits))
+    return out

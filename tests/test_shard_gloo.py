@@ -88,3 +88,57 @@ def test_sharded_replay_equals_single_peer(world, key_bits):
         assert np.array_equal(lpath, np.concatenate(want_path))
         assert np.array_equal(user, np.concatenate(want_user))
         assert np.array_equal(decision, np.concatenate(want_dec))
+
+
+def _worker_pieces(rank, world, port, q, key_bits, pieces):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        table = synth.make_table(N_REC, synth.rng_for(3))
+        batch = synth.make_batch(table, N_UPD, synth.rng_for(3, salt=10 + rank), keys="zipf")
+        ids, rows = _shard_ids(rank, world, key_bits)
+        orc = TypedOracle(capi.make_config(shard.shard_capacity(world, key_bits, N_REC) + 1, **synth.synth_ranks(N_REC)))
+        orc.load(rows, table.rows[ids])
+        res = shard.merge_batch_on_host(world, rank, batch, dist, orc.merge, pieces, key_bits)
+        q.put((rank, orc.table[rows.astype(np.int64)].copy(), np.concatenate([ch.decision for ch, _ in res]),
+               np.concatenate([got.head["user"] for _, got in res])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_piecewise_host_entry_order():
+    """The replay order of bb_router_merge_batch (piece by piece, inside a piece by source rank), on 2 ranks over gloo:
+    equal to ONE oracle replaying rank 0's piece 0, rank 1's piece 0, rank 0's piece 1, ..."""
+    world, pieces, key_bits = 2, 3, KEY_BITS
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pieces, args=(r, world, port, q, key_bits, pieces)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        r = q.get(timeout=120)
+        results[r[0]] = r[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    table = synth.make_table(N_REC, synth.rng_for(3))
+    ref = TypedOracle(capi.make_config(N_REC, **synth.synth_ranks(N_REC)))
+    ref.load(np.arange(N_REC), table.rows)
+    batches = [synth.make_batch(table, N_UPD, synth.rng_for(3, salt=10 + r), keys="zipf") for r in range(world)]
+    chunk = -(-N_UPD // pieces)
+    want = {r: ([], []) for r in range(world)}
+    for j in range(pieces):
+        for src in range(world):
+            b = batches[src].slice(j * chunk, min((j + 1) * chunk, N_UPD))
+            dec = ref.merge(b).decision
+            for r in range(world):
+                mine = np.nonzero(shard.owner_of(b.path_id, world, key_bits) == r)[0]
+                want[r][0].append(dec[mine])
+                want[r][1].append(b.head["user"][mine])
+    for r in range(world):
+        rows, decision, user = results[r]
+        ids, _ = _shard_ids(r, world, key_bits)
+        assert np.array_equal(rows, ref.table[ids])
+        assert np.array_equal(decision, np.concatenate(want[r][0])) and np.array_equal(user, np.concatenate(want[r][1]))
