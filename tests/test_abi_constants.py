@@ -30,3 +30,14 @@ def test_row_and_batch_sizes_match_the_header():
     row = defines("BB_ROW_")
     assert (row["BB_ROW_M_PRESENT"], row["BB_ROW_V_PRESENT"], row["BB_ROW_ALIAS"]) == (
         codec.ROW_M_PRESENT, codec.ROW_V_PRESENT, codec.ROW_ALIAS)
+
+
+def test_slots_and_collect_flags_match_the_header():
+    slots = defines("BB_SLOT_") | defines("BB_NO_")
+    assert slots["BB_NO_SLOT"] == codec.NO_SLOT and slots["BB_SLOT_ECHO"] == codec.SLOT_ECHO == codec.NO_SLOT - 1
+    assert defines("BB_COLLECT_")["BB_COLLECT_FILTER_RECORDS"] == codec.COLLECT_FILTER_RECORDS
+    # the JS shim mirrors the flags it sets
+    js = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "js", "bullet-b200.js")).read()
+    for name in ("BB_CFG_POST_GETDATA", "BB_CFG_EXACT_ORDER"):
+        m = re.search(r"const\s+" + name + r"\s*=\s*(\d+)", js)
+        assert m and int(m.group(1)) == defines("BB_CFG_")[name], name
